@@ -1,0 +1,186 @@
+/*
+ * ba_gpu.h -- C ABI of the B200-native windowed bundle-adjustment solver.
+ *
+ * Drop-in boundary for the Ceres Problem/Solve path of
+ * martinxluptak/3dsmc-bundle-adjustment (citations relative to the reference):
+ *
+ *   ba_gpu_create   <- ceres::Problem + Solver::Options construction
+ *                      src/OptimizationUtils.cpp:218-226,
+ *                      headers/BundleAdjustmentConfig.h:44-67
+ *   ba_gpu_upload   <- AddParameterBlock / AddResidualBlock /
+ *                      SetParameterBlockConstant
+ *                      src/OptimizationUtils.cpp:236-241, 251-254, 275, 279-294, 299
+ *   ba_gpu_solve    <- ceres::Solve            src/OptimizationUtils.cpp:300
+ *   ba_gpu_download <- Ceres writing the optimum back into the caller-owned
+ *                      pose / point / intrinsics blocks
+ *                      (pose.data() :251, map_point.point.data() :275,
+ *                       intrinsics_optimized.data() :236)
+ *
+ * Plain pointers and sizes only; no C++/torch types. All doubles are IEEE fp64,
+ * all indices int32. Every function returns 0 on success and a negative
+ * BA_ERR_* code on failure (never throws, never aborts);
+ * ba_gpu_last_error() gives the message.  A context is not thread-safe; use one
+ * per host thread.  There is NO CPU fallback: without a CUDA device
+ * ba_gpu_create fails with BA_ERR_CUDA.
+ */
+#ifndef BA_GPU_H
+#define BA_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ba_gpu_ctx ba_gpu_ctx;
+
+enum {
+  BA_OK = 0,
+  BA_ERR_INVALID = -1,  /* bad argument / unsorted or out-of-range indices */
+  BA_ERR_CUDA = -2,     /* CUDA runtime error (message has the detail) */
+  BA_ERR_STATE = -3,    /* call order (e.g. solve before upload) */
+  BA_ERR_UNSUPPORTED = -4, /* option combination not implemented */
+  BA_ERR_NUMERIC = -5,  /* non-finite cost at the initial point */
+  BA_ERR_COMM = -6      /* NCCL error */
+};
+
+enum {
+  BA_SOLVER_AUTO = 0,              /* explicit if reduced dim <= explicit_max_dim */
+  BA_SOLVER_EXPLICIT_CHOLESKY = 1, /* explicit Schur complement + dense Cholesky
+                                      (== Ceres DENSE_SCHUR / SPARSE_SCHUR step) */
+  BA_SOLVER_IMPLICIT_PCG = 2       /* matrix-free Schur + block-Jacobi PCG
+                                      (== Ceres ITERATIVE_SCHUR + SCHUR_JACOBI) */
+};
+
+enum {
+  BA_TERM_NO_CONVERGENCE = 0, /* max_num_iterations reached */
+  BA_TERM_GRADIENT = 1,
+  BA_TERM_PARAMETER = 2,
+  BA_TERM_FUNCTION = 3,
+  BA_TERM_MIN_RADIUS = 4,
+  BA_TERM_FAILURE = 5
+};
+
+/* Knobs. The first block keeps the reference's names
+ * (ceresGlobalProblem, headers/BundleAdjustmentConfig.h:47-50, 64-65). */
+typedef struct ba_gpu_options {
+  double HUB_P_REPR;        /* Huber delta, reprojection      (:47) */
+  double WEIGHT_INTRINSICS; /* intrinsics prior weight         (:48) */
+  double WEIGHT_UNPR;       /* depth-prior weight              (:49) */
+  double HUB_P_UNPR;        /* Huber delta, depth prior        (:50) */
+  int32_t max_num_iterations; /* options.max_num_iterations    (:64) */
+  double eta;               /* options.eta (PCG forcing term)  (:65) */
+  /* cost model: REF mode = (1,1) is the reference's cost; NS mode = (0,0) is
+   * reprojection only with fixed intrinsics (north-star subset) */
+  int32_t use_depth_prior;
+  int32_t optimize_intrinsics;
+  int32_t solver;           /* BA_SOLVER_* */
+  int32_t explicit_max_dim; /* AUTO switch point (reduced system dimension) */
+  int64_t n_obs_total;      /* weight normaliser 1/N; 0 -> n_obs of the upload
+                               (set to the global count when point-sharded) */
+  /* Ceres 2.0.0 trust-region defaults */
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double initial_trust_region_radius, max_trust_region_radius, min_trust_region_radius;
+  double min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
+  int32_t max_num_consecutive_invalid_steps;
+  int32_t jacobi_scaling;
+  int32_t max_linear_solver_iterations, min_linear_solver_iterations;
+  int32_t residual_reset_period;
+  /* execution */
+  int32_t device;          /* CUDA ordinal; <0 = current device */
+  int32_t poll_interval;   /* host polls the device-side LM / PCG termination
+                              flag every this many iterations (>=1) */
+  int32_t use_cuda_graph;  /* capture the PCG iteration in a CUDA graph */
+} ba_gpu_options;
+
+/* Per-iteration record, written by the device-side LM controller. Mirrors
+ * ceres::IterationSummary for the fields the parity tests compare. */
+typedef struct ba_gpu_iter {
+  int32_t iteration, step_is_valid, step_is_successful, linear_iters;
+  double cost, cost_change, gradient_max_norm, step_norm, relative_decrease,
+      radius, model_cost_change;
+} ba_gpu_iter;
+
+typedef struct ba_gpu_summary {
+  int32_t termination, num_iterations, num_successful, num_unsuccessful;
+  double initial_cost, final_cost;
+  int64_t total_linear_iters;
+  int32_t solver_used;       /* BA_SOLVER_EXPLICIT_CHOLESKY or _IMPLICIT_PCG */
+  int32_t reduced_dim;
+  double solve_ms;           /* CUDA-event time of ba_gpu_solve on its stream */
+  int64_t kernel_launches;   /* kernels launched by this solve */
+} ba_gpu_summary;
+
+void ba_gpu_default_options(ba_gpu_options *o);
+
+int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **ctx);
+void ba_gpu_destroy(ba_gpu_ctx *ctx);
+/* ctx may be NULL: message of the last failed ba_gpu_create on this thread */
+const char *ba_gpu_last_error(const ba_gpu_ctx *ctx);
+/* replaces the options of an existing context (takes effect at next upload) */
+int ba_gpu_set_options(ba_gpu_ctx *ctx, const ba_gpu_options *o);
+
+/* Host buffers in, canonical reference order: observation k is
+ * the k-th admissible (keyframe, landmark) pair of the reference's loop
+ * (src/OptimizationUtils.cpp:244, 257) => cam_idx non-decreasing.
+ *   pose7 [n_cam*7]  (qx,qy,qz,qw,tx,ty,tz), camera->world, Sophus storage
+ *                    order (headers/sophus/se3.hpp:356-365)
+ *   fixed_cam        index of the constant pose (:299), or -1
+ *   pt3   [n_pt*3]   world points; pt_idx = order of first appearance (:271-276)
+ *   uv2   [n_obs*2]  pixels; depth [n_obs] metres or NULL (required iff
+ *                    use_depth_prior)
+ *   intr4 (fx,fy,cx,cy) initial value; intr_prior4 = intrinsics_initial (:238) */
+int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7,
+                  int32_t fixed_cam, int32_t n_pt, const double *pt3,
+                  int32_t n_obs, const int32_t *cam_idx, const int32_t *pt_idx,
+                  const double *uv2, const double *depth, const double intr4[4],
+                  const double intr_prior4[4]);
+
+int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary);
+/* copies up to cap trace records of the last solve; returns the count */
+int ba_gpu_get_trace(ba_gpu_ctx *ctx, ba_gpu_iter *out, int32_t cap);
+
+int ba_gpu_download(ba_gpu_ctx *ctx, double *pose7, double *pt3, double intr4[4]);
+
+/* ---- test hooks (parity tests call these through ctypes) ---- */
+/* Linearisation at the current device state, transposed back to the canonical
+ * row-major per-observation layout of the oracle: R = 2 + use_depth_prior.
+ *   r [n_obs*R], Jc [n_obs*R*6], Jp [n_obs*R*3], Jk [n_obs*2*4],
+ *   g_c [n_cam*6], g_p [n_pt*3], g_k [4]; any pointer may be NULL. */
+int ba_gpu_eval(ba_gpu_ctx *ctx, double *r, double *Jc, double *Jp, double *Jk,
+                double *cost, double *g_c, double *g_p, double *g_k);
+/* Device-built index arrays: stable point-major permutation and CSR pointers */
+int ba_gpu_get_indices(ba_gpu_ctx *ctx, int32_t *perm_pt_major,
+                       int32_t *pt_rowptr, int32_t *cam_rowptr);
+/* y = S x (reduced camera system at the current state, given radius), unscaled
+ * coordinates, x,y [n_cam*6] host buffers. Runs the implicit-Schur kernels. */
+int ba_gpu_schur_matvec(ba_gpu_ctx *ctx, double radius, const double *x, double *y);
+/* out7[i] = pose7[i] * exp(delta6[i]) on the device (Sophus semantics) */
+int ba_gpu_se3_plus(ba_gpu_ctx *ctx, int32_t n, const double *pose7,
+                    const double *delta6, double *out7);
+
+/* ---- measurement hooks (bench.py) ---- */
+enum {
+  BA_KERNEL_LINEARIZE = 0,   /* camera-major residual+Jacobian kernel */
+  BA_KERNEL_SCHUR_MATVEC = 1 /* one implicit-Schur product (both passes) */
+};
+/* Launches kernel `which` `iters` times on the context stream between two CUDA
+ * events (after `warmup` untimed launches); *ms_avg = mean ms per launch. If
+ * flush_l2 != 0 a >L2-sized buffer is rewritten before every timed launch and
+ * each launch is timed by its own event pair. */
+int ba_gpu_time_kernel(ba_gpu_ctx *ctx, int32_t which, int32_t warmup,
+                       int32_t iters, int32_t flush_l2, float *ms_avg);
+/* kernels launched by this context since creation */
+int64_t ba_gpu_launch_count(const ba_gpu_ctx *ctx);
+
+/* ---- multi-GPU: one process per GPU, points sharded ---- */
+/* rank 0 makes the id (128 bytes), the launcher broadcasts it, every rank
+ * calls comm_init before upload. Uses NCCL (dlopen'ed libnccl.so.2). */
+int ba_gpu_comm_unique_id(char id128[128]);
+int ba_gpu_comm_init(ba_gpu_ctx *ctx, const char id128[128], int32_t rank,
+                     int32_t n_ranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
