@@ -1,0 +1,1170 @@
+// ba_gpu.cu -- C-ABI of the B200-native windowed bundle-adjustment solver
+// (include/ba_gpu.h).  Host orchestration only: every floating-point operation of
+// the solve runs in the sm_100a kernels of ba_kernels.cuh; the host enqueues
+// whole LM iterations and polls a device-side termination flag.
+//
+// Boundary replaced: the ceres::Problem / ceres::Solve calls of
+// src/OptimizationUtils.cpp:218-300 (reference paths relative to /root/reference).
+// There is NO CPU fallback: without a CUDA device ba_gpu_create fails.
+#include "../../include/ba_gpu.h"
+#include "ba_kernels.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------ NCCL (dlopen)
+typedef struct ncclComm *ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclSum_ = 0, ncclMax_ = 2 };
+enum { ncclFloat64_ = 8 };
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static bool nccl_load(std::string *err) {
+  if (g_nccl.lib) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) {
+    *err = std::string("dlopen libnccl.so.2 failed: ") + dlerror();
+    return false;
+  }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+    *err = "libnccl is missing required symbols";
+    return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------ context
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct ba_gpu_ctx {
+  ba_gpu_options opt;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  bool uploaded = false, linearized = false;
+  std::vector<Buf *> bufs;
+
+  // sizes
+  int n_cam = 0, n_pt = 0, n_obs = 0, fixed_cam = -1, n_free = 0, n_items = 0;
+  int depth = 0, nk = 0;  // cost-model switches in force
+  int solver = 0, n_red = 0;
+  int nblk_obs = 0, nblk_ent = 0, nblk_cam = 0, nblk_pt = 0, n_tiles = 0, nblk_item = 0;
+  CostParams cp;
+  LmOptions lo;
+
+  // problem
+  Buf pose, pose_c, pt, pt_c, intr, intr_c, intr_prior;
+  Buf cam_idx, pt_idx, uv, depthv;
+  Buf perm, pt_rowptr, cam_rowptr, pt_cnt, cam_cnt, cursor, err_flag;
+  Buf pm_cam, pm_pt, pm_uv, pm_depth;
+  Buf items, item_ptr, item_cnt, cam_slot;
+  // Jacobian planes
+  Buf jcm, jpm;
+  JPlanes Jc_, Jp_;
+  // scaling / diag / gradient / blocks
+  Buf sc, sp, sk, dc, dp, dk, gc, gp, gk, U, Uck, Ukk, V, Vinv, Wk, tg, t, yc, yp, yk, rk, Jkk;
+  Buf one_c, one_p, one_k;
+  // PCG
+  Buf b, x, r, z, p, q, Minv;
+  // partials
+  Buf part_blk, part6, part21, part_ex, part_kk;
+  Buf pc_lin, pc_cand, pc_mcc, pe_gmax, pe_xn, pe_step, pcam_rho, pcam_bb, pcam_pq, pcam_Q;
+  // explicit solver
+  Buf W, WV, S, rhs, blk_i, blk_j, blk_cam, pair_ptr, pair_a, pair_b;
+  int n_blk = 0;
+  // controller
+  Buf st, trace;
+  LmState *h_st = nullptr;  // pinned
+  ba_gpu_summary last_summary;
+  std::vector<BaIterRec> h_trace;
+  // L2 flush scratch for ba_gpu_time_kernel
+  Buf flush;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_ranks = 1;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(ba_gpu_ctx *c, int code, const char *fmt, ...) {
+  char tmp[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tmp, sizeof(tmp), fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = tmp;
+  else
+    g_create_err = tmp;
+  return code;
+}
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(ctx, BA_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                               \
+  } while (0)
+
+static int buf_reserve(ba_gpu_ctx *ctx, Buf &b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.cap >= bytes) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + bytes / 8 + 256;  // head-room for sliding windows
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) return fail(ctx, BA_ERR_CUDA, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+  b.cap = want;
+  if (std::find(ctx->bufs.begin(), ctx->bufs.end(), &b) == ctx->bufs.end()) ctx->bufs.push_back(&b);
+  return 0;
+}
+#define RES(buf, bytes)                                      \
+  do {                                                       \
+    int rc_ = buf_reserve(ctx, ctx->buf, (size_t)(bytes));   \
+    if (rc_) return rc_;                                     \
+  } while (0)
+
+template <class T>
+static T *P(const Buf &b) {
+  return reinterpret_cast<T *>(b.p);
+}
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+#define LAUNCH(kern, grid, block, smem, ...)                              \
+  do {                                                                    \
+    if ((grid) > 0) {                                                     \
+      kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);        \
+      ctx->launches++;                                                    \
+    }                                                                     \
+  } while (0)
+
+// dispatch on the cost-model switches (template parameters of the kernels)
+#define DISPATCH_DK(D, K, ...)          \
+  do {                                  \
+    if ((D) && (K)) {                   \
+      constexpr int DD = 1, KK = 4;     \
+      __VA_ARGS__;                      \
+    } else if ((D)) {                   \
+      constexpr int DD = 1, KK = 0;     \
+      __VA_ARGS__;                      \
+    } else if ((K)) {                   \
+      constexpr int DD = 0, KK = 4;     \
+      __VA_ARGS__;                      \
+    } else {                            \
+      constexpr int DD = 0, KK = 0;     \
+      __VA_ARGS__;                      \
+    }                                   \
+  } while (0)
+#define DISPATCH_D(D, ...)          \
+  do {                              \
+    if ((D)) {                      \
+      constexpr int DD = 1;         \
+      __VA_ARGS__;                  \
+    } else {                        \
+      constexpr int DD = 0;         \
+      __VA_ARGS__;                  \
+    }                               \
+  } while (0)
+
+// ------------------------------------------------------------------ options
+extern "C" void ba_gpu_default_options(ba_gpu_options *o) {
+  memset(o, 0, sizeof(*o));
+  // headers/BundleAdjustmentConfig.h:47-50, 64-65
+  o->HUB_P_REPR = 1e-3;
+  o->WEIGHT_INTRINSICS = 1e-6;
+  o->WEIGHT_UNPR = 10.0;
+  o->HUB_P_UNPR = 1e-3;
+  o->max_num_iterations = 75;
+  o->eta = 1e-6;
+  o->use_depth_prior = 1;
+  o->optimize_intrinsics = 1;
+  o->solver = BA_SOLVER_AUTO;
+  o->explicit_max_dim = 160;
+  o->n_obs_total = 0;
+  // ceres 2.0.0 Solver::Options defaults
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->max_linear_solver_iterations = 500;
+  o->min_linear_solver_iterations = 0;
+  o->residual_reset_period = 10;
+  o->device = -1;
+  o->poll_interval = 10;
+  o->use_cuda_graph = 0;
+}
+
+static int check_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
+  if (!(o->HUB_P_REPR > 0.0) || !(o->HUB_P_UNPR > 0.0) || !(o->WEIGHT_UNPR >= 0.0) || !(o->WEIGHT_INTRINSICS >= 0.0))
+    return fail(ctx, BA_ERR_INVALID, "Huber deltas must be > 0 and weights >= 0");
+  if (o->max_num_iterations < 0 || o->poll_interval < 1) return fail(ctx, BA_ERR_INVALID, "bad iteration options");
+  if (o->solver < BA_SOLVER_AUTO || o->solver > BA_SOLVER_IMPLICIT_PCG) return fail(ctx, BA_ERR_INVALID, "bad solver");
+  if (!(o->initial_trust_region_radius > 0.0)) return fail(ctx, BA_ERR_INVALID, "bad trust-region radius");
+  return 0;
+}
+
+extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
+  if (!o || !out) return fail(nullptr, BA_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, BA_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+  ba_gpu_ctx *ctx = new ba_gpu_ctx();
+  int rc = check_options(ctx, o);
+  if (rc) {
+    g_create_err = ctx->err;
+    delete ctx;
+    return rc;
+  }
+  ctx->opt = *o;
+  int dev = o->device;
+  if (dev < 0) cudaGetDevice(&dev);
+  ctx->device = dev;
+  auto bail = [&](const char *what, cudaError_t ce) {
+    fail(nullptr, BA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
+    delete ctx;
+    return BA_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(dev)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (prop.major < 10) {
+    fail(nullptr, BA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    delete ctx;
+    return BA_ERR_CUDA;
+  }
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaMallocHost((void **)&ctx->h_st, sizeof(LmState))) != cudaSuccess) return bail("cudaMallocHost", e);
+  cudaFuncSetAttribute(k_cholesky_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  *out = ctx;
+  return BA_OK;
+}
+
+extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  for (Buf *b : ctx->bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->h_st) cudaFreeHost(ctx->h_st);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *ba_gpu_last_error(const ba_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int ba_gpu_set_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
+  if (!ctx || !o) return BA_ERR_INVALID;
+  int rc = check_options(ctx, o);
+  if (rc) return rc;
+  const int dev = ctx->opt.device;
+  ctx->opt = *o;
+  ctx->opt.device = dev;
+  ctx->uploaded = false;
+  return BA_OK;
+}
+
+extern "C" int64_t ba_gpu_launch_count(const ba_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------ upload
+static void set_planes(JPlanes &J, double *base, size_t n_pad, int depth, int nk) {
+  // every plane is n_pad double2 (or double) long and 256-byte aligned
+  size_t off = 0;
+  auto take2 = [&]() {
+    double2 *p = reinterpret_cast<double2 *>(base + off);
+    off += 2 * n_pad;
+    return p;
+  };
+  auto take1 = [&]() {
+    double *p = base + off;
+    off += n_pad;
+    return p;
+  };
+  memset(&J, 0, sizeof(J));
+  J.r = take2();
+  for (int k = 0; k < 6; ++k) J.Jc[k] = take2();
+  for (int k = 0; k < 3; ++k) J.Jp[k] = take2();
+  if (depth) {
+    J.r3 = take1();
+    for (int k = 0; k < 6; ++k) J.Jc3[k] = take1();
+    for (int k = 0; k < 3; ++k) J.Jp3[k] = take1();
+  }
+  if (nk) {
+    J.Jk[0] = take2();
+    J.Jk[1] = take2();
+  }
+}
+static size_t planes_doubles(size_t n_pad, int depth, int nk) { return n_pad * (20 + (depth ? 10 : 0) + (nk ? 4 : 0)); }
+
+__global__ void k_fill(double *p, size_t n, double v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_slots(int n_cam, int fixed_cam, int32_t *slot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_cam) slot[c] = (c == fixed_cam) ? -1 : (fixed_cam >= 0 && c > fixed_cam ? c - 1 : c);
+}
+
+// host-side pair list of the explicit Schur complement: for every block pair
+// (i <= j) of free-camera slots the (obs_a, obs_b) pairs that share a point, in
+// point-major order.  Pure index plumbing; values never touch the host.
+static int build_pair_list(ba_gpu_ctx *ctx, const int32_t *cam_idx, const int32_t *pt_idx) {
+  const int n_obs = ctx->n_obs, n_pt = ctx->n_pt, nf = ctx->n_free;
+  std::vector<int32_t> rowptr((size_t)n_pt + 1, 0), perm((size_t)n_obs);
+  for (int i = 0; i < n_obs; ++i) rowptr[pt_idx[i] + 1]++;
+  for (int p = 0; p < n_pt; ++p) rowptr[p + 1] += rowptr[p];
+  {
+    std::vector<int32_t> cur(rowptr.begin(), rowptr.end() - 1);
+    for (int i = 0; i < n_obs; ++i) perm[cur[pt_idx[i]]++] = i;
+  }
+  auto slot = [&](int c) { return c == ctx->fixed_cam ? -1 : (ctx->fixed_cam >= 0 && c > ctx->fixed_cam ? c - 1 : c); };
+  const size_t nb_all = (size_t)nf * (nf + 1) / 2;
+  auto bidx = [&](int i, int j) { return (size_t)i * nf - (size_t)i * (i - 1) / 2 + (j - i); };
+  std::vector<int64_t> cnt(nb_all + 1, 0);
+  for (int p = 0; p < n_pt; ++p)
+    for (int a = rowptr[p]; a < rowptr[p + 1]; ++a) {
+      const int sa = slot(cam_idx[perm[a]]);
+      if (sa < 0) continue;
+      for (int b = rowptr[p]; b < rowptr[p + 1]; ++b) {
+        const int sb = slot(cam_idx[perm[b]]);
+        if (sb < sa) continue;
+        cnt[bidx(sa, sb) + 1]++;
+      }
+    }
+  // keep every diagonal block (damping only when a camera has no observation)
+  std::vector<int32_t> bi, bj, bc, pptr;
+  std::vector<int64_t> start(nb_all, -1);
+  int64_t total = 0;
+  std::vector<int> slot_cam(nf);
+  for (int c = 0; c < ctx->n_cam; ++c)
+    if (slot(c) >= 0) slot_cam[slot(c)] = c;
+  for (int i = 0; i < nf; ++i)
+    for (int j = i; j < nf; ++j) {
+      const size_t k = bidx(i, j);
+      if (cnt[k + 1] == 0 && i != j) continue;
+      start[k] = total;
+      bi.push_back(i);
+      bj.push_back(j);
+      bc.push_back(slot_cam[i]);
+      pptr.push_back((int32_t)total);
+      total += cnt[k + 1];
+    }
+  if (total > 0x7fffffff) return fail(ctx, BA_ERR_UNSUPPORTED, "explicit Schur pair list too large");
+  pptr.push_back((int32_t)total);
+  std::vector<int32_t> pa((size_t)total), pb((size_t)total);
+  std::vector<int64_t> cur(start);
+  for (int p = 0; p < n_pt; ++p)
+    for (int a = rowptr[p]; a < rowptr[p + 1]; ++a) {
+      const int sa = slot(cam_idx[perm[a]]);
+      if (sa < 0) continue;
+      for (int b = rowptr[p]; b < rowptr[p + 1]; ++b) {
+        const int sb = slot(cam_idx[perm[b]]);
+        if (sb < sa) continue;
+        const int64_t w = cur[bidx(sa, sb)]++;
+        pa[w] = perm[a];
+        pb[w] = perm[b];
+      }
+    }
+  ctx->n_blk = (int)bi.size();
+  RES(blk_i, bi.size() * 4);
+  RES(blk_j, bi.size() * 4);
+  RES(blk_cam, bi.size() * 4);
+  RES(pair_ptr, pptr.size() * 4);
+  RES(pair_a, pa.size() * 4);
+  RES(pair_b, pb.size() * 4);
+  CK(cudaMemcpyAsync(ctx->blk_i.p, bi.data(), bi.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->blk_j.p, bj.data(), bj.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->blk_cam.p, bc.data(), bc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->pair_ptr.p, pptr.data(), pptr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (total) {
+    CK(cudaMemcpyAsync(ctx->pair_a.p, pa.data(), pa.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->pair_b.p, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));  // host vectors die here
+  return 0;
+}
+
+extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7, int32_t fixed_cam, int32_t n_pt,
+                             const double *pt3, int32_t n_obs, const int32_t *cam_idx, const int32_t *pt_idx,
+                             const double *uv2, const double *depth, const double intr4[4], const double intr_prior4[4]) {
+  if (!ctx) return BA_ERR_INVALID;
+  ctx->uploaded = false;
+  ctx->linearized = false;
+  const ba_gpu_options &o = ctx->opt;
+  if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !pose7 || !intr4 || (n_pt > 0 && !pt3) ||
+      (n_obs > 0 && (!cam_idx || !pt_idx || !uv2)))
+    return fail(ctx, BA_ERR_INVALID, "bad sizes or null buffers");
+  if (fixed_cam >= n_cam) return fail(ctx, BA_ERR_INVALID, "fixed_cam out of range");
+  if (o.use_depth_prior && n_obs > 0 && !depth) return fail(ctx, BA_ERR_INVALID, "depth required when use_depth_prior");
+  if (o.optimize_intrinsics && !intr_prior4) return fail(ctx, BA_ERR_INVALID, "intr_prior4 required when optimize_intrinsics");
+  CK(cudaSetDevice(ctx->device));
+  ctx->n_cam = n_cam;
+  ctx->n_pt = n_pt;
+  ctx->n_obs = n_obs;
+  ctx->fixed_cam = fixed_cam < 0 ? -1 : fixed_cam;
+  ctx->n_free = n_cam - (fixed_cam >= 0 ? 1 : 0);
+  ctx->depth = o.use_depth_prior ? 1 : 0;
+  ctx->nk = o.optimize_intrinsics ? 4 : 0;
+  ctx->n_red = 6 * ctx->n_free + ctx->nk;
+  int solver = o.solver;
+  if (solver == BA_SOLVER_AUTO)
+    solver = (ctx->n_red <= o.explicit_max_dim || ctx->nk) ? BA_SOLVER_EXPLICIT_CHOLESKY : BA_SOLVER_IMPLICIT_PCG;
+  if (solver == BA_SOLVER_IMPLICIT_PCG && ctx->nk)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "optimize_intrinsics needs the explicit solver (as ITERATIVE_SCHUR needs points only)");
+  if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_red > 1024)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "explicit Cholesky supports reduced dimension <= 1024 (got %d)", ctx->n_red);
+  if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks > 1)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "the explicit solver is single-GPU (windowed problems stay on one GPU)");
+  ctx->solver = solver;
+
+  const int64_t N = o.n_obs_total > 0 ? o.n_obs_total : (int64_t)n_obs;
+  // src/OptimizationUtils.cpp:280, 290: weights 1/N and WEIGHT_UNPR/N; residual = sqrt(weight) * ...
+  ctx->cp.sw_repr = sqrt(1.0 / (double)(N > 0 ? N : 1));
+  ctx->cp.sw_unpr = sqrt(o.WEIGHT_UNPR / (double)(N > 0 ? N : 1));
+  ctx->cp.hub_repr = o.HUB_P_REPR;
+  ctx->cp.hub_unpr = o.HUB_P_UNPR;
+  ctx->cp.sw_intr = sqrt(o.WEIGHT_INTRINSICS);
+  ctx->cp.fixed_cam = ctx->fixed_cam;
+  ctx->cp.pad = 0;
+  LmOptions &lo = ctx->lo;
+  lo.function_tolerance = o.function_tolerance;
+  lo.gradient_tolerance = o.gradient_tolerance;
+  lo.parameter_tolerance = o.parameter_tolerance;
+  lo.max_radius = o.max_trust_region_radius;
+  lo.min_radius = o.min_trust_region_radius;
+  lo.min_relative_decrease = o.min_relative_decrease;
+  lo.min_lm_diagonal = o.min_lm_diagonal;
+  lo.max_lm_diagonal = o.max_lm_diagonal;
+  lo.eta = o.eta;
+  lo.max_num_iterations = o.max_num_iterations;
+  lo.max_invalid = o.max_num_consecutive_invalid_steps;
+  lo.max_pcg = o.max_linear_solver_iterations;
+  lo.min_pcg = o.min_linear_solver_iterations;
+  lo.reset_period = o.residual_reset_period;
+  lo.trace_cap = o.max_num_iterations + 2;
+
+  const size_t nc = (size_t)n_cam, np = (size_t)n_pt, no = (size_t)n_obs;
+  const int n_ent = n_cam + n_pt + 1;
+  ctx->nblk_obs = cdiv(n_obs, BA_THREADS);
+  ctx->nblk_ent = cdiv(n_ent, BA_THREADS);
+  ctx->nblk_cam = cdiv(n_cam, BA_THREADS);
+  ctx->nblk_pt = cdiv(n_pt, BA_THREADS);
+  ctx->n_tiles = cdiv(n_pt, BA_TILE_PTS);
+
+  RES(pose, nc * 56);
+  RES(pose_c, nc * 56);
+  RES(pt, np * 24);
+  RES(pt_c, np * 24);
+  RES(intr, 32);
+  RES(intr_c, 32);
+  RES(intr_prior, 32);
+  RES(cam_idx, no * 4);
+  RES(pt_idx, no * 4);
+  RES(uv, no * 16);
+  RES(depthv, no * 8);
+  RES(perm, no * 4);
+  RES(pt_rowptr, (np + 1) * 4);
+  RES(cam_rowptr, (nc + 1) * 4);
+  RES(pt_cnt, (np + 1) * 4);
+  RES(cam_cnt, (nc + 1) * 4);
+  RES(cursor, (np + 1) * 4);
+  RES(err_flag, 16);
+  RES(pm_cam, no * 4);
+  RES(pm_pt, no * 4);
+  RES(pm_uv, no * 16);
+  RES(pm_depth, no * 8);
+  RES(item_ptr, (nc + 1) * 4);
+  RES(item_cnt, (nc + 1) * 4);
+  RES(cam_slot, nc * 4);
+  const size_t n_pad = (no + 31) / 32 * 32 + 32;
+  RES(jcm, planes_doubles(n_pad, ctx->depth, ctx->nk) * 8);
+  RES(jpm, planes_doubles(n_pad, ctx->depth, ctx->nk) * 8);
+  set_planes(ctx->Jc_, P<double>(ctx->jcm), n_pad, ctx->depth, ctx->nk);
+  set_planes(ctx->Jp_, P<double>(ctx->jpm), n_pad, ctx->depth, ctx->nk);
+  RES(sc, nc * 48);
+  RES(sp, np * 24);
+  RES(sk, 32);
+  RES(one_c, nc * 48);
+  RES(one_p, np * 24);
+  RES(one_k, 32);
+  RES(dc, nc * 48);
+  RES(dp, np * 24);
+  RES(dk, 32);
+  RES(gc, nc * 48);
+  RES(gp, np * 24);
+  RES(gk, 32);
+  RES(U, nc * 288);
+  RES(Uck, nc * 192);
+  RES(Ukk, 128);
+  RES(V, np * 48);
+  RES(Vinv, np * 48);
+  RES(Wk, ctx->nk ? np * 96 : 16);
+  RES(tg, np * 24);
+  RES(t, np * 24);
+  RES(yc, nc * 48);
+  RES(yp, np * 24);
+  RES(yk, 32);
+  RES(rk, 32);
+  RES(Jkk, 32);
+  RES(b, nc * 48);
+  RES(x, nc * 48);
+  RES(r, nc * 48);
+  RES(z, nc * 48);
+  RES(p, nc * 48);
+  RES(q, nc * 48);
+  RES(Minv, nc * 288);
+  RES(pc_lin, (size_t)ctx->nblk_obs * 8);
+  RES(pc_cand, (size_t)ctx->nblk_obs * 8);
+  RES(pc_mcc, (size_t)ctx->nblk_obs * 8);
+  RES(pe_gmax, (size_t)ctx->nblk_ent * 8);
+  RES(pe_xn, (size_t)ctx->nblk_ent * 8);
+  RES(pe_step, (size_t)ctx->nblk_ent * 8);
+  RES(pcam_rho, (size_t)ctx->nblk_cam * 8);
+  RES(pcam_bb, (size_t)ctx->nblk_cam * 8);
+  RES(pcam_pq, (size_t)ctx->nblk_cam * 8);
+  RES(pcam_Q, (size_t)ctx->nblk_cam * 8);
+  RES(part_kk, (size_t)(ctx->nblk_pt + 1) * 14 * 8);
+  RES(st, sizeof(LmState));
+  RES(trace, (size_t)lo.trace_cap * sizeof(BaIterRec));
+
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->pose.p, pose7, nc * 56, cudaMemcpyHostToDevice, s));
+  if (np) CK(cudaMemcpyAsync(ctx->pt.p, pt3, np * 24, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->intr.p, intr4, 32, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->intr_prior.p, intr_prior4 ? intr_prior4 : intr4, 32, cudaMemcpyHostToDevice, s));
+  if (no) {
+    CK(cudaMemcpyAsync(ctx->cam_idx.p, cam_idx, no * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->pt_idx.p, pt_idx, no * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->uv.p, uv2, no * 16, cudaMemcpyHostToDevice, s));
+    if (depth) CK(cudaMemcpyAsync(ctx->depthv.p, depth, no * 8, cudaMemcpyHostToDevice, s));
+  }
+  // ---- device-built indices
+  CK(cudaMemsetAsync(ctx->pt_cnt.p, 0, (np + 1) * 4, s));
+  CK(cudaMemsetAsync(ctx->cam_cnt.p, 0, (nc + 1) * 4, s));
+  CK(cudaMemsetAsync(ctx->cursor.p, 0, (np + 1) * 4, s));
+  CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, s));
+  LAUNCH(k_index_count, ctx->nblk_obs, BA_THREADS, 0, n_obs, n_cam, n_pt, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+         P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->cam_cnt), P<int32_t>(ctx->err_flag));
+  LAUNCH(k_exclusive_scan, 1, 1024, 0, n_pt, P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->pt_rowptr));
+  LAUNCH(k_exclusive_scan, 1, 1024, 0, n_cam, P<int32_t>(ctx->cam_cnt), P<int32_t>(ctx->cam_rowptr));
+  LAUNCH(k_index_fill, ctx->nblk_obs, BA_THREADS, 0, n_obs, P<int32_t>(ctx->pt_idx), P<int32_t>(ctx->pt_rowptr),
+         P<int32_t>(ctx->cursor), P<int32_t>(ctx->perm));
+  LAUNCH(k_index_sort, ctx->nblk_pt, BA_THREADS, 0, n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->perm));
+  LAUNCH(k_index_gather, ctx->nblk_pt, BA_THREADS, 0, n_pt, n_obs, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->perm),
+         P<int32_t>(ctx->cam_idx), P<double2>(ctx->uv), depth ? P<double>(ctx->depthv) : (double *)nullptr,
+         P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt), P<double2>(ctx->pm_uv), P<double>(ctx->pm_depth));
+  LAUNCH(k_item_count, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->item_cnt));
+  LAUNCH(k_exclusive_scan, 1, 1024, 0, n_cam, P<int32_t>(ctx->item_cnt), P<int32_t>(ctx->item_ptr));
+  LAUNCH(k_slots, ctx->nblk_cam, BA_THREADS, 0, n_cam, ctx->fixed_cam, P<int32_t>(ctx->cam_slot));
+  int32_t h_items = 0, h_err = 0;
+  CK(cudaMemcpyAsync(&h_items, P<int32_t>(ctx->item_ptr) + n_cam, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_err, ctx->err_flag.p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h_err) return fail(ctx, BA_ERR_INVALID, "observation indices out of range or cam_idx not non-decreasing");
+  ctx->n_items = h_items;
+  ctx->nblk_item = cdiv(h_items * 32, BA_THREADS);
+  RES(items, (size_t)(h_items + 1) * sizeof(BaItem));
+  LAUNCH(k_item_fill, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->item_ptr),
+         P<BaItem>(ctx->items));
+  RES(part_blk, (size_t)(h_items + 1) * 61 * 8);
+  RES(part6, (size_t)(h_items + 1) * 6 * 8);
+  RES(part21, (size_t)(h_items + 1) * 21 * 8);
+  RES(part_ex, (size_t)(h_items + 1) * 30 * 8);
+  // unit scale vectors (jacobi_scaling off, and the un-scaled evaluation hook)
+  LAUNCH(k_fill, cdiv(6 * n_cam, 256), 256, 0, P<double>(ctx->one_c), (size_t)6 * nc, 1.0);
+  LAUNCH(k_fill, cdiv(3 * n_pt, 256), 256, 0, P<double>(ctx->one_p), (size_t)3 * np, 1.0);
+  LAUNCH(k_fill, 1, 256, 0, P<double>(ctx->one_k), (size_t)4, 1.0);
+  if (solver == BA_SOLVER_EXPLICIT_CHOLESKY) {
+    RES(W, (no + 1) * 144);
+    RES(WV, (no + 1) * 144);
+    RES(S, (size_t)ctx->n_red * ctx->n_red * 8 + 64);
+    RES(rhs, (size_t)ctx->n_red * 8 + 64);
+    int rc = build_pair_list(ctx, cam_idx, pt_idx);
+    if (rc) return rc;
+  }
+  CK(cudaGetLastError());
+  ctx->uploaded = true;
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------ pipeline pieces
+// linearise at the current point in both orders + normal-equation blocks
+static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk) {
+  const int D = ctx->depth, K = ctx->nk;
+  LmState *st = P<LmState>(ctx->st);
+  DISPATCH_DK(D, K, {
+    LAUNCH((k_linearize<DD, KK, 1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+           P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc, sp,
+           sk, ctx->cp, ctx->Jc_, P<double>(ctx->pc_lin), st, gate);
+    LAUNCH((k_linearize<DD, KK, 0>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt),
+           P<double2>(ctx->pm_uv), P<double>(ctx->pm_depth), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc,
+           sp, sk, ctx->cp, ctx->Jp_, (double *)nullptr, st, gate);
+    LAUNCH((k_cam_blocks<DD, KK>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), ctx->Jc_,
+           P<double>(ctx->part_blk), st, gate);
+    LAUNCH((k_cam_blocks_fin<KK>), ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part_blk),
+           P<double>(ctx->U), P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
+    LAUNCH((k_pt_blocks<DD, KK>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), ctx->Jp_, P<double>(ctx->V),
+           P<double>(ctx->gp), P<double>(ctx->Wk), P<double>(ctx->dp), ctx->lo, st, gate);
+  });
+  if (K)
+    LAUNCH(k_kk_fin, 1, BA_THREADS, 0, ctx->n_items, P<double>(ctx->part_blk), P<double>(ctx->intr), P<double>(ctx->intr_prior),
+           sk, ctx->cp, ctx->lo, P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->rk),
+           P<double>(ctx->Jkk), st, gate);
+}
+static void enqueue_state_norms(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk) {
+  LAUNCH(k_state_norms, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, ctx->nk, ctx->fixed_cam, P<double>(ctx->pose),
+         P<double>(ctx->pt), P<double>(ctx->intr), P<double>(ctx->gc), P<double>(ctx->gp), P<double>(ctx->gk), sc, sp, sk,
+         P<double>(ctx->pe_gmax), P<double>(ctx->pe_xn), P<LmState>(ctx->st), gate);
+}
+
+// IterationZero of the trust-region minimizer
+static void enqueue_iteration_zero(ba_gpu_ctx *ctx) {
+  LmState *st = P<LmState>(ctx->st);
+  LAUNCH(k_lm_init, 1, 1, 0, st, ctx->opt.initial_trust_region_radius);
+  const bool js = ctx->opt.jacobi_scaling != 0;
+  // first pass un-scaled: cost, gradient norm, column norms
+  enqueue_linearize(ctx, GATE_RUN, P<double>(ctx->one_c), P<double>(ctx->one_p), P<double>(ctx->one_k));
+  enqueue_state_norms(ctx, GATE_RUN, P<double>(ctx->one_c), P<double>(ctx->one_p), P<double>(ctx->one_k));
+  if (js) {
+    LAUNCH(k_make_scale, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, ctx->nk, P<double>(ctx->U), P<double>(ctx->V),
+           P<double>(ctx->Ukk), P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk), st, GATE_RUN);
+    enqueue_linearize(ctx, GATE_RUN, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk));
+  } else {
+    cudaMemcpyAsync(ctx->sc.p, ctx->one_c.p, (size_t)ctx->n_cam * 48, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->sp.p, ctx->one_p.p, (size_t)ctx->n_pt * 24, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->sk.p, ctx->one_k.p, 32, cudaMemcpyDeviceToDevice, ctx->stream);
+  }
+  LAUNCH(k_set_have_scale, 1, 1, 0, st);
+  LAUNCH(k_lm_iter0, 1, BA_THREADS, 0, ctx->nblk_obs, ctx->nblk_ent, ctx->nk, P<double>(ctx->pc_lin), P<double>(ctx->pe_gmax),
+         P<double>(ctx->pe_xn), P<double>(ctx->rk), ctx->lo, st, P<BaIterRec>(ctx->trace));
+  ctx->linearized = true;
+}
+
+// one implicit-Schur product: part6 <- sum Jc^T (alpha Jc v - Jp t), t <- pass 1 of v
+static void enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate) {
+  LmState *st = P<LmState>(ctx->st);
+  const int rp = ctx->lo.reset_period;
+  DISPATCH_D(ctx->depth, {
+    LAUNCH((k_schur_pass1<DD, 0, 0>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+           ctx->Jp_, v, (const double *)nullptr, P<double>(ctx->Vinv), (const double *)nullptr, P<double>(ctx->t), st, gate, rp);
+    LAUNCH((k_schur_pass2<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
+           ctx->Jc_, v, P<double>(ctx->t), 1.0, P<double>(ctx->part6), st, gate, rp);
+  });
+}
+
+static int poll_state(ba_gpu_ctx *ctx) {
+  CK(cudaMemcpyAsync(ctx->h_st, ctx->st.p, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static void enqueue_pcg_iteration(ba_gpu_ctx *ctx) {
+  LmState *st = P<LmState>(ctx->st);
+  const int rp = ctx->lo.reset_period;
+  LAUNCH(k_pcg_dir, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, P<double>(ctx->pcam_rho), P<double>(ctx->z),
+         P<double>(ctx->p), st, GATE_PCG);
+  enqueue_matvec(ctx, P<double>(ctx->p), GATE_PCG);
+  LAUNCH(k_pcg_q, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part6), P<double>(ctx->dc),
+         P<double>(ctx->p), P<double>(ctx->q), P<double>(ctx->pcam_pq), st, GATE_PCG);
+  LAUNCH(k_pcg_step, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, P<double>(ctx->pcam_pq), P<double>(ctx->p),
+         P<double>(ctx->q), P<double>(ctx->b), P<double>(ctx->Minv), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z),
+         P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), st, GATE_PCG, rp);
+  if (rp > 0) {
+    enqueue_matvec(ctx, P<double>(ctx->x), GATE_PCG_RESET);
+    LAUNCH(k_pcg_reset, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part6),
+           P<double>(ctx->dc), P<double>(ctx->x), P<double>(ctx->b), P<double>(ctx->Minv), P<double>(ctx->r), P<double>(ctx->z),
+           P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), st, GATE_PCG_RESET, rp);
+  }
+  LAUNCH(k_pcg_ctl, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_Q), ctx->lo, st, GATE_PCG);
+}
+
+// reduced system solve by implicit Schur + block-Jacobi PCG; host polls the
+// device-side PCG controller every poll_interval iterations
+static int solve_implicit(ba_gpu_ctx *ctx) {
+  LmState *st = P<LmState>(ctx->st);
+  DISPATCH_D(ctx->depth, {
+    // rhs = -g_c + sum Jc^T Jp V^-1 g_p
+    LAUNCH((k_schur_pass2<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
+           ctx->Jc_, P<double>(ctx->gc), P<double>(ctx->tg), 0.0, P<double>(ctx->part6), st, GATE_RUN, 0);
+    LAUNCH((k_schur_diag<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Jc_,
+           P<double>(ctx->Vinv), P<double>(ctx->part21), st, GATE_RUN);
+  });
+  LAUNCH(k_schur_diag_fin, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part21),
+         P<double>(ctx->U), P<double>(ctx->dc), P<double>(ctx->Minv), st, GATE_RUN);
+  LAUNCH(k_pcg_init, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part6), P<double>(ctx->gc),
+         P<double>(ctx->Minv), P<double>(ctx->b), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z), P<double>(ctx->pcam_rho),
+         P<double>(ctx->pcam_bb), st, GATE_RUN);
+  LAUNCH(k_pcg_start, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_bb), st, GATE_RUN);
+  const int batch = std::max(1, ctx->opt.poll_interval);
+  int launched = 0;
+  for (;;) {
+    for (int k = 0; k < batch; ++k) enqueue_pcg_iteration(ctx);
+    launched += batch;
+    int rc = poll_state(ctx);
+    if (rc) return rc;
+    if (ctx->h_st->pcg_done || ctx->h_st->done) break;
+    if (launched > ctx->lo.max_pcg + batch) return fail(ctx, BA_ERR_STATE, "PCG controller did not terminate");
+  }
+  LAUNCH(k_pcg_finish, cdiv(6 * ctx->n_cam, BA_THREADS), BA_THREADS, 0, 6 * ctx->n_cam, P<double>(ctx->x), P<double>(ctx->yc), st,
+         GATE_RUN);
+  return 0;
+}
+
+// reduced system by explicit Schur complement + dense Cholesky (windowed problems)
+static int solve_explicit(ba_gpu_ctx *ctx) {
+  LmState *st = P<LmState>(ctx->st);
+  const int n = ctx->n_red;
+  if (n == 0) return 0;
+  cudaMemsetAsync(ctx->S.p, 0, (size_t)n * n * 8, ctx->stream);
+  DISPATCH_D(ctx->depth, {
+    LAUNCH((k_obs_W<DD>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pt_idx), ctx->Jc_, P<double>(ctx->Vinv),
+           P<double>(ctx->W), P<double>(ctx->WV), st, GATE_RUN);
+  });
+  if (ctx->nk) {
+    LAUNCH((k_explicit_cam<4>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
+           P<double>(ctx->W), P<double>(ctx->WV), P<double>(ctx->tg), P<double>(ctx->Wk), P<double>(ctx->part_ex), st, GATE_RUN);
+    LAUNCH(k_explicit_kk, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->Wk), P<double>(ctx->Vinv), P<double>(ctx->tg),
+           P<double>(ctx->part_kk), st, GATE_RUN);
+    LAUNCH((k_explicit_assemble<4>), cdiv(ctx->n_cam + 1, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ctx->n_free, n,
+           P<int32_t>(ctx->cam_slot), P<int32_t>(ctx->item_ptr), P<double>(ctx->part_ex), ctx->nblk_pt, P<double>(ctx->part_kk),
+           P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->S),
+           P<double>(ctx->rhs), st, GATE_RUN);
+  } else {
+    LAUNCH((k_explicit_cam<0>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
+           P<double>(ctx->W), P<double>(ctx->WV), P<double>(ctx->tg), P<double>(ctx->Wk), P<double>(ctx->part_ex), st, GATE_RUN);
+    LAUNCH((k_explicit_assemble<0>), cdiv(ctx->n_cam + 1, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ctx->n_free, n,
+           P<int32_t>(ctx->cam_slot), P<int32_t>(ctx->item_ptr), P<double>(ctx->part_ex), ctx->nblk_pt, P<double>(ctx->part_kk),
+           P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->S),
+           P<double>(ctx->rhs), st, GATE_RUN);
+  }
+  LAUNCH(k_schur_pairs, ctx->n_blk, BA_THREADS, 0, n, P<int32_t>(ctx->blk_i), P<int32_t>(ctx->blk_j), P<int32_t>(ctx->blk_cam),
+         P<int32_t>(ctx->pair_ptr), P<int32_t>(ctx->pair_a), P<int32_t>(ctx->pair_b), P<double>(ctx->W), P<double>(ctx->WV),
+         P<double>(ctx->U), P<double>(ctx->dc), P<double>(ctx->S), st, GATE_RUN);
+  if (n <= 160) {
+    const size_t smem = ((size_t)n * n + n + 8) * 8;
+    LAUNCH((k_cholesky_solve<1>), 1, 256, smem, n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
+           P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
+  } else {
+    LAUNCH((k_cholesky_solve<0>), 1, 1024, 0, n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
+           P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
+  }
+  return 0;
+}
+
+static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
+  LmState *st = P<LmState>(ctx->st);
+  const int D = ctx->depth, K = ctx->nk;
+  LAUNCH(k_lm_begin, 1, 1, 0, ctx->lo, st);
+  LAUNCH(k_point_inverse, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->V), P<double>(ctx->dp), P<double>(ctx->gp),
+         P<double>(ctx->Vinv), P<double>(ctx->tg), st, GATE_RUN);
+  int rc = ctx->solver == BA_SOLVER_IMPLICIT_PCG ? solve_implicit(ctx) : solve_explicit(ctx);
+  if (rc) return rc;
+  DISPATCH_DK(D, K, {
+    // back-substitution y_p = V^-1 (-g_p - W^T y_c)
+    LAUNCH((k_schur_pass1<DD, KK, 1>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+           ctx->Jp_, P<double>(ctx->yc), P<double>(ctx->yk), P<double>(ctx->Vinv), P<double>(ctx->gp), P<double>(ctx->yp), st,
+           GATE_RUN, 0);
+    LAUNCH((k_model_cost<DD, KK>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+           ctx->Jc_, P<double>(ctx->yc), P<double>(ctx->yp), P<double>(ctx->yk), P<double>(ctx->pc_mcc), st, GATE_RUN);
+  });
+  LAUNCH(k_candidate, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, K, ctx->fixed_cam, P<double>(ctx->pose), P<double>(ctx->pt),
+         P<double>(ctx->intr), P<double>(ctx->yc), P<double>(ctx->yp), P<double>(ctx->yk), P<double>(ctx->sc), P<double>(ctx->sp),
+         P<double>(ctx->sk), P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c), P<double>(ctx->pe_step), st,
+         GATE_RUN);
+  DISPATCH_D(D, {
+    LAUNCH((k_cost<DD>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+           P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c),
+           ctx->cp, P<double>(ctx->pc_cand), st, GATE_RUN);
+  });
+  LAUNCH(k_lm_control, 1, BA_THREADS, 0, ctx->nblk_obs, ctx->nblk_ent, K, P<double>(ctx->pc_mcc), P<double>(ctx->pe_step),
+         P<double>(ctx->pc_cand), P<double>(ctx->rk), P<double>(ctx->Jkk), P<double>(ctx->yk), P<double>(ctx->intr_c),
+         P<double>(ctx->intr_prior), ctx->cp.sw_intr, ctx->lo, st, P<BaIterRec>(ctx->trace));
+  // accepted: x <- x+, relinearise (all gated on the device-side decision)
+  LAUNCH(k_accept, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr),
+         P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c), st, GATE_ACCEPTED);
+  enqueue_linearize(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk));
+  enqueue_state_norms(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk));
+  LAUNCH(k_lm_post, 1, BA_THREADS, 0, ctx->nblk_obs, ctx->nblk_ent, K, P<double>(ctx->pc_lin), P<double>(ctx->pe_gmax),
+         P<double>(ctx->pe_xn), P<double>(ctx->rk), ctx->lo, st, P<BaIterRec>(ctx->trace), GATE_ACCEPTED);
+  return 0;
+}
+
+extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
+  if (!ctx) return BA_ERR_INVALID;
+  if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_solve before ba_gpu_upload");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t l0 = ctx->launches;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  enqueue_iteration_zero(ctx);
+  const int poll = std::max(1, ctx->opt.poll_interval);
+  int rc = 0;
+  for (int it = 1;; ++it) {
+    rc = enqueue_lm_iteration(ctx);
+    if (rc) return rc;
+    const bool implicit = ctx->solver == BA_SOLVER_IMPLICIT_PCG;
+    if (!implicit && (it % poll) != 0 && it <= ctx->lo.max_num_iterations) continue;
+    rc = poll_state(ctx);
+    if (rc) return rc;
+    if (ctx->h_st->done) break;
+    if (it > ctx->lo.max_num_iterations + 2) return fail(ctx, BA_ERR_STATE, "LM controller did not terminate");
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  const LmState &h = *ctx->h_st;
+  ba_gpu_summary s;
+  memset(&s, 0, sizeof(s));
+  s.termination = h.termination;
+  s.num_iterations = h.iter > 0 ? (h.termination == BA_TERM_NO_CONVERGENCE || h.termination == BA_TERM_GRADIENT ||
+                                           h.termination == BA_TERM_MIN_RADIUS
+                                       ? h.iter - 1
+                                       : h.iter)
+                                : 0;
+  s.num_successful = h.num_successful;
+  s.num_unsuccessful = h.num_unsuccessful;
+  s.initial_cost = h.initial_cost;
+  s.final_cost = h.x_cost;
+  s.total_linear_iters = h.total_lin_iters;
+  s.solver_used = ctx->solver;
+  s.reduced_dim = ctx->n_red;
+  s.solve_ms = ms;
+  s.kernel_launches = ctx->launches - l0;
+  const int nt = std::min(h.n_trace, ctx->lo.trace_cap);
+  ctx->h_trace.resize(nt);
+  if (nt) CK(cudaMemcpy(ctx->h_trace.data(), ctx->trace.p, (size_t)nt * sizeof(BaIterRec), cudaMemcpyDeviceToHost));
+  ctx->last_summary = s;
+  if (summary) *summary = s;
+  if (h.termination == BA_TERM_FAILURE && h.n_trace <= 1 && h.eval_fail)
+    return fail(ctx, BA_ERR_NUMERIC, "non-finite cost or Jacobian at the initial point");
+  return BA_OK;
+}
+
+extern "C" int ba_gpu_get_trace(ba_gpu_ctx *ctx, ba_gpu_iter *out, int32_t cap) {
+  if (!ctx || (!out && cap > 0)) return BA_ERR_INVALID;
+  const int n = std::min<int>(cap, (int)ctx->h_trace.size());
+  static_assert(sizeof(ba_gpu_iter) == sizeof(BaIterRec), "trace record layout");
+  if (n > 0) memcpy(out, ctx->h_trace.data(), (size_t)n * sizeof(BaIterRec));
+  return n;
+}
+
+extern "C" int ba_gpu_download(ba_gpu_ctx *ctx, double *pose7, double *pt3, double intr4[4]) {
+  if (!ctx) return BA_ERR_INVALID;
+  if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_download before ba_gpu_upload");
+  CK(cudaSetDevice(ctx->device));
+  if (pose7) CK(cudaMemcpyAsync(pose7, ctx->pose.p, (size_t)ctx->n_cam * 56, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pt3 && ctx->n_pt) CK(cudaMemcpyAsync(pt3, ctx->pt.p, (size_t)ctx->n_pt * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  if (intr4) CK(cudaMemcpyAsync(intr4, ctx->intr.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------ test hooks
+extern "C" int ba_gpu_eval(ba_gpu_ctx *ctx, double *r, double *Jc, double *Jp, double *Jk, double *cost, double *g_c,
+                           double *g_p, double *g_k) {
+  if (!ctx) return BA_ERR_INVALID;
+  if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_eval before ba_gpu_upload");
+  CK(cudaSetDevice(ctx->device));
+  LmState *st = P<LmState>(ctx->st);
+  LAUNCH(k_lm_init, 1, 1, 0, st, ctx->opt.initial_trust_region_radius);
+  enqueue_linearize(ctx, GATE_RUN, P<double>(ctx->one_c), P<double>(ctx->one_p), P<double>(ctx->one_k));
+  ctx->linearized = false;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  const size_t n = ctx->n_obs;
+  const int R = 2 + ctx->depth;
+  std::vector<double> h(n * 2 + 1);
+  auto get2 = [&](const double2 *src) -> int {
+    if (n) CK(cudaMemcpy(h.data(), src, n * 16, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  auto get1 = [&](const double *src) -> int {
+    if (n) CK(cudaMemcpy(h.data(), src, n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  int rc;
+  const JPlanes &J = ctx->Jc_;
+  if (r) {
+    if ((rc = get2(J.r))) return rc;
+    for (size_t i = 0; i < n; ++i) {
+      r[i * R] = h[2 * i];
+      r[i * R + 1] = h[2 * i + 1];
+    }
+    if (ctx->depth) {
+      if ((rc = get1(J.r3))) return rc;
+      for (size_t i = 0; i < n; ++i) r[i * R + 2] = h[i];
+    }
+  }
+  if (Jc)
+    for (int k = 0; k < 6; ++k) {
+      if ((rc = get2(J.Jc[k]))) return rc;
+      for (size_t i = 0; i < n; ++i) {
+        Jc[(i * R + 0) * 6 + k] = h[2 * i];
+        Jc[(i * R + 1) * 6 + k] = h[2 * i + 1];
+      }
+      if (ctx->depth) {
+        if ((rc = get1(J.Jc3[k]))) return rc;
+        for (size_t i = 0; i < n; ++i) Jc[(i * R + 2) * 6 + k] = h[i];
+      }
+    }
+  if (Jp)
+    for (int k = 0; k < 3; ++k) {
+      if ((rc = get2(J.Jp[k]))) return rc;
+      for (size_t i = 0; i < n; ++i) {
+        Jp[(i * R + 0) * 3 + k] = h[2 * i];
+        Jp[(i * R + 1) * 3 + k] = h[2 * i + 1];
+      }
+      if (ctx->depth) {
+        if ((rc = get1(J.Jp3[k]))) return rc;
+        for (size_t i = 0; i < n; ++i) Jp[(i * R + 2) * 3 + k] = h[i];
+      }
+    }
+  if (Jk) {
+    memset(Jk, 0, n * 8 * sizeof(double));
+    if (ctx->nk)
+      for (int k = 0; k < 2; ++k) {
+        if ((rc = get2(J.Jk[k]))) return rc;
+        for (size_t i = 0; i < n; ++i) {
+          Jk[(i * 2 + 0) * 4 + 2 * k] = h[2 * i];          // row0: fx (k=0) / cx (k=1) column
+          Jk[(i * 2 + 1) * 4 + 2 * k + 1] = h[2 * i + 1];  // row1: fy / cy column
+        }
+      }
+  }
+  if (cost) {
+    std::vector<double> pc(ctx->nblk_obs + 1);
+    if (ctx->nblk_obs) CK(cudaMemcpy(pc.data(), ctx->pc_lin.p, (size_t)ctx->nblk_obs * 8, cudaMemcpyDeviceToHost));
+    double c = 0.0;
+    for (int i = 0; i < ctx->nblk_obs; ++i) c += pc[i];
+    if (ctx->nk) {
+      double rk[4];
+      CK(cudaMemcpy(rk, ctx->rk.p, 32, cudaMemcpyDeviceToHost));
+      double s = 0.0;
+      for (int k = 0; k < 4; ++k) s += rk[k] * rk[k];
+      c = 0.5 * s + c;
+    }
+    *cost = c;
+  }
+  if (g_c) CK(cudaMemcpy(g_c, ctx->gc.p, (size_t)ctx->n_cam * 48, cudaMemcpyDeviceToHost));
+  if (g_p && ctx->n_pt) CK(cudaMemcpy(g_p, ctx->gp.p, (size_t)ctx->n_pt * 24, cudaMemcpyDeviceToHost));
+  if (g_k) {
+    memset(g_k, 0, 32);
+    if (ctx->nk) CK(cudaMemcpy(g_k, ctx->gk.p, 32, cudaMemcpyDeviceToHost));
+  }
+  if ((rc = poll_state(ctx))) return rc;
+  if (ctx->h_st->eval_fail) return fail(ctx, BA_ERR_NUMERIC, "non-finite residual or Jacobian");
+  return BA_OK;
+}
+
+extern "C" int ba_gpu_get_indices(ba_gpu_ctx *ctx, int32_t *perm_pt_major, int32_t *pt_rowptr, int32_t *cam_rowptr) {
+  if (!ctx) return BA_ERR_INVALID;
+  if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_get_indices before ba_gpu_upload");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (perm_pt_major && ctx->n_obs) CK(cudaMemcpy(perm_pt_major, ctx->perm.p, (size_t)ctx->n_obs * 4, cudaMemcpyDeviceToHost));
+  if (pt_rowptr) CK(cudaMemcpy(pt_rowptr, ctx->pt_rowptr.p, ((size_t)ctx->n_pt + 1) * 4, cudaMemcpyDeviceToHost));
+  if (cam_rowptr) CK(cudaMemcpy(cam_rowptr, ctx->cam_rowptr.p, ((size_t)ctx->n_cam + 1) * 4, cudaMemcpyDeviceToHost));
+  return BA_OK;
+}
+
+__global__ void k_set_radius(LmState *st, double radius) { st->radius = radius; }
+
+// brings the device to "linearised at the current point" with a given radius:
+// iteration zero (scaling included) + damped point-block inverses
+static int prepare_linear_system(ba_gpu_ctx *ctx, double radius) {
+  enqueue_iteration_zero(ctx);
+  LmState *st = P<LmState>(ctx->st);
+  LAUNCH(k_set_radius, 1, 1, 0, st, radius);
+  LAUNCH(k_point_inverse, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->V), P<double>(ctx->dp), P<double>(ctx->gp),
+         P<double>(ctx->Vinv), P<double>(ctx->tg), st, GATE_RUN);
+  int rc = poll_state(ctx);
+  if (rc) return rc;
+  if (ctx->h_st->eval_fail) return fail(ctx, BA_ERR_NUMERIC, "non-finite residual or Jacobian");
+  if (ctx->h_st->lin_fail) return fail(ctx, BA_ERR_NUMERIC, "singular point block");
+  return 0;
+}
+__global__ void k_clear_done(LmState *st) {
+  st->done = 0;
+  st->pcg_done = 0;
+  st->pcg_it = 1;
+}
+
+extern "C" int ba_gpu_schur_matvec(ba_gpu_ctx *ctx, double radius, const double *x, double *y) {
+  if (!ctx || !x || !y) return BA_ERR_INVALID;
+  if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_schur_matvec before ba_gpu_upload");
+  if (ctx->nk) return fail(ctx, BA_ERR_UNSUPPORTED, "implicit Schur product needs optimize_intrinsics = 0");
+  CK(cudaSetDevice(ctx->device));
+  int rc = prepare_linear_system(ctx, radius);
+  if (rc) return rc;
+  LmState *st = P<LmState>(ctx->st);
+  LAUNCH(k_clear_done, 1, 1, 0, st);
+  const size_t n = (size_t)6 * ctx->n_cam;
+  std::vector<double> sc(n), xs(n);
+  CK(cudaMemcpy(sc.data(), ctx->sc.p, n * 8, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) xs[i] = x[i] / sc[i];
+  CK(cudaMemcpyAsync(ctx->p.p, xs.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  enqueue_matvec(ctx, P<double>(ctx->p), GATE_RUN);
+  LAUNCH(k_pcg_q, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part6), P<double>(ctx->dc),
+         P<double>(ctx->p), P<double>(ctx->q), P<double>(ctx->pcam_pq), st, GATE_RUN);
+  CK(cudaMemcpyAsync(xs.data(), ctx->q.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  for (size_t i = 0; i < n; ++i) y[i] = xs[i] / sc[i];
+  return BA_OK;
+}
+
+__global__ void k_se3_plus(int n, const double *__restrict__ pose, const double *__restrict__ delta, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double T[7], d[6], o[7];
+  for (int k = 0; k < 7; ++k) T[k] = pose[7 * (size_t)i + k];
+  for (int k = 0; k < 6; ++k) d[k] = delta[6 * (size_t)i + k];
+  se3_plus(T, d, o);
+  for (int k = 0; k < 7; ++k) out[7 * (size_t)i + k] = o[k];
+}
+
+extern "C" int ba_gpu_se3_plus(ba_gpu_ctx *ctx, int32_t n, const double *pose7, const double *delta6, double *out7) {
+  if (!ctx || n < 0 || (n > 0 && (!pose7 || !delta6 || !out7))) return BA_ERR_INVALID;
+  if (n == 0) return BA_OK;
+  CK(cudaSetDevice(ctx->device));
+  double *d = nullptr;
+  CK(cudaMalloc(&d, (size_t)n * 20 * 8));
+  double *dp = d, *dd = d + (size_t)7 * n, *dout = dd + (size_t)6 * n;
+  cudaMemcpyAsync(dp, pose7, (size_t)n * 56, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dd, delta6, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream);
+  LAUNCH(k_se3_plus, cdiv(n, 256), 256, 0, n, dp, dd, dout);
+  cudaMemcpyAsync(out7, dout, (size_t)n * 56, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, BA_ERR_CUDA, "se3_plus: %s", cudaGetErrorString(e));
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------ measurement hooks
+__global__ void k_flush(double *p, size_t n, double v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+extern "C" int ba_gpu_time_kernel(ba_gpu_ctx *ctx, int32_t which, int32_t warmup, int32_t iters, int32_t flush_l2,
+                                  float *ms_avg) {
+  if (!ctx || !ms_avg || iters <= 0 || warmup < 0) return BA_ERR_INVALID;
+  if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_time_kernel before ba_gpu_upload");
+  if (which == BA_KERNEL_SCHUR_MATVEC && ctx->nk) return fail(ctx, BA_ERR_UNSUPPORTED, "matvec needs optimize_intrinsics = 0");
+  CK(cudaSetDevice(ctx->device));
+  int rc = prepare_linear_system(ctx, ctx->opt.initial_trust_region_radius);
+  if (rc) return rc;
+  LmState *st = P<LmState>(ctx->st);
+  LAUNCH(k_clear_done, 1, 1, 0, st);
+  if (which == BA_KERNEL_SCHUR_MATVEC) CK(cudaMemcpyAsync(ctx->p.p, ctx->gc.p, (size_t)ctx->n_cam * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+  const size_t flush_n = (size_t)512 * 1024 * 1024 / 8;  // 512 MiB > 126 MB L2
+  if (flush_l2) RES(flush, flush_n * 8);
+  auto one = [&]() {
+    if (which == BA_KERNEL_LINEARIZE) {
+      DISPATCH_DK(ctx->depth, ctx->nk, {
+        LAUNCH((k_linearize<DD, KK, 1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx),
+               P<int32_t>(ctx->pt_idx), P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose), P<double>(ctx->pt),
+               P<double>(ctx->intr), P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk), ctx->cp, ctx->Jc_,
+               P<double>(ctx->pc_lin), st, GATE_RUN);
+      });
+    } else {
+      enqueue_matvec(ctx, P<double>(ctx->p), GATE_RUN);
+    }
+  };
+  for (int i = 0; i < warmup; ++i) one();
+  double total = 0.0;
+  if (flush_l2) {
+    for (int i = 0; i < iters; ++i) {
+      k_flush<<<1184, 256, 0, ctx->stream>>>(P<double>(ctx->flush), flush_n, (double)i);
+      CK(cudaEventRecord(ctx->ev0, ctx->stream));
+      one();
+      CK(cudaEventRecord(ctx->ev1, ctx->stream));
+      CK(cudaEventSynchronize(ctx->ev1));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      total += ms;
+    }
+  } else {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int i = 0; i < iters; ++i) one();
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    total = ms;
+  }
+  CK(cudaGetLastError());
+  *ms_avg = (float)(total / iters);
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+extern "C" int ba_gpu_comm_unique_id(char id128[128]) {
+  std::string err;
+  if (!id128) return BA_ERR_INVALID;
+  if (!nccl_load(&err)) return fail(nullptr, BA_ERR_COMM, "%s", err.c_str());
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail(nullptr, BA_ERR_COMM, "ncclGetUniqueId: %d", r);
+  memcpy(id128, id.internal, 128);
+  return BA_OK;
+}
+
+extern "C" int ba_gpu_comm_init(ba_gpu_ctx *ctx, const char id128[128], int32_t rank, int32_t n_ranks) {
+  if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return BA_ERR_INVALID;
+  std::string err;
+  if (!nccl_load(&err)) return fail(ctx, BA_ERR_COMM, "%s", err.c_str());
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(id.internal, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank);
+  if (r != 0) return fail(ctx, BA_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  ctx->rank = rank;
+  ctx->n_ranks = n_ranks;
+  return BA_OK;
+}

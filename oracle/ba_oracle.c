@@ -470,7 +470,7 @@ typedef struct {
   double *Jp; /* [n_obs*R*3] */
   double *Jk; /* [n_obs*2*4] reprojection rows only */
   double rk[4];
-  double Jkk; /* prior Jacobian = Jkk * I4 */
+  double Jkk[4]; /* prior Jacobian = diag(Jkk); column-scaled with the rest of J */
   double *cam_cost; /* [n_cam] per-camera cost partials (deterministic sum) */
 } ora_jac;
 
@@ -566,12 +566,12 @@ static int evaluate_full(const ora_problem *p, const ora_options *o,
     /* IntrinsicsPrior, squared loss (nullptr)  src/OptimizationUtils.cpp:237-241 */
     double Jkk[16];
     ora_intrinsics_prior(intr, p->intr_prior, o->weight_intrinsics, J->rk, Jkk);
-    J->Jkk = Jkk[0];
+    for (int i = 0; i < 4; ++i) J->Jkk[i] = Jkk[i * 4 + i];
     double s = 0.0;
     for (int i = 0; i < 4; ++i) s += J->rk[i] * J->rk[i];
     total += 0.5 * s;
   } else {
-    J->Jkk = 0.0;
+    memset(J->Jkk, 0, sizeof(J->Jkk));
     memset(J->rk, 0, sizeof(J->rk));
   }
   for (int c = 0; c < p->n_cam; ++c) total += J->cam_cost[c];
@@ -655,7 +655,7 @@ static void compute_gradient(const ora_problem *p, const ora_layout *L,
           const double *jk = J->Jk + ((size_t)i * 2 + row) * 4;
           for (int k = 0; k < 4; ++k) g[k] += jk[k] * r;
         }
-      for (int k = 0; k < 4; ++k) g[k] += J->Jkk * J->rk[k];
+      for (int k = 0; k < 4; ++k) g[k] += J->Jkk[k] * J->rk[k];
     }
     memcpy(g_k, g, sizeof(g));
   }
@@ -797,7 +797,7 @@ static void column_sqnorms(const ora_ws *w, double *nc, double *np, double nk[4]
         const double *jk = w->J.Jk + ((size_t)i * 2 + row) * 4;
         for (int k = 0; k < 4; ++k) nk[k] += jk[k] * jk[k];
       }
-    for (int k = 0; k < 4; ++k) nk[k] += w->J.Jkk * w->J.Jkk;
+    for (int k = 0; k < 4; ++k) nk[k] += w->J.Jkk[k] * w->J.Jkk[k];
   }
 }
 
@@ -805,6 +805,8 @@ static void column_sqnorms(const ora_ws *w, double *nc, double *np, double nk[4]
 static void scale_columns(ora_ws *w) {
   const ora_problem *p = w->p;
   const int R = w->L.R;
+  if (w->L.nk)
+    for (int k = 0; k < 4; ++k) w->J.Jkk[k] *= w->sk[k];
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < p->n_obs; ++i) {
     const double *sc = w->sc + 6 * p->cam_idx[i];
@@ -939,8 +941,8 @@ static int solve_dense_schur(ora_ws *w, double radius) {
   }
   if (nk)
     for (int k = 0; k < 4; ++k) {
-      S[(size_t)(koff + k) * n + koff + k] += w->J.Jkk * w->J.Jkk;
-      rhs[koff + k] -= w->J.Jkk * w->J.rk[k];
+      S[(size_t)(koff + k) * n + koff + k] += w->J.Jkk[k] * w->J.Jkk[k];
+      rhs[koff + k] -= w->J.Jkk[k] * w->J.rk[k];
     }
   for (int c = 0; c < p->n_cam; ++c) {
     const int slot = L->cam_slot[c];
@@ -1346,7 +1348,7 @@ static double model_cost_change(const ora_ws *w) {
   double total = 0.0;
   if (L->nk)
     for (int k = 0; k < 4; ++k) {
-      const double m = w->J.Jkk * w->yk[k];
+      const double m = w->J.Jkk[k] * w->yk[k];
       total += m * (w->J.rk[k] + m / 2.0);
     }
   for (int c = 0; c < p->n_cam; ++c) total += part[c];

@@ -1,0 +1,284 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the
+mpmath golden vectors.  Tolerances are the north star's: indices bit-exact;
+residuals / Jacobians 1e-12 relative; final cost 1e-8 relative; poses
+1e-6 m / 1e-6 rad after a fixed LM iteration count."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import ba_b200, mode_opts, ora, pose_err, rel_err, to_oracle
+
+pytestmark = pytest.mark.gpu
+syn = ba_b200.synthetic
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "residual_jacobian_golden.json")))
+
+
+def _problem(name):
+    if name == "cfg1":
+        return syn.make_config(1)
+    if name == "cfg1_small":
+        return syn.make_config(1, scale=0.1)
+    if name == "cfg3_small":
+        return syn.make_config(3, scale=0.02)
+    if name == "cfg4_small":
+        return syn.make_config(4, scale=0.02)
+    if name == "window20":
+        seq = syn.make_tum_sequence(40, 4000, 24000, seed=5)
+        return syn.window_problem(seq, 10, 29).problem
+    raise KeyError(name)
+
+
+@pytest.fixture(scope="module")
+def solver_cache():
+    cache = {}
+    yield cache
+    for s in cache.values():
+        s.close()
+
+
+def _solver(cache, **kw):
+    key = tuple(sorted(kw.items()))
+    if key not in cache:
+        cache[key] = ba_b200.GpuSolver(**kw)
+    return cache[key]
+
+
+# ---------------------------------------------------------------- indices
+@pytest.mark.parametrize("name", ["cfg1", "cfg3_small", "cfg4_small", "window20"])
+def test_indices_bit_exact(name, solver_cache):
+    p = _problem(name)
+    g, _ = mode_opts("NS")
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    perm, pt_rowptr, cam_rowptr = s.indices()
+    operm, opt, ocam = ora.build_indices(to_oracle(p))
+    assert np.array_equal(perm, operm)
+    assert np.array_equal(pt_rowptr, opt)
+    assert np.array_equal(cam_rowptr, ocam)
+    # stable counting sort property, independently of the oracle
+    assert np.array_equal(perm, np.argsort(p.pt_idx, kind="stable").astype(np.int32))
+
+
+def test_upload_rejects_unsorted(solver_cache):
+    p = _problem("cfg1_small")
+    p.cam_idx = p.cam_idx[::-1].copy()
+    s = _solver(solver_cache, **mode_opts("NS")[0])
+    with pytest.raises(ba_b200.BAError) as e:
+        s.upload(p)
+    assert e.value.code == ba_b200.capi.BA_ERR_INVALID
+
+
+# ---------------------------------------------------------------- residuals / Jacobians
+@pytest.mark.parametrize("mode", ["REF", "NS", "DEPTH", "INTR"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg4_small"])
+def test_eval_vs_oracle(name, mode, solver_cache):
+    p = _problem(name)
+    if p.depth is None and mode in ("REF", "DEPTH"):
+        pytest.skip("no depth in this config")
+    g, o = mode_opts(mode)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    out = s.eval()
+    ref = ora.evaluate(to_oracle(p), ora.default_options(**o))
+    assert ref["rc"] == 0
+    sw = np.sqrt(1.0 / p.n_obs)
+    # residuals: differences of O(640 px) quantities -> scale by the pixel magnitude
+    assert rel_err(out["r"][:, :2], ref["r"][:, :2], scale=sw * 640.0) < 1e-12
+    if g["use_depth_prior"]:
+        assert rel_err(out["r"][:, 2], ref["r"][:, 2], scale=np.sqrt(10.0 / p.n_obs) * 4.0) < 1e-12
+    for key in ("Jc", "Jp"):
+        assert rel_err(out[key], ref[key]) < 1e-12, key
+    if g["optimize_intrinsics"]:
+        assert rel_err(out["Jk"], ref["Jk"]) < 1e-12
+    assert abs(out["cost"] - ref["cost"]) <= 1e-12 * abs(ref["cost"])
+    assert rel_err(out["g_c"], ref["g_c"]) < 1e-11
+    assert rel_err(out["g_p"], ref["g_p"]) < 1e-11
+    if g["optimize_intrinsics"]:
+        assert rel_err(out["g_k"], ref["g_k"]) < 1e-11
+
+
+def test_eval_vs_mpmath_golden(solver_cache):
+    """One-observation problems built from the 60-digit golden vectors."""
+    s = _solver(solver_cache, **mode_opts("REF", HUB_P_REPR=1e30, HUB_P_UNPR=1e30)[0])
+    for g in GOLD["residual_jacobian"]:
+        n = int(round(1.0 / g["w_repr"]))
+        assert abs(1.0 / n - g["w_repr"]) < 1e-18 and abs(10.0 / n - g["w_unpr"]) < 1e-15
+        p = ba_b200.BAProblem(np.array([g["pose"]]), np.array([g["pt"]]), [0], [0], np.array([g["uv"]]),
+                              np.array([g["depth"]]), np.array(g["intr"]), None, -1)
+        s.set_options(n_obs_total=n)
+        s.upload(p)
+        out = s.eval()
+        sw = np.sqrt(g["w_repr"])
+        assert rel_err(out["r"][0, :2], g["r"][:2], scale=sw * 640.0) < 1e-12
+        assert rel_err(out["r"][0, 2:], g["r"][2:], scale=np.sqrt(g["w_unpr"]) * max(1.0, g["depth"])) < 1e-12
+        for row in range(3):
+            assert rel_err(out["Jc"][0, row], g["Jpose"][row]) < 1e-12
+        assert rel_err(out["Jp"][0], g["Jpt"]) < 1e-12
+        assert rel_err(out["Jk"][0], np.array(g["Jintr"])[:2]) < 1e-12
+
+
+def test_huber_region_active(solver_cache):
+    """Most residuals sit in Huber's linear region: make sure
+    both branches are exercised by the parity problems."""
+    p = _problem("cfg1")
+    ref = ora.evaluate(to_oracle(p), ora.default_options())
+    s2 = np.sum(ref["r"][:, :2] ** 2, axis=1)
+    assert np.count_nonzero(s2 > 0.9e-6) > 100
+
+
+def test_se3_plus_vs_oracle(solver_cache):
+    s = _solver(solver_cache, **mode_opts("NS")[0])
+    rng = np.random.default_rng(7)
+    n = 200
+    pose = ba_b200.se3.exp(rng.normal(size=(n, 6)))
+    delta = rng.normal(size=(n, 6)) * (10.0 ** rng.uniform(-13, 0, size=(n, 1)))
+    delta[0] = 0.0
+    out = s.se3_plus(pose, delta)
+    for i in range(n):
+        ref = ora.se3_mul(pose[i], ora.se3_exp(delta[i]))
+        assert np.max(np.abs(out[i] - ref)) < 4e-15, i
+
+
+# ---------------------------------------------------------------- implicit Schur product
+@pytest.mark.parametrize("name", ["cfg1", "cfg4_small", "cfg3_small"])
+def test_schur_matvec_vs_oracle(name, solver_cache):
+    p = _problem(name)
+    g, o = mode_opts("NS", solver=2)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    rng = np.random.default_rng(1)
+    for radius in (1e4, 3.7):
+        x = rng.normal(size=6 * p.n_cam)
+        y = s.schur_matvec(radius, x)
+        yref = ora.schur_matvec(to_oracle(p), ora.default_options(**o), radius, x)
+        assert rel_err(y, yref) < 1e-10
+    # linearity and symmetry of S (size-independent properties)
+    x1, x2 = rng.normal(size=6 * p.n_cam), rng.normal(size=6 * p.n_cam)
+    y1, y2 = s.schur_matvec(1e4, x1), s.schur_matvec(1e4, x2)
+    y12 = s.schur_matvec(1e4, 2.0 * x1 - 3.0 * x2)
+    assert rel_err(y12, 2.0 * y1 - 3.0 * y2) < 1e-11
+    assert abs(x1 @ y2 - x2 @ y1) <= 1e-10 * (abs(x1 @ y2) + np.linalg.norm(y1) * np.linalg.norm(x2))
+
+
+# ---------------------------------------------------------------- full LM solves
+def _compare_solve(p, mode, solver, iters, cache, lockstep=True, cost_tol=1e-8):
+    g, o = mode_opts(mode, solver=solver, max_num_iterations=iters)
+    s = _solver(cache, **g)
+    s.upload(p)
+    summ = s.solve()
+    pose, pt, intr = s.download()
+    tr = s.trace()
+    op = to_oracle(p)
+    rc, osum, otr = ora.solve(op, ora.default_options(**o))
+    assert rc == 0
+    assert summ.termination == osum.termination
+    assert summ.num_iterations == osum.num_iterations
+    assert summ.num_successful == osum.num_successful and summ.num_unsuccessful == osum.num_unsuccessful
+    assert abs(summ.initial_cost - osum.initial_cost) <= 1e-12 * osum.initial_cost
+    assert abs(summ.final_cost - osum.final_cost) <= cost_tol * osum.final_cost
+    dt, dr = pose_err(pose, op.pose7)
+    assert dt < 1e-6 and dr < 1e-6, (dt, dr)
+    assert np.max(np.abs(pt - op.pt3)) < 1e-5
+    if mode in ("REF", "INTR"):
+        assert np.max(np.abs(intr - op.intr)) < 1e-5
+    if lockstep:
+        assert len(tr) == len(otr)
+        for a, b in zip(tr, otr):
+            assert a["iteration"] == b["iteration"]
+            assert a["step_is_valid"] == b["step_is_valid"] and a["step_is_successful"] == b["step_is_successful"]
+            assert abs(a["cost"] - b["cost"]) <= 1e-8 * abs(b["cost"]), (a, b)
+            assert abs(a["radius"] - b["radius"]) <= 1e-6 * abs(b["radius"]), (a, b)
+    return summ, osum
+
+
+@pytest.mark.parametrize("mode", ["REF", "NS", "DEPTH", "INTR"])
+def test_solve_explicit_cfg1(mode, solver_cache):
+    summ, _ = _compare_solve(_problem("cfg1"), mode, 1, 10, solver_cache)
+    assert summ.solver_used == ba_b200.capi.BA_SOLVER_EXPLICIT_CHOLESKY
+    assert summ.final_cost < 0.5 * summ.initial_cost
+
+
+def test_solve_explicit_window20_ref(solver_cache):
+    summ, _ = _compare_solve(_problem("window20"), "REF", 0, 10, solver_cache)
+    assert summ.reduced_dim == 6 * 19 + 4 and summ.solver_used == ba_b200.capi.BA_SOLVER_EXPLICIT_CHOLESKY
+
+
+def test_solve_to_convergence_ref(solver_cache):
+    """Reference settings (75 iterations, tolerances on): same termination."""
+    _compare_solve(_problem("cfg1"), "REF", 1, 75, solver_cache)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3_small", "cfg4_small"])
+def test_solve_implicit_pcg(name, solver_cache):
+    """Implicit Schur + block-Jacobi PCG against the oracle's own PCG."""
+    summ, osum = _compare_solve(_problem(name), "NS", 2, 8, solver_cache)
+    assert summ.solver_used == ba_b200.capi.BA_SOLVER_IMPLICIT_PCG
+    assert summ.total_linear_iters == osum.total_linear_iters
+
+
+def test_explicit_and_implicit_agree(solver_cache):
+    """A converged PCG step equals the Cholesky step: same optimum."""
+    p = _problem("cfg3_small")
+    res = []
+    for solver in (1, 2):
+        g, _ = mode_opts("NS", solver=solver, max_num_iterations=30, explicit_max_dim=1024)
+        s = _solver(solver_cache, **g)
+        s.upload(p)
+        summ = s.solve()
+        res.append((summ.final_cost, s.download()[0]))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * res[0][0]
+    dt, dr = pose_err(res[0][1], res[1][1])
+    assert dt < 1e-4 and dr < 1e-4
+
+
+def test_noise_free_problem_reaches_zero_cost(solver_cache):
+    """Known-answer: exact observations, perturbed start -> cost ~ 0, poses -> truth."""
+    seq = syn.make_tum_sequence(7, 300, 1800, seed=21, noise=False)
+    truth = syn.window_problem(seq, 0, 6, use_depth=False).problem
+    rng = np.random.default_rng(2)
+    p = truth.copy()
+    d = np.concatenate([0.01 * rng.normal(size=(7, 3)), 0.005 * rng.normal(size=(7, 3))], axis=1)
+    d[0] = 0
+    p.pose7 = ba_b200.se3.mul(truth.pose7, ba_b200.se3.exp(d))
+    p.pt3 = truth.pt3 + 0.01 * rng.normal(size=truth.pt3.shape)
+    # float-rounded pixels keep the optimum ~1e-5 px away from the truth
+    g, _ = mode_opts("NS", solver=1, max_num_iterations=50, function_tolerance=1e-14, HUB_P_REPR=1.0)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    summ = s.solve()
+    assert summ.final_cost < 1e-9 * summ.initial_cost
+
+
+def test_repeated_solves_are_deterministic(solver_cache):
+    p = _problem("cfg3_small")
+    g, _ = mode_opts("NS", solver=2, max_num_iterations=5)
+    s = _solver(solver_cache, **g)
+    out = []
+    for _ in range(2):
+        s.upload(p)
+        summ = s.solve()
+        out.append((summ.final_cost, s.download()[0].copy()))
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+
+
+def test_window_optimize_mirror(solver_cache):
+    """windowOptimize drop-in semantics: in-place mutation + frame change."""
+    seq = syn.make_tum_sequence(30, 3000, 18000, seed=9)
+    seq_o = syn.make_tum_sequence(30, 3000, 18000, seed=9)
+    gp = ba_b200.CeresGlobalProblem(max_num_iterations=10)
+    intr = seq.K.copy()
+    ok, summ = ba_b200.window_optimize(gp, 10, 29, seq, seq.K.copy(), intr, return_summary=True)
+    assert ok and summ.final_cost < summ.initial_cost
+    # oracle on the same window
+    win = syn.window_problem(seq_o, 10, 29)
+    op = to_oracle(win.problem)
+    rc, osum, _ = ora.solve(op, ora.default_options(max_num_iterations=10))
+    syn.write_back(seq_o, win, op.pose7, op.pt3)
+    assert abs(summ.final_cost - osum.final_cost) <= 1e-8 * osum.final_cost
+    dt, dr = pose_err(seq.pose, seq_o.pose)
+    assert dt < 1e-6 and dr < 1e-6
+    assert np.max(np.abs(intr - op.intr)) < 1e-5
+    # poses outside the window untouched
+    assert np.array_equal(seq.pose[:10], seq_o.pose[:10])
