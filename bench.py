@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s (and Jacobian-eval observations/s) of the B200 BA
+solver on BASELINE.json's synthetic configs, with the kernel roofline and the
+CPU baseline beside it.
+
+  python bench.py --gpus N --steps K --warmup W [--workload cfg5] [--impl reference]
+
+A "step" is one Levenberg-Marquardt iteration (linearisation + Schur linear
+solve + step evaluation) of the fixed-iteration-count solve on the workload.
+Default workload: cfg5 of BASELINE.json (10k cameras, 2M points, 8M
+observations, reprojection only, implicit-Schur PCG) -- the config the metric's
+"1/2/4/8 B200" refers to; it fits one GPU.  With N > 1 (torchrun, one rank per
+GPU) the points and their observations are sharded across ranks and the
+camera-sized partial vectors are combined with NCCL all-reduce: total work is
+fixed => "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg1": dict(cfg=1, mode=(1, 1), desc="7-keyframe TUM-shaped window, 500 landmarks, 3000 obs, REF cost, explicit Schur + Cholesky"),
+    "cfg2": dict(cfg=2, mode=(1, 1), desc="sliding 20-keyframe windows over 800 keyframes, REF cost, explicit Schur + Cholesky"),
+    "cfg3": dict(cfg=3, mode=(0, 0), desc="global BA 800 keyframes, 60k landmarks, 400k obs, NS cost, implicit-Schur PCG"),
+    "cfg4": dict(cfg=4, mode=(0, 0), desc="BAL-shaped loop 1723 cameras, 156k points, 680k obs, NS cost, implicit-Schur PCG"),
+    "cfg5": dict(cfg=5, mode=(0, 0), desc="large synthetic 10k cameras, 2M points, 8M obs, NS cost, implicit-Schur PCG"),
+}
+# algorithmic bytes: NS mode, fp64, int32 indices
+B_LINEARIZE = 208          # per observation
+B_PASS1 = (148, 72, 48)    # per observation, per point, per camera
+B_PASS2 = (172, 0, 96)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_sample(problem, mode, pcg_counts, threads, budget_s=25.0):
+    """Times the CPU oracle (the Ceres-equivalent restatement, all host cores) on
+    a bounded sample of the same problem: ONE LM iteration whose PCG is capped so
+    the sample stays within ~budget_s, then prices the full K-iteration solve
+    with the GPU run's own PCG iteration counts:
+        t_cpu = (K + 2) * t_linearize + sum_it n_pcg(it) * t_pcg_iteration
+    """
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ora
+    op = ora.Problem(problem.pose7, problem.pt3, problem.cam_idx, problem.pt_idx, problem.uv2, problem.depth, problem.intr,
+                     problem.intr_prior, problem.fixed_cam)
+    implicit = mode == (0, 0) and 6 * problem.n_cam > 160
+    # calibrate the cap from the problem size (~60 ns per observation and PCG iteration and core)
+    cap = 500
+    if implicit:
+        est_iter = max(1e-4, problem.n_obs * 150e-9 / max(1, threads) * 2.0)
+        cap = int(max(4, min(500, budget_s / est_iter)))
+    o = ora.default_options(use_depth_prior=mode[0], optimize_intrinsics=mode[1], solver=1 if implicit else 0,
+                            num_threads=threads, max_num_iterations=1, max_pcg_iterations=cap)
+    t0 = time.time()
+    rc, s, tr = ora.solve(op, o)
+    wall = time.time() - t0
+    n_pcg = max(1, int(s.total_linear_iters))
+    t_lin = s.seconds_linearize / 2.0  # iteration zero + the accepted step's relinearisation (or candidate cost)
+    if implicit:
+        t_pcg = s.seconds_linear_solve / n_pcg
+        total = (len(pcg_counts) + 2) * t_lin + float(np.sum(pcg_counts)) * t_pcg
+    else:
+        t_pcg = s.seconds_linear_solve
+        total = (len(pcg_counts) + 2) * t_lin + len(pcg_counts) * t_pcg
+    return {"value": len(pcg_counts) / total, "unit": "LM iterations/s", "cores": threads, "kind": "port",
+            "sample": "oracle (C restatement of Ceres 2.0.0 LM + %s, OpenMP %d threads) timed on 1 LM iteration of the same problem "
+                      "(PCG capped at %d its, %.1f s wall); priced for the K-iteration solve with the GPU run's PCG counts: "
+                      "t_linearize=%.4fs, t_%s=%.5fs" % ("implicit-Schur PCG" if implicit else "dense Schur", threads, cap, wall,
+                                                         t_lin, "pcg_iter" if implicit else "schur_solve", t_pcg),
+            "t_linearize_s": t_lin, "t_linear_unit_s": t_pcg, "jacobian_obs_per_s": problem.n_obs / max(t_lin, 1e-12)}
+
+
+def pinned_copy(a):
+    """numpy view of pinned host memory holding a copy of `a` (H2D at full PCIe speed)."""
+    import torch
+    if a is None:
+        return None
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t.numpy()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; reported in config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    K, W = args.steps, max(args.warmup, 0)
+
+    import ba_b200
+    syn = ba_b200.synthetic
+
+    if args.impl == "reference":
+        # the reference's CPU implementation of the path = the oracle port (Ceres itself cannot be built here)
+        if rank != 0:
+            return 0
+        problem = syn.make_config(wl["cfg"], scale=args.scale)
+        if wl["cfg"] == 2:
+            problem = syn.window_problem(problem, 0, 19).problem
+        threads = os.cpu_count() or 1
+        base = cpu_reference_sample(problem, wl["mode"], [60] * K if wl["mode"] == (0, 0) else [0] * K, threads)
+        line = {"metric": "LM iterations/s", "value": base["value"], "unit": "LM iterations/s", "n_gpus": args.gpus, "steps": K,
+                "warmup": W, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": args.workload + ": " + wl["desc"], "scale": args.scale,
+                           "note": "PCG iterations per LM iteration priced at 60 (the b200 arm reports its own counts)"},
+                "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "LM iterations/s", "h2d_bytes_per_step": 0,
+                                              "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t_gen = time.time()
+    full = syn.make_config(wl["cfg"], scale=args.scale)
+    if wl["cfg"] == 2:
+        full = syn.window_problem(full, 0, 19).problem
+    t_gen = time.time() - t_gen
+    if world > 1 and wl["mode"] != (0, 0):
+        raise SystemExit("windowed (explicit) workloads are single-GPU; use --workload cfg4/cfg5 with --gpus > 1")
+    problem, _ = syn.shard_points(full, rank, world)
+    opts = dict(use_depth_prior=wl["mode"][0], optimize_intrinsics=wl["mode"][1], function_tolerance=0.0,
+                parameter_tolerance=0.0, gradient_tolerance=0.0, device=local_rank, n_obs_total=full.n_obs)
+    s = ba_b200.GpuSolver(max_num_iterations=max(W, 1), **opts)
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idbuf.copy_(torch.frombuffer(bytearray(ba_b200.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        s.comm_init(bytes(idbuf.cpu().numpy().tobytes()), rank, world)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # pinned host copies for the end-to-end leg
+    hp = problem.copy()
+    for f in ("pose7", "pt3", "cam_idx", "pt_idx", "uv2", "depth"):
+        setattr(hp, f, pinned_copy(getattr(hp, f)))
+
+    # ---- warm-up: W LM iterations (plus kernel warm-up of the timing hooks)
+    s.upload(hp)
+    if W > 0:
+        s.solve()
+    # ---- timed: K LM iterations, inputs resident in HBM (upload outside the region)
+    s.set_options(max_num_iterations=K)
+    s.upload(hp)
+    sync_all()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.time()
+    summ = s.solve()
+    sync_all()
+    wall_solve = time.time() - t0
+    solve_ms = maxr(summ.solve_ms)
+    trace = s.trace()
+    n_iter = summ.num_iterations
+    pcg_counts = [t["linear_iters"] for t in trace[1:]]
+    # ---- end to end through the C-ABI with host buffers: upload + solve + download
+    sync_all()
+    t0 = time.time()
+    s.upload(hp)
+    summ2 = s.solve()
+    pose, pt, intr = s.download()
+    sync_all()
+    e2e_s = maxr(time.time() - t0)
+    clk = clocks.stop() if clocks else None
+    h2d = sum(int(a.nbytes) for a in (hp.pose7, hp.pt3, hp.cam_idx, hp.pt_idx, hp.uv2, hp.intr, hp.intr_prior) if a is not None)
+    if hp.depth is not None and wl["mode"][0]:
+        h2d += int(hp.depth.nbytes)
+    d2h = int(pose.nbytes + pt.nbytes + intr.nbytes)
+
+    # ---- kernel timings for the roofline (CUDA events on the solver's stream, inputs >> L2 at cfg4/5;
+    #      L2 flushed between launches otherwise)
+    peak, peak_src = peaks()
+    flush = full.n_obs * 160 < 512e6
+    ms_lin = s.time_kernel(ba_b200.capi.BA_KERNEL_LINEARIZE, 3, 20, flush)
+    roof = {}
+    n_o, n_p, n_c = problem.n_obs, problem.n_pt, problem.n_cam
+    roof["k_linearize"] = (B_LINEARIZE * n_o, ms_lin)
+    if wl["mode"] == (0, 0):
+        ms_p1 = s.time_kernel(ba_b200.capi.BA_KERNEL_SCHUR_PASS1, 3, 20, flush)
+        ms_p2 = s.time_kernel(ba_b200.capi.BA_KERNEL_SCHUR_PASS2, 3, 20, flush)
+        roof["k_schur_pass1"] = (B_PASS1[0] * n_o + B_PASS1[1] * n_p + B_PASS1[2] * n_c, ms_p1)
+        roof["k_schur_pass2"] = (B_PASS2[0] * n_o + B_PASS2[1] * n_p + B_PASS2[2] * n_c, ms_p2)
+    kernels = {k: {"bytes": b, "ms": ms, "achieved_gbs": b / ms / 1e6, "frac": b / ms / 1e6 / peak} for k, (b, ms) in roof.items()}
+    dom = max(kernels, key=lambda k: kernels[k]["ms"] * (sum(pcg_counts) if "schur" in k else (n_iter + 2)))
+    jac_obs_s = maxr(0.0) if False else full.n_obs / (maxr(ms_lin) * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    line = {
+        "metric": "LM iterations/s", "value": n_iter / (solve_ms * 1e-3), "unit": "LM iterations/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": solve_ms / max(n_iter, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "n_cam": full.n_cam, "n_pt": full.n_pt, "n_obs": full.n_obs,
+                   "scale": args.scale, "lm_iterations": n_iter, "pcg_iterations_total": int(summ.total_linear_iters),
+                   "pcg_iterations_per_lm": pcg_counts, "tolerances": "disabled (fixed iteration count)",
+                   "parallelism": "points sharded x%d, NCCL all-reduce of camera-sized vectors" % world if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (Jacobian planes %.0f MB per pass)" % (full.n_obs * 144 / 1e6) if not flush
+                         else "L2 flushed (512 MiB write) between timed kernel launches",
+                   "generate_s": round(t_gen, 2)},
+        "jacobian_eval_obs_per_s": jac_obs_s,
+        "final_cost": summ.final_cost, "initial_cost": summ.initial_cost,
+        "solve_wall_ms": wall_solve * 1e3,
+        "e2e": {"value": summ2.num_iterations / e2e_s, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d // max(K, 1),
+                "d2h_bytes_per_step": d2h // max(K, 1), "seconds": e2e_s,
+                "note": "upload (pinned host -> HBM, index build) + solve + download through ba_gpu_* with host buffers"},
+        "gpu_launches": int(summ.kernel_launches),
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                     "timing": "CUDA events on the solver stream, mean of 20 launches after 3 warm-ups"},
+        "roofline_kernels": kernels,
+        "clocks": clk,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference_sample(full, wl["mode"], pcg_counts, os.cpu_count() or 1)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -161,8 +161,10 @@ int ba_gpu_se3_plus(ba_gpu_ctx *ctx, int32_t n, const double *pose7,
 
 /* ---- measurement hooks (bench.py) ---- */
 enum {
-  BA_KERNEL_LINEARIZE = 0,   /* camera-major residual+Jacobian kernel */
-  BA_KERNEL_SCHUR_MATVEC = 1 /* one implicit-Schur product (both passes) */
+  BA_KERNEL_LINEARIZE = 0,    /* camera-major residual+Jacobian kernel */
+  BA_KERNEL_SCHUR_MATVEC = 1, /* one implicit-Schur product (both passes) */
+  BA_KERNEL_SCHUR_PASS1 = 2,  /* point-major pass  t = V^-1 W^T x only */
+  BA_KERNEL_SCHUR_PASS2 = 3   /* camera-major pass y = U x - W t only */
 };
 /* Launches kernel `which` `iters` times on the context stream between two CUDA
  * events (after `warmup` untimed launches); *ms_avg = mean ms per launch. If
