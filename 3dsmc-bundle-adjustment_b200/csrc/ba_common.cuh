@@ -74,8 +74,8 @@ struct LmState {
   int32_t have_scale;
   int64_t total_lin_iters;
   // PCG controller
-  int32_t pcg_it, pcg_done, pcg_fail, pcg_break, pcg_iters_last, pad0;
-  double pcg_rho_hist[2], pcg_Q0;
+  int32_t pcg_it, pcg_done, pcg_fail, pcg_break, pcg_iters_last, pcg_counter;
+  double pcg_rho, pcg_beta, pcg_Q0;
   BaIterRec pending;     // record of an accepted step, completed after relinearisation
 };
 

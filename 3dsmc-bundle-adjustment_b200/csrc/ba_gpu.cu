@@ -100,6 +100,8 @@ struct ba_gpu_ctx {
   // partials
   Buf part_blk, part6, part21, part_ex, part_kk;
   Buf pc_lin, pc_cand, pc_mcc, pe_gmax, pe_xn, pe_step, pcam_rho, pcam_bb, pcam_pq, pcam_Q;
+  // multi-GPU staging (dense per-camera sums, scalars, identity item_ptr)
+  Buf red_blk, red6, red21, scal, ident;
   // explicit solver
   Buf W, WV, S, rhs, blk_i, blk_j, blk_cam, pair_ptr, pair_a, pair_b;
   int n_blk = 0;
@@ -113,6 +115,8 @@ struct ba_gpu_ctx {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, n_ranks = 1;
+  int64_t collectives = 0;
+  bool comm_error = false;
 };
 
 static thread_local std::string g_create_err;
@@ -570,6 +574,11 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   RES(pcam_pq, (size_t)ctx->nblk_cam * 8);
   RES(pcam_Q, (size_t)ctx->nblk_cam * 8);
   RES(part_kk, (size_t)(ctx->nblk_pt + 1) * 14 * 8);
+  RES(red_blk, nc * 27 * 8);
+  RES(red6, nc * 48);
+  RES(red21, nc * 21 * 8);
+  RES(scal, 64 * 8);
+  RES(ident, (nc + 1) * 4);
   RES(st, sizeof(LmState));
   RES(trace, (size_t)lo.trace_cap * sizeof(BaIterRec));
 
@@ -602,6 +611,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   LAUNCH(k_item_count, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->item_cnt));
   LAUNCH(k_exclusive_scan, 1, 1024, 0, n_cam, P<int32_t>(ctx->item_cnt), P<int32_t>(ctx->item_ptr));
   LAUNCH(k_slots, ctx->nblk_cam, BA_THREADS, 0, n_cam, ctx->fixed_cam, P<int32_t>(ctx->cam_slot));
+  LAUNCH(k_iota, cdiv(n_cam + 1, 256), 256, 0, n_cam + 1, P<int32_t>(ctx->ident));
   int32_t h_items = 0, h_err = 0;
   CK(cudaMemcpyAsync(&h_items, P<int32_t>(ctx->item_ptr) + n_cam, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&h_err, ctx->err_flag.p, 4, cudaMemcpyDeviceToHost, s));
@@ -633,6 +643,52 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   return BA_OK;
 }
 
+// ------------------------------------------------------------------ multi-GPU reductions
+static int nccl_allreduce(ba_gpu_ctx *ctx, double *buf, size_t n, bool is_max) {
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, n, ncclFloat64_, is_max ? ncclMax_ : ncclSum_, ctx->comm, ctx->stream);
+  if (r != 0) return fail(ctx, BA_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  ctx->collectives++;
+  return 0;
+}
+// scalar from per-CTA partials: single GPU -> the partial array itself (summed by
+// the consumer in fixed order); sharded -> local sum, all-reduce, 1-entry array
+struct PartRef {
+  const double *p;
+  int n;
+};
+static PartRef reduce_scalar(ba_gpu_ctx *ctx, const double *part, int nblk, int slot, bool is_max, int gate) {
+  if (ctx->n_ranks == 1) return PartRef{part, nblk};
+  double *out = P<double>(ctx->scal) + slot;
+  k_reduce_partials<<<1, BA_THREADS, 0, ctx->stream>>>(nblk, part, out, is_max ? 1 : 0, P<LmState>(ctx->st), gate);
+  ctx->launches++;
+  if (nccl_allreduce(ctx, out, 1, is_max)) ctx->comm_error = true;
+  return PartRef{out, 1};
+}
+// per-camera sums of item partials: single GPU -> (item_ptr, part); sharded ->
+// dense local sums, all-reduce, (identity, dense)
+struct ItemRef {
+  const int32_t *ptr;
+  const double *part;
+};
+template <int NV>
+static ItemRef reduce_items(ba_gpu_ctx *ctx, const double *part, Buf &dense, int gate) {
+  if (ctx->n_ranks == 1) return ItemRef{P<int32_t>(ctx->item_ptr), part};
+  k_sum_items<NV><<<cdiv(ctx->n_cam * NV, BA_THREADS), BA_THREADS, 0, ctx->stream>>>(
+      ctx->n_cam, P<int32_t>(ctx->item_ptr), part, P<double>(dense), P<LmState>(ctx->st), gate);
+  ctx->launches++;
+  if (nccl_allreduce(ctx, P<double>(dense), (size_t)ctx->n_cam * NV, false)) ctx->comm_error = true;
+  return ItemRef{P<int32_t>(ctx->ident), P<double>(dense)};
+}
+// failure flags must agree on every rank (they steer the control flow)
+static void sync_flags(ba_gpu_ctx *ctx) {
+  if (ctx->n_ranks == 1) return;
+  double *out = P<double>(ctx->scal) + 32;
+  k_flags_pack<<<1, 1, 0, ctx->stream>>>(P<LmState>(ctx->st), out);
+  if (nccl_allreduce(ctx, out, 2, true)) ctx->comm_error = true;
+  k_flags_unpack<<<1, 1, 0, ctx->stream>>>(P<LmState>(ctx->st), out);
+  ctx->launches += 2;
+}
+
 // ------------------------------------------------------------------ pipeline pieces
 // linearise at the current point in both orders + normal-equation blocks
 static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk) {
@@ -647,7 +703,9 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
            sp, sk, ctx->cp, ctx->Jp_, (double *)nullptr, st, gate);
     LAUNCH((k_cam_blocks<DD, KK>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), ctx->Jc_,
            P<double>(ctx->part_blk), st, gate);
-    LAUNCH((k_cam_blocks_fin<KK>), ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part_blk),
+    ItemRef ir = ItemRef{P<int32_t>(ctx->item_ptr), P<double>(ctx->part_blk)};
+    if (KK == 0) ir = reduce_items<27>(ctx, P<double>(ctx->part_blk), ctx->red_blk, gate);
+    LAUNCH((k_cam_blocks_fin<KK>), ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part,
            P<double>(ctx->U), P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
     LAUNCH((k_pt_blocks<DD, KK>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), ctx->Jp_, P<double>(ctx->V),
            P<double>(ctx->gp), P<double>(ctx->Wk), P<double>(ctx->dp), ctx->lo, st, gate);
@@ -660,7 +718,7 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
 static void enqueue_state_norms(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk) {
   LAUNCH(k_state_norms, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, ctx->nk, ctx->fixed_cam, P<double>(ctx->pose),
          P<double>(ctx->pt), P<double>(ctx->intr), P<double>(ctx->gc), P<double>(ctx->gp), P<double>(ctx->gk), sc, sp, sk,
-         P<double>(ctx->pe_gmax), P<double>(ctx->pe_xn), P<LmState>(ctx->st), gate);
+         P<double>(ctx->pe_gmax), P<double>(ctx->pe_xn), P<LmState>(ctx->st), gate, ctx->rank == 0 ? 1.0 : 0.0);
 }
 
 // IterationZero of the trust-region minimizer
@@ -681,8 +739,12 @@ static void enqueue_iteration_zero(ba_gpu_ctx *ctx) {
     cudaMemcpyAsync(ctx->sk.p, ctx->one_k.p, 32, cudaMemcpyDeviceToDevice, ctx->stream);
   }
   LAUNCH(k_set_have_scale, 1, 1, 0, st);
-  LAUNCH(k_lm_iter0, 1, BA_THREADS, 0, ctx->nblk_obs, ctx->nblk_ent, ctx->nk, P<double>(ctx->pc_lin), P<double>(ctx->pe_gmax),
-         P<double>(ctx->pe_xn), P<double>(ctx->rk), ctx->lo, st, P<BaIterRec>(ctx->trace));
+  sync_flags(ctx);
+  const PartRef rc_ = reduce_scalar(ctx, P<double>(ctx->pc_lin), ctx->nblk_obs, 0, false, GATE_RUN);
+  const PartRef rg_ = reduce_scalar(ctx, P<double>(ctx->pe_gmax), ctx->nblk_ent, 1, true, GATE_RUN);
+  const PartRef rx_ = reduce_scalar(ctx, P<double>(ctx->pe_xn), ctx->nblk_ent, 2, false, GATE_RUN);
+  LAUNCH(k_lm_iter0, 1, BA_THREADS, 0, rc_.n, rg_.n, ctx->nk, rc_.p, rg_.p, rx_.p, P<double>(ctx->rk), ctx->lo, st,
+         P<BaIterRec>(ctx->trace));
   ctx->linearized = true;
 }
 
@@ -706,24 +768,27 @@ static int poll_state(ba_gpu_ctx *ctx) {
   return 0;
 }
 
-static void enqueue_pcg_iteration(ba_gpu_ctx *ctx) {
+// one PCG iteration; `it` mirrors the device-side iteration counter (they agree
+// while the controller has not finished; afterwards every kernel is gated off)
+static void enqueue_pcg_iteration(ba_gpu_ctx *ctx, int it) {
   LmState *st = P<LmState>(ctx->st);
   const int rp = ctx->lo.reset_period;
-  LAUNCH(k_pcg_dir, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, P<double>(ctx->pcam_rho), P<double>(ctx->z),
-         P<double>(ctx->p), st, GATE_PCG);
+  const int reset = (rp > 0 && (it % rp) == 0) ? 1 : 0;
+  LAUNCH(k_pcg_dir, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<double>(ctx->z), P<double>(ctx->p), st, GATE_PCG);
   enqueue_matvec(ctx, P<double>(ctx->p), GATE_PCG);
-  LAUNCH(k_pcg_q, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part6), P<double>(ctx->dc),
-         P<double>(ctx->p), P<double>(ctx->q), P<double>(ctx->pcam_pq), st, GATE_PCG);
+  ItemRef ir = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_PCG);
+  LAUNCH(k_pcg_q, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->dc), P<double>(ctx->p),
+         P<double>(ctx->q), P<double>(ctx->pcam_pq), st, GATE_PCG);
   LAUNCH(k_pcg_step, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, P<double>(ctx->pcam_pq), P<double>(ctx->p),
          P<double>(ctx->q), P<double>(ctx->b), P<double>(ctx->Minv), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z),
-         P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), st, GATE_PCG, rp);
-  if (rp > 0) {
-    enqueue_matvec(ctx, P<double>(ctx->x), GATE_PCG_RESET);
-    LAUNCH(k_pcg_reset, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part6),
-           P<double>(ctx->dc), P<double>(ctx->x), P<double>(ctx->b), P<double>(ctx->Minv), P<double>(ctx->r), P<double>(ctx->z),
-           P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), st, GATE_PCG_RESET, rp);
+         P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), ctx->lo, st, GATE_PCG, reset);
+  if (reset) {
+    enqueue_matvec(ctx, P<double>(ctx->x), GATE_PCG);
+    ir = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_PCG);
+    LAUNCH(k_pcg_reset, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, ir.ptr, ir.part, P<double>(ctx->dc),
+           P<double>(ctx->x), P<double>(ctx->b), P<double>(ctx->Minv), P<double>(ctx->r), P<double>(ctx->z),
+           P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), ctx->lo, st, GATE_PCG);
   }
-  LAUNCH(k_pcg_ctl, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_Q), ctx->lo, st, GATE_PCG);
 }
 
 // reduced system solve by implicit Schur + block-Jacobi PCG; host polls the
@@ -737,21 +802,24 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
     LAUNCH((k_schur_diag<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Jc_,
            P<double>(ctx->Vinv), P<double>(ctx->part21), st, GATE_RUN);
   });
-  LAUNCH(k_schur_diag_fin, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part21),
-         P<double>(ctx->U), P<double>(ctx->dc), P<double>(ctx->Minv), st, GATE_RUN);
-  LAUNCH(k_pcg_init, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part6), P<double>(ctx->gc),
-         P<double>(ctx->Minv), P<double>(ctx->b), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z), P<double>(ctx->pcam_rho),
+  sync_flags(ctx);
+  ItemRef i21 = reduce_items<21>(ctx, P<double>(ctx->part21), ctx->red21, GATE_RUN);
+  LAUNCH(k_schur_diag_fin, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i21.ptr, i21.part, P<double>(ctx->U), P<double>(ctx->dc),
+         P<double>(ctx->Minv), st, GATE_RUN);
+  ItemRef i6 = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_RUN);
+  LAUNCH(k_pcg_init, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i6.ptr, i6.part, P<double>(ctx->gc), P<double>(ctx->Minv),
+         P<double>(ctx->b), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z), P<double>(ctx->pcam_rho),
          P<double>(ctx->pcam_bb), st, GATE_RUN);
-  LAUNCH(k_pcg_start, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_bb), st, GATE_RUN);
+  LAUNCH(k_pcg_start, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_bb), P<double>(ctx->pcam_rho), st, GATE_RUN);
   const int batch = std::max(1, ctx->opt.poll_interval);
-  int launched = 0;
+  int it = 1;
   for (;;) {
-    for (int k = 0; k < batch; ++k) enqueue_pcg_iteration(ctx);
-    launched += batch;
+    for (int k = 0; k < batch; ++k, ++it) enqueue_pcg_iteration(ctx, it);
     int rc = poll_state(ctx);
     if (rc) return rc;
+    if (ctx->comm_error) return BA_ERR_COMM;
     if (ctx->h_st->pcg_done || ctx->h_st->done) break;
-    if (launched > ctx->lo.max_pcg + batch) return fail(ctx, BA_ERR_STATE, "PCG controller did not terminate");
+    if (it > ctx->lo.max_pcg + batch + 1) return fail(ctx, BA_ERR_STATE, "PCG controller did not terminate");
   }
   LAUNCH(k_pcg_finish, cdiv(6 * ctx->n_cam, BA_THREADS), BA_THREADS, 0, 6 * ctx->n_cam, P<double>(ctx->x), P<double>(ctx->yc), st,
          GATE_RUN);
@@ -818,22 +886,34 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
   LAUNCH(k_candidate, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, K, ctx->fixed_cam, P<double>(ctx->pose), P<double>(ctx->pt),
          P<double>(ctx->intr), P<double>(ctx->yc), P<double>(ctx->yp), P<double>(ctx->yk), P<double>(ctx->sc), P<double>(ctx->sp),
          P<double>(ctx->sk), P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c), P<double>(ctx->pe_step), st,
-         GATE_RUN);
+         GATE_RUN, ctx->rank == 0 ? 1.0 : 0.0);
   DISPATCH_D(D, {
     LAUNCH((k_cost<DD>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
            P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c),
            ctx->cp, P<double>(ctx->pc_cand), st, GATE_RUN);
   });
-  LAUNCH(k_lm_control, 1, BA_THREADS, 0, ctx->nblk_obs, ctx->nblk_ent, K, P<double>(ctx->pc_mcc), P<double>(ctx->pe_step),
-         P<double>(ctx->pc_cand), P<double>(ctx->rk), P<double>(ctx->Jkk), P<double>(ctx->yk), P<double>(ctx->intr_c),
-         P<double>(ctx->intr_prior), ctx->cp.sw_intr, ctx->lo, st, P<BaIterRec>(ctx->trace));
+  sync_flags(ctx);
+  {
+    const PartRef rm = reduce_scalar(ctx, P<double>(ctx->pc_mcc), ctx->nblk_obs, 3, false, GATE_RUN);
+    const PartRef rs = reduce_scalar(ctx, P<double>(ctx->pe_step), ctx->nblk_ent, 4, false, GATE_RUN);
+    const PartRef rc2 = reduce_scalar(ctx, P<double>(ctx->pc_cand), ctx->nblk_obs, 5, false, GATE_RUN);
+    LAUNCH(k_lm_control, 1, BA_THREADS, 0, rm.n, rs.n, K, rm.p, rs.p, rc2.p, P<double>(ctx->rk), P<double>(ctx->Jkk),
+           P<double>(ctx->yk), P<double>(ctx->intr_c), P<double>(ctx->intr_prior), ctx->cp.sw_intr, ctx->lo, st,
+           P<BaIterRec>(ctx->trace));
+  }
   // accepted: x <- x+, relinearise (all gated on the device-side decision)
   LAUNCH(k_accept, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr),
          P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c), st, GATE_ACCEPTED);
   enqueue_linearize(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk));
   enqueue_state_norms(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk));
-  LAUNCH(k_lm_post, 1, BA_THREADS, 0, ctx->nblk_obs, ctx->nblk_ent, K, P<double>(ctx->pc_lin), P<double>(ctx->pe_gmax),
-         P<double>(ctx->pe_xn), P<double>(ctx->rk), ctx->lo, st, P<BaIterRec>(ctx->trace), GATE_ACCEPTED);
+  sync_flags(ctx);
+  {
+    const PartRef rc3 = reduce_scalar(ctx, P<double>(ctx->pc_lin), ctx->nblk_obs, 6, false, GATE_ACCEPTED);
+    const PartRef rg = reduce_scalar(ctx, P<double>(ctx->pe_gmax), ctx->nblk_ent, 7, true, GATE_ACCEPTED);
+    const PartRef rx = reduce_scalar(ctx, P<double>(ctx->pe_xn), ctx->nblk_ent, 8, false, GATE_ACCEPTED);
+    LAUNCH(k_lm_post, 1, BA_THREADS, 0, rc3.n, rg.n, K, rc3.p, rg.p, rx.p, P<double>(ctx->rk), ctx->lo, st,
+           P<BaIterRec>(ctx->trace), GATE_ACCEPTED);
+  }
   return 0;
 }
 

@@ -939,48 +939,40 @@ k_pcg_init(int n_cam, const int32_t *__restrict__ item_ptr, const double *__rest
 
 // single CTA: PCG controller reset ("Convergence. |b| = 0" shortcut included)
 __global__ void __launch_bounds__(BA_THREADS)
-k_pcg_start(int nblk, const double *__restrict__ part_bb, LmState *st, int gate) {
+k_pcg_start(int nblk, const double *__restrict__ part_bb, const double *__restrict__ part_rho, LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
   __shared__ double red[BA_WARPS + 2];
   const double bb = block_sum_array(part_bb, nblk, red);
+  const double rho = block_sum_array(part_rho, nblk, red);
   if (threadIdx.x == 0) {
     st->pcg_it = 1;
     st->pcg_fail = 0;
     st->pcg_break = 0;
     st->pcg_Q0 = 0.0;
-    st->pcg_rho_hist[0] = 1.0;
-    st->pcg_rho_hist[1] = 1.0;
+    st->pcg_rho = rho;
+    st->pcg_beta = 0.0;
+    st->pcg_counter = 0;
     st->pcg_iters_last = 0;
     st->pcg_done = (bb == 0.0 || st->lin_fail) ? 1 : 0;
     if (!isfinite(bb)) {
       st->pcg_done = 1;
       st->lin_fail = 1;
+    } else if (bb != 0.0 && (rho == 0.0 || !isfinite(rho))) {  // IsZeroOrInfinity(rho): solver failure
+      st->pcg_done = 1;
+      st->lin_fail = 1;
+      st->pcg_iters_last = 1;
     }
   }
 }
 
-// direction update: rho = r.z, beta = rho / last_rho, p = z + beta p
+// direction update p = z + beta p (beta = rho / last_rho from the controller)
 __global__ void __launch_bounds__(BA_THREADS)
-k_pcg_dir(int n_cam, int nblk, const double *__restrict__ part_rho, const double *__restrict__ z, double *__restrict__ p,
-          LmState *st, int gate) {
+k_pcg_dir(int n_cam, const double *__restrict__ z, double *__restrict__ p, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  __shared__ double red[BA_WARPS + 2];
-  const int it = st->pcg_it;
-  const double last_rho = st->pcg_rho_hist[(it - 1) & 1];
-  const double rho = block_sum_array(part_rho, nblk, red);
-  bool fail = (rho == 0.0) || !isfinite(rho);
-  double beta = 0.0;
-  if (it > 1) {
-    beta = rho / last_rho;
-    if (beta == 0.0 || !isfinite(beta)) fail = true;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    st->pcg_rho_hist[it & 1] = rho;
-    if (fail) st->pcg_fail = 1;
-  }
-  if (fail) return;
   const int c = blockIdx.x * BA_THREADS + threadIdx.x;
   if (c >= n_cam) return;
+  const int it = st->pcg_it;
+  const double beta = st->pcg_beta;
   double zv[6], pv[6];
   load6(z + 6 * (size_t)c, zv);
   if (it > 1) {
@@ -1020,29 +1012,96 @@ k_pcg_q(int n_cam, const int32_t *__restrict__ item_ptr, const double *__restric
   if (threadIdx.x == 0) part_pq[blockIdx.x] = s1;
 }
 
-// alpha = rho / p.q ; x += alpha p ; r -= alpha q (unless this is a residual
-// reset iteration) ; z = M^-1 r ; partials of r.z and x.(b + r)
+// Tail of a PCG iteration, run by the LAST CTA to finish (integer ticket, the
+// floating-point sums stay in fixed order): quadratic-model termination of
+// conjugate_gradients_solver.cc, then rho / beta of the next iteration.
+__device__ __forceinline__ void pcg_controller(int nblk, double *part_rho, double *part_Q, double *red, const LmOptions &lo,
+                                               LmState *st) {
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int t = atomicAdd(&st->pcg_counter, 1);
+    is_last = (t == nblk - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double v = 0.0, w = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    v += __ldcg(part_rho + i);
+    w += __ldcg(part_Q + i);
+  }
+  v = warp_sum(v);
+  w = warp_sum(w);
+  const int wid = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) {
+    red[wid] = v;
+    red[BA_WARPS + 2 + wid] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double rho_new = 0.0, xq = 0.0;
+  for (int i = 0; i < BA_WARPS; ++i) {
+    rho_new += red[i];
+    xq += red[BA_WARPS + 2 + i];
+  }
+  st->pcg_counter = 0;
+  const int it = st->pcg_it;
+  st->pcg_iters_last = it;
+  const double Q1 = -1.0 * xq;
+  const double zeta = it * (Q1 - st->pcg_Q0) / Q1;
+  if (zeta < lo.eta && it >= lo.min_pcg) {
+    st->pcg_done = 1;
+    return;
+  }
+  st->pcg_Q0 = Q1;
+  if (it >= lo.max_pcg) {
+    st->pcg_done = 1;
+    return;
+  }
+  // next iteration: rho = r.z, beta = rho / last_rho (IsZeroOrInfinity -> failure)
+  const double beta = rho_new / st->pcg_rho;
+  if (rho_new == 0.0 || !isfinite(rho_new) || beta == 0.0 || !isfinite(beta)) {
+    st->pcg_iters_last = it + 1;
+    st->pcg_done = 1;
+    st->lin_fail = 1;
+    return;
+  }
+  st->pcg_rho = rho_new;
+  st->pcg_beta = beta;
+  st->pcg_it = it + 1;
+}
+
+// alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = M^-1 r ; partials of r.z and
+// x.(b + r); the last CTA runs the controller.  On a residual-reset iteration only x
+// is updated here (r is recomputed from b - S x by k_pcg_reset).
 __global__ void __launch_bounds__(BA_THREADS)
 k_pcg_step(int n_cam, int nblk, const double *__restrict__ part_pq, const double *__restrict__ p,
            const double *__restrict__ q, const double *__restrict__ b, const double *__restrict__ Minv,
-           double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *__restrict__ part_rho,
-           double *__restrict__ part_Q, LmState *st, int gate, int reset_period) {
+           double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *part_rho, double *part_Q,
+           LmOptions lo, LmState *st, int gate, int reset) {
   if (!gate_open(st, gate)) return;
-  __shared__ double red[BA_WARPS + 2];
-  const int it = st->pcg_it;
-  if (st->pcg_fail) return;
+  __shared__ double red[2 * BA_WARPS + 4];
   const double pq = block_sum_array(part_pq, nblk, red);
-  const double rho = st->pcg_rho_hist[it & 1];
-  if (pq <= 0.0 || isinf(pq) || isnan(pq)) {  // NO_CONVERGENCE: keep x
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->pcg_break = 1;
+  const double rho = st->pcg_rho;
+  if (pq <= 0.0 || isinf(pq) || isnan(pq)) {  // NO_CONVERGENCE: keep x, stop
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st->pcg_iters_last = st->pcg_it;
+      st->pcg_break = 1;
+      st->pcg_done = 1;  // safe: every CTA takes this branch from its own (identical) sum
+    }
     return;
   }
   const double alpha = rho / pq;
   if (isinf(alpha)) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->pcg_fail = 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st->pcg_iters_last = st->pcg_it;
+      st->pcg_done = 1;
+      st->lin_fail = 1;
+    }
     return;
   }
-  const bool reset = reset_period > 0 && (it % reset_period) == 0;
   const int c = blockIdx.x * BA_THREADS + threadIdx.x;
   double rz = 0.0, xq = 0.0;
   if (c < n_cam) {
@@ -1069,25 +1128,24 @@ k_pcg_step(int n_cam, int nblk, const double *__restrict__ part_pq, const double
       }
     }
   }
-  if (!reset) {
-    const double s1 = block_sum(rz, red);
-    const double s2 = block_sum(xq, red);
-    if (threadIdx.x == 0) {
-      part_rho[blockIdx.x] = s1;
-      part_Q[blockIdx.x] = s2;
-    }
+  if (reset) return;
+  const double s1 = block_sum(rz, red);
+  const double s2 = block_sum(xq, red);
+  if (threadIdx.x == 0) {
+    part_rho[blockIdx.x] = s1;
+    part_Q[blockIdx.x] = s2;
   }
+  pcg_controller(nblk, part_rho, part_Q, red, lo, st);
 }
 
 // residual reset (every residual_reset_period iterations): r = b - S x
 __global__ void __launch_bounds__(BA_THREADS)
-k_pcg_reset(int n_cam, const int32_t *__restrict__ item_ptr, const double *__restrict__ part, const double *__restrict__ dc,
-            const double *__restrict__ x, const double *__restrict__ b, const double *__restrict__ Minv,
-            double *__restrict__ r, double *__restrict__ z, double *__restrict__ part_rho, double *__restrict__ part_Q,
-            const LmState *st, int gate, int reset_period) {
-  if (!gate_open(st, gate, reset_period)) return;
-  if (st->pcg_fail || st->pcg_break) return;
-  __shared__ double red[BA_WARPS + 1];
+k_pcg_reset(int n_cam, int nblk, const int32_t *__restrict__ item_ptr, const double *__restrict__ part,
+            const double *__restrict__ dc, const double *__restrict__ x, const double *__restrict__ b,
+            const double *__restrict__ Minv, double *__restrict__ r, double *__restrict__ z, double *part_rho,
+            double *part_Q, LmOptions lo, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  __shared__ double red[2 * BA_WARPS + 4];
   const int c = blockIdx.x * BA_THREADS + threadIdx.x;
   const double radius = st->radius;
   double rz = 0.0, xq = 0.0;
@@ -1118,38 +1176,7 @@ k_pcg_reset(int n_cam, const int32_t *__restrict__ item_ptr, const double *__res
     part_rho[blockIdx.x] = s1;
     part_Q[blockIdx.x] = s2;
   }
-}
-
-// single CTA: quadratic-model termination of conjugate_gradients_solver.cc
-__global__ void __launch_bounds__(BA_THREADS)
-k_pcg_ctl(int nblk, const double *__restrict__ part_Q, LmOptions lo, LmState *st, int gate) {
-  if (!gate_open(st, gate)) return;
-  __shared__ double red[BA_WARPS + 2];
-  const double xq = block_sum_array(part_Q, nblk, red);
-  if (threadIdx.x != 0) return;
-  const int it = st->pcg_it;
-  st->pcg_iters_last = it;
-  if (st->pcg_fail) {
-    st->pcg_done = 1;
-    st->lin_fail = 1;
-    return;
-  }
-  if (st->pcg_break) {
-    st->pcg_done = 1;
-    return;
-  }
-  const double Q1 = -1.0 * xq;
-  const double zeta = it * (Q1 - st->pcg_Q0) / Q1;
-  if (zeta < lo.eta && it >= lo.min_pcg) {
-    st->pcg_done = 1;
-    return;
-  }
-  st->pcg_Q0 = Q1;
-  if (it >= lo.max_pcg) {
-    st->pcg_done = 1;
-    return;
-  }
-  st->pcg_it = it + 1;
+  pcg_controller(nblk, part_rho, part_Q, red, lo, st);
 }
 
 // y_c = x (PCG solution); non-finite solution = linear solver failure
@@ -1174,7 +1201,7 @@ k_state_norms(int n_cam, int n_pt, int nk, int fixed_cam, const double *__restri
               const double *__restrict__ intr, const double *__restrict__ gc, const double *__restrict__ gp,
               const double *__restrict__ gk, const double *__restrict__ sc, const double *__restrict__ sp,
               const double *__restrict__ sk, double *__restrict__ part_gmax, double *__restrict__ part_xn,
-              const LmState *st, int gate) {
+              const LmState *st, int gate, double cam_weight) {
   if (!gate_open(st, gate)) return;
   __shared__ double red[BA_WARPS + 1];
   const int e = blockIdx.x * BA_THREADS + threadIdx.x;
@@ -1190,7 +1217,7 @@ k_state_norms(int n_cam, int n_pt, int nk, int fixed_cam, const double *__restri
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
         gm = fmax(gm, fabs(T[k] - o[k]));
-        xn += T[k] * T[k];
+        xn += cam_weight * (T[k] * T[k]);
       }
     }
   } else if (e < n_cam + n_pt) {
@@ -1204,7 +1231,7 @@ k_state_norms(int n_cam, int n_pt, int nk, int fixed_cam, const double *__restri
   } else if (e == n_cam + n_pt && nk) {
     for (int k = 0; k < 4; ++k) {
       gm = fmax(gm, fabs(gk[k] / sk[k]));
-      xn += intr[k] * intr[k];
+      xn += cam_weight * (intr[k] * intr[k]);
     }
   }
   const double m = block_max(gm, red);
@@ -1247,7 +1274,7 @@ k_candidate(int n_cam, int n_pt, int nk, int fixed_cam, const double *__restrict
             const double *__restrict__ intr, const double *__restrict__ yc, const double *__restrict__ yp,
             const double *__restrict__ yk, const double *__restrict__ sc, const double *__restrict__ sp,
             const double *__restrict__ sk, double *__restrict__ pose_c, double *__restrict__ pt_c,
-            double *__restrict__ intr_c, double *__restrict__ part_step, const LmState *st, int gate) {
+            double *__restrict__ intr_c, double *__restrict__ part_step, const LmState *st, int gate, double cam_weight) {
   if (!gate_open(st, gate)) return;
   __shared__ double red[BA_WARPS + 1];
   const int e = blockIdx.x * BA_THREADS + threadIdx.x;
@@ -1264,7 +1291,7 @@ k_candidate(int n_cam, int n_pt, int nk, int fixed_cam, const double *__restrict
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
         const double df = T[k] - o[k];
-        sn += df * df;
+        sn += cam_weight * (df * df);
       }
     } else {
 #pragma unroll
@@ -1288,7 +1315,7 @@ k_candidate(int n_cam, int n_pt, int nk, int fixed_cam, const double *__restrict
       const double c = nk ? x + yk[k] * sk[k] : x;
       intr_c[k] = c;
       const double df = x - c;
-      sn += df * df;
+      sn += cam_weight * (df * df);
     }
   }
   const double s = block_sum(sn, red);
@@ -1874,4 +1901,43 @@ k_cholesky_solve(int n, double *__restrict__ Sg, const double *__restrict__ rhs,
     }
   }
   if (tid < 4) yk[tid] = nk ? bv[6 * n_free + tid] : 0.0;
+}
+
+
+// =====================================================================
+// Multi-GPU glue (points sharded across ranks): local
+// per-camera sums / scalars are packed into dense buffers that NCCL all-reduces
+// in place; the single-GPU kernels then consume them through an identity
+// item_ptr (one "item" per camera) or a 1-entry partial array.
+// =====================================================================
+template <int NV>
+__global__ void __launch_bounds__(BA_THREADS)
+k_sum_items(int n_cam, const int32_t *__restrict__ item_ptr, const double *__restrict__ part, double *__restrict__ out,
+            const LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  const int idx = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (idx >= n_cam * NV) return;
+  const int c = idx / NV, k = idx - c * NV;
+  double s = 0.0;
+  for (int it = item_ptr[c]; it < item_ptr[c + 1]; ++it) s += part[(size_t)it * NV + k];
+  out[idx] = s;
+}
+__global__ void __launch_bounds__(BA_THREADS)
+k_reduce_partials(int n, const double *__restrict__ part, double *__restrict__ out, int is_max, const LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  __shared__ double red[BA_WARPS + 2];
+  const double v = is_max ? block_max_array(part, n, red) : block_sum_array(part, n, red);
+  if (threadIdx.x == 0) out[0] = v;
+}
+__global__ void k_flags_pack(const LmState *st, double *out) {
+  out[0] = (double)st->eval_fail;
+  out[1] = (double)st->lin_fail;
+}
+__global__ void k_flags_unpack(LmState *st, const double *in) {
+  if (in[0] != 0.0) st->eval_fail = 1;
+  if (in[1] != 0.0) st->lin_fail = 1;
+}
+__global__ void k_iota(int n, int32_t *p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
 }

@@ -1,0 +1,26 @@
+"""Point-sharded multi-GPU solve == single-GPU solve (needs >= 2 GPUs)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("cfg", [3, 4])
+@pytest.mark.parametrize("world", [2])
+def test_sharded_solve_matches_single_gpu(world, cfg):
+    if _n_gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(cfg), "0.05", "6"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "MULTI_GPU_PARITY OK" in out.stdout
