@@ -1,0 +1,182 @@
+// OptimizationUtils_gpu.cpp -- drop-in replacement for the Ceres-facing half of
+// the reference's src/OptimizationUtils.cpp: countConstraints (:184-213) and
+// windowOptimize (:215-313) keep their signatures (headers/OptimizationUtils.h:42,
+// 55) and their observable behaviour -- enumeration order, in-place frame change
+// and write-back -- while ceres::Problem / ceres::Solve (:218-300) are replaced by
+// ba_gpu_upload / ba_gpu_solve / ba_gpu_download (include/ba_gpu.h).
+//
+// Inside the reference tree: compile with -DBA_USE_REFERENCE_HEADERS in place of
+// the cost-functor / Ceres part of src/OptimizationUtils.cpp.
+#ifdef BA_USE_REFERENCE_HEADERS
+#include "OptimizationUtils.h"
+#else
+#include "compat/reference_types.h"
+#endif
+
+#include <cstdio>
+#include <set>
+#include <vector>
+
+#include "../../include/ba_gpu.h"
+#include "ba_host_debug.h"
+
+using std::vector;
+
+namespace {
+// one solver context per host thread, reused across windows (device buffers are
+// kept; sliding windows repeat every frame_frequency keyframes, src/main.cpp:163-168)
+struct Ctx {
+  ba_gpu_ctx *ctx = nullptr;
+  ~Ctx() {
+    if (ctx) ba_gpu_destroy(ctx);
+  }
+};
+thread_local Ctx g_ctx;
+thread_local BaHostLastProblem g_last;
+}  // namespace
+
+const BaHostLastProblem &ba_host_last_problem() { return g_last; }
+
+int countConstraints(const Map3D &map, const vector<KeyFrame> &keyframes, int kf_i, int kf_f) {
+  (void)map;
+  int admissible_obs = 0;
+  for (int kf_n = kf_i; kf_n <= kf_f; kf_n++) {
+    const KeyFrame &kf = keyframes[kf_n];
+    for (const auto &index_pair : kf.global_points_map) {
+      const double depth = kf.points3d_local[index_pair.first](2);
+      if (depth <= 1e-15) {
+        // the reference prints here (:202); kept quiet on purpose: same count
+        continue;
+      }
+      admissible_obs++;
+    }
+  }
+  return admissible_obs;
+}
+
+bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vector<KeyFrame> &keyframes, Map3D &map,
+                    const Vector4d &intrinsics_initial, Vector4d &intrinsics_optimized) {
+  const int n_cam = kf_f - kf_i + 1;
+  if (n_cam <= 0) return true;
+
+  // ---- options: ceresGlobalProblem knobs (:47-50, :64-65) -> ba_gpu_options
+  ba_gpu_options opt;
+  ba_gpu_default_options(&opt);
+  opt.HUB_P_REPR = globalProblem.HUB_P_REPR;
+  opt.HUB_P_UNPR = globalProblem.HUB_P_UNPR;
+  opt.WEIGHT_UNPR = globalProblem.WEIGHT_UNPR;
+  opt.WEIGHT_INTRINSICS = globalProblem.WEIGHT_INTRINSICS;
+  opt.max_num_iterations = globalProblem.options.max_num_iterations;
+  opt.eta = globalProblem.options.eta;
+  opt.use_depth_prior = 1;       // DepthPrior residual per observation (:288-294)
+  opt.optimize_intrinsics = 1;   // intrinsics are a free block with a prior (:236-241)
+  opt.solver = BA_SOLVER_AUTO;   // SPARSE_SCHUR == exact Schur step
+
+  // ---- snapshot for the error path: inputs stay untouched on failure
+  vector<Sophus::SE3d> pose_backup(n_cam);
+  for (int k = 0; k < n_cam; ++k) pose_backup[k] = keyframes[kf_i + k].T_w_c;
+  vector<std::pair<int, Vector3d>> point_backup;
+
+  const Sophus::SE3d initialPose = keyframes[kf_i].T_w_c;          // :231
+  const Sophus::SE3d initialPoseInv = keyframes[kf_i].T_w_c.inverse();  // :232
+  const int admissible_obs = countConstraints(map, keyframes, kf_i, kf_f);  // :242
+
+  // ---- canonical enumeration (:244-294): container order, first-appearance point ids
+  std::set<int> already_observed_pts;
+  std::unordered_map<int, int> pt_of_landmark;
+  vector<int> landmark_of_pt;
+  vector<int32_t> cam_idx, pt_idx;
+  vector<double> uv2, depthv, pose7((size_t)n_cam * 7), pt3;
+  cam_idx.reserve(admissible_obs);
+  pt_idx.reserve(admissible_obs);
+  uv2.reserve((size_t)admissible_obs * 2);
+  depthv.reserve(admissible_obs);
+  bool missing_landmark = false;
+  for (int kf_n = kf_i; kf_n <= kf_f && !missing_landmark; kf_n++) {
+    KeyFrame &curr_kf = keyframes[kf_n];
+    curr_kf.T_w_c = Sophus::SE3d(initialPoseInv * curr_kf.T_w_c);  // :248, in place
+    for (const auto &index_pair : curr_kf.global_points_map) {
+      const int landmarkId = index_pair.second;
+      const int localId = index_pair.first;
+      const double depth = curr_kf.points3d_local[localId](2);
+      if (depth <= 1e-15) continue;  // :265-268
+      auto found = map.find(landmarkId);
+      if (found == map.end()) {  // the reference would throw from map.at (:270)
+        missing_landmark = true;
+        break;
+      }
+      Landmark &map_point = found->second;
+      if (already_observed_pts.find(landmarkId) == already_observed_pts.end()) {
+        already_observed_pts.insert(landmarkId);
+        point_backup.emplace_back(landmarkId, map_point.point);
+        map_point.point = initialPoseInv * map_point.point;  // :274, in place
+        pt_of_landmark[landmarkId] = (int)landmark_of_pt.size();
+        landmark_of_pt.push_back(landmarkId);
+      }
+      cam_idx.push_back(kf_n - kf_i);
+      pt_idx.push_back(pt_of_landmark[landmarkId]);
+      uv2.push_back((double)curr_kf.keypoints[localId].pt.x);  // float -> double (:262)
+      uv2.push_back((double)curr_kf.keypoints[localId].pt.y);
+      depthv.push_back(depth);
+    }
+  }
+  auto restore = [&]() {
+    for (int k = 0; k < n_cam; ++k) keyframes[kf_i + k].T_w_c = pose_backup[k];
+    for (auto &pb : point_backup) map.at(pb.first).point = pb.second;
+  };
+  if (missing_landmark) {
+    std::fprintf(stderr, "windowOptimize: keyframe references a landmark that is not in the map\n");
+    restore();
+    return false;
+  }
+  const int n_pt = (int)landmark_of_pt.size(), n_obs = (int)cam_idx.size();
+  for (int k = 0; k < n_cam; ++k)
+    for (int j = 0; j < 7; ++j) pose7[(size_t)k * 7 + j] = keyframes[kf_i + k].T_w_c.data()[j];
+  pt3.resize((size_t)n_pt * 3);
+  for (int p = 0; p < n_pt; ++p)
+    for (int j = 0; j < 3; ++j) pt3[(size_t)p * 3 + j] = map.at(landmark_of_pt[p]).point(j);
+  double intr[4], prior[4];
+  for (int j = 0; j < 4; ++j) {
+    intr[j] = intrinsics_optimized(j);
+    prior[j] = intrinsics_initial(j);
+  }
+  g_last.cam_idx = cam_idx;
+  g_last.pt_idx = pt_idx;
+  g_last.landmark_of_pt = landmark_of_pt;
+  g_last.admissible_obs = admissible_obs;
+
+  // ---- ceres::Solve (:300) -> GPU
+  int rc = BA_OK;
+  if (!g_ctx.ctx)
+    rc = ba_gpu_create(&opt, &g_ctx.ctx);
+  else
+    rc = ba_gpu_set_options(g_ctx.ctx, &opt);
+  ba_gpu_summary summary;
+  if (rc == BA_OK)
+    rc = ba_gpu_upload(g_ctx.ctx, n_cam, pose7.data(), /*fixed_cam=*/0 /* :299 */, n_pt, pt3.data(), n_obs, cam_idx.data(),
+                       pt_idx.data(), uv2.data(), depthv.data(), intr, prior);
+  if (rc == BA_OK) rc = ba_gpu_solve(g_ctx.ctx, &summary);
+  if (rc == BA_OK) rc = ba_gpu_download(g_ctx.ctx, pose7.data(), pt3.data(), intr);
+  if (rc != BA_OK) {
+    std::fprintf(stderr, "windowOptimize: GPU solve failed (%d): %s\n", rc, ba_gpu_last_error(g_ctx.ctx));
+    restore();
+    return false;
+  }
+  g_last.summary = summary;
+
+  // ---- Ceres wrote the optimum into the caller-owned blocks: do the same
+  for (int k = 0; k < n_cam; ++k) keyframes[kf_i + k].T_w_c = Sophus::SE3d(pose7.data() + (size_t)k * 7);
+  for (int p = 0; p < n_pt; ++p) {
+    Vector3d &x = map.at(landmark_of_pt[p]).point;
+    for (int j = 0; j < 3; ++j) x(j) = pt3[(size_t)p * 3 + j];
+  }
+  for (int j = 0; j < 4; ++j) intrinsics_optimized(j) = intr[j];
+
+  // ---- back to the world frame (:303-310)
+  for (int kf_n = kf_i; kf_n <= kf_f; kf_n++) {
+    KeyFrame &curr_kf = keyframes[kf_n];
+    curr_kf.T_w_c = Sophus::SE3d(initialPose * curr_kf.T_w_c);
+  }
+  for (int lId : already_observed_pts) map.at(lId).point = initialPose * map.at(lId).point;
+  return true;
+}

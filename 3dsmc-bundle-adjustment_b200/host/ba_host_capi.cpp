@@ -1,0 +1,89 @@
+// Flat C harness around the C++ drop-in (tests drive it through ctypes): builds
+// vector<KeyFrame> + Map3D from arrays with the SAME std::unordered_map insert
+// sequence the caller specifies, runs windowOptimize / countConstraints with the
+// reference's signatures, and flattens the mutated state back.
+#include "compat/reference_types.h"
+#include "ba_host_debug.h"
+
+#include <cstring>
+
+extern "C" {
+// obs arrays are in INSERTION order per keyframe: kf_ptr[n_kf+1] CSR,
+// local ids are 0..cnt-1 in that order; landmark ids lm[]; pixels float; depth double.
+// pose7 [n_kf*7], landmark table: lm_id[n_lm], lm_pt[n_lm*3].  All in/out.
+// out_* (nullable): the enumeration windowOptimize produced and, independently,
+// the container iteration order recomputed here.
+int ba_host_window_optimize(int n_kf, double *pose7, const int32_t *kf_ptr, const int32_t *lm, const float *uv,
+                            const double *depth, int n_lm, const int32_t *lm_id, double *lm_pt, int kf_i, int kf_f,
+                            int max_num_iterations, const double *intr0, double *intr, int32_t *out_n_obs,
+                            int32_t *out_cam_idx, int32_t *out_landmark, int32_t *ref_cam_idx, int32_t *ref_landmark,
+                            int32_t *out_count, double *out_costs /*initial, final*/) {
+  std::vector<KeyFrame> keyframes(n_kf);
+  Map3D map;
+  for (int k = 0; k < n_kf; ++k) {
+    KeyFrame &kf = keyframes[k];
+    kf.frame_id = (uint)k;
+    kf.T_w_c = Sophus::SE3d(pose7 + (size_t)k * 7);
+    const int a = kf_ptr[k], b = kf_ptr[k + 1];
+    kf.keypoints.resize(b - a);
+    kf.points3d_local.resize(b - a);
+    for (int i = a; i < b; ++i) {
+      const int local = i - a;
+      kf.keypoints[local].pt.x = uv[2 * (size_t)i];
+      kf.keypoints[local].pt.y = uv[2 * (size_t)i + 1];
+      kf.points3d_local[local] = Vector3d(0.0, 0.0, depth[i]);
+      kf.global_points_map.insert({local, lm[i]});
+    }
+  }
+  for (int l = 0; l < n_lm; ++l) {
+    Landmark L;
+    L.point = Vector3d(lm_pt[3 * (size_t)l], lm_pt[3 * (size_t)l + 1], lm_pt[3 * (size_t)l + 2]);
+    map.insert({lm_id[l], L});
+  }
+  // independent walk of the containers (what the reference's loops would visit)
+  int nref = 0;
+  for (int k = kf_i; k <= kf_f; ++k)
+    for (const auto &pr : keyframes[k].global_points_map) {
+      if (keyframes[k].points3d_local[pr.first](2) <= 1e-15) continue;
+      if (ref_cam_idx) ref_cam_idx[nref] = k - kf_i;
+      if (ref_landmark) ref_landmark[nref] = pr.second;
+      ++nref;
+    }
+  if (out_count) *out_count = countConstraints(map, keyframes, kf_i, kf_f);
+  ceresGlobalProblem gp;
+  gp.options.max_num_iterations = max_num_iterations;
+  Vector4d i0(intr0[0], intr0[1], intr0[2], intr0[3]), io(intr[0], intr[1], intr[2], intr[3]);
+  const bool ok = windowOptimize(gp, kf_i, kf_f, keyframes, map, i0, io);
+  const BaHostLastProblem &last = ba_host_last_problem();
+  if (ok) {
+    if (out_n_obs) *out_n_obs = (int32_t)last.cam_idx.size();
+    for (size_t i = 0; i < last.cam_idx.size(); ++i) {
+      if (out_cam_idx) out_cam_idx[i] = last.cam_idx[i];
+      if (out_landmark) out_landmark[i] = last.landmark_of_pt[last.pt_idx[i]];
+    }
+    if (out_costs) {
+      out_costs[0] = last.summary.initial_cost;
+      out_costs[1] = last.summary.final_cost;
+    }
+  }
+  for (int k = 0; k < n_kf; ++k) std::memcpy(pose7 + (size_t)k * 7, keyframes[k].T_w_c.data(), 7 * sizeof(double));
+  for (int l = 0; l < n_lm; ++l)
+    for (int j = 0; j < 3; ++j) lm_pt[3 * (size_t)l + j] = map.at(lm_id[l]).point(j);
+  for (int j = 0; j < 4; ++j) intr[j] = io(j);
+  return ok ? 0 : -1;
+}
+
+int ba_host_count_constraints(int n_kf, const int32_t *kf_ptr, const double *depth, int kf_i, int kf_f) {
+  std::vector<KeyFrame> keyframes(n_kf);
+  Map3D map;
+  for (int k = 0; k < n_kf; ++k) {
+    const int a = kf_ptr[k], b = kf_ptr[k + 1];
+    keyframes[k].points3d_local.resize(b - a);
+    for (int i = a; i < b; ++i) {
+      keyframes[k].points3d_local[i - a] = Vector3d(0.0, 0.0, depth[i]);
+      keyframes[k].global_points_map.insert({i - a, i});
+    }
+  }
+  return countConstraints(map, keyframes, kf_i, kf_f);
+}
+}

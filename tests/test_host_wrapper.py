@@ -1,0 +1,94 @@
+"""The compiled C++ drop-in (host/OptimizationUtils_gpu.cpp): windowOptimize /
+countConstraints with the reference's signatures (headers/OptimizationUtils.h:42,
+55), driven through the flat harness libba_host.so."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import ba_b200, ora, pose_err
+
+HOST_LIB = os.path.join(os.path.dirname(ba_b200.capi.LIB_PATH), "libba_host.so")
+syn = ba_b200.synthetic
+se3 = ba_b200.se3
+
+
+def _lib():
+    ba_b200.capi.load()  # libba_gpu.so first (dependency)
+    L = C.CDLL(HOST_LIB)
+    L.ba_host_count_constraints.restype = C.c_int
+    L.ba_host_window_optimize.restype = C.c_int
+    return L
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def test_host_library_exports_and_count():
+    L = _lib()
+    assert hasattr(L, "ba_host_window_optimize") and hasattr(L, "ba_host_count_constraints")
+    seq = syn.make_tum_sequence(12, 200, 1200, seed=4)
+    seq.depth[::7] = 0.0          # inadmissible observations (depth <= 1e-15 are skipped, :265)
+    seq.depth[3::11] = -1.0
+    kf_ptr = seq.kf_ptr.astype(np.int32)
+    n = L.ba_host_count_constraints(12, _ptr(kf_ptr, C.c_int32), _ptr(seq.depth, C.c_double), 2, 9)
+    assert n == ba_b200.count_constraints(seq, 2, 9)
+    a, b = kf_ptr[2], kf_ptr[10]
+    assert n == int(np.count_nonzero(seq.depth[a:b] > 1e-15))
+
+
+@pytest.mark.gpu
+def test_window_optimize_cpp_dropin():
+    L = _lib()
+    n_kf, kf_i, kf_f, iters = 30, 8, 27, 10
+    seq = syn.make_tum_sequence(n_kf, 3000, 18000, seed=13)
+    seq.depth[5::97] = 0.0  # a few inadmissible observations
+    pose = seq.pose.copy()
+    lm_pt = seq.pt.copy()
+    lm_id = np.arange(seq.pt.shape[0], dtype=np.int32)
+    kf_ptr = seq.kf_ptr.astype(np.int32)
+    uv = seq.uv.astype(np.float32)
+    n_max = int(kf_ptr[kf_f + 1] - kf_ptr[kf_i])
+    out_n = C.c_int32(0)
+    out_count = C.c_int32(0)
+    out_cam = np.zeros(n_max, dtype=np.int32); out_lm = np.zeros(n_max, dtype=np.int32)
+    ref_cam = np.zeros(n_max, dtype=np.int32); ref_lm = np.zeros(n_max, dtype=np.int32)
+    intr0 = seq.K.copy(); intr = seq.K.copy(); costs = np.zeros(2)
+    rc = L.ba_host_window_optimize(n_kf, _ptr(pose, C.c_double), _ptr(kf_ptr, C.c_int32), _ptr(seq.lm, C.c_int32),
+                                   _ptr(uv, C.c_float), _ptr(seq.depth, C.c_double), lm_id.shape[0], _ptr(lm_id, C.c_int32),
+                                   _ptr(lm_pt, C.c_double), kf_i, kf_f, iters, _ptr(intr0, C.c_double), _ptr(intr, C.c_double),
+                                   C.byref(out_n), _ptr(out_cam, C.c_int32), _ptr(out_lm, C.c_int32), _ptr(ref_cam, C.c_int32),
+                                   _ptr(ref_lm, C.c_int32), C.byref(out_count), _ptr(costs, C.c_double))
+    assert rc == 0
+    n = out_n.value
+    assert n == out_count.value == ba_b200.count_constraints(seq, kf_i, kf_f)
+    # bit-exact enumeration: what went to the GPU == an independent walk of the same containers
+    assert np.array_equal(out_cam[:n], ref_cam[:n]) and np.array_equal(out_lm[:n], ref_lm[:n])
+    assert np.all(np.diff(out_cam[:n]) >= 0)
+    # oracle on the problem in exactly that order
+    key = {(int(k), int(l)): i for i, (k, l) in enumerate(zip(seq.kf, seq.lm))}
+    rows = np.array([key[(kf_i + int(c), int(l))] for c, l in zip(out_cam[:n], out_lm[:n])])
+    uniq, first = np.unique(out_lm[:n], return_index=True)
+    lm_order = uniq[np.argsort(first, kind="stable")]
+    new_of = {int(l): i for i, l in enumerate(lm_order)}
+    T0 = seq.pose[kf_i]
+    T0inv = se3.inverse(T0)
+    p = ba_b200.BAProblem(se3.mul(np.broadcast_to(T0inv, (kf_f - kf_i + 1, 7)), seq.pose[kf_i:kf_f + 1]),
+                          se3.act(T0inv, seq.pt[lm_order]), out_cam[:n], [new_of[int(l)] for l in out_lm[:n]],
+                          seq.uv[rows], seq.depth[rows], seq.K, seq.K, 0)
+    op = ora.Problem(p.pose7, p.pt3, p.cam_idx, p.pt_idx, p.uv2, p.depth, p.intr, p.intr_prior, 0)
+    rc, osum, _ = ora.solve(op, ora.default_options(max_num_iterations=iters))
+    assert rc == 0
+    assert abs(costs[0] - osum.initial_cost) <= 1e-12 * osum.initial_cost
+    assert abs(costs[1] - osum.final_cost) <= 1e-8 * osum.final_cost
+    want_pose = se3.mul(np.broadcast_to(T0, op.pose7.shape), op.pose7)
+    dt, dr = pose_err(pose[kf_i:kf_f + 1], want_pose)
+    assert dt < 1e-6 and dr < 1e-6
+    assert np.max(np.abs(lm_pt[lm_order] - se3.act(T0, op.pt3))) < 1e-5
+    assert np.max(np.abs(intr - op.intr)) < 1e-5
+    # untouched outside the window / for landmarks not observed in it
+    assert np.array_equal(pose[:kf_i], seq.pose[:kf_i]) and np.array_equal(pose[kf_f + 1:], seq.pose[kf_f + 1:])
+    others = np.setdiff1d(lm_id, lm_order)
+    assert np.array_equal(lm_pt[others], seq.pt[others])
