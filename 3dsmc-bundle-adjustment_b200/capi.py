@@ -18,6 +18,7 @@ c_int32_p = C.POINTER(C.c_int32)
 
 BA_OK, BA_ERR_INVALID, BA_ERR_CUDA, BA_ERR_STATE, BA_ERR_UNSUPPORTED, BA_ERR_NUMERIC, BA_ERR_COMM = 0, -1, -2, -3, -4, -5, -6
 BA_SOLVER_AUTO, BA_SOLVER_EXPLICIT_CHOLESKY, BA_SOLVER_IMPLICIT_PCG = 0, 1, 2
+BA_JAC_AUTO, BA_JAC_PLANES, BA_JAC_FACTORED = 0, 1, 2
 BA_KERNEL_LINEARIZE, BA_KERNEL_SCHUR_MATVEC, BA_KERNEL_SCHUR_PASS1, BA_KERNEL_SCHUR_PASS2 = 0, 1, 2, 3
 TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT", 2: "PARAMETER", 3: "FUNCTION", 4: "MIN_RADIUS", 5: "FAILURE"}
 
@@ -37,7 +38,7 @@ class Options(C.Structure):
         ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
         ("max_linear_solver_iterations", C.c_int32), ("min_linear_solver_iterations", C.c_int32),
         ("residual_reset_period", C.c_int32), ("device", C.c_int32), ("poll_interval", C.c_int32),
-        ("use_cuda_graph", C.c_int32),
+        ("use_cuda_graph", C.c_int32), ("jacobian_store", C.c_int32),
     ]
 
 

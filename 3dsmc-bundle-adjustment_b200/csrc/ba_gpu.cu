@@ -8,6 +8,7 @@
 // There is NO CPU fallback: without a CUDA device ba_gpu_create fails.
 #include "../../include/ba_gpu.h"
 #include "ba_kernels.cuh"
+#include "ba_kernels_fact.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -89,9 +90,13 @@ struct ba_gpu_ctx {
   Buf perm, pt_rowptr, cam_rowptr, pt_cnt, cam_cnt, cursor, err_flag;
   Buf pm_cam, pm_pt, pm_uv, pm_depth;
   Buf items, item_ptr, item_cnt, cam_slot;
-  // Jacobian planes
+  // Jacobian planes (materialised store) / factored store
   Buf jcm, jpm;
   JPlanes Jc_, Jp_;
+  bool fact = false, planes_ready = false;
+  Buf fcm, fpm, geo, camx, Vs, ts, tgs, ys, tile_lo, tile_span;
+  bool staged = false;
+  FPlanes Fc_, Fp_;
   // scaling / diag / gradient / blocks
   Buf sc, sp, sk, dc, dp, dk, gc, gp, gk, U, Uck, Ukk, V, Vinv, Wk, tg, t, yc, yp, yk, rk, Jkk;
   Buf one_c, one_p, one_k;
@@ -235,6 +240,7 @@ extern "C" void ba_gpu_default_options(ba_gpu_options *o) {
   o->device = -1;
   o->poll_interval = 10;
   o->use_cuda_graph = 0;
+  o->jacobian_store = BA_JAC_AUTO;
 }
 
 static int check_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
@@ -242,6 +248,7 @@ static int check_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
     return fail(ctx, BA_ERR_INVALID, "Huber deltas must be > 0 and weights >= 0");
   if (o->max_num_iterations < 0 || o->poll_interval < 1) return fail(ctx, BA_ERR_INVALID, "bad iteration options");
   if (o->solver < BA_SOLVER_AUTO || o->solver > BA_SOLVER_IMPLICIT_PCG) return fail(ctx, BA_ERR_INVALID, "bad solver");
+  if (o->jacobian_store < BA_JAC_AUTO || o->jacobian_store > BA_JAC_FACTORED) return fail(ctx, BA_ERR_INVALID, "bad jacobian_store");
   if (!(o->initial_trust_region_radius > 0.0)) return fail(ctx, BA_ERR_INVALID, "bad trust-region radius");
   return 0;
 }
@@ -434,6 +441,19 @@ static int build_pair_list(ba_gpu_ctx *ctx, const int32_t *cam_idx, const int32_
   return 0;
 }
 
+// materialised Jacobian planes, allocated on demand (always for the explicit /
+// REF path; lazily for the un-scaled evaluation hook when the store is factored)
+static int ensure_planes(ba_gpu_ctx *ctx) {
+  if (ctx->planes_ready) return 0;
+  const size_t n_pad = ((size_t)ctx->n_obs + 31) / 32 * 32 + 32;
+  RES(jcm, planes_doubles(n_pad, ctx->depth, ctx->nk) * 8);
+  RES(jpm, planes_doubles(n_pad, ctx->depth, ctx->nk) * 8);
+  set_planes(ctx->Jc_, P<double>(ctx->jcm), n_pad, ctx->depth, ctx->nk);
+  set_planes(ctx->Jp_, P<double>(ctx->jpm), n_pad, ctx->depth, ctx->nk);
+  ctx->planes_ready = true;
+  return 0;
+}
+
 extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7, int32_t fixed_cam, int32_t n_pt,
                              const double *pt3, int32_t n_obs, const int32_t *cam_idx, const int32_t *pt_idx,
                              const double *uv2, const double *depth, const double intr4[4], const double intr_prior4[4]) {
@@ -466,6 +486,11 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks > 1)
     return fail(ctx, BA_ERR_UNSUPPORTED, "the explicit solver is single-GPU (windowed problems stay on one GPU)");
   ctx->solver = solver;
+  const bool can_fact = (solver == BA_SOLVER_IMPLICIT_PCG && !o.use_depth_prior && !o.optimize_intrinsics);
+  if (o.jacobian_store == BA_JAC_FACTORED && !can_fact)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "the factored Jacobian store needs NS mode (no depth prior, fixed intrinsics) + implicit PCG");
+  ctx->fact = can_fact && o.jacobian_store != BA_JAC_PLANES;
+  ctx->planes_ready = false;
 
   const int64_t N = o.n_obs_total > 0 ? o.n_obs_total : (int64_t)n_obs;
   // src/OptimizationUtils.cpp:280, 290: weights 1/N and WEIGHT_UNPR/N; residual = sqrt(weight) * ...
@@ -527,10 +552,28 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   RES(item_cnt, (nc + 1) * 4);
   RES(cam_slot, nc * 4);
   const size_t n_pad = (no + 31) / 32 * 32 + 32;
-  RES(jcm, planes_doubles(n_pad, ctx->depth, ctx->nk) * 8);
-  RES(jpm, planes_doubles(n_pad, ctx->depth, ctx->nk) * 8);
-  set_planes(ctx->Jc_, P<double>(ctx->jcm), n_pad, ctx->depth, ctx->nk);
-  set_planes(ctx->Jp_, P<double>(ctx->jpm), n_pad, ctx->depth, ctx->nk);
+  if (!ctx->fact) {
+    int rcp = ensure_planes(ctx);
+    if (rcp) return rcp;
+  } else {
+    RES(fcm, n_pad * 48);
+    RES(fpm, n_pad * 48);
+    auto setf = [&](FPlanes &F, double *base) {
+      F.r = reinterpret_cast<double2 *>(base);
+      F.g0 = reinterpret_cast<double2 *>(base + 2 * n_pad);
+      F.g1 = reinterpret_cast<double2 *>(base + 4 * n_pad);
+    };
+    setf(ctx->Fc_, P<double>(ctx->fcm));
+    setf(ctx->Fp_, P<double>(ctx->fpm));
+    RES(geo, nc * BA_CAMREC * 8);
+    RES(camx, nc * BA_CAMREC * 8);
+    RES(Vs, np * 48);
+    RES(ts, (np + 1) * 32);
+    RES(tgs, (np + 1) * 32);
+    RES(ys, (np + 1) * 32);
+    RES(tile_lo, (size_t)(ctx->n_tiles + 1) * 4);
+    RES(tile_span, (size_t)(ctx->n_tiles + 1) * 4);
+  }
   RES(sc, nc * 48);
   RES(sp, np * 24);
   RES(sk, 32);
@@ -622,6 +665,16 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   RES(items, (size_t)(h_items + 1) * sizeof(BaItem));
   LAUNCH(k_item_fill, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->item_ptr),
          P<BaItem>(ctx->items));
+  if (ctx->fact) {
+    // camera span of every point tile -> shared-memory staging of pass 1
+    CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, s));
+    LAUNCH(k_tile_cam_range, ctx->n_tiles, BA_THREADS, 0, n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+           P<int32_t>(ctx->tile_lo), P<int32_t>(ctx->tile_span), P<int32_t>(ctx->err_flag));
+    int32_t h_span = 0;
+    CK(cudaMemcpyAsync(&h_span, ctx->err_flag.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->staged = h_span <= BA_STAGE_CAMS;
+  }
   RES(part_blk, (size_t)(h_items + 1) * 61 * 8);
   RES(part6, (size_t)(h_items + 1) * 6 * 8);
   RES(part21, (size_t)(h_items + 1) * 21 * 8);
@@ -691,9 +744,29 @@ static void sync_flags(ba_gpu_ctx *ctx) {
 
 // ------------------------------------------------------------------ pipeline pieces
 // linearise at the current point in both orders + normal-equation blocks
-static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk) {
+static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk,
+                              bool force_planes = false) {
   const int D = ctx->depth, K = ctx->nk;
   LmState *st = P<LmState>(ctx->st);
+  if (ctx->fact && !force_planes) {
+    const double *intr = P<double>(ctx->intr);
+    LAUNCH(k_cam_geo, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->fixed_cam, P<double>(ctx->pose), sc, P<double>(ctx->geo), st,
+           gate);
+    LAUNCH((kf_linearize<1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+           P<double2>(ctx->uv), P<double>(ctx->pose), P<double>(ctx->pt), intr, ctx->cp, ctx->Fc_, P<double>(ctx->pc_lin), st,
+           gate);
+    LAUNCH((kf_linearize<0>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt),
+           P<double2>(ctx->pm_uv), P<double>(ctx->pose), P<double>(ctx->pt), intr, ctx->cp, ctx->Fp_, (double *)nullptr, st,
+           gate);
+    LAUNCH(kf_cam_blocks, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), ctx->Fc_, P<double>(ctx->geo), intr,
+           P<double>(ctx->part_blk), st, gate);
+    ItemRef ir = reduce_items<27>(ctx, P<double>(ctx->part_blk), ctx->red_blk, gate);
+    LAUNCH((k_cam_blocks_fin<0>), ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->U), P<double>(ctx->gc),
+           P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
+    LAUNCH(kf_pt_blocks, ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam), ctx->Fp_,
+           P<double>(ctx->geo), intr, sp, P<double>(ctx->V), P<double>(ctx->gp), P<double>(ctx->dp), ctx->lo, st, gate);
+    return;
+  }
   DISPATCH_DK(D, K, {
     LAUNCH((k_linearize<DD, KK, 1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
            P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc, sp,
@@ -749,9 +822,38 @@ static void enqueue_iteration_zero(ba_gpu_ctx *ctx) {
 }
 
 // one implicit-Schur product: part6 <- sum Jc^T (alpha Jc v - Jp t), t <- pass 1 of v
+static void enqueue_point_inverse(ba_gpu_ctx *ctx, int gate) {
+  LmState *st = P<LmState>(ctx->st);
+  if (ctx->fact)
+    LAUNCH(kf_point_inverse, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->V), P<double>(ctx->dp), P<double>(ctx->gp),
+           P<double>(ctx->sp), P<double>(ctx->Vinv), P<double>(ctx->Vs), P<double>(ctx->tgs), st, gate);
+  else
+    LAUNCH(k_point_inverse, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->V), P<double>(ctx->dp), P<double>(ctx->gp),
+           P<double>(ctx->Vinv), P<double>(ctx->tg), st, gate);
+}
+
 static void enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int passes = 3) {
   LmState *st = P<LmState>(ctx->st);
   const int rp = ctx->lo.reset_period;
+  if (ctx->fact) {
+    const double *intr = P<double>(ctx->intr);
+    if (passes & 1) {
+      if (ctx->staged) {
+        LAUNCH((kf_schur_pass1<0, 1>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+               ctx->Fp_, P<double>(ctx->geo), v, P<double>(ctx->camx), P<int32_t>(ctx->tile_lo), P<int32_t>(ctx->tile_span), intr,
+               P<double>(ctx->Vinv), P<double>(ctx->sp), (const double *)nullptr, (double *)nullptr, P<double>(ctx->ts), st, gate);
+      } else {
+        LAUNCH(k_pack_camx, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, v, P<double>(ctx->geo), P<double>(ctx->camx), st, gate);
+        LAUNCH((kf_schur_pass1<0, 0>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+               ctx->Fp_, P<double>(ctx->geo), v, P<double>(ctx->camx), P<int32_t>(ctx->tile_lo), P<int32_t>(ctx->tile_span), intr,
+               P<double>(ctx->Vinv), P<double>(ctx->sp), (const double *)nullptr, (double *)nullptr, P<double>(ctx->ts), st, gate);
+      }
+    }
+    if (passes & 2)
+      LAUNCH(kf_schur_pass2, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Fc_,
+             P<double>(ctx->geo), intr, v, P<double>(ctx->ts), 1.0, P<double>(ctx->part6), st, gate);
+    return;
+  }
   DISPATCH_D(ctx->depth, {
     if (passes & 1)
     LAUNCH((k_schur_pass1<DD, 0, 0>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
@@ -795,6 +897,13 @@ static void enqueue_pcg_iteration(ba_gpu_ctx *ctx, int it) {
 // device-side PCG controller every poll_interval iterations
 static int solve_implicit(ba_gpu_ctx *ctx) {
   LmState *st = P<LmState>(ctx->st);
+  if (ctx->fact) {
+    const double *intr = P<double>(ctx->intr);
+    LAUNCH(kf_schur_pass2, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Fc_,
+           P<double>(ctx->geo), intr, P<double>(ctx->gc), P<double>(ctx->tgs), 0.0, P<double>(ctx->part6), st, GATE_RUN);
+    LAUNCH(kf_schur_diag, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Fc_,
+           P<double>(ctx->geo), intr, P<double>(ctx->Vs), P<double>(ctx->part21), st, GATE_RUN);
+  } else
   DISPATCH_D(ctx->depth, {
     // rhs = -g_c + sum Jc^T Jp V^-1 g_p
     LAUNCH((k_schur_pass2<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
@@ -871,10 +980,20 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
   LmState *st = P<LmState>(ctx->st);
   const int D = ctx->depth, K = ctx->nk;
   LAUNCH(k_lm_begin, 1, 1, 0, ctx->lo, st);
-  LAUNCH(k_point_inverse, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->V), P<double>(ctx->dp), P<double>(ctx->gp),
-         P<double>(ctx->Vinv), P<double>(ctx->tg), st, GATE_RUN);
+  enqueue_point_inverse(ctx, GATE_RUN);
   int rc = ctx->solver == BA_SOLVER_IMPLICIT_PCG ? solve_implicit(ctx) : solve_explicit(ctx);
   if (rc) return rc;
+  if (ctx->fact) {
+    const double *intr = P<double>(ctx->intr);
+    LAUNCH(k_pack_camx, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<double>(ctx->yc), P<double>(ctx->geo), P<double>(ctx->camx), st,
+           GATE_RUN);
+    LAUNCH((kf_schur_pass1<1, 0>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+           ctx->Fp_, P<double>(ctx->geo), P<double>(ctx->yc), P<double>(ctx->camx), P<int32_t>(ctx->tile_lo),
+           P<int32_t>(ctx->tile_span), intr, P<double>(ctx->Vinv), P<double>(ctx->sp), P<double>(ctx->gp), P<double>(ctx->yp),
+           P<double>(ctx->ys), st, GATE_RUN);
+    LAUNCH(kf_model_cost, ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx), ctx->Fc_,
+           P<double>(ctx->camx), intr, P<double>(ctx->ys), P<double>(ctx->pc_mcc), st, GATE_RUN);
+  } else
   DISPATCH_DK(D, K, {
     // back-substitution y_p = V^-1 (-g_p - W^T y_c)
     LAUNCH((k_schur_pass1<DD, KK, 1>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
@@ -995,8 +1114,12 @@ extern "C" int ba_gpu_eval(ba_gpu_ctx *ctx, double *r, double *Jc, double *Jp, d
   if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_eval before ba_gpu_upload");
   CK(cudaSetDevice(ctx->device));
   LmState *st = P<LmState>(ctx->st);
+  {
+    int rcp = ensure_planes(ctx);
+    if (rcp) return rcp;
+  }
   LAUNCH(k_lm_init, 1, 1, 0, st, ctx->opt.initial_trust_region_radius);
-  enqueue_linearize(ctx, GATE_RUN, P<double>(ctx->one_c), P<double>(ctx->one_p), P<double>(ctx->one_k));
+  enqueue_linearize(ctx, GATE_RUN, P<double>(ctx->one_c), P<double>(ctx->one_p), P<double>(ctx->one_k), /*force_planes=*/true);
   ctx->linearized = false;
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
@@ -1103,8 +1226,7 @@ static int prepare_linear_system(ba_gpu_ctx *ctx, double radius) {
   enqueue_iteration_zero(ctx);
   LmState *st = P<LmState>(ctx->st);
   LAUNCH(k_set_radius, 1, 1, 0, st, radius);
-  LAUNCH(k_point_inverse, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->V), P<double>(ctx->dp), P<double>(ctx->gp),
-         P<double>(ctx->Vinv), P<double>(ctx->tg), st, GATE_RUN);
+  enqueue_point_inverse(ctx, GATE_RUN);
   int rc = poll_state(ctx);
   if (rc) return rc;
   if (ctx->h_st->eval_fail) return fail(ctx, BA_ERR_NUMERIC, "non-finite residual or Jacobian");
@@ -1192,7 +1314,11 @@ extern "C" int ba_gpu_time_kernel(ba_gpu_ctx *ctx, int32_t which, int32_t warmup
   const size_t flush_n = (size_t)512 * 1024 * 1024 / 8;  // 512 MiB > 126 MB L2
   if (flush_l2) RES(flush, flush_n * 8);
   auto one = [&]() {
-    if (which == BA_KERNEL_LINEARIZE) {
+    if (which == BA_KERNEL_LINEARIZE && ctx->fact) {
+      LAUNCH((kf_linearize<1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+             P<double2>(ctx->uv), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), ctx->cp, ctx->Fc_,
+             P<double>(ctx->pc_lin), st, GATE_RUN);
+    } else if (which == BA_KERNEL_LINEARIZE) {
       DISPATCH_DK(ctx->depth, ctx->nk, {
         LAUNCH((k_linearize<DD, KK, 1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx),
                P<int32_t>(ctx->pt_idx), P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose), P<double>(ctx->pt),

@@ -53,6 +53,13 @@ enum {
 };
 
 enum {
+  BA_JAC_AUTO = 0,     /* factored for NS mode + implicit PCG, planes otherwise */
+  BA_JAC_PLANES = 1,   /* materialised r, Jc (2x6), Jp (2x3) planes: 160 B/obs per ordering */
+  BA_JAC_FACTORED = 2  /* r + (X/Z, Y/Z, 1/Z, w): 48 B/obs; Jacobian entries rebuilt in registers
+                          (NS mode + implicit PCG only) */
+};
+
+enum {
   BA_TERM_NO_CONVERGENCE = 0, /* max_num_iterations reached */
   BA_TERM_GRADIENT = 1,
   BA_TERM_PARAMETER = 2,
@@ -91,6 +98,7 @@ typedef struct ba_gpu_options {
   int32_t poll_interval;   /* host polls the device-side LM / PCG termination
                               flag every this many iterations (>=1) */
   int32_t use_cuda_graph;  /* capture the PCG iteration in a CUDA graph */
+  int32_t jacobian_store;  /* BA_JAC_AUTO / _PLANES / _FACTORED */
 } ba_gpu_options;
 
 /* Per-iteration record, written by the device-side LM controller. Mirrors

@@ -25,6 +25,8 @@ def mode_opts(mode, **kw):
         if key == "solver":
             g["solver"] = v
             o["solver"] = 0 if v in (0, 1) else 1
+        elif key == "jacobian_store":
+            g[key] = v
         elif key == "max_num_iterations":
             g[key] = v
             o[key] = v

@@ -146,10 +146,11 @@ def test_se3_plus_vs_oracle(solver_cache):
 
 
 # ---------------------------------------------------------------- implicit Schur product
+@pytest.mark.parametrize("store", [1, 2], ids=["planes", "factored"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg4_small", "cfg3_small"])
-def test_schur_matvec_vs_oracle(name, solver_cache):
+def test_schur_matvec_vs_oracle(name, store, solver_cache):
     p = _problem(name)
-    g, o = mode_opts("NS", solver=2)
+    g, o = mode_opts("NS", solver=2, jacobian_store=store)
     s = _solver(solver_cache, **g)
     s.upload(p)
     rng = np.random.default_rng(1)
@@ -167,8 +168,9 @@ def test_schur_matvec_vs_oracle(name, solver_cache):
 
 
 # ---------------------------------------------------------------- full LM solves
-def _compare_solve(p, mode, solver, iters, cache, lockstep=True, cost_tol=1e-8, pose_tol=1e-6, pt_tol=1e-5, trace_tol=1e-8):
-    g, o = mode_opts(mode, solver=solver, max_num_iterations=iters)
+def _compare_solve(p, mode, solver, iters, cache, lockstep=True, cost_tol=1e-8, pose_tol=1e-6, pt_tol=1e-5, trace_tol=1e-8,
+                   **extra):
+    g, o = mode_opts(mode, solver=solver, max_num_iterations=iters, **extra)
     s = _solver(cache, **g)
     s.upload(p)
     summ = s.solve()
@@ -214,17 +216,19 @@ def test_solve_to_convergence_ref(solver_cache):
     _compare_solve(_problem("cfg1"), "REF", 1, 75, solver_cache)
 
 
+@pytest.mark.parametrize("store", [1, 2], ids=["planes", "factored"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg3_small"])
-def test_solve_implicit_pcg(name, solver_cache):
+def test_solve_implicit_pcg(name, store, solver_cache):
     """Implicit Schur + block-Jacobi PCG against the oracle's own PCG, in lock
     step: same PCG iteration counts, cost 1e-8, poses 1e-6 (well-conditioned
     TUM-shaped problems)."""
-    summ, osum = _compare_solve(_problem(name), "NS", 2, 8, solver_cache)
+    summ, osum = _compare_solve(_problem(name), "NS", 2, 8, solver_cache, jacobian_store=store)
     assert summ.solver_used == ba_b200.capi.BA_SOLVER_IMPLICIT_PCG
     assert summ.total_linear_iters == osum.total_linear_iters
 
 
-def test_solve_implicit_pcg_ill_conditioned(solver_cache):
+@pytest.mark.parametrize("store", [1, 2], ids=["planes", "factored"])
+def test_solve_implicit_pcg_ill_conditioned(store, solver_cache):
     """BAL-shaped loop: the reduced system is so ill-conditioned that PCG stops on
     its iteration cap / eta = 1e-6 far from the exact step, and summation-order
     round-off (1e-16) is amplified by cond(S) into 1e-6 relative cost differences
@@ -232,7 +236,7 @@ def test_solve_implicit_pcg_ill_conditioned(solver_cache):
     included).  Parity here: same accept/reject sequence, cost to 1e-5, poses to
     1e-4 of the 30 m scene."""
     p = _problem("cfg4_small")
-    g, o = mode_opts("NS", solver=2, max_num_iterations=8)
+    g, o = mode_opts("NS", solver=2, max_num_iterations=8, jacobian_store=store)
     s = _solver(solver_cache, **g)
     s.upload(p)
     summ = s.solve()
@@ -313,3 +317,25 @@ def test_window_optimize_mirror(solver_cache):
     assert np.max(np.abs(intr - op.intr)) < 1e-5
     # poses outside the window untouched
     assert np.array_equal(seq.pose[:10], seq_o.pose[:10])
+
+
+def test_factored_store_rejected_outside_ns_implicit(solver_cache):
+    p = _problem("cfg1_small")
+    s = _solver(solver_cache, use_depth_prior=1, optimize_intrinsics=1, jacobian_store=2)
+    with pytest.raises(ba_b200.BAError) as e:
+        s.upload(p)
+    assert e.value.code == ba_b200.capi.BA_ERR_UNSUPPORTED
+
+
+def test_eval_hook_with_factored_store(solver_cache):
+    """The un-scaled evaluation hook materialises planes on demand."""
+    p = _problem("cfg3_small")
+    g, o = mode_opts("NS", solver=2, jacobian_store=2)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    out = s.eval()
+    ref = ora.evaluate(to_oracle(p), ora.default_options(**o))
+    free = p.cam_idx != p.fixed_cam
+    assert rel_err(out["Jc"][free], ref["Jc"][free]) < 1e-12 and rel_err(out["Jp"], ref["Jp"]) < 1e-12
+    summ = s.solve()
+    assert summ.final_cost < summ.initial_cost
