@@ -18,7 +18,7 @@ c_int32_p = C.POINTER(C.c_int32)
 
 BA_OK, BA_ERR_INVALID, BA_ERR_CUDA, BA_ERR_STATE, BA_ERR_UNSUPPORTED, BA_ERR_NUMERIC, BA_ERR_COMM = 0, -1, -2, -3, -4, -5, -6
 BA_SOLVER_AUTO, BA_SOLVER_EXPLICIT_CHOLESKY, BA_SOLVER_IMPLICIT_PCG = 0, 1, 2
-BA_JAC_AUTO, BA_JAC_PLANES, BA_JAC_FACTORED = 0, 1, 2
+BA_JAC_AUTO, BA_JAC_PLANES, BA_JAC_FACTORED, BA_JAC_TILED = 0, 1, 2, 3
 BA_KERNEL_LINEARIZE, BA_KERNEL_SCHUR_MATVEC, BA_KERNEL_SCHUR_PASS1, BA_KERNEL_SCHUR_PASS2 = 0, 1, 2, 3
 TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT", 2: "PARAMETER", 3: "FUNCTION", 4: "MIN_RADIUS", 5: "FAILURE"}
 
@@ -64,7 +64,7 @@ EXPORTS = [
     "ba_gpu_default_options", "ba_gpu_create", "ba_gpu_destroy", "ba_gpu_last_error", "ba_gpu_set_options",
     "ba_gpu_upload", "ba_gpu_solve", "ba_gpu_get_trace", "ba_gpu_download", "ba_gpu_eval", "ba_gpu_get_indices",
     "ba_gpu_schur_matvec", "ba_gpu_se3_plus", "ba_gpu_time_kernel", "ba_gpu_launch_count", "ba_gpu_comm_unique_id",
-    "ba_gpu_comm_init",
+    "ba_gpu_comm_init", "ba_gpu_jacobian_store_used",
 ]
 
 _LIB = None
@@ -100,6 +100,7 @@ def load():
     L.ba_gpu_time_kernel.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     L.ba_gpu_launch_count.argtypes = [vp]
     L.ba_gpu_launch_count.restype = C.c_int64
+    L.ba_gpu_jacobian_store_used.argtypes = [vp]
     L.ba_gpu_comm_unique_id.argtypes = [C.c_char_p]
     L.ba_gpu_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
     for name in EXPORTS:

@@ -9,6 +9,7 @@
 #include "../../include/ba_gpu.h"
 #include "ba_kernels.cuh"
 #include "ba_kernels_fact.cuh"
+#include "ba_kernels_tile.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -68,7 +69,7 @@ struct Buf {
 
 struct ba_gpu_ctx {
   ba_gpu_options opt;
-  int device = 0;
+  int device = 0, n_sm = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -97,6 +98,11 @@ struct ba_gpu_ctx {
   Buf fcm, fpm, geo, camx, Vs, ts, tgs, ys, tile_lo, tile_span;
   bool staged = false;
   FPlanes Fc_, Fp_;
+  // tile-fused product (ba_kernels_tile.cuh)
+  Buf tmeta, tseg, tout, taux, tm_cam, tm_pt, tm_uv, ftm, cam_tmin, cam_tmax, tcnt, tpart_ptr, part6t;
+  bool tiled = false;
+  int tile_npt = 0, n_tparts = 0;
+  double2 *Tg0 = nullptr, *Tg1 = nullptr;
   // scaling / diag / gradient / blocks
   Buf sc, sp, sk, dc, dp, dk, gc, gp, gk, U, Uck, Ukk, V, Vinv, Wk, tg, t, yc, yp, yk, rk, Jkk;
   Buf one_c, one_p, one_k;
@@ -170,6 +176,9 @@ static T *P(const Buf &b) {
   return reinterpret_cast<T *>(b.p);
 }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static size_t tile_smem_bytes(int npt) {
+  return ((size_t)6 * (npt * BA_THREADS + 8) + 3 * BA_TILE_PTS + BA_TILE_MAXSPAN * BA_TILE_QREC + BA_TILE_MAXSPAN * 6) * 8;
+}
 
 #define LAUNCH(kern, grid, block, smem, ...)                              \
   do {                                                                    \
@@ -248,7 +257,7 @@ static int check_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
     return fail(ctx, BA_ERR_INVALID, "Huber deltas must be > 0 and weights >= 0");
   if (o->max_num_iterations < 0 || o->poll_interval < 1) return fail(ctx, BA_ERR_INVALID, "bad iteration options");
   if (o->solver < BA_SOLVER_AUTO || o->solver > BA_SOLVER_IMPLICIT_PCG) return fail(ctx, BA_ERR_INVALID, "bad solver");
-  if (o->jacobian_store < BA_JAC_AUTO || o->jacobian_store > BA_JAC_FACTORED) return fail(ctx, BA_ERR_INVALID, "bad jacobian_store");
+  if (o->jacobian_store < BA_JAC_AUTO || o->jacobian_store > BA_JAC_TILED) return fail(ctx, BA_ERR_INVALID, "bad jacobian_store");
   if (!(o->initial_trust_region_radius > 0.0)) return fail(ctx, BA_ERR_INVALID, "bad trust-region radius");
   return 0;
 }
@@ -280,6 +289,7 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if ((e = cudaSetDevice(dev)) != cudaSuccess) return bail("cudaSetDevice", e);
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  ctx->n_sm = prop.multiProcessorCount;
   if (prop.major < 10) {
     fail(nullptr, BA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
     delete ctx;
@@ -290,6 +300,11 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMallocHost((void **)&ctx->h_st, sizeof(LmState))) != cudaSuccess) return bail("cudaMallocHost", e);
   cudaFuncSetAttribute(k_cholesky_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  cudaFuncSetAttribute(kt_schur_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2));
+  cudaFuncSetAttribute(kt_schur_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(3));
+  cudaFuncSetAttribute(kt_schur_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(4));
+  cudaFuncSetAttribute(kt_schur_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(6));
+  cudaFuncSetAttribute(kt_schur_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(8));
   *out = ctx;
   return BA_OK;
 }
@@ -322,6 +337,10 @@ extern "C" int ba_gpu_set_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
 }
 
 extern "C" int64_t ba_gpu_launch_count(const ba_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int ba_gpu_jacobian_store_used(const ba_gpu_ctx *ctx) {
+  if (!ctx || !ctx->uploaded) return BA_ERR_STATE;
+  return ctx->tiled ? BA_JAC_TILED : (ctx->fact ? BA_JAC_FACTORED : BA_JAC_PLANES);
+}
 
 // ------------------------------------------------------------------ upload
 static void set_planes(JPlanes &J, double *base, size_t n_pad, int depth, int nk) {
@@ -675,6 +694,58 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     CK(cudaStreamSynchronize(s));
     ctx->staged = h_span <= BA_STAGE_CAMS;
   }
+  ctx->tiled = false;
+  if (ctx->fact && o.jacobian_store != BA_JAC_FACTORED && ctx->n_tiles > 0) {
+    // tile-fused product: tile metadata, then (if the locality bounds hold) the tile-camera-major store
+    RES(tmeta, (size_t)ctx->n_tiles * sizeof(TileMeta));
+    CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, s));
+    LAUNCH(kt_tile_meta, ctx->n_tiles, BA_THREADS, 0, n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam), P<TileMeta>(ctx->tmeta),
+           P<int32_t>(ctx->err_flag));
+    int32_t h_max[2] = {0, 0};
+    CK(cudaMemcpyAsync(h_max, ctx->err_flag.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const bool ok = h_max[0] <= BA_TILE_MAXSPAN && h_max[1] <= BA_TILE_MAXCAP;
+    if (!ok && o.jacobian_store == BA_JAC_TILED)
+      return fail(ctx, BA_ERR_UNSUPPORTED, "tiled store: a point tile spans %d cameras / holds %d observations (limits %d / %d)",
+                  h_max[0], h_max[1], BA_TILE_MAXSPAN, BA_TILE_MAXCAP);
+    if (ok) {
+      const int need = std::max(1, cdiv(h_max[1], BA_THREADS));
+      ctx->tile_npt = need <= 2 ? 2 : need <= 3 ? 3 : need <= 4 ? 4 : need <= 6 ? 6 : 8;
+      RES(tseg, (size_t)ctx->n_tiles * (BA_TILE_MAXSPAN + 1) * 2);
+      RES(tout, (size_t)ctx->n_tiles * BA_TILE_MAXSPAN * 4);
+      RES(taux, no * 4);
+      RES(tm_cam, no * 4);
+      RES(tm_pt, no * 4);
+      RES(tm_uv, no * 16);
+      RES(ftm, n_pad * 32);
+      ctx->Tg0 = P<double2>(ctx->ftm);
+      ctx->Tg1 = P<double2>(ctx->ftm) + n_pad;
+      RES(cam_tmin, nc * 4);
+      RES(cam_tmax, nc * 4);
+      RES(tcnt, (nc + 1) * 4);
+      RES(tpart_ptr, (nc + 1) * 4);
+      LAUNCH(k_fill_i32, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->cam_tmin), 0x7fffffff);
+      LAUNCH(k_fill_i32, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->cam_tmax), -1);
+      LAUNCH(k_fill_i32, cdiv(ctx->n_tiles * BA_TILE_MAXSPAN, BA_THREADS), BA_THREADS, 0, ctx->n_tiles * BA_TILE_MAXSPAN,
+             P<int32_t>(ctx->tout), -1);
+      LAUNCH(kt_tile_build, ctx->n_tiles, BA_THREADS, (size_t)(h_max[1] + 1) * 4, P<TileMeta>(ctx->tmeta), P<int32_t>(ctx->pm_cam),
+             P<int32_t>(ctx->pm_pt), P<double2>(ctx->pm_uv), P<int32_t>(ctx->tm_cam), P<int32_t>(ctx->tm_pt), P<double2>(ctx->tm_uv),
+             P<uint32_t>(ctx->taux), P<uint16_t>(ctx->tseg), P<int32_t>(ctx->cam_tmin), P<int32_t>(ctx->cam_tmax));
+      LAUNCH((kt_cam_tiles<0>), ctx->nblk_cam, BA_THREADS, 0, n_cam, P<TileMeta>(ctx->tmeta), P<uint16_t>(ctx->tseg),
+             P<int32_t>(ctx->cam_tmin), P<int32_t>(ctx->cam_tmax), (const int32_t *)nullptr, P<int32_t>(ctx->tcnt),
+             (int32_t *)nullptr);
+      LAUNCH(k_exclusive_scan, 1, 1024, 0, n_cam, P<int32_t>(ctx->tcnt), P<int32_t>(ctx->tpart_ptr));
+      LAUNCH((kt_cam_tiles<1>), ctx->nblk_cam, BA_THREADS, 0, n_cam, P<TileMeta>(ctx->tmeta), P<uint16_t>(ctx->tseg),
+             P<int32_t>(ctx->cam_tmin), P<int32_t>(ctx->cam_tmax), P<int32_t>(ctx->tpart_ptr), (int32_t *)nullptr,
+             P<int32_t>(ctx->tout));
+      int32_t h_parts = 0;
+      CK(cudaMemcpyAsync(&h_parts, P<int32_t>(ctx->tpart_ptr) + n_cam, 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      ctx->n_tparts = h_parts;
+      RES(part6t, (size_t)(h_parts + 1) * 48);
+      ctx->tiled = true;
+    }
+  }
   RES(part_blk, (size_t)(h_items + 1) * 61 * 8);
   RES(part6, (size_t)(h_items + 1) * 6 * 8);
   RES(part21, (size_t)(h_items + 1) * 21 * 8);
@@ -724,10 +795,11 @@ struct ItemRef {
   const double *part;
 };
 template <int NV>
-static ItemRef reduce_items(ba_gpu_ctx *ctx, const double *part, Buf &dense, int gate) {
-  if (ctx->n_ranks == 1) return ItemRef{P<int32_t>(ctx->item_ptr), part};
+static ItemRef reduce_items(ba_gpu_ctx *ctx, const double *part, Buf &dense, int gate, const int32_t *ptr = nullptr) {
+  if (!ptr) ptr = P<int32_t>(ctx->item_ptr);
+  if (ctx->n_ranks == 1) return ItemRef{ptr, part};
   k_sum_items<NV><<<cdiv(ctx->n_cam * NV, BA_THREADS), BA_THREADS, 0, ctx->stream>>>(
-      ctx->n_cam, P<int32_t>(ctx->item_ptr), part, P<double>(dense), P<LmState>(ctx->st), gate);
+      ctx->n_cam, ptr, part, P<double>(dense), P<LmState>(ctx->st), gate);
   ctx->launches++;
   if (nccl_allreduce(ctx, P<double>(dense), (size_t)ctx->n_cam * NV, false)) ctx->comm_error = true;
   return ItemRef{P<int32_t>(ctx->ident), P<double>(dense)};
@@ -758,6 +830,9 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
     LAUNCH((kf_linearize<0>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt),
            P<double2>(ctx->pm_uv), P<double>(ctx->pose), P<double>(ctx->pt), intr, ctx->cp, ctx->Fp_, (double *)nullptr, st,
            gate);
+    if (ctx->tiled)
+      LAUNCH(kt_linearize, ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->tm_cam), P<int32_t>(ctx->tm_pt),
+             P<double2>(ctx->tm_uv), P<double>(ctx->pose), P<double>(ctx->pt), intr, ctx->cp, ctx->Tg0, ctx->Tg1, st, gate);
     LAUNCH(kf_cam_blocks, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), ctx->Fc_, P<double>(ctx->geo), intr,
            P<double>(ctx->part_blk), st, gate);
     ItemRef ir = reduce_items<27>(ctx, P<double>(ctx->part_blk), ctx->red_blk, gate);
@@ -832,9 +907,32 @@ static void enqueue_point_inverse(ba_gpu_ctx *ctx, int gate) {
            P<double>(ctx->Vinv), P<double>(ctx->tg), st, gate);
 }
 
-static void enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int passes = 3) {
+template <int NPT>
+static void launch_fused(ba_gpu_ctx *ctx, const double *v, int gate) {
+  LAUNCH((kt_schur_fused<NPT>), ctx->n_tiles, BA_THREADS, tile_smem_bytes(NPT), ctx->n_pt, P<int32_t>(ctx->pt_rowptr),
+         P<TileMeta>(ctx->tmeta), P<uint16_t>(ctx->tseg), P<int32_t>(ctx->tout), P<uint32_t>(ctx->taux), ctx->Tg0, ctx->Tg1,
+         P<double>(ctx->geo), P<double>(ctx->pose), v, P<double>(ctx->intr), P<double>(ctx->Vs), P<double>(ctx->part6t),
+         P<LmState>(ctx->st), gate);
+}
+
+// One implicit-Schur product of v (without the LM damping term): enqueues the
+// kernels and returns the per-camera partial list that k_pcg_q / k_pcg_reset add up.
+// passes: 3 = product (fused kernel if the store is tiled), 1 / 2 = one pass of the
+// two-pass form, 7 = force the two-pass form.
+static ItemRef enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int passes = 3) {
   LmState *st = P<LmState>(ctx->st);
   const int rp = ctx->lo.reset_period;
+  if (ctx->tiled && passes == 3) {
+    switch (ctx->tile_npt) {
+      case 2: launch_fused<2>(ctx, v, gate); break;
+      case 3: launch_fused<3>(ctx, v, gate); break;
+      case 4: launch_fused<4>(ctx, v, gate); break;
+      case 6: launch_fused<6>(ctx, v, gate); break;
+      default: launch_fused<8>(ctx, v, gate); break;
+    }
+    return ItemRef{P<int32_t>(ctx->tpart_ptr), P<double>(ctx->part6t)};
+  }
+  const ItemRef items_ref{P<int32_t>(ctx->item_ptr), P<double>(ctx->part6)};
   if (ctx->fact) {
     const double *intr = P<double>(ctx->intr);
     if (passes & 1) {
@@ -852,7 +950,7 @@ static void enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int passe
     if (passes & 2)
       LAUNCH(kf_schur_pass2, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Fc_,
              P<double>(ctx->geo), intr, v, P<double>(ctx->ts), 1.0, P<double>(ctx->part6), st, gate);
-    return;
+    return items_ref;
   }
   DISPATCH_D(ctx->depth, {
     if (passes & 1)
@@ -862,6 +960,7 @@ static void enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int passe
     LAUNCH((k_schur_pass2<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
            ctx->Jc_, v, P<double>(ctx->t), 1.0, P<double>(ctx->part6), st, gate, rp);
   });
+  return items_ref;
 }
 
 static int poll_state(ba_gpu_ctx *ctx) {
@@ -877,16 +976,16 @@ static void enqueue_pcg_iteration(ba_gpu_ctx *ctx, int it) {
   const int rp = ctx->lo.reset_period;
   const int reset = (rp > 0 && (it % rp) == 0) ? 1 : 0;
   LAUNCH(k_pcg_dir, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<double>(ctx->z), P<double>(ctx->p), st, GATE_PCG);
-  enqueue_matvec(ctx, P<double>(ctx->p), GATE_PCG);
-  ItemRef ir = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_PCG);
+  ItemRef ir = enqueue_matvec(ctx, P<double>(ctx->p), GATE_PCG);
+  ir = reduce_items<6>(ctx, ir.part, ctx->red6, GATE_PCG, ir.ptr);
   LAUNCH(k_pcg_q, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->dc), P<double>(ctx->p),
          P<double>(ctx->q), P<double>(ctx->pcam_pq), st, GATE_PCG);
   LAUNCH(k_pcg_step, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, P<double>(ctx->pcam_pq), P<double>(ctx->p),
          P<double>(ctx->q), P<double>(ctx->b), P<double>(ctx->Minv), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z),
          P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), ctx->lo, st, GATE_PCG, reset);
   if (reset) {
-    enqueue_matvec(ctx, P<double>(ctx->x), GATE_PCG);
-    ir = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_PCG);
+    ir = enqueue_matvec(ctx, P<double>(ctx->x), GATE_PCG);
+    ir = reduce_items<6>(ctx, ir.part, ctx->red6, GATE_PCG, ir.ptr);
     LAUNCH(k_pcg_reset, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, ir.ptr, ir.part, P<double>(ctx->dc),
            P<double>(ctx->x), P<double>(ctx->b), P<double>(ctx->Minv), P<double>(ctx->r), P<double>(ctx->z),
            P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), ctx->lo, st, GATE_PCG);
@@ -1253,8 +1352,8 @@ extern "C" int ba_gpu_schur_matvec(ba_gpu_ctx *ctx, double radius, const double 
   CK(cudaMemcpy(sc.data(), ctx->sc.p, n * 8, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < n; ++i) xs[i] = x[i] / sc[i];
   CK(cudaMemcpyAsync(ctx->p.p, xs.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  enqueue_matvec(ctx, P<double>(ctx->p), GATE_RUN);
-  LAUNCH(k_pcg_q, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->item_ptr), P<double>(ctx->part6), P<double>(ctx->dc),
+  const ItemRef mv = enqueue_matvec(ctx, P<double>(ctx->p), GATE_RUN);
+  LAUNCH(k_pcg_q, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, mv.ptr, mv.part, P<double>(ctx->dc),
          P<double>(ctx->p), P<double>(ctx->q), P<double>(ctx->pcam_pq), st, GATE_RUN);
   CK(cudaMemcpyAsync(xs.data(), ctx->q.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1309,7 +1408,7 @@ extern "C" int ba_gpu_time_kernel(ba_gpu_ctx *ctx, int32_t which, int32_t warmup
   if (which != BA_KERNEL_LINEARIZE) {
     // t must hold a finite pass-1 result before a pass-2-only timing
     CK(cudaMemcpyAsync(ctx->p.p, ctx->gc.p, (size_t)ctx->n_cam * 48, cudaMemcpyDeviceToDevice, ctx->stream));
-    enqueue_matvec(ctx, P<double>(ctx->p), GATE_RUN);
+    enqueue_matvec(ctx, P<double>(ctx->p), GATE_RUN, 7);
   }
   const size_t flush_n = (size_t)512 * 1024 * 1024 / 8;  // 512 MiB > 126 MB L2
   if (flush_l2) RES(flush, flush_n * 8);

@@ -165,6 +165,13 @@ class GpuSolver:
     def launch_count(self):
         return int(self.lib.ba_gpu_launch_count(self._ctx))
 
+    def jacobian_store_used(self):
+        """BA_JAC_* in force after the last upload (what BA_JAC_AUTO resolved to)."""
+        rc = int(self.lib.ba_gpu_jacobian_store_used(self._ctx))
+        if rc < 0:
+            self._check(rc)
+        return rc
+
     def comm_init(self, id128: bytes, rank: int, n_ranks: int):
         self._check(self.lib.ba_gpu_comm_init(self._ctx, id128, rank, n_ranks))
 

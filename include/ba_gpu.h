@@ -53,10 +53,14 @@ enum {
 };
 
 enum {
-  BA_JAC_AUTO = 0,     /* factored for NS mode + implicit PCG, planes otherwise */
+  BA_JAC_AUTO = 0,     /* NS mode + implicit PCG: tiled if the index locality allows, else factored;
+                          planes otherwise */
   BA_JAC_PLANES = 1,   /* materialised r, Jc (2x6), Jp (2x3) planes: 160 B/obs per ordering */
-  BA_JAC_FACTORED = 2  /* r + (X/Z, Y/Z, 1/Z, w): 48 B/obs; Jacobian entries rebuilt in registers
-                          (NS mode + implicit PCG only) */
+  BA_JAC_FACTORED = 2, /* r + (X/Z, Y/Z, 1/Z, w): 48 B/obs; Jacobian entries rebuilt in registers
+                          (NS mode + implicit PCG only); two-pass Schur product */
+  BA_JAC_TILED = 3     /* factored store + a tile-local camera-major copy of (X/Z, Y/Z, 1/Z, w): the
+                          Schur product is ONE pass, 36 B/obs (needs point tiles that span <= 64
+                          cameras and hold <= 2048 observations; BA_ERR_UNSUPPORTED otherwise) */
 };
 
 enum {
@@ -173,6 +177,8 @@ enum {
   BA_KERNEL_SCHUR_MATVEC = 1, /* one implicit-Schur product (both passes) */
   BA_KERNEL_SCHUR_PASS1 = 2,  /* point-major pass  t = V^-1 W^T x only */
   BA_KERNEL_SCHUR_PASS2 = 3   /* camera-major pass y = U x - W t only */
+  /* with the tiled store MATVEC is the single fused kernel and PASS1/PASS2 time the
+     two-pass kernels over the same data */
 };
 /* Launches kernel `which` `iters` times on the context stream between two CUDA
  * events (after `warmup` untimed launches); *ms_avg = mean ms per launch. If
@@ -182,6 +188,8 @@ int ba_gpu_time_kernel(ba_gpu_ctx *ctx, int32_t which, int32_t warmup,
                        int32_t iters, int32_t flush_l2, float *ms_avg);
 /* kernels launched by this context since creation */
 int64_t ba_gpu_launch_count(const ba_gpu_ctx *ctx);
+/* BA_JAC_* in force after the last upload (what BA_JAC_AUTO resolved to) */
+int ba_gpu_jacobian_store_used(const ba_gpu_ctx *ctx);
 
 /* ---- multi-GPU: one process per GPU, points sharded ---- */
 /* rank 0 makes the id (128 bytes), the launcher broadcasts it, every rank

@@ -146,7 +146,7 @@ def test_se3_plus_vs_oracle(solver_cache):
 
 
 # ---------------------------------------------------------------- implicit Schur product
-@pytest.mark.parametrize("store", [1, 2], ids=["planes", "factored"])
+@pytest.mark.parametrize("store", [1, 2, 3], ids=["planes", "factored", "tiled"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg4_small", "cfg3_small"])
 def test_schur_matvec_vs_oracle(name, store, solver_cache):
     p = _problem(name)
@@ -216,7 +216,7 @@ def test_solve_to_convergence_ref(solver_cache):
     _compare_solve(_problem("cfg1"), "REF", 1, 75, solver_cache)
 
 
-@pytest.mark.parametrize("store", [1, 2], ids=["planes", "factored"])
+@pytest.mark.parametrize("store", [1, 2, 3], ids=["planes", "factored", "tiled"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg3_small"])
 def test_solve_implicit_pcg(name, store, solver_cache):
     """Implicit Schur + block-Jacobi PCG against the oracle's own PCG, in lock
@@ -227,7 +227,7 @@ def test_solve_implicit_pcg(name, store, solver_cache):
     assert summ.total_linear_iters == osum.total_linear_iters
 
 
-@pytest.mark.parametrize("store", [1, 2], ids=["planes", "factored"])
+@pytest.mark.parametrize("store", [1, 2, 3], ids=["planes", "factored", "tiled"])
 def test_solve_implicit_pcg_ill_conditioned(store, solver_cache):
     """BAL-shaped loop: the reduced system is so ill-conditioned that PCG stops on
     its iteration cap / eta = 1e-6 far from the exact step, and summation-order
@@ -325,6 +325,41 @@ def test_factored_store_rejected_outside_ns_implicit(solver_cache):
     with pytest.raises(ba_b200.BAError) as e:
         s.upload(p)
     assert e.value.code == ba_b200.capi.BA_ERR_UNSUPPORTED
+
+
+def test_tiled_store_needs_index_locality(solver_cache):
+    """Point ids relabelled at random: a 128-point tile then spans every camera.
+    The tiled store refuses (explicit request) / AUTO falls back to the two-pass
+    factored product, which still matches the oracle."""
+    p = syn.make_config(4, scale=0.1)
+    assert p.n_cam > 64
+    rng = np.random.default_rng(3)
+    relabel = rng.permutation(p.n_pt).astype(np.int32)
+    p.pt_idx = relabel[p.pt_idx]
+    inv = np.empty_like(relabel)
+    inv[relabel] = np.arange(p.n_pt, dtype=np.int32)
+    p.pt3 = p.pt3[inv].copy()
+    g, o = mode_opts("NS", solver=2, jacobian_store=3)
+    s = _solver(solver_cache, **g)
+    with pytest.raises(ba_b200.BAError) as e:
+        s.upload(p)
+    assert e.value.code == ba_b200.capi.BA_ERR_UNSUPPORTED
+    g, o = mode_opts("NS", solver=2, jacobian_store=0)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    assert s.jacobian_store_used() == ba_b200.capi.BA_JAC_FACTORED
+    x = rng.normal(size=6 * p.n_cam)
+    y = s.schur_matvec(1e4, x)
+    yref = ora.schur_matvec(to_oracle(p), ora.default_options(**o), 1e4, x)
+    assert rel_err(y, yref) < 1e-10
+
+
+def test_auto_store_is_tiled_on_sequential_data(solver_cache):
+    p = _problem("cfg3_small")
+    g, _ = mode_opts("NS", solver=2)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    assert s.jacobian_store_used() == ba_b200.capi.BA_JAC_TILED
 
 
 def test_eval_hook_with_factored_store(solver_cache):
