@@ -10,6 +10,11 @@
 #include "ba_kernels.cuh"
 #include "ba_kernels_fact.cuh"
 #include "ba_kernels_tile.cuh"
+#include "ba_kernels_sparse.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <dlfcn.h>
 #include <math.h>
@@ -103,6 +108,11 @@ struct ba_gpu_ctx {
   bool tiled = false;
   int tile_npt = 0, n_tparts = 0;
   double2 *Tg0 = nullptr, *Tg1 = nullptr;
+  // explicit block-sparse Schur complement (ba_kernels_sparse.cuh)
+  Buf sp_cnt, sp_off, sp_keys, sp_vals, sp_keys2, sp_pairs, sp_ukeys, sp_ucnt, sp_nruns, sb_ptr, sb_i, sb_j, row_ucnt, row_tcnt,
+      row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent_blk, ent_col, Sblk, ysp, cub_tmp;
+  int n_sblk = 0, n_ent = 0;
+  long long n_pairs = 0;
   // scaling / diag / gradient / blocks
   Buf sc, sp, sk, dc, dp, dk, gc, gp, gk, U, Uck, Ukk, V, Vinv, Wk, tg, t, yc, yp, yk, rk, Jkk;
   Buf one_c, one_p, one_k;
@@ -256,7 +266,7 @@ static int check_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
   if (!(o->HUB_P_REPR > 0.0) || !(o->HUB_P_UNPR > 0.0) || !(o->WEIGHT_UNPR >= 0.0) || !(o->WEIGHT_INTRINSICS >= 0.0))
     return fail(ctx, BA_ERR_INVALID, "Huber deltas must be > 0 and weights >= 0");
   if (o->max_num_iterations < 0 || o->poll_interval < 1) return fail(ctx, BA_ERR_INVALID, "bad iteration options");
-  if (o->solver < BA_SOLVER_AUTO || o->solver > BA_SOLVER_IMPLICIT_PCG) return fail(ctx, BA_ERR_INVALID, "bad solver");
+  if (o->solver < BA_SOLVER_AUTO || o->solver > BA_SOLVER_SPARSE_SCHUR_PCG) return fail(ctx, BA_ERR_INVALID, "bad solver");
   if (o->jacobian_store < BA_JAC_AUTO || o->jacobian_store > BA_JAC_TILED) return fail(ctx, BA_ERR_INVALID, "bad jacobian_store");
   if (!(o->initial_trust_region_radius > 0.0)) return fail(ctx, BA_ERR_INVALID, "bad trust-region radius");
   return 0;
@@ -473,6 +483,89 @@ static int ensure_planes(ba_gpu_ctx *ctx) {
   return 0;
 }
 
+// structure of the explicit block-sparse Schur complement (integer-only, device-built;
+// the radix sort / scan / run-length steps are CUB library calls, setup only)
+#define CUBCALL(fn, ...)                                                  \
+  do {                                                                    \
+    size_t tb_ = 0;                                                       \
+    CK(fn(nullptr, tb_, __VA_ARGS__, ctx->stream));                       \
+    RES(cub_tmp, tb_ + 16);                                               \
+    CK(fn(ctx->cub_tmp.p, tb_, __VA_ARGS__, ctx->stream));                \
+  } while (0)
+static int build_sparse_structure(ba_gpu_ctx *ctx) {
+  const int n_pt = ctx->n_pt, n_cam = ctx->n_cam;
+  cudaStream_t s = ctx->stream;
+  typedef unsigned long long u64;
+  RES(sp_cnt, ((size_t)n_pt + 2) * 8);
+  RES(sp_off, ((size_t)n_pt + 2) * 8);
+  LAUNCH(k_sp_count, cdiv(n_pt + 1, BA_THREADS), BA_THREADS, 0, n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+         ctx->fixed_cam, P<long long>(ctx->sp_cnt));
+  CUBCALL(cub::DeviceScan::ExclusiveSum, P<long long>(ctx->sp_cnt), P<long long>(ctx->sp_off), n_pt + 1);
+  long long n_pairs = 0;
+  CK(cudaMemcpyAsync(&n_pairs, P<long long>(ctx->sp_off) + n_pt, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (n_pairs > 0x7fffffffLL) return fail(ctx, BA_ERR_UNSUPPORTED, "sparse Schur: %lld observation pairs (limit 2^31-1)", n_pairs);
+  ctx->n_pairs = n_pairs;
+  const size_t np8 = ((size_t)n_pairs + 1) * 8;
+  RES(sp_keys, np8);
+  RES(sp_vals, np8);
+  RES(sp_keys2, np8);
+  RES(sp_pairs, np8);
+  LAUNCH(k_sp_emit, ctx->nblk_pt, BA_THREADS, 0, n_pt, n_cam, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam), ctx->fixed_cam,
+         P<long long>(ctx->sp_off), P<u64>(ctx->sp_keys), P<u64>(ctx->sp_vals));
+  int bits = 1;
+  while (bits < 64 && ((u64)1 << bits) < (u64)n_cam * (u64)n_cam) ++bits;
+  CUBCALL(cub::DeviceRadixSort::SortPairs, P<u64>(ctx->sp_keys), P<u64>(ctx->sp_keys2), P<u64>(ctx->sp_vals), P<u64>(ctx->sp_pairs),
+          (int)n_pairs, 0, bits);
+  RES(sp_ukeys, np8);
+  RES(sp_ucnt, ((size_t)n_pairs + 2) * 4);
+  RES(sp_nruns, 16);
+  CUBCALL(cub::DeviceRunLengthEncode::Encode, P<u64>(ctx->sp_keys2), P<u64>(ctx->sp_ukeys), P<int32_t>(ctx->sp_ucnt),
+          P<int32_t>(ctx->sp_nruns), (int)n_pairs);
+  int32_t n_blk = 0;
+  CK(cudaMemcpyAsync(&n_blk, ctx->sp_nruns.p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (n_pairs == 0) n_blk = 0;
+  ctx->n_sblk = n_blk;
+  const size_t nb = (size_t)n_blk;
+  RES(sb_ptr, (nb + 2) * 4);
+  CK(cudaMemsetAsync(P<int32_t>(ctx->sp_ucnt) + nb, 0, 4, s));
+  CUBCALL(cub::DeviceScan::ExclusiveSum, P<int32_t>(ctx->sp_ucnt), P<int32_t>(ctx->sb_ptr), n_blk + 1);
+  RES(sb_i, (nb + 1) * 4);
+  RES(sb_j, (nb + 1) * 4);
+  RES(row_ucnt, ((size_t)n_cam + 2) * 4);
+  RES(row_tcnt, ((size_t)n_cam + 2) * 4);
+  RES(row_ustart, ((size_t)n_cam + 2) * 4);
+  RES(row_tstart, ((size_t)n_cam + 2) * 4);
+  RES(sp_tkeys, (nb + 1) * 8);
+  RES(sp_tkeys2, (nb + 1) * 8);
+  RES(sp_tvals, (nb + 1) * 4);
+  RES(sp_tvals2, (nb + 1) * 4);
+  CK(cudaMemsetAsync(ctx->row_ucnt.p, 0, ((size_t)n_cam + 2) * 4, s));
+  CK(cudaMemsetAsync(ctx->row_tcnt.p, 0, ((size_t)n_cam + 2) * 4, s));
+  LAUNCH(k_sp_blocks, cdiv(n_blk, BA_THREADS), BA_THREADS, 0, n_blk, n_cam, P<u64>(ctx->sp_ukeys), P<int32_t>(ctx->sb_i),
+         P<int32_t>(ctx->sb_j), P<int32_t>(ctx->row_ucnt), P<int32_t>(ctx->row_tcnt), P<u64>(ctx->sp_tkeys), P<int32_t>(ctx->sp_tvals));
+  if (n_blk > 0)
+    CUBCALL(cub::DeviceRadixSort::SortPairs, P<u64>(ctx->sp_tkeys), P<u64>(ctx->sp_tkeys2), P<int32_t>(ctx->sp_tvals),
+            P<int32_t>(ctx->sp_tvals2), n_blk, 0, 64);
+  CUBCALL(cub::DeviceScan::ExclusiveSum, P<int32_t>(ctx->row_ucnt), P<int32_t>(ctx->row_ustart), n_cam + 1);
+  CUBCALL(cub::DeviceScan::ExclusiveSum, P<int32_t>(ctx->row_tcnt), P<int32_t>(ctx->row_tstart), n_cam + 1);
+  int32_t n_t = 0;
+  CK(cudaMemcpyAsync(&n_t, P<int32_t>(ctx->row_tstart) + n_cam, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->n_ent = n_blk + n_t;
+  RES(ent_ptr, ((size_t)n_cam + 2) * 4);
+  RES(ent_blk, ((size_t)ctx->n_ent + 1) * 4);
+  RES(ent_col, ((size_t)ctx->n_ent + 1) * 4);
+  LAUNCH(k_sp_entries, cdiv(n_cam + 1, BA_THREADS), BA_THREADS, 0, n_cam, P<int32_t>(ctx->row_ustart), P<int32_t>(ctx->row_tstart),
+         P<int32_t>(ctx->sp_tvals2), P<int32_t>(ctx->sb_i), P<int32_t>(ctx->sb_j), P<int32_t>(ctx->ent_ptr),
+         P<uint32_t>(ctx->ent_blk), P<int32_t>(ctx->ent_col));
+  RES(Sblk, (nb + 1) * 288);
+  RES(ysp, ((size_t)n_cam + 1) * 48);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7, int32_t fixed_cam, int32_t n_pt,
                              const double *pt3, int32_t n_obs, const int32_t *cam_idx, const int32_t *pt_idx,
                              const double *uv2, const double *depth, const double intr4[4], const double intr_prior4[4]) {
@@ -498,14 +591,19 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   int solver = o.solver;
   if (solver == BA_SOLVER_AUTO)
     solver = (ctx->n_red <= o.explicit_max_dim || ctx->nk) ? BA_SOLVER_EXPLICIT_CHOLESKY : BA_SOLVER_IMPLICIT_PCG;
-  if (solver == BA_SOLVER_IMPLICIT_PCG && ctx->nk)
+  if ((solver == BA_SOLVER_IMPLICIT_PCG || solver == BA_SOLVER_SPARSE_SCHUR_PCG) && ctx->nk)
     return fail(ctx, BA_ERR_UNSUPPORTED, "optimize_intrinsics needs the explicit solver (as ITERATIVE_SCHUR needs points only)");
+  if (solver == BA_SOLVER_SPARSE_SCHUR_PCG && o.use_depth_prior)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "the block-sparse Schur solver needs NS mode (no depth prior, fixed intrinsics)");
   if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_red > 1024)
     return fail(ctx, BA_ERR_UNSUPPORTED, "explicit Cholesky supports reduced dimension <= 1024 (got %d)", ctx->n_red);
   if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks > 1)
     return fail(ctx, BA_ERR_UNSUPPORTED, "the explicit solver is single-GPU (windowed problems stay on one GPU)");
   ctx->solver = solver;
-  const bool can_fact = (solver == BA_SOLVER_IMPLICIT_PCG && !o.use_depth_prior && !o.optimize_intrinsics);
+  const bool sparse = solver == BA_SOLVER_SPARSE_SCHUR_PCG;
+  const bool can_fact = ((solver == BA_SOLVER_IMPLICIT_PCG || sparse) && !o.use_depth_prior && !o.optimize_intrinsics);
+  if (sparse && o.jacobian_store == BA_JAC_PLANES)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "the block-sparse Schur solver rebuilds its blocks from the factored store");
   if (o.jacobian_store == BA_JAC_FACTORED && !can_fact)
     return fail(ctx, BA_ERR_UNSUPPORTED, "the factored Jacobian store needs NS mode (no depth prior, fixed intrinsics) + implicit PCG");
   ctx->fact = can_fact && o.jacobian_store != BA_JAC_PLANES;
@@ -695,7 +793,11 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     ctx->staged = h_span <= BA_STAGE_CAMS;
   }
   ctx->tiled = false;
-  if (ctx->fact && o.jacobian_store != BA_JAC_FACTORED && ctx->n_tiles > 0) {
+  if (sparse) {
+    int rcs = build_sparse_structure(ctx);
+    if (rcs) return rcs;
+  }
+  if (ctx->fact && !sparse && o.jacobian_store != BA_JAC_FACTORED && ctx->n_tiles > 0) {
     // tile-fused product: tile metadata, then (if the locality bounds hold) the tile-camera-major store
     RES(tmeta, (size_t)ctx->n_tiles * sizeof(TileMeta));
     CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, s));
@@ -922,6 +1024,11 @@ static void launch_fused(ba_gpu_ctx *ctx, const double *v, int gate) {
 static ItemRef enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int passes = 3) {
   LmState *st = P<LmState>(ctx->st);
   const int rp = ctx->lo.reset_period;
+  if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && passes == 3) {
+    LAUNCH(k_bsr_spmv, cdiv(ctx->n_cam * 32, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->ent_ptr),
+           P<uint32_t>(ctx->ent_blk), P<int32_t>(ctx->ent_col), P<double>(ctx->Sblk), v, P<double>(ctx->ysp), st, gate);
+    return ItemRef{P<int32_t>(ctx->ident), P<double>(ctx->ysp)};
+  }
   if (ctx->tiled && passes == 3) {
     switch (ctx->tile_npt) {
       case 2: launch_fused<2>(ctx, v, gate); break;
@@ -961,6 +1068,14 @@ static ItemRef enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int pa
            ctx->Jc_, v, P<double>(ctx->t), 1.0, P<double>(ctx->part6), st, gate, rp);
   });
   return items_ref;
+}
+
+// values of the explicit block-sparse Schur complement (needs V^-1 of this radius)
+static void enqueue_sparse_values(ba_gpu_ctx *ctx, int gate) {
+  if (ctx->solver != BA_SOLVER_SPARSE_SCHUR_PCG) return;
+  LAUNCH(k_sp_schur, cdiv(ctx->n_sblk * 32, BA_THREADS), BA_THREADS, 0, ctx->n_sblk, P<int32_t>(ctx->sb_ptr), P<int32_t>(ctx->sb_i),
+         P<int32_t>(ctx->sb_j), P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->pm_pt), ctx->Fp_, P<double>(ctx->geo),
+         P<double>(ctx->intr), P<double>(ctx->Vs), P<double>(ctx->U), P<double>(ctx->Sblk), P<LmState>(ctx->st), gate);
 }
 
 static int poll_state(ba_gpu_ctx *ctx) {
@@ -1010,6 +1125,7 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
     LAUNCH((k_schur_diag<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Jc_,
            P<double>(ctx->Vinv), P<double>(ctx->part21), st, GATE_RUN);
   });
+  enqueue_sparse_values(ctx, GATE_RUN);
   sync_flags(ctx);
   ItemRef i21 = reduce_items<21>(ctx, P<double>(ctx->part21), ctx->red21, GATE_RUN);
   LAUNCH(k_schur_diag_fin, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i21.ptr, i21.part, P<double>(ctx->U), P<double>(ctx->dc),
@@ -1080,7 +1196,7 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
   const int D = ctx->depth, K = ctx->nk;
   LAUNCH(k_lm_begin, 1, 1, 0, ctx->lo, st);
   enqueue_point_inverse(ctx, GATE_RUN);
-  int rc = ctx->solver == BA_SOLVER_IMPLICIT_PCG ? solve_implicit(ctx) : solve_explicit(ctx);
+  int rc = ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY ? solve_implicit(ctx) : solve_explicit(ctx);
   if (rc) return rc;
   if (ctx->fact) {
     const double *intr = P<double>(ctx->intr);
@@ -1147,7 +1263,7 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   for (int it = 1;; ++it) {
     rc = enqueue_lm_iteration(ctx);
     if (rc) return rc;
-    const bool implicit = ctx->solver == BA_SOLVER_IMPLICIT_PCG;
+    const bool implicit = ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY;
     if (!implicit && (it % poll) != 0 && it <= ctx->lo.max_num_iterations) continue;
     rc = poll_state(ctx);
     if (rc) return rc;
@@ -1326,6 +1442,7 @@ static int prepare_linear_system(ba_gpu_ctx *ctx, double radius) {
   LmState *st = P<LmState>(ctx->st);
   LAUNCH(k_set_radius, 1, 1, 0, st, radius);
   enqueue_point_inverse(ctx, GATE_RUN);
+  enqueue_sparse_values(ctx, GATE_RUN);
   int rc = poll_state(ctx);
   if (rc) return rc;
   if (ctx->h_st->eval_fail) return fail(ctx, BA_ERR_NUMERIC, "non-finite residual or Jacobian");

@@ -48,8 +48,12 @@ enum {
   BA_SOLVER_AUTO = 0,              /* explicit if reduced dim <= explicit_max_dim */
   BA_SOLVER_EXPLICIT_CHOLESKY = 1, /* explicit Schur complement + dense Cholesky
                                       (== Ceres DENSE_SCHUR / SPARSE_SCHUR step) */
-  BA_SOLVER_IMPLICIT_PCG = 2       /* matrix-free Schur + block-Jacobi PCG
+  BA_SOLVER_IMPLICIT_PCG = 2,      /* matrix-free Schur + block-Jacobi PCG
                                       (== Ceres ITERATIVE_SCHUR + SCHUR_JACOBI) */
+  BA_SOLVER_SPARSE_SCHUR_PCG = 3   /* explicit BLOCK-SPARSE Schur complement (6x6 blocks, symmetric
+                                      storage, device-built structure) + the same PCG
+                                      (== ITERATIVE_SCHUR with use_explicit_schur_complement;
+                                      the matrix Ceres SPARSE_SCHUR factorises). NS mode only. */
 };
 
 enum {

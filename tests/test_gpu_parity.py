@@ -251,6 +251,63 @@ def test_solve_implicit_pcg_ill_conditioned(store, solver_cache):
     assert abs(summ.total_linear_iters - osum.total_linear_iters) <= 0.05 * osum.total_linear_iters
 
 
+# ---------------------------------------------------------------- explicit block-sparse Schur complement + PCG
+@pytest.mark.parametrize("name", ["cfg1", "cfg4_small", "cfg3_small"])
+def test_sparse_schur_product_vs_oracle(name, solver_cache):
+    """The block-sparse S times x equals the oracle's implicit product (and is symmetric)."""
+    p = _problem(name)
+    g, o = mode_opts("NS", solver=3)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    rng = np.random.default_rng(2)
+    for radius in (1e4, 3.7):
+        x = rng.normal(size=6 * p.n_cam)
+        y = s.schur_matvec(radius, x)
+        yref = ora.schur_matvec(to_oracle(p), ora.default_options(**o), radius, x)
+        assert rel_err(y, yref) < 1e-10
+    x1, x2 = rng.normal(size=6 * p.n_cam), rng.normal(size=6 * p.n_cam)
+    y1, y2 = s.schur_matvec(1e4, x1), s.schur_matvec(1e4, x2)
+    assert abs(x1 @ y2 - x2 @ y1) <= 1e-10 * (abs(x1 @ y2) + np.linalg.norm(y1) * np.linalg.norm(x2))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3_small"])
+def test_solve_sparse_schur_pcg(name, solver_cache):
+    """Explicit block-sparse S + PCG against the oracle's PCG, in lock step on the
+    well-conditioned TUM-shaped problems."""
+    summ, osum = _compare_solve(_problem(name), "NS", 3, 8, solver_cache)
+    assert summ.solver_used == ba_b200.capi.BA_SOLVER_SPARSE_SCHUR_PCG
+    assert abs(summ.total_linear_iters - osum.total_linear_iters) <= max(2, 0.02 * osum.total_linear_iters)
+
+
+def test_sparse_schur_duplicate_camera_observations(solver_cache):
+    """A camera that observes the same landmark twice: the diagonal block needs both
+    orders of the pair."""
+    p = _problem("cfg1")
+    # duplicate the first 40 observations of camera 3 (same landmark, shifted pixel), keep camera-major order
+    idx = np.flatnonzero(p.cam_idx == 3)[:40]
+    ins = idx[-1] + 1
+    p.cam_idx = np.insert(p.cam_idx, ins, p.cam_idx[idx])
+    p.pt_idx = np.insert(p.pt_idx, ins, p.pt_idx[idx])
+    p.uv2 = np.insert(p.uv2, ins, p.uv2[idx] + 0.25, axis=0)
+    if p.depth is not None:
+        p.depth = np.insert(p.depth, ins, p.depth[idx])
+    g, o = mode_opts("NS", solver=3)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    x = np.random.default_rng(5).normal(size=6 * p.n_cam)
+    y = s.schur_matvec(1e4, x)
+    yref = ora.schur_matvec(to_oracle(p), ora.default_options(**o), 1e4, x)
+    assert rel_err(y, yref) < 1e-10
+
+
+def test_sparse_schur_rejected_outside_ns(solver_cache):
+    p = _problem("cfg1_small")
+    s = _solver(solver_cache, use_depth_prior=1, optimize_intrinsics=0, solver=3)
+    with pytest.raises(ba_b200.BAError) as e:
+        s.upload(p)
+    assert e.value.code == ba_b200.capi.BA_ERR_UNSUPPORTED
+
+
 def test_explicit_and_implicit_agree(solver_cache):
     """A converged PCG step equals the Cholesky step: same optimum."""
     p = _problem("cfg3_small")
