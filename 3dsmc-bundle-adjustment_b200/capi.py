@@ -38,7 +38,7 @@ class Options(C.Structure):
         ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
         ("max_linear_solver_iterations", C.c_int32), ("min_linear_solver_iterations", C.c_int32),
         ("residual_reset_period", C.c_int32), ("device", C.c_int32), ("poll_interval", C.c_int32),
-        ("use_cuda_graph", C.c_int32), ("jacobian_store", C.c_int32),
+        ("persistent_pcg", C.c_int32), ("jacobian_store", C.c_int32),
     ]
 
 

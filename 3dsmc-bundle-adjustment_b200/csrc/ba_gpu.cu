@@ -20,6 +20,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -110,9 +111,10 @@ struct ba_gpu_ctx {
   double2 *Tg0 = nullptr, *Tg1 = nullptr;
   // explicit block-sparse Schur complement (ba_kernels_sparse.cuh)
   Buf sp_cnt, sp_off, sp_keys, sp_vals, sp_keys2, sp_pairs, sp_ukeys, sp_ucnt, sp_nruns, sb_ptr, sb_i, sb_j, row_ucnt, row_tcnt,
-      row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent_blk, ent_col, Sblk, ysp, cub_tmp;
-  int n_sblk = 0, n_ent = 0;
+      row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
+  int n_sblk = 0, n_ent = 0, pcg_grid = 0;
   long long n_pairs = 0;
+  Buf p2, pcg_bar, wb_rho, wb_Q;
   // scaling / diag / gradient / blocks
   Buf sc, sp, sk, dc, dp, dk, gc, gp, gk, U, Uck, Ukk, V, Vinv, Wk, tg, t, yc, yp, yk, rk, Jkk;
   Buf one_c, one_p, one_k;
@@ -258,7 +260,7 @@ extern "C" void ba_gpu_default_options(ba_gpu_options *o) {
   o->residual_reset_period = 10;
   o->device = -1;
   o->poll_interval = 10;
-  o->use_cuda_graph = 0;
+  o->persistent_pcg = 1;
   o->jacobian_store = BA_JAC_AUTO;
 }
 
@@ -555,13 +557,24 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   CK(cudaStreamSynchronize(s));
   ctx->n_ent = n_blk + n_t;
   RES(ent_ptr, ((size_t)n_cam + 2) * 4);
-  RES(ent_blk, ((size_t)ctx->n_ent + 1) * 4);
-  RES(ent_col, ((size_t)ctx->n_ent + 1) * 4);
+  RES(ent, ((size_t)ctx->n_ent + 1) * 8);
   LAUNCH(k_sp_entries, cdiv(n_cam + 1, BA_THREADS), BA_THREADS, 0, n_cam, P<int32_t>(ctx->row_ustart), P<int32_t>(ctx->row_tstart),
          P<int32_t>(ctx->sp_tvals2), P<int32_t>(ctx->sb_i), P<int32_t>(ctx->sb_j), P<int32_t>(ctx->ent_ptr),
-         P<uint32_t>(ctx->ent_blk), P<int32_t>(ctx->ent_col));
+         P<int2>(ctx->ent));
   RES(Sblk, (nb + 1) * 288);
   RES(ysp, ((size_t)n_cam + 1) * 48);
+  RES(p2, ((size_t)n_cam + 1) * 48);
+  RES(row_pq, ((size_t)n_cam + 1) * 8);
+  RES(wb_rho, ((size_t)cdiv(n_cam, 32) + 1) * 8);
+  RES(wb_Q, ((size_t)cdiv(n_cam, 32) + 1) * 8);
+  RES(dsq, ((size_t)n_cam + 1) * 48);
+  RES(pcg_bar, 128);
+  CK(cudaMemsetAsync(ctx->pcg_bar.p, 0, 128, s));
+  {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_sparse_persistent, BA_THREADS, 0));
+    ctx->pcg_grid = ctx->n_sm * std::min(per_sm, 2);
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1026,7 +1039,7 @@ static ItemRef enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int pa
   const int rp = ctx->lo.reset_period;
   if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && passes == 3) {
     LAUNCH(k_bsr_spmv, cdiv(ctx->n_cam * 32, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->ent_ptr),
-           P<uint32_t>(ctx->ent_blk), P<int32_t>(ctx->ent_col), P<double>(ctx->Sblk), v, P<double>(ctx->ysp), st, gate);
+           P<int2>(ctx->ent), P<double>(ctx->Sblk), v, P<double>(ctx->ysp), st, gate);
     return ItemRef{P<int32_t>(ctx->ident), P<double>(ctx->ysp)};
   }
   if (ctx->tiled && passes == 3) {
@@ -1129,12 +1142,32 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
   sync_flags(ctx);
   ItemRef i21 = reduce_items<21>(ctx, P<double>(ctx->part21), ctx->red21, GATE_RUN);
   LAUNCH(k_schur_diag_fin, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i21.ptr, i21.part, P<double>(ctx->U), P<double>(ctx->dc),
-         P<double>(ctx->Minv), st, GATE_RUN);
+         P<double>(ctx->Minv), ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG ? P<double>(ctx->dsq) : (double *)nullptr, st, GATE_RUN);
   ItemRef i6 = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_RUN);
   LAUNCH(k_pcg_init, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i6.ptr, i6.part, P<double>(ctx->gc), P<double>(ctx->Minv),
          P<double>(ctx->b), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z), P<double>(ctx->pcam_rho),
          P<double>(ctx->pcam_bb), st, GATE_RUN);
   LAUNCH(k_pcg_start, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_bb), P<double>(ctx->pcam_rho), st, GATE_RUN);
+  if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && ctx->n_ranks == 1 && ctx->opt.persistent_pcg && ctx->pcg_grid > 0) {
+    // the whole PCG solve in one cooperative launch (ba_kernels_sparse.cuh)
+    cudaMemsetAsync(ctx->pcg_bar.p, 0, 16, ctx->stream);  // (profile counters at +64 accumulate over the solve)
+    int n_cam = ctx->n_cam;
+    const int32_t *ent_ptr = P<int32_t>(ctx->ent_ptr);
+    const int2 *ent = P<int2>(ctx->ent);
+    const double *Sb = P<double>(ctx->Sblk), *dsq = P<double>(ctx->dsq), *bb = P<double>(ctx->b), *Minv = P<double>(ctx->Minv);
+    double *x = P<double>(ctx->x), *r = P<double>(ctx->r), *z = P<double>(ctx->z), *p0 = P<double>(ctx->p), *p1 = P<double>(ctx->p2),
+           *q = P<double>(ctx->q), *rpq = P<double>(ctx->row_pq), *prho = P<double>(ctx->wb_rho), *pQ = P<double>(ctx->wb_Q);
+    unsigned int *bar = P<unsigned int>(ctx->pcg_bar);
+    LmOptions lo = ctx->lo;
+    unsigned long long *prof = getenv("BA_PCG_PROF") ? P<unsigned long long>(ctx->pcg_bar) + 8 : nullptr;
+    void *args[] = {&n_cam, &ent_ptr, &ent, &Sb, &dsq, &bb, &Minv, &x, &r, &z, &p0, &p1, &q, &rpq, &prho, &pQ, &bar, &lo, &st, &prof};
+    const int grid = std::max(1, std::min(ctx->pcg_grid, cdiv(ctx->n_cam, BA_WARPS)));
+    CK(cudaLaunchCooperativeKernel((const void *)k_pcg_sparse_persistent, dim3(grid), dim3(BA_THREADS), args, 0, ctx->stream));
+    ctx->launches++;
+    LAUNCH(k_pcg_finish, cdiv(6 * ctx->n_cam, BA_THREADS), BA_THREADS, 0, 6 * ctx->n_cam, P<double>(ctx->x), P<double>(ctx->yc), st,
+           GATE_RUN);
+    return 0;
+  }
   const int batch = std::max(1, ctx->opt.poll_interval);
   int it = 1;
   for (;;) {
@@ -1298,6 +1331,14 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   if (nt) CK(cudaMemcpy(ctx->h_trace.data(), ctx->trace.p, (size_t)nt * sizeof(BaIterRec), cudaMemcpyDeviceToHost));
   ctx->last_summary = s;
   if (summary) *summary = s;
+  if (getenv("BA_PCG_PROF") && ctx->pcg_bar.p && ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG) {
+    unsigned long long pr[6];
+    cudaMemcpy(pr, P<unsigned long long>(ctx->pcg_bar) + 8, 48, cudaMemcpyDeviceToHost);
+    cudaMemset(P<unsigned long long>(ctx->pcg_bar) + 8, 0, 48);
+    const double n = (double)std::max<int64_t>(1, s.total_linear_iters);
+    fprintf(stderr, "[BA_PCG_PROF] us/iteration (CTA 0): product %.2f | barrier %.2f | sum+alpha %.2f | update %.2f | barrier %.2f | reset+controller %.2f\n",
+            pr[0] / n / 1e3, pr[1] / n / 1e3, pr[2] / n / 1e3, pr[3] / n / 1e3, pr[4] / n / 1e3, pr[5] / n / 1e3);
+  }
   if (h.termination == BA_TERM_FAILURE && h.n_trace <= 1 && h.eval_fail)
     return fail(ctx, BA_ERR_NUMERIC, "non-finite cost or Jacobian at the initial point");
   return BA_OK;

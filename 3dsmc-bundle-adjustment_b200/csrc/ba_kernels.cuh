@@ -833,8 +833,8 @@ __device__ __forceinline__ bool spd6_inverse(const double A[36], double Ai[36]) 
 
 __global__ void __launch_bounds__(BA_THREADS)
 k_schur_diag_fin(int n_cam, const int32_t *__restrict__ item_ptr, const double *__restrict__ part,
-                 const double *__restrict__ U, const double *__restrict__ dc, double *__restrict__ Minv, LmState *st,
-                 int gate) {
+                 const double *__restrict__ U, const double *__restrict__ dc, double *__restrict__ Minv,
+                 double *__restrict__ dsq /* D^2 per column, may be null */, LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
   const int c = blockIdx.x * BA_THREADS + threadIdx.x;
   if (c >= n_cam) return;
@@ -860,6 +860,7 @@ k_schur_diag_fin(int n_cam, const int32_t *__restrict__ item_ptr, const double *
   for (int k = 0; k < 6; ++k) {
     const double D = sqrt(dc[6 * (size_t)c + k] / radius);
     B[k * 6 + k] += D * D;
+    if (dsq) dsq[6 * (size_t)c + k] = D * D;
   }
   if (!spd6_inverse(B, Bi)) st->lin_fail = 1;
 #pragma unroll

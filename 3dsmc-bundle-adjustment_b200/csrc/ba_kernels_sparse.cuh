@@ -89,11 +89,11 @@ k_sp_blocks(int n_blk, int n_cam, const unsigned long long *__restrict__ ukeys, 
 }
 
 // row r: transposed entries (columns < r, ascending) then upper entries (columns >= r, ascending)
-// entry = block index, bit 31 set when the block is used transposed
+// entry = (block index with bit 31 set when the block is used transposed, column)
 __global__ void __launch_bounds__(BA_THREADS)
 k_sp_entries(int n_cam, const int32_t *__restrict__ row_ustart, const int32_t *__restrict__ row_tstart,
              const int32_t *__restrict__ tvals_sorted, const int32_t *__restrict__ blk_i, const int32_t *__restrict__ blk_j,
-             int32_t *__restrict__ ent_ptr, uint32_t *__restrict__ ent_blk, int32_t *__restrict__ ent_col) {
+             int32_t *__restrict__ ent_ptr, int2 *__restrict__ ent) {
   const int r = blockIdx.x * BA_THREADS + threadIdx.x;
   if (r > n_cam) return;
   const int base = row_ustart[r] + row_tstart[r];
@@ -102,13 +102,9 @@ k_sp_entries(int n_cam, const int32_t *__restrict__ row_ustart, const int32_t *_
   int w = base;
   for (int e = row_tstart[r]; e < row_tstart[r + 1]; ++e, ++w) {
     const int b = tvals_sorted[e];
-    ent_blk[w] = (uint32_t)b | 0x80000000u;
-    ent_col[w] = blk_i[b];
+    ent[w] = make_int2((int)((uint32_t)b | 0x80000000u), blk_i[b]);
   }
-  for (int b = row_ustart[r]; b < row_ustart[r + 1]; ++b, ++w) {
-    ent_blk[w] = (uint32_t)b;
-    ent_col[w] = blk_j[b];
-  }
+  for (int b = row_ustart[r]; b < row_ustart[r + 1]; ++b, ++w) ent[w] = make_int2(b, blk_j[b]);
 }
 
 // ------------------------------------------------------------------ values
@@ -186,27 +182,43 @@ k_sp_schur(int n_blk, const int32_t *__restrict__ blk_ptr, const int32_t *__rest
 
 // ------------------------------------------------------------------ y = S x  (without the LM damping)
 // One warp per camera row; a lane multiplies whole 6x6 blocks (256-bit loads), the
-// lane partials are combined by a fixed butterfly.
+// lane partials are combined by a fixed butterfly.  v = za (+ beta * pb) is formed on the
+// fly (PCG direction update fused into the product); CG = 1 reads the vectors through L2
+// (ld.global.cg) because other CTAs of the same launch wrote them.
 __device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c, double &d) {
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
-__global__ void __launch_bounds__(BA_THREADS)
-k_bsr_spmv(int n_cam, const int32_t *__restrict__ ent_ptr, const uint32_t *__restrict__ ent_blk,
-           const int32_t *__restrict__ ent_col, const double *__restrict__ S, const double *__restrict__ x,
-           double *__restrict__ y, const LmState *st, int gate) {
-  if (!gate_open(st, gate)) return;
-  const int r = (blockIdx.x * BA_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (r >= n_cam) return;
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int e = ent_ptr[r] + lane; e < ent_ptr[r + 1]; e += 32) {
-    const uint32_t eb = __ldg(ent_blk + e);
-    const int col = __ldg(ent_col + e);
-    const double *B = S + 36 * (size_t)(eb & 0x7fffffffu);
+__device__ __forceinline__ void load6cg(const double *p, double v[6]) {
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  const double2 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+template <int CG>
+__device__ __forceinline__ void bsr_row(int r, int lane, const int32_t *__restrict__ ent_ptr, const int2 *__restrict__ ent,
+                                        const double *__restrict__ S, const double *za, const double *pb, double beta, bool use_pb,
+                                        double acc[6]) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+  for (int e = __ldg(ent_ptr + r) + lane; e < __ldg(ent_ptr + r + 1); e += 32) {
+    const int2 en = __ldg(ent + e);
+    const double *B = S + 36 * (size_t)((uint32_t)en.x & 0x7fffffffu);
     double m[36], xv[6];
 #pragma unroll
     for (int k = 0; k < 9; ++k) ld256(B + 4 * k, m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
-    load6(x + 6 * (size_t)col, xv);
-    if (eb & 0x80000000u) {
+    if (CG)
+      load6cg(za + 6 * (size_t)en.y, xv);
+    else
+      load6(za + 6 * (size_t)en.y, xv);
+    if (use_pb) {
+      double pv[6];
+      if (CG)
+        load6cg(pb + 6 * (size_t)en.y, pv);
+      else
+        load6(pb + 6 * (size_t)en.y, pv);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) xv[k] = xv[k] + beta * pv[k];
+    }
+    if ((uint32_t)en.x & 0x80000000u) {
 #pragma unroll
       for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -220,5 +232,357 @@ k_bsr_spmv(int n_cam, const int32_t *__restrict__ ent_ptr, const uint32_t *__res
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+}
+__device__ __forceinline__ double pick6(const double a[6], int k) {
+  return k == 0 ? a[0] : k == 1 ? a[1] : k == 2 ? a[2] : k == 3 ? a[3] : k == 4 ? a[4] : a[5];
+}
+
+__global__ void __launch_bounds__(BA_THREADS)
+k_bsr_spmv(int n_cam, const int32_t *__restrict__ ent_ptr, const int2 *__restrict__ ent, const double *__restrict__ S,
+           const double *__restrict__ x, double *__restrict__ y, const LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  const int r = (blockIdx.x * BA_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n_cam) return;
+  double acc[6];
+  bsr_row<0>(r, lane, ent_ptr, ent, S, x, x, 0.0, false, acc);
   if (lane == 0) store6(y + 6 * (size_t)r, acc);
+}
+
+// ------------------------------------------------------------------ persistent PCG
+// The whole preconditioned-CG solve of one LM iteration in ONE cooperative launch:
+// with S explicit a PCG iteration is ~10 us of work, so four launches per iteration
+// (direction, product, q, step) plus a host poll every few iterations would leave the
+// GPU idle most of the time.  Persistent CTAs (all co-resident) run
+//     phase I   p = z + beta p_old (ping-pong buffers), q = S p + D^2 p, per-row p.q
+//               (warps walk rows independently: no CTA barrier inside the phase)
+//     phase II  alpha, x += alpha p, r -= alpha q, z = M^-1 r, partials of r.z and x.(b + r)
+// separated by grid barriers (monotonic arrival counter, release/acquire through L2);
+// every CTA then evaluates the Ceres CG controller (conjugate_gradients_solver.cc: quadratic
+// model termination, rho / beta) from the same partials in the same order, so all CTAs
+// take identical decisions with no broadcast.  Every residual_reset_period iterations
+// r = b - S x is recomputed (one extra product).  Partials have a fixed granularity
+// (rows, 256-camera blocks) => results do not depend on the grid size.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*((volatile unsigned int *)bar) < epoch) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// every thread of the CTA gets sum(part[0..n)), part written by other CTAs
+__device__ __forceinline__ double block_sum_array_cg(const double *part, int n, double *smem /*>=BA_WARPS+1*/) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += __ldcg(part + i);
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < BA_WARPS; ++i) s += smem[i];
+    smem[BA_WARPS] = s;
+  }
+  __syncthreads();
+  return smem[BA_WARPS];
+}
+
+// one 6x6 block (or its transpose) times v = za[col] (+ beta pb[col]), accumulated into acc
+__device__ __forceinline__ void bsr_entry(const int2 en, const double *__restrict__ S, const double *za, const double *pb,
+                                          double beta, bool use_pb, double acc[6]) {
+  const double *B = S + 36 * (size_t)((uint32_t)en.x & 0x7fffffffu);
+  double m[36], xv[6];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) ld256(B + 4 * k, m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
+  load6cg(za + 6 * (size_t)en.y, xv);
+  if (use_pb) {
+    double pv[6];
+    load6cg(pb + 6 * (size_t)en.y, pv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xv[k] = xv[k] + beta * pv[k];
+  }
+  if ((uint32_t)en.x & 0x80000000u) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[a] += m[k * 6 + a] * xv[k];
+  } else {
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[a] += m[a * 6 + k] * xv[k];
+  }
+}
+
+// rows gw, gw + nw, ... of out = S v + dsq .* v with v = za (+ beta pb).  The row pointers
+// are fetched two rows ahead and the first 32 entries one row ahead, so a row costs one
+// dependent L2 round trip (its blocks).  MODE 0 (PCG direction): also writes v to pnew and
+// the row's v.out to row_pq.  MODE 1 (residual reset): only out.
+template <int MODE>
+__device__ __forceinline__ void bsr_rows(int n_cam, int gw, int nw, int lane, const int32_t *__restrict__ ent_ptr,
+                                         const int2 *__restrict__ ent, const double *__restrict__ S,
+                                         const double *__restrict__ dsq, const double *za, const double *pb, double beta,
+                                         bool use_pb, double *pnew, double *out, double *row_pq) {
+  const int2 none = make_int2(0, 0);
+  int row = gw;
+  if (row >= n_cam) return;
+  int b0 = __ldg(ent_ptr + row), e0 = __ldg(ent_ptr + row + 1);
+  int b1 = 0, e1 = 0;
+  if (row + nw < n_cam) {
+    b1 = __ldg(ent_ptr + row + nw);
+    e1 = __ldg(ent_ptr + row + nw + 1);
+  }
+  int2 en0 = b0 + lane < e0 ? __ldg(ent + b0 + lane) : none;
+  int2 en0b = b0 + lane + 32 < e0 ? __ldg(ent + b0 + lane + 32) : none;
+  for (; row < n_cam; row += nw) {
+    // prefetch: first 64 entries of the next row, pointers of the one after
+    const int2 en1 = b1 + lane < e1 ? __ldg(ent + b1 + lane) : none;
+    const int2 en1b = b1 + lane + 32 < e1 ? __ldg(ent + b1 + lane + 32) : none;
+    int b2 = 0, e2 = 0;
+    if (row + 2 * nw < n_cam) {
+      b2 = __ldg(ent_ptr + row + 2 * nw);
+      e2 = __ldg(ent_ptr + row + 2 * nw + 1);
+    }
+    double zk = 0.0, pk = 0.0, dk = 0.0;
+    if (lane < 6) {
+      zk = __ldcg(za + 6 * (size_t)row + lane);
+      if (use_pb) pk = __ldcg(pb + 6 * (size_t)row + lane);
+      dk = __ldg(dsq + 6 * (size_t)row + lane);
+    }
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (b0 + lane < e0) bsr_entry(en0, S, za, pb, beta, use_pb, acc);
+    if (b0 + lane + 32 < e0) bsr_entry(en0b, S, za, pb, beta, use_pb, acc);
+    for (int e = b0 + lane + 64; e < e0; e += 32) bsr_entry(__ldg(ent + e), S, za, pb, beta, use_pb, acc);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+    const double pv = use_pb ? zk + beta * pk : zk;
+    const double qv = pick6(acc, lane) + dk * pv;
+    if (lane < 6) {
+      if (MODE == 0) pnew[6 * (size_t)row + lane] = pv;
+      out[6 * (size_t)row + lane] = qv;
+    }
+    if (MODE == 0) {
+      // v.out of the row, components added in order 0..5 (as k_pcg_q)
+      const double t = pv * qv;
+      double s = __shfl_sync(BA_FULL, t, 0);
+#pragma unroll
+      for (int k = 1; k < 6; ++k) s += __shfl_sync(BA_FULL, t, k);
+      if (lane == 0) row_pq[row] = s;
+    }
+    b0 = b1; e0 = e1; en0 = en1; en0b = en1b;
+    b1 = b2; e1 = e2;
+  }
+}
+
+// sum of n doubles written by other CTAs; every thread of the CTA gets it.  Fixed order:
+// thread t adds elements t, t + 256, ... into 4 interleaved accumulators (loads in flight),
+// then the usual butterfly / warp order.
+__device__ __forceinline__ double block_sum_wide_cg(const double *part, int n, double *smem /*>=BA_WARPS+1*/) {
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  int i = threadIdx.x;
+  for (; i + 3 * BA_THREADS < n; i += 4 * BA_THREADS) {
+    const double a = __ldcg(part + i), b = __ldcg(part + i + BA_THREADS), c = __ldcg(part + i + 2 * BA_THREADS),
+                 d = __ldcg(part + i + 3 * BA_THREADS);
+    v0 += a;
+    v1 += b;
+    v2 += c;
+    v3 += d;
+  }
+  for (; i < n; i += BA_THREADS) v0 += __ldcg(part + i);
+  double v = (v0 + v1) + (v2 + v3);
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < BA_WARPS; ++k) s += smem[k];
+    smem[BA_WARPS] = s;
+  }
+  __syncthreads();
+  return smem[BA_WARPS];
+}
+
+// two sums in one pass (the controller's r.z and x.(b + r)); red >= 2 * BA_WARPS + 2
+__device__ __forceinline__ void block_sum2_cg(const double *pa, const double *pb, int n, double *red, double &sa, double &sb) {
+  double v = 0.0, w = 0.0;
+  for (int i = threadIdx.x; i < n; i += BA_THREADS) {
+    v += __ldcg(pa + i);
+    w += __ldcg(pb + i);
+  }
+  v = warp_sum(v);
+  w = warp_sum(w);
+  const int wid = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) {
+    red[wid] = v;
+    red[BA_WARPS + wid] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0, t = 0.0;
+    for (int k = 0; k < BA_WARPS; ++k) {
+      s += red[k];
+      t += red[BA_WARPS + k];
+    }
+    red[2 * BA_WARPS] = s;
+    red[2 * BA_WARPS + 1] = t;
+  }
+  __syncthreads();
+  sa = red[2 * BA_WARPS];
+  sb = red[2 * BA_WARPS + 1];
+}
+
+// phase II for one warp-block of 32 cameras (lane = camera): no CTA barrier
+template <int RESET>
+__device__ __forceinline__ void pcg_update_warp(int n_cam, int wb, int lane, double alpha, bool skip_r,
+                                                const double *__restrict__ b, const double *__restrict__ Minv, double *x,
+                                                double *r, double *z, const double *pnew, const double *q, double *part_rho,
+                                                double *part_Q) {
+  const int c = wb * 32 + lane;
+  double rz = 0.0, xq = 0.0;
+  if (c < n_cam) {
+    double xv[6], rv[6], qv[6], bv[6], zv[6];
+    load6cg(x + 6 * (size_t)c, xv);
+    if (!RESET) {
+      double pv[6];
+      load6cg(pnew + 6 * (size_t)c, pv);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) xv[k] = xv[k] + alpha * pv[k];
+      store6(x + 6 * (size_t)c, xv);
+    }
+    if (!skip_r) {
+      load6cg(q + 6 * (size_t)c, qv);
+      load6(b + 6 * (size_t)c, bv);
+      if (RESET) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rv[k] = bv[k] - qv[k];
+      } else {
+        load6cg(r + 6 * (size_t)c, rv);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rv[k] = rv[k] - alpha * qv[k];
+      }
+      store6(r + 6 * (size_t)c, rv);
+      minv_mul(Minv, c, rv, zv);
+      store6(z + 6 * (size_t)c, zv);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        rz += rv[k] * zv[k];
+        xq += xv[k] * (bv[k] + rv[k]);
+      }
+    }
+  }
+  if (!skip_r) {
+    rz = warp_sum(rz);
+    xq = warp_sum(xq);
+    if (lane == 0) {
+      part_rho[wb] = rz;
+      part_Q[wb] = xq;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BA_THREADS, 1)
+k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ ent_ptr, const int2 *__restrict__ ent,
+                        const double *__restrict__ S, const double *__restrict__ dsq, const double *__restrict__ b,
+                        const double *__restrict__ Minv, double *x, double *r, double *z, double *pbuf0, double *pbuf1,
+                        double *q, double *row_pq, double *part_rho, double *part_Q, unsigned int *bar, LmOptions lo,
+                        LmState *st, unsigned long long *prof /* nullable: ns per phase, CTA 0 */) {
+  if (st->done || st->pcg_done) return;  // identical on every CTA: the state is only written back after the last barrier
+  __shared__ double red[2 * BA_WARPS + 4];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gw = (blockIdx.x * BA_THREADS + tid) >> 5, nw = (gridDim.x * BA_THREADS) >> 5;
+  const int n_wb = (n_cam + 31) / 32;
+  int it = st->pcg_it;
+  double rho = st->pcg_rho, beta = st->pcg_beta, Q0 = st->pcg_Q0;
+  int fail = 0, brk = 0, iters_last = 0;
+  unsigned int epoch = 0;
+  double *pold = pbuf0, *pnew = pbuf1;
+  unsigned long long t0 = 0, tacc[6] = {0, 0, 0, 0, 0, 0};
+#define PROF_TICK(slot)                                             \
+  if (prof && blockIdx.x == 0 && tid == 0) {                        \
+    unsigned long long t1_;                                         \
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1_));          \
+    tacc[slot] += t1_ - t0;                                         \
+    t0 = t1_;                                                       \
+  }
+  if (prof && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+
+  for (;;) {
+    // ---- phase I: p = z (+ beta p_old), q = S p + D^2 p, per-row p.q
+    bsr_rows<0>(n_cam, gw, nw, lane, ent_ptr, ent, S, dsq, z, pold, beta, it > 1, pnew, q, row_pq);
+    PROF_TICK(0)
+    grid_barrier(bar, epoch);
+    PROF_TICK(1)
+
+    // ---- phase II: alpha; x += alpha p; r -= alpha q; z = M^-1 r; warp-block partials
+    const double pq = block_sum_wide_cg(row_pq, n_cam, red);
+    if (pq <= 0.0 || isinf(pq) || isnan(pq)) {  // NO_CONVERGENCE: keep x, stop
+      iters_last = it;
+      brk = 1;
+      break;
+    }
+    const double alpha = rho / pq;
+    if (isinf(alpha)) {
+      iters_last = it;
+      fail = 1;
+      break;
+    }
+    const bool reset = lo.reset_period > 0 && (it % lo.reset_period) == 0;
+    PROF_TICK(2)
+    for (int wb = gw; wb < n_wb; wb += nw)
+      pcg_update_warp<0>(n_cam, wb, lane, alpha, reset, b, Minv, x, r, z, pnew, q, part_rho, part_Q);
+    PROF_TICK(3)
+    grid_barrier(bar, epoch);
+    PROF_TICK(4)
+    if (reset) {
+      // ---- residual reset: q = S x + D^2 x, then r = b - q, z = M^-1 r
+      bsr_rows<1>(n_cam, gw, nw, lane, ent_ptr, ent, S, dsq, x, x, 0.0, false, nullptr, q, nullptr);
+      grid_barrier(bar, epoch);
+      for (int wb = gw; wb < n_wb; wb += nw)
+        pcg_update_warp<1>(n_cam, wb, lane, 0.0, false, b, Minv, x, r, z, pnew, q, part_rho, part_Q);
+      grid_barrier(bar, epoch);
+    }
+
+    // ---- controller (every CTA, identical inputs, identical order)
+    double rho_new, xq;
+    block_sum2_cg(part_rho, part_Q, n_wb, red, rho_new, xq);
+    iters_last = it;
+    const double Q1 = -1.0 * xq;
+    const double zeta = it * (Q1 - Q0) / Q1;
+    if (zeta < lo.eta && it >= lo.min_pcg) break;
+    Q0 = Q1;
+    if (it >= lo.max_pcg) break;
+    const double beta_new = rho_new / rho;
+    if (rho_new == 0.0 || !isfinite(rho_new) || beta_new == 0.0 || !isfinite(beta_new)) {
+      iters_last = it + 1;
+      fail = 1;
+      break;
+    }
+    rho = rho_new;
+    beta = beta_new;
+    ++it;
+    double *t = pold;
+    pold = pnew;
+    pnew = t;
+    PROF_TICK(5)
+  }
+  if (prof && blockIdx.x == 0 && tid == 0)
+    for (int k = 0; k < 6; ++k) prof[k] += tacc[k];
+  if (blockIdx.x == 0 && tid == 0) {
+    st->pcg_it = it;
+    st->pcg_rho = rho;
+    st->pcg_beta = beta;
+    st->pcg_Q0 = Q0;
+    st->pcg_iters_last = iters_last;
+    st->pcg_break = brk;
+    if (fail) st->lin_fail = 1;
+    st->pcg_done = 1;
+  }
 }

@@ -105,7 +105,8 @@ typedef struct ba_gpu_options {
   int32_t device;          /* CUDA ordinal; <0 = current device */
   int32_t poll_interval;   /* host polls the device-side LM / PCG termination
                               flag every this many iterations (>=1) */
-  int32_t use_cuda_graph;  /* capture the PCG iteration in a CUDA graph */
+  int32_t persistent_pcg;  /* 1: run the whole PCG solve of an LM iteration in one persistent
+                              cooperative kernel when the solver supports it (block-sparse Schur) */
   int32_t jacobian_store;  /* BA_JAC_AUTO / _PLANES / _FACTORED */
 } ba_gpu_options;
 

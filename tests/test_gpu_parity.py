@@ -270,11 +270,13 @@ def test_sparse_schur_product_vs_oracle(name, solver_cache):
     assert abs(x1 @ y2 - x2 @ y1) <= 1e-10 * (abs(x1 @ y2) + np.linalg.norm(y1) * np.linalg.norm(x2))
 
 
+@pytest.mark.parametrize("persistent", [0, 1], ids=["launch-per-step", "persistent"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg3_small"])
-def test_solve_sparse_schur_pcg(name, solver_cache):
+def test_solve_sparse_schur_pcg(name, persistent, solver_cache):
     """Explicit block-sparse S + PCG against the oracle's PCG, in lock step on the
-    well-conditioned TUM-shaped problems."""
-    summ, osum = _compare_solve(_problem(name), "NS", 3, 8, solver_cache)
+    well-conditioned TUM-shaped problems; the PCG loop as one persistent
+    cooperative kernel or as one launch per step."""
+    summ, osum = _compare_solve(_problem(name), "NS", 3, 8, solver_cache, persistent_pcg=persistent)
     assert summ.solver_used == ba_b200.capi.BA_SOLVER_SPARSE_SCHUR_PCG
     assert abs(summ.total_linear_iters - osum.total_linear_iters) <= max(2, 0.02 * osum.total_linear_iters)
 
