@@ -39,6 +39,7 @@ class Options(C.Structure):
         ("max_linear_solver_iterations", C.c_int32), ("min_linear_solver_iterations", C.c_int32),
         ("residual_reset_period", C.c_int32), ("device", C.c_int32), ("poll_interval", C.c_int32),
         ("persistent_pcg", C.c_int32), ("jacobian_store", C.c_int32),
+        ("sparse_max_pairs_per_obs", C.c_int32),
     ]
 
 
@@ -64,7 +65,7 @@ EXPORTS = [
     "ba_gpu_default_options", "ba_gpu_create", "ba_gpu_destroy", "ba_gpu_last_error", "ba_gpu_set_options",
     "ba_gpu_upload", "ba_gpu_solve", "ba_gpu_get_trace", "ba_gpu_download", "ba_gpu_eval", "ba_gpu_get_indices",
     "ba_gpu_schur_matvec", "ba_gpu_se3_plus", "ba_gpu_time_kernel", "ba_gpu_launch_count", "ba_gpu_comm_unique_id",
-    "ba_gpu_comm_init", "ba_gpu_jacobian_store_used",
+    "ba_gpu_comm_init", "ba_gpu_jacobian_store_used", "ba_gpu_sparse_stats",
 ]
 
 _LIB = None
@@ -101,6 +102,7 @@ def load():
     L.ba_gpu_launch_count.argtypes = [vp]
     L.ba_gpu_launch_count.restype = C.c_int64
     L.ba_gpu_jacobian_store_used.argtypes = [vp]
+    L.ba_gpu_sparse_stats.argtypes = [vp, C.POINTER(C.c_int64), c_int32_p, c_int32_p]
     L.ba_gpu_comm_unique_id.argtypes = [C.c_char_p]
     L.ba_gpu_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
     for name in EXPORTS:

@@ -262,6 +262,7 @@ extern "C" void ba_gpu_default_options(ba_gpu_options *o) {
   o->poll_interval = 10;
   o->persistent_pcg = 1;
   o->jacobian_store = BA_JAC_AUTO;
+  o->sparse_max_pairs_per_obs = 16;
 }
 
 static int check_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
@@ -349,6 +350,14 @@ extern "C" int ba_gpu_set_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
 }
 
 extern "C" int64_t ba_gpu_launch_count(const ba_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int ba_gpu_sparse_stats(const ba_gpu_ctx *ctx, int64_t *n_pairs, int32_t *n_blocks, int32_t *n_entries) {
+  if (!ctx || !ctx->uploaded) return BA_ERR_STATE;
+  const bool sp = ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG;
+  if (n_pairs) *n_pairs = sp ? ctx->n_pairs : 0;
+  if (n_blocks) *n_blocks = sp ? ctx->n_sblk : 0;
+  if (n_entries) *n_entries = sp ? ctx->n_ent : 0;
+  return BA_OK;
+}
 extern "C" int ba_gpu_jacobian_store_used(const ba_gpu_ctx *ctx) {
   if (!ctx || !ctx->uploaded) return BA_ERR_STATE;
   return ctx->tiled ? BA_JAC_TILED : (ctx->fact ? BA_JAC_FACTORED : BA_JAC_PLANES);
@@ -494,6 +503,18 @@ static int ensure_planes(ba_gpu_ctx *ctx) {
     RES(cub_tmp, tb_ + 16);                                               \
     CK(fn(ctx->cub_tmp.p, tb_, __VA_ARGS__, ctx->stream));                \
   } while (0)
+static int sparse_count_pairs(ba_gpu_ctx *ctx, long long *n_pairs_out) {
+  const int n_pt = ctx->n_pt;
+  cudaStream_t s = ctx->stream;
+  RES(sp_cnt, ((size_t)n_pt + 2) * 8);
+  RES(sp_off, ((size_t)n_pt + 2) * 8);
+  LAUNCH(k_sp_count, cdiv(n_pt + 1, BA_THREADS), BA_THREADS, 0, n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+         ctx->fixed_cam, P<long long>(ctx->sp_cnt));
+  CUBCALL(cub::DeviceScan::ExclusiveSum, P<long long>(ctx->sp_cnt), P<long long>(ctx->sp_off), n_pt + 1);
+  CK(cudaMemcpyAsync(n_pairs_out, P<long long>(ctx->sp_off) + n_pt, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
 static int build_sparse_structure(ba_gpu_ctx *ctx) {
   const int n_pt = ctx->n_pt, n_cam = ctx->n_cam;
   cudaStream_t s = ctx->stream;
@@ -613,7 +634,11 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks > 1)
     return fail(ctx, BA_ERR_UNSUPPORTED, "the explicit solver is single-GPU (windowed problems stay on one GPU)");
   ctx->solver = solver;
-  const bool sparse = solver == BA_SOLVER_SPARSE_SCHUR_PCG;
+  // AUTO on a large NS-mode problem, single GPU: block-sparse explicit S if the co-visibility
+  // is sparse enough (decided after the index build, from the pair count), else implicit
+  const bool auto_large = o.solver == BA_SOLVER_AUTO && solver == BA_SOLVER_IMPLICIT_PCG && !o.use_depth_prior &&
+                          ctx->n_ranks == 1 && o.jacobian_store != BA_JAC_PLANES;
+  bool sparse = solver == BA_SOLVER_SPARSE_SCHUR_PCG;
   const bool can_fact = ((solver == BA_SOLVER_IMPLICIT_PCG || sparse) && !o.use_depth_prior && !o.optimize_intrinsics);
   if (sparse && o.jacobian_store == BA_JAC_PLANES)
     return fail(ctx, BA_ERR_UNSUPPORTED, "the block-sparse Schur solver rebuilds its blocks from the factored store");
@@ -806,6 +831,15 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     ctx->staged = h_span <= BA_STAGE_CAMS;
   }
   ctx->tiled = false;
+  if (auto_large) {
+    long long n_pairs = 0;
+    int rcs = sparse_count_pairs(ctx, &n_pairs);
+    if (rcs) return rcs;
+    if (n_pairs <= (long long)o.sparse_max_pairs_per_obs * (long long)n_obs && n_pairs <= 0x7fffffffLL) {
+      sparse = true;
+      ctx->solver = BA_SOLVER_SPARSE_SCHUR_PCG;
+    }
+  }
   if (sparse) {
     int rcs = build_sparse_structure(ctx);
     if (rcs) return rcs;

@@ -165,6 +165,13 @@ class GpuSolver:
     def launch_count(self):
         return int(self.lib.ba_gpu_launch_count(self._ctx))
 
+    def sparse_stats(self):
+        """(row entries, stored upper blocks) of the block-sparse Schur complement; zeros for other solvers."""
+        import ctypes as C
+        npairs, nblk, nent = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.ba_gpu_sparse_stats(self._ctx, C.byref(npairs), C.byref(nblk), C.byref(nent)))
+        return int(nent.value), int(nblk.value)
+
     def jacobian_store_used(self):
         """BA_JAC_* in force after the last upload (what BA_JAC_AUTO resolved to)."""
         rc = int(self.lib.ba_gpu_jacobian_store_used(self._ctx))

@@ -45,7 +45,9 @@ enum {
 };
 
 enum {
-  BA_SOLVER_AUTO = 0,              /* explicit if reduced dim <= explicit_max_dim */
+  BA_SOLVER_AUTO = 0,              /* dense explicit if reduced dim <= explicit_max_dim (or free intrinsics);
+                                      else block-sparse if the co-visibility is sparse (one GPU, NS mode);
+                                      else implicit */
   BA_SOLVER_EXPLICIT_CHOLESKY = 1, /* explicit Schur complement + dense Cholesky
                                       (== Ceres DENSE_SCHUR / SPARSE_SCHUR step) */
   BA_SOLVER_IMPLICIT_PCG = 2,      /* matrix-free Schur + block-Jacobi PCG
@@ -107,7 +109,10 @@ typedef struct ba_gpu_options {
                               flag every this many iterations (>=1) */
   int32_t persistent_pcg;  /* 1: run the whole PCG solve of an LM iteration in one persistent
                               cooperative kernel when the solver supports it (block-sparse Schur) */
-  int32_t jacobian_store;  /* BA_JAC_AUTO / _PLANES / _FACTORED */
+  int32_t jacobian_store;  /* BA_JAC_AUTO / _PLANES / _FACTORED / _TILED */
+  int32_t sparse_max_pairs_per_obs; /* BA_SOLVER_AUTO on a large NS-mode problem (one GPU) picks the
+                              block-sparse Schur solver when the number of same-point observation
+                              pairs is at most this many per observation, else the implicit one */
 } ba_gpu_options;
 
 /* Per-iteration record, written by the device-side LM controller. Mirrors
@@ -195,6 +200,9 @@ int ba_gpu_time_kernel(ba_gpu_ctx *ctx, int32_t which, int32_t warmup,
 int64_t ba_gpu_launch_count(const ba_gpu_ctx *ctx);
 /* BA_JAC_* in force after the last upload (what BA_JAC_AUTO resolved to) */
 int ba_gpu_jacobian_store_used(const ba_gpu_ctx *ctx);
+/* block-sparse Schur structure of the last upload (zeros for the other solvers): same-point
+ * observation pairs, stored upper blocks, row entries (each off-diagonal block appears twice) */
+int ba_gpu_sparse_stats(const ba_gpu_ctx *ctx, int64_t *n_pairs, int32_t *n_blocks, int32_t *n_entries);
 
 /* ---- multi-GPU: one process per GPU, points sharded ---- */
 /* rank 0 makes the id (128 bytes), the launcher broadcasts it, every rank
