@@ -34,13 +34,14 @@ typedef struct {
 } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclSum_ = 0, ncclMax_ = 2 };
-enum { ncclFloat64_ = 8 };
+enum { ncclUint64_ = 5, ncclFloat64_ = 8 };
 struct NcclApi {
   void *lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -59,8 +60,9 @@ static bool nccl_load(std::string *err) {
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather) {
     *err = "libnccl is missing required symbols";
     return false;
   }
@@ -112,7 +114,8 @@ struct ba_gpu_ctx {
   // explicit block-sparse Schur complement (ba_kernels_sparse.cuh)
   Buf sp_cnt, sp_off, sp_keys, sp_vals, sp_keys2, sp_pairs, sp_ukeys, sp_ucnt, sp_nruns, sb_ptr, sb_i, sb_j, row_ucnt, row_tcnt,
       row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
-  int n_sblk = 0, n_ent = 0, pcg_grid = 0;
+  int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0;
+  Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   long long n_pairs = 0;
   Buf p2, pcg_bar, wb_rho, wb_Q;
   // scaling / diag / gradient / blocks
@@ -503,6 +506,18 @@ static int ensure_planes(ba_gpu_ctx *ctx) {
     RES(cub_tmp, tb_ + 16);                                               \
     CK(fn(ctx->cub_tmp.p, tb_, __VA_ARGS__, ctx->stream));                \
   } while (0)
+static int nccl_allreduce(ba_gpu_ctx *ctx, double *buf, size_t n, bool is_max);
+// host scalar combined over the ranks (setup only)
+static int allreduce_host_scalar(ba_gpu_ctx *ctx, double *v, bool is_max) {
+  if (ctx->n_ranks == 1) return 0;
+  RES(sp_scal, 64);
+  CK(cudaMemcpyAsync(ctx->sp_scal.p, v, 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = nccl_allreduce(ctx, P<double>(ctx->sp_scal), 1, is_max);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(v, ctx->sp_scal.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 static int sparse_count_pairs(ba_gpu_ctx *ctx, long long *n_pairs_out) {
   const int n_pt = ctx->n_pt;
   cudaStream_t s = ctx->stream;
@@ -549,11 +564,45 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   CK(cudaMemcpyAsync(&n_blk, ctx->sp_nruns.p, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (n_pairs == 0) n_blk = 0;
+  // pair list pointers of the LOCAL blocks
+  ctx->n_sblk_local = n_blk;
+  RES(sb_ptr, ((size_t)n_blk + 2) * 4);
+  CK(cudaMemsetAsync(P<int32_t>(ctx->sp_ucnt) + n_blk, 0, 4, s));
+  CUBCALL(cub::DeviceScan::ExclusiveSum, P<int32_t>(ctx->sp_ucnt), P<int32_t>(ctx->sb_ptr), n_blk + 1);
+  RES(sp_lkeys, ((size_t)n_blk + 1) * 8);
+  RES(sp_gid, ((size_t)n_blk + 1) * 4);
+  CK(cudaMemcpyAsync(ctx->sp_lkeys.p, ctx->sp_ukeys.p, (size_t)n_blk * 8, cudaMemcpyDeviceToDevice, s));
+  if (ctx->n_ranks > 1) {
+    // point-sharded: every rank holds the blocks its own points touch.  The block structure must be the
+    // same everywhere (S is all-reduced, PCG runs replicated): all-gather the key lists, sort, unique.
+    double mx = (double)n_blk;
+    int rcm = allreduce_host_scalar(ctx, &mx, true);
+    if (rcm) return rcm;
+    const size_t slot = (size_t)mx + 1, all = slot * ctx->n_ranks;
+    if (all > 0x7fffffffull) return fail(ctx, BA_ERR_UNSUPPORTED, "sparse Schur: too many blocks to gather");
+    RES(sp_gather, (all + 1) * 8);
+    RES(sp_gsorted, (all + 1) * 8);
+    CK(cudaMemsetAsync(P<u64>(ctx->sp_gather) + slot * ctx->rank, 0xff, slot * 8, s));
+    CK(cudaMemcpyAsync(P<u64>(ctx->sp_gather) + slot * ctx->rank, ctx->sp_lkeys.p, (size_t)n_blk * 8, cudaMemcpyDeviceToDevice, s));
+    ncclResult_t nr = g_nccl.AllGather(P<u64>(ctx->sp_gather) + slot * ctx->rank, ctx->sp_gather.p, slot, ncclUint64_, ctx->comm, s);
+    if (nr != 0) return fail(ctx, BA_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    ctx->collectives++;
+    CUBCALL(cub::DeviceRadixSort::SortKeys, P<u64>(ctx->sp_gather), P<u64>(ctx->sp_gsorted), (int)all, 0, 64);
+    RES(sp_ukeys, (all + 1) * 8);
+    RES(sp_ucnt, (all + 2) * 4);
+    CUBCALL(cub::DeviceRunLengthEncode::Encode, P<u64>(ctx->sp_gsorted), P<u64>(ctx->sp_ukeys), P<int32_t>(ctx->sp_ucnt),
+            P<int32_t>(ctx->sp_nruns), (int)all);
+    int32_t n_all = 0;
+    CK(cudaMemcpyAsync(&n_all, ctx->sp_nruns.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    n_blk = n_all - 1;  // the padding key ~0 sorts last (every rank pads at least one slot)
+    LAUNCH(k_sp_lookup, cdiv(ctx->n_sblk_local, BA_THREADS), BA_THREADS, 0, ctx->n_sblk_local, P<u64>(ctx->sp_lkeys), n_blk,
+           P<u64>(ctx->sp_ukeys), P<int32_t>(ctx->sp_gid));
+  } else {
+    LAUNCH(k_iota, cdiv(n_blk + 1, 256), 256, 0, n_blk + 1, P<int32_t>(ctx->sp_gid));
+  }
   ctx->n_sblk = n_blk;
   const size_t nb = (size_t)n_blk;
-  RES(sb_ptr, (nb + 2) * 4);
-  CK(cudaMemsetAsync(P<int32_t>(ctx->sp_ucnt) + nb, 0, 4, s));
-  CUBCALL(cub::DeviceScan::ExclusiveSum, P<int32_t>(ctx->sp_ucnt), P<int32_t>(ctx->sb_ptr), n_blk + 1);
   RES(sb_i, (nb + 1) * 4);
   RES(sb_j, (nb + 1) * 4);
   RES(row_ucnt, ((size_t)n_cam + 2) * 4);
@@ -582,6 +631,9 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   LAUNCH(k_sp_entries, cdiv(n_cam + 1, BA_THREADS), BA_THREADS, 0, n_cam, P<int32_t>(ctx->row_ustart), P<int32_t>(ctx->row_tstart),
          P<int32_t>(ctx->sp_tvals2), P<int32_t>(ctx->sb_i), P<int32_t>(ctx->sb_j), P<int32_t>(ctx->ent_ptr),
          P<int2>(ctx->ent));
+  RES(sp_diag, ((size_t)n_cam + 1) * 4);
+  LAUNCH(k_sp_diag_index, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->row_ustart), P<int32_t>(ctx->sb_j),
+         P<int32_t>(ctx->sp_diag));
   RES(Sblk, (nb + 1) * 288);
   RES(ysp, ((size_t)n_cam + 1) * 48);
   RES(p2, ((size_t)n_cam + 1) * 48);
@@ -637,7 +689,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   // AUTO on a large NS-mode problem, single GPU: block-sparse explicit S if the co-visibility
   // is sparse enough (decided after the index build, from the pair count), else implicit
   const bool auto_large = o.solver == BA_SOLVER_AUTO && solver == BA_SOLVER_IMPLICIT_PCG && !o.use_depth_prior &&
-                          ctx->n_ranks == 1 && o.jacobian_store != BA_JAC_PLANES;
+                          o.jacobian_store != BA_JAC_PLANES;
   bool sparse = solver == BA_SOLVER_SPARSE_SCHUR_PCG;
   const bool can_fact = ((solver == BA_SOLVER_IMPLICIT_PCG || sparse) && !o.use_depth_prior && !o.optimize_intrinsics);
   if (sparse && o.jacobian_store == BA_JAC_PLANES)
@@ -835,7 +887,11 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     long long n_pairs = 0;
     int rcs = sparse_count_pairs(ctx, &n_pairs);
     if (rcs) return rcs;
-    if (n_pairs <= (long long)o.sparse_max_pairs_per_obs * (long long)n_obs && n_pairs <= 0x7fffffffLL) {
+    double tot_pairs = (double)n_pairs, tot_obs = (double)n_obs, max_pairs = (double)n_pairs;  // same decision on every rank
+    if ((rcs = allreduce_host_scalar(ctx, &tot_pairs, false)) || (rcs = allreduce_host_scalar(ctx, &tot_obs, false)) ||
+        (rcs = allreduce_host_scalar(ctx, &max_pairs, true)))
+      return rcs;
+    if (tot_pairs <= (double)o.sparse_max_pairs_per_obs * tot_obs && max_pairs <= 2147483647.0) {
       sparse = true;
       ctx->solver = BA_SOLVER_SPARSE_SCHUR_PCG;
     }
@@ -1117,12 +1173,19 @@ static ItemRef enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int pa
   return items_ref;
 }
 
-// values of the explicit block-sparse Schur complement (needs V^-1 of this radius)
+// values of the explicit block-sparse Schur complement (needs V^-1 of this radius).  Point-sharded:
+// every rank fills the blocks of its own points into the common structure, the values are all-reduced,
+// then the (already reduced) camera blocks U go onto the diagonal.
 static void enqueue_sparse_values(ba_gpu_ctx *ctx, int gate) {
   if (ctx->solver != BA_SOLVER_SPARSE_SCHUR_PCG) return;
-  LAUNCH(k_sp_schur, cdiv(ctx->n_sblk * 32, BA_THREADS), BA_THREADS, 0, ctx->n_sblk, P<int32_t>(ctx->sb_ptr), P<int32_t>(ctx->sb_i),
-         P<int32_t>(ctx->sb_j), P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->pm_pt), ctx->Fp_, P<double>(ctx->geo),
-         P<double>(ctx->intr), P<double>(ctx->Vs), P<double>(ctx->U), P<double>(ctx->Sblk), P<LmState>(ctx->st), gate);
+  LmState *st = P<LmState>(ctx->st);
+  if (ctx->n_ranks > 1) cudaMemsetAsync(ctx->Sblk.p, 0, (size_t)ctx->n_sblk * 288, ctx->stream);
+  LAUNCH(k_sp_schur, cdiv(ctx->n_sblk_local * 32, BA_THREADS), BA_THREADS, 0, ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr),
+         P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid), P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->pm_pt),
+         ctx->Fp_, P<double>(ctx->geo), P<double>(ctx->intr), P<double>(ctx->Vs), P<double>(ctx->Sblk), st, gate);
+  if (ctx->n_ranks > 1 && nccl_allreduce(ctx, P<double>(ctx->Sblk), (size_t)ctx->n_sblk * 36, false)) ctx->comm_error = true;
+  LAUNCH(k_sp_add_diag, cdiv(ctx->n_cam * 36, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->sp_diag), P<double>(ctx->U),
+         P<double>(ctx->Sblk), st, gate);
 }
 
 static int poll_state(ba_gpu_ctx *ctx) {
@@ -1138,8 +1201,9 @@ static void enqueue_pcg_iteration(ba_gpu_ctx *ctx, int it) {
   const int rp = ctx->lo.reset_period;
   const int reset = (rp > 0 && (it % rp) == 0) ? 1 : 0;
   LAUNCH(k_pcg_dir, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<double>(ctx->z), P<double>(ctx->p), st, GATE_PCG);
+  const bool replicated = ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG;  // S is complete on every rank: no exchange in PCG
   ItemRef ir = enqueue_matvec(ctx, P<double>(ctx->p), GATE_PCG);
-  ir = reduce_items<6>(ctx, ir.part, ctx->red6, GATE_PCG, ir.ptr);
+  if (!replicated) ir = reduce_items<6>(ctx, ir.part, ctx->red6, GATE_PCG, ir.ptr);
   LAUNCH(k_pcg_q, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->dc), P<double>(ctx->p),
          P<double>(ctx->q), P<double>(ctx->pcam_pq), st, GATE_PCG);
   LAUNCH(k_pcg_step, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, P<double>(ctx->pcam_pq), P<double>(ctx->p),
@@ -1147,7 +1211,7 @@ static void enqueue_pcg_iteration(ba_gpu_ctx *ctx, int it) {
          P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), ctx->lo, st, GATE_PCG, reset);
   if (reset) {
     ir = enqueue_matvec(ctx, P<double>(ctx->x), GATE_PCG);
-    ir = reduce_items<6>(ctx, ir.part, ctx->red6, GATE_PCG, ir.ptr);
+    if (!replicated) ir = reduce_items<6>(ctx, ir.part, ctx->red6, GATE_PCG, ir.ptr);
     LAUNCH(k_pcg_reset, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->nblk_cam, ir.ptr, ir.part, P<double>(ctx->dc),
            P<double>(ctx->x), P<double>(ctx->b), P<double>(ctx->Minv), P<double>(ctx->r), P<double>(ctx->z),
            P<double>(ctx->pcam_rho), P<double>(ctx->pcam_Q), ctx->lo, st, GATE_PCG);
@@ -1182,7 +1246,7 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
          P<double>(ctx->b), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z), P<double>(ctx->pcam_rho),
          P<double>(ctx->pcam_bb), st, GATE_RUN);
   LAUNCH(k_pcg_start, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_bb), P<double>(ctx->pcam_rho), st, GATE_RUN);
-  if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && ctx->n_ranks == 1 && ctx->opt.persistent_pcg && ctx->pcg_grid > 0) {
+  if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && ctx->opt.persistent_pcg && ctx->pcg_grid > 0) {
     // the whole PCG solve in one cooperative launch (ba_kernels_sparse.cuh)
     cudaMemsetAsync(ctx->pcg_bar.p, 0, 16, ctx->stream);  // (profile counters at +64 accumulate over the solve)
     int n_cam = ctx->n_cam;

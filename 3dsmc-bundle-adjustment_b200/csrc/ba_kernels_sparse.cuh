@@ -108,7 +108,7 @@ k_sp_entries(int n_cam, const int32_t *__restrict__ row_ustart, const int32_t *_
 }
 
 // ------------------------------------------------------------------ values
-// One warp per block.  S_b = [i == j] U_i - diag(s_i) (sum_pairs W_a Vs_p W_b^T) diag(s_j),
+// One warp per (local) block.  S_b = [i == j] U_i - diag(s_i) (sum_pairs W_a Vs_p W_b^T) diag(s_j),
 // W_o = jr0_o (x) p0_o + jr1_o (x) p1_o (un-scaled rows rebuilt from the factored store).
 // Through the 2x2 core M = P_a Vs P_b^T:  W_a Vs W_b^T = [jr0_a jr1_a] M [jr0_b jr1_b]^T.
 __device__ __forceinline__ void sp_rows(const ObsGeo &o, const double R[9], double jr0[6], double jr1[6], double p0[3],
@@ -125,15 +125,52 @@ __device__ __forceinline__ void sp_rows(const ObsGeo &o, const double R[9], doub
   }
 }
 
+// local block -> index in the common (all-rank) block list
 __global__ void __launch_bounds__(BA_THREADS)
-k_sp_schur(int n_blk, const int32_t *__restrict__ blk_ptr, const int32_t *__restrict__ blk_i, const int32_t *__restrict__ blk_j,
-           const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ pm_pt, FPlanes F,
-           const double *__restrict__ geo, const double *__restrict__ intr, const double *__restrict__ Vs,
-           const double *__restrict__ U, double *__restrict__ S, const LmState *st, int gate) {
+k_sp_lookup(int n_local, const unsigned long long *__restrict__ lkeys, int n_global, const unsigned long long *__restrict__ gkeys,
+            int32_t *__restrict__ gid) {
+  const int b = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (b >= n_local) return;
+  const unsigned long long k = lkeys[b];
+  int lo = 0, hi = n_global - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (gkeys[mid] < k)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  gid[b] = lo;
+}
+// diagonal block of every camera row (its first upper entry, if that is (c, c)), else -1
+__global__ void __launch_bounds__(BA_THREADS)
+k_sp_diag_index(int n_cam, const int32_t *__restrict__ row_ustart, const int32_t *__restrict__ blk_j, int32_t *__restrict__ diag) {
+  const int c = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (c >= n_cam) return;
+  const int b = row_ustart[c];
+  diag[c] = (b < row_ustart[c + 1] && blk_j[b] == c) ? b : -1;
+}
+__global__ void __launch_bounds__(BA_THREADS)
+k_sp_add_diag(int n_cam, const int32_t *__restrict__ diag, const double *__restrict__ U, double *__restrict__ S, const LmState *st,
+              int gate) {
+  if (!gate_open(st, gate)) return;
+  const int i = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (i >= n_cam * 36) return;
+  const int c = i / 36, k = i - 36 * c;
+  const int b = diag[c];
+  if (b >= 0) S[36 * (size_t)b + k] += U[36 * (size_t)c + k];
+}
+
+__global__ void __launch_bounds__(BA_THREADS)
+k_sp_schur(int n_blk, int n_cam, const int32_t *__restrict__ blk_ptr, const unsigned long long *__restrict__ lkeys,
+           const int32_t *__restrict__ gid, const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ pm_pt,
+           FPlanes F, const double *__restrict__ geo, const double *__restrict__ intr, const double *__restrict__ Vs,
+           double *__restrict__ S, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
   const int b = (blockIdx.x * BA_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= n_blk) return;
-  const int ci = blk_i[b], cj = blk_j[b];
+  const unsigned long long key = lkeys[b];
+  const int ci = (int)(key / (unsigned long long)n_cam), cj = (int)(key % (unsigned long long)n_cam);
   const double fx = ldg1(intr), fy = ldg1(intr + 1);
   CamRec ri, rj;
   load_camrec(geo, ci, ri);
@@ -169,13 +206,12 @@ k_sp_schur(int n_blk, const int32_t *__restrict__ blk_ptr, const int32_t *__rest
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
   // lanes 0..35 -> lane k writes entry k (two rounds)
-  double *Sb = S + 36 * (size_t)b;
+  double *Sb = S + 36 * (size_t)gid[b];
 #pragma unroll
   for (int k = 0; k < 36; ++k) {
     if (lane == (k & 31)) {
       const int r = k / 6, c = k - 6 * (k / 6);
-      const double u = ci == cj ? U[36 * (size_t)ci + k] : 0.0;
-      Sb[k] = u - acc[k] * (ri.s[r] * rj.s[c]);
+      Sb[k] = -(acc[k] * (ri.s[r] * rj.s[c]));  // k_sp_add_diag puts U on the diagonal blocks
     }
   }
 }

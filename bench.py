@@ -257,7 +257,7 @@ def main():
                 parameter_tolerance=0.0, gradient_tolerance=0.0, device=local_rank, n_obs_total=full.n_obs,
                 jacobian_store=args.store)
     if wl["mode"] == (0, 0):
-        opts["solver"] = SOLVERS[args.solver] if world == 1 else 2
+        opts["solver"] = SOLVERS[args.solver]
     s = ba_b200.GpuSolver(max_num_iterations=max(W, 1), **opts)
     if world > 1:
         idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -353,7 +353,10 @@ def main():
                    "n_cam": full.n_cam, "n_pt": full.n_pt, "n_obs": full.n_obs,
                    "scale": args.scale, "lm_iterations": n_iter, "pcg_iterations_total": int(summ.total_linear_iters),
                    "pcg_iterations_per_lm": pcg_counts, "tolerances": "disabled (fixed iteration count)",
-                   "parallelism": "points sharded x%d, NCCL all-reduce of camera-sized vectors" % world if world > 1 else "single GPU",
+                   "parallelism": ("single GPU" if world == 1 else
+                                   ("points sharded x%d: linearisation, point blocks and S formation per shard, NCCL all-reduce of the "
+                                    "block-sparse S (once per LM iteration), PCG replicated" % world) if solver_used == 3 else
+                                   ("points sharded x%d, NCCL all-reduce of camera-sized vectors (one per PCG iteration)" % world)),
                    "l2": ("block-sparse S is L2-resident by design (the product is timed warm, as it runs inside PCG); "
                           if solver_used == 3 else "") +
                          ("streaming inputs larger than L2 (factored store %.0f MB per pass)" % (full.n_obs * 36 / 1e6) if not flush

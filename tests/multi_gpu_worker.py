@@ -1,7 +1,7 @@
 """torchrun worker: point-sharded solve on WORLD_SIZE GPUs vs the same solve on
 one GPU (rank 0 checks).  Launched by tests/test_gpu_multi.py and by hand:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-      tests/multi_gpu_worker.py [cfg] [scale] [iters]"""
+      tests/multi_gpu_worker.py [cfg] [scale] [iters] [solver: 2 implicit, 3 block-sparse]"""
 import os
 import sys
 
@@ -17,12 +17,13 @@ def main():
     cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     scale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.05
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+    solver = int(sys.argv[4]) if len(sys.argv) > 4 else 2
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     full = ba_b200.synthetic.make_config(cfg, scale=scale)
     shard, ids = ba_b200.synthetic.shard_points(full, rank, world)
-    opts = dict(use_depth_prior=0, optimize_intrinsics=0, solver=2, max_num_iterations=iters, device=local)
+    opts = dict(use_depth_prior=0, optimize_intrinsics=0, solver=solver, max_num_iterations=iters, device=local)
     s = ba_b200.GpuSolver(n_obs_total=full.n_obs, **opts)
     idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
@@ -53,8 +54,8 @@ def main():
         dcost = abs(summ.final_cost - sum1.final_cost) / sum1.final_cost
         dpose = float(np.max(np.abs(pose - pose1)))
         dpt = float(np.max(np.abs(allpt.cpu().numpy() - pt1)))
-        print("world=%d cfg%d scale=%g: LM its %d/%d, PCG its %d/%d, final cost %.12g vs %.12g (rel %.2e), max|dpose| %.2e, max|dpt| %.2e"
-              % (world, cfg, scale, summ.num_iterations, sum1.num_iterations, summ.total_linear_iters, sum1.total_linear_iters,
+        print("world=%d solver=%d cfg%d scale=%g: LM its %d/%d, PCG its %d/%d, final cost %.12g vs %.12g (rel %.2e), max|dpose| %.2e, max|dpt| %.2e"
+              % (world, solver, cfg, scale, summ.num_iterations, sum1.num_iterations, summ.total_linear_iters, sum1.total_linear_iters,
                  summ.final_cost, sum1.final_cost, dcost, dpose, dpt))
         # well-conditioned TUM-shaped problems (cfg3): strict; the ill-conditioned loop (cfg4/5) amplifies the
         # different summation order of the sharded reduction (see test_solve_implicit_pcg_ill_conditioned)
