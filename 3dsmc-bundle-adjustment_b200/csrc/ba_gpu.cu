@@ -645,7 +645,8 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   CK(cudaMemsetAsync(ctx->pcg_bar.p, 0, 128, s));
   {
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_sparse_persistent, BA_THREADS, 0));
+    CK(cudaFuncSetAttribute(k_pcg_sparse_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_WARPS * BA_PCG_SMEM_PER_WARP));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_sparse_persistent, BA_THREADS, (size_t)BA_WARPS * BA_PCG_SMEM_PER_WARP));
     ctx->pcg_grid = ctx->n_sm * std::min(per_sm, 2);
   }
   CK(cudaGetLastError());
@@ -1260,7 +1261,8 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
     unsigned long long *prof = getenv("BA_PCG_PROF") ? P<unsigned long long>(ctx->pcg_bar) + 8 : nullptr;
     void *args[] = {&n_cam, &ent_ptr, &ent, &Sb, &dsq, &bb, &Minv, &x, &r, &z, &p0, &p1, &q, &rpq, &prho, &pQ, &bar, &lo, &st, &prof};
     const int grid = std::max(1, std::min(ctx->pcg_grid, cdiv(ctx->n_cam, BA_WARPS)));
-    CK(cudaLaunchCooperativeKernel((const void *)k_pcg_sparse_persistent, dim3(grid), dim3(BA_THREADS), args, 0, ctx->stream));
+    CK(cudaLaunchCooperativeKernel((const void *)k_pcg_sparse_persistent, dim3(grid), dim3(BA_THREADS), args,
+                                   (size_t)BA_WARPS * BA_PCG_SMEM_PER_WARP, ctx->stream));
     ctx->launches++;
     LAUNCH(k_pcg_finish, cdiv(6 * ctx->n_cam, BA_THREADS), BA_THREADS, 0, 6 * ctx->n_cam, P<double>(ctx->x), P<double>(ctx->yc), st,
            GATE_RUN);

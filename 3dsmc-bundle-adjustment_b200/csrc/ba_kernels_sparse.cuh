@@ -415,21 +415,71 @@ __device__ __forceinline__ void bsr_rows(int n_cam, int gw, int nw, int lane, co
   }
 }
 
+// The structure is constant over the PCG solve and a warp owns the same rows in every iteration:
+// the entries of its first rows live in a per-warp shared-memory cache (BA_PCG_ENT_SLOTS trips of 32
+// entries, BA_PCG_ROWS row records), so a cached row costs ONE dependent L2 round trip (its blocks).
+#define BA_PCG_ENT_SLOTS 16
+#define BA_PCG_ROWS 16
+#define BA_PCG_SMEM_PER_WARP (36 * 32 * 8 + BA_PCG_ENT_SLOTS * 32 * 8 + BA_PCG_ROWS * 8)
+template <int MODE>
+__device__ __forceinline__ void bsr_rows_cached(int n_cam, int gw, int nw, int lane, int n_cached, const int2 *rowinfo,
+                                                const int2 *ecache, const double *__restrict__ S,
+                                                const double *__restrict__ dsq, const double *za, const double *pb, double beta,
+                                                bool use_pb, double *pnew, double *out, double *row_pq) {
+  int slot = 0;
+  for (int i = 0, row = gw; i < n_cached; ++i, row += nw) {
+    const int2 be = rowinfo[i];
+    double zk = 0.0, pk = 0.0, dk = 0.0;
+    if (lane < 6) {
+      zk = __ldcg(za + 6 * (size_t)row + lane);
+      if (use_pb) pk = __ldcg(pb + 6 * (size_t)row + lane);
+      dk = __ldg(dsq + 6 * (size_t)row + lane);
+    }
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int e = be.x; e < be.y; e += 32, ++slot) {
+      const int2 en = ecache[slot * 32 + lane];
+      if (e + lane < be.y) bsr_entry(en, S, za, pb, beta, use_pb, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+    const double pv = use_pb ? zk + beta * pk : zk;
+    const double qv = pick6(acc, lane) + dk * pv;
+    if (lane < 6) {
+      if (MODE == 0) pnew[6 * (size_t)row + lane] = pv;
+      out[6 * (size_t)row + lane] = qv;
+    }
+    if (MODE == 0) {
+      const double t = pv * qv;
+      double sum = __shfl_sync(BA_FULL, t, 0);
+#pragma unroll
+      for (int k = 1; k < 6; ++k) sum += __shfl_sync(BA_FULL, t, k);
+      if (lane == 0) row_pq[row] = sum;
+    }
+  }
+}
+
 // sum of n doubles written by other CTAs; every thread of the CTA gets it.  Fixed order:
 // thread t adds elements t, t + 256, ... into 4 interleaved accumulators (loads in flight),
 // then the usual butterfly / warp order.
 __device__ __forceinline__ double block_sum_wide_cg(const double *part, int n, double *smem /*>=BA_WARPS+1*/) {
+  // 16-byte loads, 4 in flight per thread; element order per thread is fixed (pairs t, t + 256, ...)
+  const double2 *p2 = reinterpret_cast<const double2 *>(part);
+  const int n2 = n >> 1;
   double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
   int i = threadIdx.x;
-  for (; i + 3 * BA_THREADS < n; i += 4 * BA_THREADS) {
-    const double a = __ldcg(part + i), b = __ldcg(part + i + BA_THREADS), c = __ldcg(part + i + 2 * BA_THREADS),
-                 d = __ldcg(part + i + 3 * BA_THREADS);
-    v0 += a;
-    v1 += b;
-    v2 += c;
-    v3 += d;
+  for (; i + 3 * BA_THREADS < n2; i += 4 * BA_THREADS) {
+    const double2 a = __ldcg(p2 + i), b = __ldcg(p2 + i + BA_THREADS), c = __ldcg(p2 + i + 2 * BA_THREADS),
+                  d = __ldcg(p2 + i + 3 * BA_THREADS);
+    v0 += a.x + a.y;
+    v1 += b.x + b.y;
+    v2 += c.x + c.y;
+    v3 += d.x + d.y;
   }
-  for (; i < n; i += BA_THREADS) v0 += __ldcg(part + i);
+  for (; i < n2; i += BA_THREADS) {
+    const double2 a = __ldcg(p2 + i);
+    v0 += a.x + a.y;
+  }
+  if ((n & 1) && threadIdx.x == 0) v1 += __ldcg(part + n - 1);
   double v = (v0 + v1) + (v2 + v3);
   v = warp_sum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -475,12 +525,14 @@ __device__ __forceinline__ void block_sum2_cg(const double *pa, const double *pb
   sb = red[2 * BA_WARPS + 1];
 }
 
-// phase II for one warp-block of 32 cameras (lane = camera): no CTA barrier
-template <int RESET>
+// phase II for one warp-block of 32 cameras (lane = camera): no CTA barrier.  CACHED: M^-1 of the
+// camera comes from the warp's shared-memory copy ([36][32] doubles, conflict-free) and b from registers
+// (both constant during the solve, and a warp owns the same cameras in every iteration).
+template <int RESET, int CACHED>
 __device__ __forceinline__ void pcg_update_warp(int n_cam, int wb, int lane, double alpha, bool skip_r,
-                                                const double *__restrict__ b, const double *__restrict__ Minv, double *x,
-                                                double *r, double *z, const double *pnew, const double *q, double *part_rho,
-                                                double *part_Q) {
+                                                const double *__restrict__ b, const double *__restrict__ Minv,
+                                                const double *minv_s, const double breg[6], double *x, double *r, double *z,
+                                                const double *pnew, const double *q, double *part_rho, double *part_Q) {
   const int c = wb * 32 + lane;
   double rz = 0.0, xq = 0.0;
   if (c < n_cam) {
@@ -495,7 +547,11 @@ __device__ __forceinline__ void pcg_update_warp(int n_cam, int wb, int lane, dou
     }
     if (!skip_r) {
       load6cg(q + 6 * (size_t)c, qv);
-      load6(b + 6 * (size_t)c, bv);
+      if (CACHED) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bv[k] = breg[k];
+      } else
+        load6(b + 6 * (size_t)c, bv);
       if (RESET) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) rv[k] = bv[k] - qv[k];
@@ -505,7 +561,16 @@ __device__ __forceinline__ void pcg_update_warp(int n_cam, int wb, int lane, dou
         for (int k = 0; k < 6; ++k) rv[k] = rv[k] - alpha * qv[k];
       }
       store6(r + 6 * (size_t)c, rv);
-      minv_mul(Minv, c, rv, zv);
+      if (CACHED) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sacc += minv_s[(a * 6 + k) * 32 + lane] * rv[k];
+          zv[a] = sacc;
+        }
+      } else
+        minv_mul(Minv, c, rv, zv);
       store6(z + 6 * (size_t)c, zv);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
@@ -532,9 +597,38 @@ k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ ent_ptr, const in
                         LmState *st, unsigned long long *prof /* nullable: ns per phase, CTA 0 */) {
   if (st->done || st->pcg_done) return;  // identical on every CTA: the state is only written back after the last barrier
   __shared__ double red[2 * BA_WARPS + 4];
+  extern __shared__ double minv_all[];  // per warp: M^-1 [36][32] doubles, entry cache [SLOTS][32] int2, row records [ROWS] int2
   const int tid = threadIdx.x, lane = tid & 31;
   const int gw = (blockIdx.x * BA_THREADS + tid) >> 5, nw = (gridDim.x * BA_THREADS) >> 5;
   const int n_wb = (n_cam + 31) / 32;
+  // the warp's first camera block: M^-1 into shared memory, b into registers
+  char *wsm = reinterpret_cast<char *>(minv_all) + (size_t)(tid >> 5) * BA_PCG_SMEM_PER_WARP;
+  double *minv_s = reinterpret_cast<double *>(wsm);
+  int2 *ecache = reinterpret_cast<int2 *>(wsm + 36 * 32 * 8);
+  int2 *rowinfo = ecache + BA_PCG_ENT_SLOTS * 32;
+  // the warp's first rows: entries into the shared-memory cache
+  int n_cached = 0;
+  {
+    int slot = 0;
+    for (int row = gw; row < n_cam && n_cached < BA_PCG_ROWS; row += nw) {
+      const int b0 = ent_ptr[row], e0 = ent_ptr[row + 1];
+      const int trips = (e0 - b0 + 31) >> 5;
+      if (slot + trips > BA_PCG_ENT_SLOTS) break;
+      if (lane == 0) rowinfo[n_cached] = make_int2(b0, e0);
+      for (int e = b0; e < e0; e += 32, ++slot) ecache[slot * 32 + lane] = e + lane < e0 ? ent[e + lane] : make_int2(0, 0);
+      ++n_cached;
+    }
+  }
+  double breg[6] = {0, 0, 0, 0, 0, 0};
+  if (gw < n_wb) {
+    const int c = gw * 32 + lane;
+    if (c < n_cam) {
+#pragma unroll
+      for (int k = 0; k < 36; ++k) minv_s[k * 32 + lane] = Minv[36 * (size_t)c + k];
+      load6(b + 6 * (size_t)c, breg);
+    }
+  }
+  __syncwarp();
   int it = st->pcg_it;
   double rho = st->pcg_rho, beta = st->pcg_beta, Q0 = st->pcg_Q0;
   int fail = 0, brk = 0, iters_last = 0;
@@ -552,7 +646,8 @@ k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ ent_ptr, const in
 
   for (;;) {
     // ---- phase I: p = z (+ beta p_old), q = S p + D^2 p, per-row p.q
-    bsr_rows<0>(n_cam, gw, nw, lane, ent_ptr, ent, S, dsq, z, pold, beta, it > 1, pnew, q, row_pq);
+    bsr_rows_cached<0>(n_cam, gw, nw, lane, n_cached, rowinfo, ecache, S, dsq, z, pold, beta, it > 1, pnew, q, row_pq);
+    bsr_rows<0>(n_cam, gw + n_cached * nw, nw, lane, ent_ptr, ent, S, dsq, z, pold, beta, it > 1, pnew, q, row_pq);
     PROF_TICK(0)
     grid_barrier(bar, epoch);
     PROF_TICK(1)
@@ -572,17 +667,20 @@ k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ ent_ptr, const in
     }
     const bool reset = lo.reset_period > 0 && (it % lo.reset_period) == 0;
     PROF_TICK(2)
-    for (int wb = gw; wb < n_wb; wb += nw)
-      pcg_update_warp<0>(n_cam, wb, lane, alpha, reset, b, Minv, x, r, z, pnew, q, part_rho, part_Q);
+    if (gw < n_wb) pcg_update_warp<0, 1>(n_cam, gw, lane, alpha, reset, b, Minv, minv_s, breg, x, r, z, pnew, q, part_rho, part_Q);
+    for (int wb = gw + nw; wb < n_wb; wb += nw)
+      pcg_update_warp<0, 0>(n_cam, wb, lane, alpha, reset, b, Minv, minv_s, breg, x, r, z, pnew, q, part_rho, part_Q);
     PROF_TICK(3)
     grid_barrier(bar, epoch);
     PROF_TICK(4)
     if (reset) {
       // ---- residual reset: q = S x + D^2 x, then r = b - q, z = M^-1 r
-      bsr_rows<1>(n_cam, gw, nw, lane, ent_ptr, ent, S, dsq, x, x, 0.0, false, nullptr, q, nullptr);
+      bsr_rows_cached<1>(n_cam, gw, nw, lane, n_cached, rowinfo, ecache, S, dsq, x, x, 0.0, false, nullptr, q, nullptr);
+      bsr_rows<1>(n_cam, gw + n_cached * nw, nw, lane, ent_ptr, ent, S, dsq, x, x, 0.0, false, nullptr, q, nullptr);
       grid_barrier(bar, epoch);
-      for (int wb = gw; wb < n_wb; wb += nw)
-        pcg_update_warp<1>(n_cam, wb, lane, 0.0, false, b, Minv, x, r, z, pnew, q, part_rho, part_Q);
+      if (gw < n_wb) pcg_update_warp<1, 1>(n_cam, gw, lane, 0.0, false, b, Minv, minv_s, breg, x, r, z, pnew, q, part_rho, part_Q);
+      for (int wb = gw + nw; wb < n_wb; wb += nw)
+        pcg_update_warp<1, 0>(n_cam, wb, lane, 0.0, false, b, Minv, minv_s, breg, x, r, z, pnew, q, part_rho, part_Q);
       grid_barrier(bar, epoch);
     }
 
