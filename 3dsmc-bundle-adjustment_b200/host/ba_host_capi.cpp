@@ -86,4 +86,35 @@ int ba_host_count_constraints(int n_kf, const int32_t *kf_ptr, const double *dep
   }
   return countConstraints(map, keyframes, kf_i, kf_f);
 }
+
+// ---- flat wrappers of host/TrajectoryIO.cpp (tests/test_trajectory_eval.py)
+int ba_host_read_intrinsics(const char *path, double out4[4]) {
+  const Vector4d k = read_camera_intrinsics_from_file(path);
+  for (int i = 0; i < 4; ++i) out4[i] = k[i];
+  return 0;
+}
+int ba_host_get_first_pose(const char *first_timestamp, const char *gt_path, double out7[7]) {
+  const Sophus::SE3d T = getFirstPose(first_timestamp, gt_path);
+  std::memcpy(out7, T.data(), 7 * sizeof(double));
+  return 0;
+}
+// timestamps: n NUL-terminated strings back to back
+int ba_host_write_poses(const char *path, int n, const char *timestamps, const double *pose7) {
+  std::vector<KeyFrame> kfs(n);
+  const char *t = timestamps;
+  for (int i = 0; i < n; ++i) {
+    kfs[i].timestamp = t;
+    t += kfs[i].timestamp.size() + 1;
+    kfs[i].T_w_c = Sophus::SE3d(pose7 + (size_t)i * 7);
+  }
+  write_keyframe_poses_to_file(path, kfs);
+  return 0;
+}
+int ba_host_pose_offset(int n, double *pose7, const double *initial7) {
+  std::vector<KeyFrame> kfs(n);
+  for (int i = 0; i < n; ++i) kfs[i].T_w_c = Sophus::SE3d(pose7 + (size_t)i * 7);
+  poseOffset(kfs, Sophus::SE3d(initial7));
+  for (int i = 0; i < n; ++i) std::memcpy(pose7 + (size_t)i * 7, kfs[i].T_w_c.data(), 7 * sizeof(double));
+  return 0;
+}
 }

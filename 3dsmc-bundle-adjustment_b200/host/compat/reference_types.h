@@ -169,6 +169,12 @@ class ceresGlobalProblem {
   }
 };
 
+// I/O and gauge helpers around the hot path (headers/OptimizationUtils.h), host/TrajectoryIO.cpp
+Vector4d read_camera_intrinsics_from_file(const std::string &file_path);
+void write_keyframe_poses_to_file(const std::string &file_path, const std::vector<KeyFrame> &keyframes);
+Sophus::SE3d getFirstPose(const std::string &first_timestamp, const std::string &ground_truth_file_path);
+void poseOffset(std::vector<KeyFrame> &keyframes, const Sophus::SE3d &initial_pose);
+
 // the two entry points of the hot path (headers/OptimizationUtils.h:42, 55)
 int countConstraints(const Map3D &map, const std::vector<KeyFrame> &keyframes, int kf_i, int kf_f);
 bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, std::vector<KeyFrame> &keyframes, Map3D &map,
