@@ -65,7 +65,7 @@ EXPORTS = [
     "ba_gpu_default_options", "ba_gpu_create", "ba_gpu_destroy", "ba_gpu_last_error", "ba_gpu_set_options",
     "ba_gpu_upload", "ba_gpu_solve", "ba_gpu_get_trace", "ba_gpu_download", "ba_gpu_eval", "ba_gpu_get_indices",
     "ba_gpu_schur_matvec", "ba_gpu_se3_plus", "ba_gpu_time_kernel", "ba_gpu_launch_count", "ba_gpu_comm_unique_id",
-    "ba_gpu_comm_init", "ba_gpu_jacobian_store_used", "ba_gpu_sparse_stats",
+    "ba_gpu_comm_init", "ba_gpu_jacobian_store_used", "ba_gpu_sparse_stats", "ba_gpu_backproject",
 ]
 
 _LIB = None
@@ -101,6 +101,8 @@ def load():
     L.ba_gpu_time_kernel.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     L.ba_gpu_launch_count.argtypes = [vp]
     L.ba_gpu_launch_count.restype = C.c_int64
+    L.ba_gpu_backproject.argtypes = [vp, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_int32, c_double_p,
+                                     c_double_p, c_double_p, c_double_p]
     L.ba_gpu_jacobian_store_used.argtypes = [vp]
     L.ba_gpu_sparse_stats.argtypes = [vp, C.POINTER(C.c_int64), c_int32_p, c_int32_p]
     L.ba_gpu_comm_unique_id.argtypes = [C.c_char_p]

@@ -117,7 +117,7 @@ struct ba_gpu_ctx {
   int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0;
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   long long n_pairs = 0;
-  Buf p2, pcg_bar, wb_rho, wb_Q;
+  Buf p2, pcg_bar, wb_rho, wb_Q, bp_buf, err_flag_bp, row_keys, row_keys2, row_ids, row_order;
   // scaling / diag / gradient / blocks
   Buf sc, sp, sk, dc, dp, dk, gc, gp, gk, U, Uck, Ukk, V, Vinv, Wk, tg, t, yc, yp, yk, rk, Jkk;
   Buf one_c, one_p, one_k;
@@ -631,6 +631,14 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   LAUNCH(k_sp_entries, cdiv(n_cam + 1, BA_THREADS), BA_THREADS, 0, n_cam, P<int32_t>(ctx->row_ustart), P<int32_t>(ctx->row_tstart),
          P<int32_t>(ctx->sp_tvals2), P<int32_t>(ctx->sb_i), P<int32_t>(ctx->sb_j), P<int32_t>(ctx->ent_ptr),
          P<int2>(ctx->ent));
+  // PCG row order: rows sorted by decreasing entry count, dealt round-robin to the persistent warps
+  RES(row_keys, ((size_t)n_cam + 1) * 8);
+  RES(row_keys2, ((size_t)n_cam + 1) * 8);
+  RES(row_ids, ((size_t)n_cam + 1) * 4);
+  RES(row_order, ((size_t)n_cam + 1) * 4);
+  LAUNCH(k_sp_row_keys, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->ent_ptr), P<u64>(ctx->row_keys), P<int32_t>(ctx->row_ids));
+  CUBCALL(cub::DeviceRadixSort::SortPairs, P<u64>(ctx->row_keys), P<u64>(ctx->row_keys2), P<int32_t>(ctx->row_ids),
+          P<int32_t>(ctx->row_order), n_cam, 0, 64);
   RES(sp_diag, ((size_t)n_cam + 1) * 4);
   LAUNCH(k_sp_diag_index, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->row_ustart), P<int32_t>(ctx->sb_j),
          P<int32_t>(ctx->sp_diag));
@@ -1251,7 +1259,7 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
     // the whole PCG solve in one cooperative launch (ba_kernels_sparse.cuh)
     cudaMemsetAsync(ctx->pcg_bar.p, 0, 16, ctx->stream);  // (profile counters at +64 accumulate over the solve)
     int n_cam = ctx->n_cam;
-    const int32_t *ent_ptr = P<int32_t>(ctx->ent_ptr);
+    const int32_t *ent_ptr = P<int32_t>(ctx->ent_ptr), *row_order = P<int32_t>(ctx->row_order);
     const int2 *ent = P<int2>(ctx->ent);
     const double *Sb = P<double>(ctx->Sblk), *dsq = P<double>(ctx->dsq), *bb = P<double>(ctx->b), *Minv = P<double>(ctx->Minv);
     double *x = P<double>(ctx->x), *r = P<double>(ctx->r), *z = P<double>(ctx->z), *p0 = P<double>(ctx->p), *p1 = P<double>(ctx->p2),
@@ -1259,7 +1267,7 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
     unsigned int *bar = P<unsigned int>(ctx->pcg_bar);
     LmOptions lo = ctx->lo;
     unsigned long long *prof = getenv("BA_PCG_PROF") ? P<unsigned long long>(ctx->pcg_bar) + 8 : nullptr;
-    void *args[] = {&n_cam, &ent_ptr, &ent, &Sb, &dsq, &bb, &Minv, &x, &r, &z, &p0, &p1, &q, &rpq, &prho, &pQ, &bar, &lo, &st, &prof};
+    void *args[] = {&n_cam, &row_order, &ent_ptr, &ent, &Sb, &dsq, &bb, &Minv, &x, &r, &z, &p0, &p1, &q, &rpq, &prho, &pQ, &bar, &lo, &st, &prof};
     const int grid = std::max(1, std::min(ctx->pcg_grid, cdiv(ctx->n_cam, BA_WARPS)));
     CK(cudaLaunchCooperativeKernel((const void *)k_pcg_sparse_persistent, dim3(grid), dim3(BA_THREADS), args,
                                    (size_t)BA_WARPS * BA_PCG_SMEM_PER_WARP, ctx->stream));
@@ -1644,6 +1652,82 @@ extern "C" int ba_gpu_se3_plus(ba_gpu_ctx *ctx, int32_t n, const double *pose7, 
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d);
   if (e != cudaSuccess) return fail(ctx, BA_ERR_CUDA, "se3_plus: %s", cudaGetErrorString(e));
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------ back-projection
+// The step right before BA in the reference: getLocalPoints3D (src/Map3D.cpp:76-97) turns every key
+// point into a camera-frame point from the depth image, addNewLandmark (:44) moves it to the world
+// frame with the key frame's pose.  One thread per key point; explicit _rn intrinsics so that no FMA
+// contraction changes a bit relative to the reference's plain C++ (Eigen _transformVector order).
+__device__ __forceinline__ void cross_rn(const double a[3], const double b[3], double o[3]) {
+  o[0] = __dsub_rn(__dmul_rn(a[1], b[2]), __dmul_rn(a[2], b[1]));
+  o[1] = __dsub_rn(__dmul_rn(a[2], b[0]), __dmul_rn(a[0], b[2]));
+  o[2] = __dsub_rn(__dmul_rn(a[0], b[1]), __dmul_rn(a[1], b[0]));
+}
+__global__ void __launch_bounds__(BA_THREADS)
+k_backproject(int n, const float2 *__restrict__ uv, const float *__restrict__ depth, int width, int height, double fx, double fy,
+              double cx, double cy, const double *__restrict__ pose7, double *__restrict__ local3, double *__restrict__ world3,
+              int32_t *err) {
+  const int i = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const float2 p = uv[i];
+  const double u = (double)p.x, v = (double)p.y;
+  const int col = (int)truncf(p.x), row = (int)truncf(p.y);  // depth_frame.at<float>(trunc(v), trunc(u))
+  if (col < 0 || col >= width || row < 0 || row >= height) {
+    atomicOr(err, 1);
+    return;
+  }
+  const double z = (double)depth[(size_t)row * width + col];
+  const double l[3] = {__ddiv_rn(__dmul_rn(z, __dsub_rn(u, cx)), fx), __ddiv_rn(__dmul_rn(z, __dsub_rn(v, cy)), fy), z};
+  if (local3) {
+    local3[3 * (size_t)i] = l[0];
+    local3[3 * (size_t)i + 1] = l[1];
+    local3[3 * (size_t)i + 2] = l[2];
+  }
+  if (world3) {
+    // T * p = q._transformVector(p) + t: uv = 2 (q.vec x p); p + w uv + q.vec x uv
+    const double q[3] = {pose7[0], pose7[1], pose7[2]}, w = pose7[3];
+    double t2[3], c3[3];
+    cross_rn(q, l, t2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t2[k] = __dadd_rn(t2[k], t2[k]);
+    cross_rn(q, t2, c3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      world3[3 * (size_t)i + k] = __dadd_rn(__dadd_rn(__dadd_rn(l[k], __dmul_rn(w, t2[k])), c3[k]), pose7[4 + k]);
+  }
+}
+
+extern "C" int ba_gpu_backproject(ba_gpu_ctx *ctx, int32_t n, const float *uv2f, const float *depth_img, int32_t width, int32_t height,
+                                  const double intr4[4], const double *pose7, double *local3, double *world3) {
+  if (!ctx || n < 0 || width <= 0 || height <= 0 || !intr4 || (n > 0 && (!uv2f || !depth_img)) || (world3 && !pose7))
+    return fail(ctx, BA_ERR_INVALID, "backproject: bad arguments");
+  if (n == 0) return BA_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t img = (size_t)width * height;
+  RES(bp_buf, (size_t)n * 8 + img * 4 + 64 + (size_t)n * 48 + 64);
+  char *base = P<char>(ctx->bp_buf);
+  float2 *d_uv = reinterpret_cast<float2 *>(base);
+  float *d_img = reinterpret_cast<float *>(base + (size_t)n * 8);
+  size_t off = ((size_t)n * 8 + img * 4 + 63) / 64 * 64;
+  double *d_pose = reinterpret_cast<double *>(base + off);
+  double *d_local = d_pose + 8, *d_world = d_local + 3 * (size_t)n;
+  cudaStream_t s = ctx->stream;
+  RES(err_flag_bp, 16);
+  CK(cudaMemsetAsync(ctx->err_flag_bp.p, 0, 16, s));
+  CK(cudaMemcpyAsync(d_uv, uv2f, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_img, depth_img, img * 4, cudaMemcpyHostToDevice, s));
+  if (pose7) CK(cudaMemcpyAsync(d_pose, pose7, 56, cudaMemcpyHostToDevice, s));
+  LAUNCH(k_backproject, cdiv(n, BA_THREADS), BA_THREADS, 0, n, d_uv, d_img, width, height, intr4[0], intr4[1], intr4[2], intr4[3],
+         d_pose, local3 ? d_local : (double *)nullptr, world3 ? d_world : (double *)nullptr, P<int32_t>(ctx->err_flag_bp));
+  int32_t h_err = 0;
+  if (local3) CK(cudaMemcpyAsync(local3, d_local, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
+  if (world3) CK(cudaMemcpyAsync(world3, d_world, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_err, ctx->err_flag_bp.p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  if (h_err) return fail(ctx, BA_ERR_INVALID, "backproject: a key point lies outside the %d x %d depth image", width, height);
   return BA_OK;
 }
 

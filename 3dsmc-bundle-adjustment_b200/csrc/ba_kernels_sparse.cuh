@@ -107,6 +107,16 @@ k_sp_entries(int n_cam, const int32_t *__restrict__ row_ustart, const int32_t *_
   for (int b = row_ustart[r]; b < row_ustart[r + 1]; ++b, ++w) ent[w] = make_int2(b, blk_j[b]);
 }
 
+// sort keys of the PCG row order: rows by DECREASING entry count (ties by row index)
+__global__ void __launch_bounds__(BA_THREADS)
+k_sp_row_keys(int n_cam, const int32_t *__restrict__ ent_ptr, unsigned long long *__restrict__ keys, int32_t *__restrict__ vals) {
+  const int r = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (r >= n_cam) return;
+  const unsigned int cnt = (unsigned int)(ent_ptr[r + 1] - ent_ptr[r]);
+  keys[r] = ((unsigned long long)(0xffffffffu - cnt) << 32) | (unsigned int)r;
+  vals[r] = r;
+}
+
 // ------------------------------------------------------------------ values
 // One warp per (local) block.  S_b = [i == j] U_i - diag(s_i) (sum_pairs W_a Vs_p W_b^T) diag(s_j),
 // W_o = jr0_o (x) p0_o + jr1_o (x) p1_o (un-scaled rows rebuilt from the factored store).
@@ -360,29 +370,35 @@ __device__ __forceinline__ void bsr_entry(const int2 en, const double *__restric
 // dependent L2 round trip (its blocks).  MODE 0 (PCG direction): also writes v to pnew and
 // the row's v.out to row_pq.  MODE 1 (residual reset): only out.
 template <int MODE>
-__device__ __forceinline__ void bsr_rows(int n_cam, int gw, int nw, int lane, const int32_t *__restrict__ ent_ptr,
-                                         const int2 *__restrict__ ent, const double *__restrict__ S,
-                                         const double *__restrict__ dsq, const double *za, const double *pb, double beta,
-                                         bool use_pb, double *pnew, double *out, double *row_pq) {
+__device__ __forceinline__ void bsr_rows(int n_cam, int gw, int nw, int lane, const int32_t *__restrict__ order,
+                                         const int32_t *__restrict__ ent_ptr, const int2 *__restrict__ ent,
+                                         const double *__restrict__ S, const double *__restrict__ dsq, const double *za,
+                                         const double *pb, double beta, bool use_pb, double *pnew, double *out,
+                                         double *row_pq) {
+  // rows order[gw], order[gw + nw], ...: `order` lists the rows by decreasing entry count, so the
+  // round-robin deal gives every warp nearly the same number of blocks
   const int2 none = make_int2(0, 0);
-  int row = gw;
-  if (row >= n_cam) return;
+  int idx = gw;
+  if (idx >= n_cam) return;
+  int row = __ldg(order + idx);
+  int row1 = idx + nw < n_cam ? __ldg(order + idx + nw) : -1;
   int b0 = __ldg(ent_ptr + row), e0 = __ldg(ent_ptr + row + 1);
   int b1 = 0, e1 = 0;
-  if (row + nw < n_cam) {
-    b1 = __ldg(ent_ptr + row + nw);
-    e1 = __ldg(ent_ptr + row + nw + 1);
+  if (row1 >= 0) {
+    b1 = __ldg(ent_ptr + row1);
+    e1 = __ldg(ent_ptr + row1 + 1);
   }
   int2 en0 = b0 + lane < e0 ? __ldg(ent + b0 + lane) : none;
   int2 en0b = b0 + lane + 32 < e0 ? __ldg(ent + b0 + lane + 32) : none;
-  for (; row < n_cam; row += nw) {
+  for (; idx < n_cam; idx += nw) {
     // prefetch: first 64 entries of the next row, pointers of the one after
     const int2 en1 = b1 + lane < e1 ? __ldg(ent + b1 + lane) : none;
     const int2 en1b = b1 + lane + 32 < e1 ? __ldg(ent + b1 + lane + 32) : none;
-    int b2 = 0, e2 = 0;
-    if (row + 2 * nw < n_cam) {
-      b2 = __ldg(ent_ptr + row + 2 * nw);
-      e2 = __ldg(ent_ptr + row + 2 * nw + 1);
+    int b2 = 0, e2 = 0, row2 = -1;
+    if (idx + 2 * nw < n_cam) {
+      row2 = __ldg(order + idx + 2 * nw);
+      b2 = __ldg(ent_ptr + row2);
+      e2 = __ldg(ent_ptr + row2 + 1);
     }
     double zk = 0.0, pk = 0.0, dk = 0.0;
     if (lane < 6) {
@@ -410,6 +426,7 @@ __device__ __forceinline__ void bsr_rows(int n_cam, int gw, int nw, int lane, co
       for (int k = 1; k < 6; ++k) s += __shfl_sync(BA_FULL, t, k);
       if (lane == 0) row_pq[row] = s;
     }
+    row = row1; row1 = row2;
     b0 = b1; e0 = e1; en0 = en1; en0b = en1b;
     b1 = b2; e1 = e2;
   }
@@ -420,15 +437,16 @@ __device__ __forceinline__ void bsr_rows(int n_cam, int gw, int nw, int lane, co
 // entries, BA_PCG_ROWS row records), so a cached row costs ONE dependent L2 round trip (its blocks).
 #define BA_PCG_ENT_SLOTS 16
 #define BA_PCG_ROWS 16
-#define BA_PCG_SMEM_PER_WARP (36 * 32 * 8 + BA_PCG_ENT_SLOTS * 32 * 8 + BA_PCG_ROWS * 8)
+#define BA_PCG_SMEM_PER_WARP (36 * 32 * 8 + BA_PCG_ENT_SLOTS * 32 * 8 + BA_PCG_ROWS * 16)
 template <int MODE>
-__device__ __forceinline__ void bsr_rows_cached(int n_cam, int gw, int nw, int lane, int n_cached, const int2 *rowinfo,
+__device__ __forceinline__ void bsr_rows_cached(int n_cam, int gw, int nw, int lane, int n_cached, const int4 *rowinfo,
                                                 const int2 *ecache, const double *__restrict__ S,
                                                 const double *__restrict__ dsq, const double *za, const double *pb, double beta,
                                                 bool use_pb, double *pnew, double *out, double *row_pq) {
   int slot = 0;
-  for (int i = 0, row = gw; i < n_cached; ++i, row += nw) {
-    const int2 be = rowinfo[i];
+  for (int i = 0; i < n_cached; ++i) {
+    const int4 be = rowinfo[i];  // (first entry, end, row, -)
+    const int row = be.z;
     double zk = 0.0, pk = 0.0, dk = 0.0;
     if (lane < 6) {
       zk = __ldcg(za + 6 * (size_t)row + lane);
@@ -590,7 +608,8 @@ __device__ __forceinline__ void pcg_update_warp(int n_cam, int wb, int lane, dou
 }
 
 __global__ void __launch_bounds__(BA_THREADS, 1)
-k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ ent_ptr, const int2 *__restrict__ ent,
+k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ row_order, const int32_t *__restrict__ ent_ptr,
+                        const int2 *__restrict__ ent,
                         const double *__restrict__ S, const double *__restrict__ dsq, const double *__restrict__ b,
                         const double *__restrict__ Minv, double *x, double *r, double *z, double *pbuf0, double *pbuf1,
                         double *q, double *row_pq, double *part_rho, double *part_Q, unsigned int *bar, LmOptions lo,
@@ -605,16 +624,17 @@ k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ ent_ptr, const in
   char *wsm = reinterpret_cast<char *>(minv_all) + (size_t)(tid >> 5) * BA_PCG_SMEM_PER_WARP;
   double *minv_s = reinterpret_cast<double *>(wsm);
   int2 *ecache = reinterpret_cast<int2 *>(wsm + 36 * 32 * 8);
-  int2 *rowinfo = ecache + BA_PCG_ENT_SLOTS * 32;
+  int4 *rowinfo = reinterpret_cast<int4 *>(ecache + BA_PCG_ENT_SLOTS * 32);
   // the warp's first rows: entries into the shared-memory cache
   int n_cached = 0;
   {
     int slot = 0;
-    for (int row = gw; row < n_cam && n_cached < BA_PCG_ROWS; row += nw) {
+    for (int idx = gw; idx < n_cam && n_cached < BA_PCG_ROWS; idx += nw) {
+      const int row = row_order[idx];
       const int b0 = ent_ptr[row], e0 = ent_ptr[row + 1];
       const int trips = (e0 - b0 + 31) >> 5;
       if (slot + trips > BA_PCG_ENT_SLOTS) break;
-      if (lane == 0) rowinfo[n_cached] = make_int2(b0, e0);
+      if (lane == 0) rowinfo[n_cached] = make_int4(b0, e0, row, 0);
       for (int e = b0; e < e0; e += 32, ++slot) ecache[slot * 32 + lane] = e + lane < e0 ? ent[e + lane] : make_int2(0, 0);
       ++n_cached;
     }
@@ -647,7 +667,7 @@ k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ ent_ptr, const in
   for (;;) {
     // ---- phase I: p = z (+ beta p_old), q = S p + D^2 p, per-row p.q
     bsr_rows_cached<0>(n_cam, gw, nw, lane, n_cached, rowinfo, ecache, S, dsq, z, pold, beta, it > 1, pnew, q, row_pq);
-    bsr_rows<0>(n_cam, gw + n_cached * nw, nw, lane, ent_ptr, ent, S, dsq, z, pold, beta, it > 1, pnew, q, row_pq);
+    bsr_rows<0>(n_cam, gw + n_cached * nw, nw, lane, row_order, ent_ptr, ent, S, dsq, z, pold, beta, it > 1, pnew, q, row_pq);
     PROF_TICK(0)
     grid_barrier(bar, epoch);
     PROF_TICK(1)
@@ -676,7 +696,7 @@ k_pcg_sparse_persistent(int n_cam, const int32_t *__restrict__ ent_ptr, const in
     if (reset) {
       // ---- residual reset: q = S x + D^2 x, then r = b - q, z = M^-1 r
       bsr_rows_cached<1>(n_cam, gw, nw, lane, n_cached, rowinfo, ecache, S, dsq, x, x, 0.0, false, nullptr, q, nullptr);
-      bsr_rows<1>(n_cam, gw + n_cached * nw, nw, lane, ent_ptr, ent, S, dsq, x, x, 0.0, false, nullptr, q, nullptr);
+      bsr_rows<1>(n_cam, gw + n_cached * nw, nw, lane, row_order, ent_ptr, ent, S, dsq, x, x, 0.0, false, nullptr, q, nullptr);
       grid_barrier(bar, epoch);
       if (gw < n_wb) pcg_update_warp<1, 1>(n_cam, gw, lane, 0.0, false, b, Minv, minv_s, breg, x, r, z, pnew, q, part_rho, part_Q);
       for (int wb = gw + nw; wb < n_wb; wb += nw)

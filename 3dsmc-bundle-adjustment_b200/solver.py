@@ -165,6 +165,23 @@ class GpuSolver:
     def launch_count(self):
         return int(self.lib.ba_gpu_launch_count(self._ctx))
 
+    def backproject(self, uv, depth_img, intr, pose7=None):
+        """Batched getLocalPoints3D (src/Map3D.cpp:76-97) [+ world-frame landmark initialisation (:44)
+        when pose7 is given]: uv [n,2] float32 pixels, depth_img [H,W] float32 metres.
+        Returns local [n,3] (and world [n,3])."""
+        import ctypes as C
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        img = np.ascontiguousarray(depth_img, dtype=np.float32)
+        k = capi.f64(intr)
+        n = uv.shape[0]
+        local = np.empty((n, 3), dtype=np.float64)
+        world = np.empty((n, 3), dtype=np.float64) if pose7 is not None else None
+        p = capi.f64(pose7) if pose7 is not None else None
+        fp = C.POINTER(C.c_float)
+        self._check(self.lib.ba_gpu_backproject(self._ctx, n, uv.ctypes.data_as(fp), img.ctypes.data_as(fp), img.shape[1], img.shape[0],
+                                                capi.dp(k), capi.dp(p), capi.dp(local), capi.dp(world)))
+        return (local, world) if pose7 is not None else local
+
     def sparse_stats(self):
         """(row entries, stored upper blocks) of the block-sparse Schur complement; zeros for other solvers."""
         import ctypes as C

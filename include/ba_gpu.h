@@ -181,6 +181,18 @@ int ba_gpu_schur_matvec(ba_gpu_ctx *ctx, double radius, const double *x, double 
 int ba_gpu_se3_plus(ba_gpu_ctx *ctx, int32_t n, const double *pose7,
                     const double *delta6, double *out7);
 
+/* ---- the step before BA: batched back-projection and landmark initialisation ----
+ * Replaces the per-key-point loop of getLocalPoints3D (src/Map3D.cpp:76-97) and the world-frame
+ * transform of addNewLandmark (src/Map3D.cpp:44).  Host buffers:
+ *   uv2f [n*2] float pixels (cv::KeyPoint::pt); depth_img [height*width] float metres, row-major
+ *   (depth_frame.at<float>(trunc(v), trunc(u))); intr4 (fx,fy,cx,cy);
+ *   local3 [n*3] = (z (u-cx)/fx, z (v-cy)/fy, z)            (nullable)
+ *   world3 [n*3] = pose7 * local3, needs pose7 (qx..tz)     (nullable)
+ * Bit-exact with the reference's plain fp64 arithmetic (no FMA contraction).  A key point outside the
+ * image -> BA_ERR_INVALID (cv::Mat::at would read out of bounds). */
+int ba_gpu_backproject(ba_gpu_ctx *ctx, int32_t n, const float *uv2f, const float *depth_img, int32_t width,
+                       int32_t height, const double intr4[4], const double *pose7, double *local3, double *world3);
+
 /* ---- measurement hooks (bench.py) ---- */
 enum {
   BA_KERNEL_LINEARIZE = 0,    /* camera-major residual+Jacobian kernel */

@@ -334,6 +334,25 @@ void ora_se3_act(const double a[7], const double p[3], double out[3]) {
   quat_rotate(a, p, r);
   for (int i = 0; i < 3; ++i) out[i] = r[i] + a[4 + i];
 }
+/* getLocalPoints3D (src/Map3D.cpp:76-97): camera-frame point of every key point from the depth image
+ * (depth_frame.at<float>(trunc(v), trunc(u)), pixels are float), and, when pose7 is given, the world-frame
+ * landmark of addNewLandmark (src/Map3D.cpp:44): T_w_c * p_local.  Returns -1 if a pixel is outside. */
+int ora_backproject(int n, const float *uv2f, const float *depth_img, int width, int height, const double intr4[4],
+                    const double *pose7, double *local3, double *world3) {
+  for (int i = 0; i < n; ++i) {
+    const double u = (double)uv2f[2 * i], v = (double)uv2f[2 * i + 1];
+    const int col = (int)truncf(uv2f[2 * i]), row = (int)truncf(uv2f[2 * i + 1]);
+    if (col < 0 || col >= width || row < 0 || row >= height) return -1;
+    const double z = (double)depth_img[(size_t)row * width + col];
+    double l[3];
+    l[0] = z * (u - intr4[2]) / intr4[0];
+    l[1] = z * (v - intr4[3]) / intr4[1];
+    l[2] = z;
+    if (local3) memcpy(local3 + 3 * (size_t)i, l, sizeof(l));
+    if (world3 && pose7) ora_se3_act(pose7, l, world3 + 3 * (size_t)i);
+  }
+  return 0;
+}
 /* SE3::exp  se3.hpp:725-746 with SO3::expAndTheta so3.hpp:537-571 */
 void ora_se3_exp(const double d[6], double out[7]) {
   const double *ups = d, *om = d + 3;

@@ -98,6 +98,9 @@ void ora_se3_exp(const double delta6[6], double out7[7]);
 void ora_se3_mul(const double a7[7], const double b7[7], double out7[7]);
 void ora_se3_inverse(const double a7[7], double out7[7]);
 void ora_se3_act(const double a7[7], const double p[3], double out[3]);
+/* src/Map3D.cpp:76-97 (+ :44 when pose7 != NULL); -1 if a key point is outside the image */
+int ora_backproject(int n, const float *uv2f, const float *depth_img, int width, int height, const double intr4[4],
+                    const double *pose7, double *local3, double *world3);
 void ora_se3_dx_this_mul_exp_x_at_0(const double a7[7], double J7x6[42]);
 
 /* ---- cost functors with ambient (autodiff-equivalent) Jacobians ----

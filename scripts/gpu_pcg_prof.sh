@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "sparse" > gpurun_out/gputests.log 2>&1; echo rc=$? >> gpurun_out/gputests.log
+python -m pytest tests/test_gpu_parity.py tests/test_backproject.py -m gpu -x -q -k "sparse or backproject" > gpurun_out/gputests.log 2>&1; echo rc=$? >> gpurun_out/gputests.log
 for c in 5 3 4; do BA_PCG_PROF=1 python profiles/profile_target.py $c 2 500 3 ; done > gpurun_out/plain_sp.log 2>&1

@@ -224,6 +224,19 @@ def se3_act(a, p):
     lib().ora_se3_act(_dp(a), _dp(p), _dp(o)); return o
 
 
+def backproject(uv, depth_img, intr, pose7=None):
+    uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+    img = np.ascontiguousarray(depth_img, dtype=np.float32)
+    k = np.ascontiguousarray(intr, dtype=np.float64)
+    n = uv.shape[0]
+    local, world = np.zeros((n, 3)), np.zeros((n, 3))
+    fp = C.POINTER(C.c_float)
+    p = np.ascontiguousarray(pose7, dtype=np.float64) if pose7 is not None else None
+    rc = lib().ora_backproject(n, uv.ctypes.data_as(fp), img.ctypes.data_as(fp), img.shape[1], img.shape[0], _dp(k),
+                               _dp(p) if p is not None else None, _dp(local), _dp(world) if p is not None else None)
+    return rc, local, (world if p is not None else None)
+
+
 def se3_dx(a):
     a = np.ascontiguousarray(a, dtype=np.float64); o = np.zeros((7, 6))
     lib().ora_se3_dx_this_mul_exp_x_at_0(_dp(a), _dp(o)); return o
