@@ -11,6 +11,7 @@
 #include "ba_kernels_fact.cuh"
 #include "ba_kernels_tile.cuh"
 #include "ba_kernels_sparse.cuh"
+#include "ba_kernels_dist.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -116,6 +117,15 @@ struct ba_gpu_ctx {
       row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
   int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0;
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
+  // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
+  Buf my_rows, row_flag, row_pos, ipc_stage;
+  void *xch = nullptr;          // own exchange buffer (cudaMalloc, cudaIpc-exported)
+  size_t xch_cap = 0;
+  int xch_ncam = 0;
+  void *xch_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  PcgFan fan;
+  bool dist_pcg = false;
+  int n_my_rows = 0, dist_grid = 0;
   long long n_pairs = 0;
   Buf p2, pcg_bar, wb_rho, wb_Q, bp_buf, err_flag_bp, row_keys, row_keys2, row_ids, row_order;
   // scaling / diag / gradient / blocks
@@ -330,6 +340,9 @@ extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  for (int k = 0; k < 8; ++k)
+    if (ctx->xch_peer[k] && k != ctx->rank) cudaIpcCloseMemHandle(ctx->xch_peer[k]);
+  if (ctx->xch) cudaFree(ctx->xch);
   for (Buf *b : ctx->bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_st) cudaFreeHost(ctx->h_st);
@@ -661,6 +674,96 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   return 0;
 }
 
+// exchange buffers of the row-sharded PCG: one cudaMalloc per rank, handles all-gathered through NCCL,
+// peers mapped with cudaIpcOpenMemHandle (NVLink peer access)
+static int setup_dist_pcg(ba_gpu_ctx *ctx) {
+  const int n_cam = ctx->n_cam, n_wb = cdiv(n_cam, 32), N = ctx->n_ranks;
+  cudaStream_t s = ctx->stream;
+  ctx->dist_pcg = false;
+  if (N > BA_MAX_RANKS) return 0;
+  // layout (doubles): z[6n] x[6n] row_pq[n] wb_rho[n_wb] wb_Q[n_wb] | flags[8] epoch[1] (u64)
+  const size_t n6 = (size_t)6 * n_cam, nd = 2 * n6 + n_cam + 2 * (size_t)n_wb;
+  const size_t bytes = (nd + 16) * 8;
+  if (ctx->xch_ncam != n_cam || !ctx->xch) {
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < 8; ++k) {
+      if (ctx->xch_peer[k] && k != ctx->rank) cudaIpcCloseMemHandle(ctx->xch_peer[k]);
+      ctx->xch_peer[k] = nullptr;
+    }
+    if (ctx->xch) cudaFree(ctx->xch);
+    ctx->xch = nullptr;
+    CK(cudaMalloc(&ctx->xch, bytes));
+    CK(cudaMemset(ctx->xch, 0, bytes));
+    ctx->xch_cap = bytes;
+    ctx->xch_ncam = n_cam;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->xch));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    RES(ipc_stage, (size_t)64 * (N + 1));
+    CK(cudaMemcpyAsync(P<char>(ctx->ipc_stage) + 64 * ctx->rank, &h, 64, cudaMemcpyHostToDevice, s));
+    ncclResult_t nr = g_nccl.AllGather(P<char>(ctx->ipc_stage) + 64 * ctx->rank, ctx->ipc_stage.p, 8, ncclUint64_, ctx->comm, s);
+    if (nr != 0) return fail(ctx, BA_ERR_COMM, "ncclAllGather(ipc handles): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    ctx->collectives++;
+    std::vector<cudaIpcMemHandle_t> all(N);
+    CK(cudaMemcpyAsync(all.data(), ctx->ipc_stage.p, (size_t)64 * N, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < N; ++k) {
+      if (k == ctx->rank) {
+        ctx->xch_peer[k] = ctx->xch;
+        continue;
+      }
+      cudaError_t e = cudaIpcOpenMemHandle(&ctx->xch_peer[k], all[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        // no peer access between these GPUs: the replicated PCG is used instead (same on every rank? the
+        // decision is all-reduced below)
+        ctx->xch_peer[k] = nullptr;
+        cudaGetLastError();
+      }
+    }
+  }
+  double ok = 1.0;
+  for (int k = 0; k < N; ++k)
+    if (!ctx->xch_peer[k]) ok = 0.0;
+  ok = -ok;  // min over ranks through the max reduction
+  int rc = allreduce_host_scalar(ctx, &ok, true);
+  if (rc) return rc;
+  if (ok != -1.0) return 0;
+  PcgFan &f = ctx->fan;
+  memset(&f, 0, sizeof(f));
+  f.n_ranks = N;
+  f.rank = ctx->rank;
+  for (int k = 0; k < N; ++k) {
+    double *base = reinterpret_cast<double *>(ctx->xch_peer[k]);
+    f.z[k] = base;
+    f.x[k] = base + n6;
+    f.row_pq[k] = base + 2 * n6;
+    f.wb_rho[k] = base + 2 * n6 + n_cam;
+    f.wb_Q[k] = base + 2 * n6 + n_cam + n_wb;
+    f.flags[k] = reinterpret_cast<unsigned long long *>(base + nd);
+  }
+  f.epoch = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(ctx->xch) + nd) + 8;
+  // own rows, in the global order of decreasing entry count
+  RES(row_flag, ((size_t)n_cam + 2) * 4);
+  RES(row_pos, ((size_t)n_cam + 2) * 4);
+  RES(my_rows, ((size_t)n_cam + 2) * 4);
+  CK(cudaMemsetAsync(ctx->row_flag.p, 0, ((size_t)n_cam + 2) * 4, s));
+  LAUNCH(k_dist_flag_rows, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->row_order), ctx->rank, N, P<int32_t>(ctx->row_flag));
+  CUBCALL(cub::DeviceScan::ExclusiveSum, P<int32_t>(ctx->row_flag), P<int32_t>(ctx->row_pos), n_cam + 1);
+  LAUNCH(k_dist_pick_rows, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->row_order), P<int32_t>(ctx->row_flag),
+         P<int32_t>(ctx->row_pos), P<int32_t>(ctx->my_rows));
+  int32_t n_my = 0;
+  CK(cudaMemcpyAsync(&n_my, P<int32_t>(ctx->row_pos) + n_cam, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->n_my_rows = n_my;
+  {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_sparse_dist, BA_THREADS, 0));
+    ctx->dist_grid = per_sm > 0 ? ctx->n_sm : 0;
+  }
+  ctx->dist_pcg = ctx->dist_grid > 0;
+  return 0;
+}
+
 extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7, int32_t fixed_cam, int32_t n_pt,
                              const double *pt3, int32_t n_obs, const int32_t *cam_idx, const int32_t *pt_idx,
                              const double *uv2, const double *depth, const double intr4[4], const double intr_prior4[4]) {
@@ -908,6 +1011,8 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   if (sparse) {
     int rcs = build_sparse_structure(ctx);
     if (rcs) return rcs;
+    ctx->dist_pcg = false;
+    if (ctx->n_ranks > 1 && o.persistent_pcg == 2 && (rcs = setup_dist_pcg(ctx))) return rcs;
   }
   if (ctx->fact && !sparse && o.jacobian_store != BA_JAC_FACTORED && ctx->n_tiles > 0) {
     // tile-fused product: tile metadata, then (if the locality bounds hold) the tile-camera-major store
@@ -1255,6 +1360,33 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
          P<double>(ctx->b), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z), P<double>(ctx->pcam_rho),
          P<double>(ctx->pcam_bb), st, GATE_RUN);
   LAUNCH(k_pcg_start, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_bb), P<double>(ctx->pcam_rho), st, GATE_RUN);
+  if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && ctx->opt.persistent_pcg == 2 && ctx->dist_pcg) {
+    // row-sharded persistent PCG, exchange over NVLink peer memory inside the kernel (ba_kernels_dist.cuh)
+    const size_t n6b = (size_t)ctx->n_cam * 48;
+    cudaMemcpyAsync(ctx->fan.z[ctx->rank], ctx->z.p, n6b, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->fan.x[ctx->rank], ctx->x.p, n6b, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemsetAsync(ctx->pcg_bar.p, 0, 16, ctx->stream);
+    PcgFan fan = ctx->fan;
+    int n_cam = ctx->n_cam, n_my = ctx->n_my_rows;
+    const int32_t *my_rows = P<int32_t>(ctx->my_rows), *ent_ptr = P<int32_t>(ctx->ent_ptr);
+    const int2 *ent = P<int2>(ctx->ent);
+    const double *Sb = P<double>(ctx->Sblk), *dsq = P<double>(ctx->dsq), *bb = P<double>(ctx->b), *Minv = P<double>(ctx->Minv);
+    double *r = P<double>(ctx->r), *p0 = P<double>(ctx->p), *p1 = P<double>(ctx->p2), *q = P<double>(ctx->q);
+    unsigned int *bar = P<unsigned int>(ctx->pcg_bar);
+    int *cfail = reinterpret_cast<int *>(P<char>(ctx->pcg_bar) + 32);
+    LmOptions lo = ctx->lo;
+    unsigned long long *prof = getenv("BA_PCG_PROF") ? P<unsigned long long>(ctx->pcg_bar) + 8 : nullptr;
+    void *args[] = {&fan, &n_cam, &n_my, &my_rows, &ent_ptr, &ent, &Sb, &dsq, &bb, &Minv, &r, &p0, &p1, &q, &bar, &lo, &st, &cfail, &prof};
+    CK(cudaLaunchCooperativeKernel((const void *)k_pcg_sparse_dist, dim3(ctx->dist_grid), dim3(BA_THREADS), args, 0, ctx->stream));
+    ctx->launches++;
+    LAUNCH(k_pcg_finish, cdiv(6 * ctx->n_cam, BA_THREADS), BA_THREADS, 0, 6 * ctx->n_cam, ctx->fan.x[ctx->rank], P<double>(ctx->yc), st,
+           GATE_RUN);
+    int32_t h_cfail = 0;
+    CK(cudaMemcpyAsync(&h_cfail, cfail, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h_cfail) return fail(ctx, BA_ERR_COMM, "row-sharded PCG: a peer GPU did not reach the NVLink barrier within 4 s");
+    return 0;
+  }
   if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && ctx->opt.persistent_pcg && ctx->pcg_grid > 0) {
     // the whole PCG solve in one cooperative launch (ba_kernels_sparse.cuh)
     cudaMemsetAsync(ctx->pcg_bar.p, 0, 16, ctx->stream);  // (profile counters at +64 accumulate over the solve)

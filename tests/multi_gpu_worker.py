@@ -18,12 +18,13 @@ def main():
     scale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.05
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 6
     solver = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+    persistent = int(sys.argv[5]) if len(sys.argv) > 5 else 1
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     full = ba_b200.synthetic.make_config(cfg, scale=scale)
     shard, ids = ba_b200.synthetic.shard_points(full, rank, world)
-    opts = dict(use_depth_prior=0, optimize_intrinsics=0, solver=solver, max_num_iterations=iters, device=local)
+    opts = dict(use_depth_prior=0, optimize_intrinsics=0, solver=solver, max_num_iterations=iters, device=local, persistent_pcg=persistent)
     s = ba_b200.GpuSolver(n_obs_total=full.n_obs, **opts)
     idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
