@@ -681,9 +681,11 @@ static int setup_dist_pcg(ba_gpu_ctx *ctx) {
   cudaStream_t s = ctx->stream;
   ctx->dist_pcg = false;
   if (N > BA_MAX_RANKS) return 0;
-  // layout (doubles): z[6n] x[6n] row_pq[n] wb_rho[n_wb] wb_Q[n_wb] | flags[8] epoch[1] (u64)
-  const size_t n6 = (size_t)6 * n_cam, nd = 2 * n6 + n_cam + 2 * (size_t)n_wb;
-  const size_t bytes = (nd + 16) * 8;
+  // layout (16-byte slots): q[2][6n] pq[2][n] slice[2][n_slices] | epoch (u64) abort (int)
+  const size_t n6 = (size_t)6 * n_cam, n_slices = (size_t)cdiv(n_cam, BA_PQ_SLICE);
+  const size_t n_slots = 2 * n6 + 2 * (size_t)n_cam + 2 * n_slices;
+  const size_t bytes = n_slots * sizeof(LLSlot) + 64;
+  (void)n_wb;
   if (ctx->xch_ncam != n_cam || !ctx->xch) {
     CK(cudaStreamSynchronize(s));
     for (int k = 0; k < 8; ++k) {
@@ -733,15 +735,16 @@ static int setup_dist_pcg(ba_gpu_ctx *ctx) {
   f.n_ranks = N;
   f.rank = ctx->rank;
   for (int k = 0; k < N; ++k) {
-    double *base = reinterpret_cast<double *>(ctx->xch_peer[k]);
-    f.z[k] = base;
-    f.x[k] = base + n6;
-    f.row_pq[k] = base + 2 * n6;
-    f.wb_rho[k] = base + 2 * n6 + n_cam;
-    f.wb_Q[k] = base + 2 * n6 + n_cam + n_wb;
-    f.flags[k] = reinterpret_cast<unsigned long long *>(base + nd);
+    LLSlot *base = reinterpret_cast<LLSlot *>(ctx->xch_peer[k]);
+    f.q[k] = base;
+    f.pq[k] = base + 2 * n6;
   }
-  f.epoch = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(ctx->xch) + nd) + 8;
+  {
+    LLSlot *base = reinterpret_cast<LLSlot *>(ctx->xch);
+    f.slice = base + 2 * n6 + 2 * (size_t)n_cam;
+    f.epoch = reinterpret_cast<unsigned long long *>(base + n_slots);
+    f.abort_flag = reinterpret_cast<int *>(f.epoch + 1);
+  }
   // own rows, in the global order of decreasing entry count
   RES(row_flag, ((size_t)n_cam + 2) * 4);
   RES(row_pos, ((size_t)n_cam + 2) * 4);
@@ -757,7 +760,8 @@ static int setup_dist_pcg(ba_gpu_ctx *ctx) {
   ctx->n_my_rows = n_my;
   {
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_sparse_dist, BA_THREADS, 0));
+    CK(cudaFuncSetAttribute(k_pcg_sparse_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_WARPS * 36 * 32 * 8));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_sparse_dist, BA_THREADS, (size_t)BA_WARPS * 36 * 32 * 8));
     ctx->dist_grid = per_sm > 0 ? ctx->n_sm : 0;
   }
   ctx->dist_pcg = ctx->dist_grid > 0;
@@ -1012,7 +1016,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     int rcs = build_sparse_structure(ctx);
     if (rcs) return rcs;
     ctx->dist_pcg = false;
-    if (ctx->n_ranks > 1 && o.persistent_pcg == 2 && (rcs = setup_dist_pcg(ctx))) return rcs;
+    if (ctx->n_ranks > 1 && o.persistent_pcg == 1 && (rcs = setup_dist_pcg(ctx))) return rcs;
   }
   if (ctx->fact && !sparse && o.jacobian_store != BA_JAC_FACTORED && ctx->n_tiles > 0) {
     // tile-fused product: tile metadata, then (if the locality bounds hold) the tile-camera-major store
@@ -1360,31 +1364,31 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
          P<double>(ctx->b), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z), P<double>(ctx->pcam_rho),
          P<double>(ctx->pcam_bb), st, GATE_RUN);
   LAUNCH(k_pcg_start, 1, BA_THREADS, 0, ctx->nblk_cam, P<double>(ctx->pcam_bb), P<double>(ctx->pcam_rho), st, GATE_RUN);
-  if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && ctx->opt.persistent_pcg == 2 && ctx->dist_pcg) {
-    // row-sharded persistent PCG, exchange over NVLink peer memory inside the kernel (ba_kernels_dist.cuh)
-    const size_t n6b = (size_t)ctx->n_cam * 48;
-    cudaMemcpyAsync(ctx->fan.z[ctx->rank], ctx->z.p, n6b, cudaMemcpyDeviceToDevice, ctx->stream);
-    cudaMemcpyAsync(ctx->fan.x[ctx->rank], ctx->x.p, n6b, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && ctx->opt.persistent_pcg == 1 && ctx->dist_pcg) {
+    // persistent PCG with the product row-sharded over the ranks, exchange through flag-in-data slots in
+    // NVLink peer memory inside the kernel (ba_kernels_dist.cuh)
     cudaMemsetAsync(ctx->pcg_bar.p, 0, 16, ctx->stream);
     PcgFan fan = ctx->fan;
     int n_cam = ctx->n_cam, n_my = ctx->n_my_rows;
     const int32_t *my_rows = P<int32_t>(ctx->my_rows), *ent_ptr = P<int32_t>(ctx->ent_ptr);
     const int2 *ent = P<int2>(ctx->ent);
     const double *Sb = P<double>(ctx->Sblk), *dsq = P<double>(ctx->dsq), *bb = P<double>(ctx->b), *Minv = P<double>(ctx->Minv);
-    double *r = P<double>(ctx->r), *p0 = P<double>(ctx->p), *p1 = P<double>(ctx->p2), *q = P<double>(ctx->q);
+    double *x = P<double>(ctx->x), *r = P<double>(ctx->r), *z = P<double>(ctx->z), *p0 = P<double>(ctx->p), *p1 = P<double>(ctx->p2),
+           *prho = P<double>(ctx->wb_rho), *pQ = P<double>(ctx->wb_Q);
     unsigned int *bar = P<unsigned int>(ctx->pcg_bar);
-    int *cfail = reinterpret_cast<int *>(P<char>(ctx->pcg_bar) + 32);
     LmOptions lo = ctx->lo;
     unsigned long long *prof = getenv("BA_PCG_PROF") ? P<unsigned long long>(ctx->pcg_bar) + 8 : nullptr;
-    void *args[] = {&fan, &n_cam, &n_my, &my_rows, &ent_ptr, &ent, &Sb, &dsq, &bb, &Minv, &r, &p0, &p1, &q, &bar, &lo, &st, &cfail, &prof};
-    CK(cudaLaunchCooperativeKernel((const void *)k_pcg_sparse_dist, dim3(ctx->dist_grid), dim3(BA_THREADS), args, 0, ctx->stream));
+    void *args[] = {&fan, &n_cam, &n_my, &my_rows, &ent_ptr, &ent, &Sb, &dsq, &bb, &Minv, &x, &r, &z, &p0, &p1, &prho, &pQ, &bar, &lo, &st,
+                    &prof};
+    CK(cudaLaunchCooperativeKernel((const void *)k_pcg_sparse_dist, dim3(ctx->dist_grid), dim3(BA_THREADS), args,
+                                   (size_t)BA_WARPS * 36 * 32 * 8, ctx->stream));
     ctx->launches++;
-    LAUNCH(k_pcg_finish, cdiv(6 * ctx->n_cam, BA_THREADS), BA_THREADS, 0, 6 * ctx->n_cam, ctx->fan.x[ctx->rank], P<double>(ctx->yc), st,
+    LAUNCH(k_pcg_finish, cdiv(6 * ctx->n_cam, BA_THREADS), BA_THREADS, 0, 6 * ctx->n_cam, P<double>(ctx->x), P<double>(ctx->yc), st,
            GATE_RUN);
-    int32_t h_cfail = 0;
-    CK(cudaMemcpyAsync(&h_cfail, cfail, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t h_abort = 0;
+    CK(cudaMemcpyAsync(&h_abort, ctx->fan.abort_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (h_cfail) return fail(ctx, BA_ERR_COMM, "row-sharded PCG: a peer GPU did not reach the NVLink barrier within 4 s");
+    if (h_abort) return fail(ctx, BA_ERR_COMM, "row-sharded PCG: a peer GPU did not deliver its slots within 4 s");
     return 0;
   }
   if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && ctx->opt.persistent_pcg && ctx->pcg_grid > 0) {

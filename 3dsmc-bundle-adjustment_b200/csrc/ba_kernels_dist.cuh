@@ -1,88 +1,99 @@
-// ba_kernels_dist.cuh -- the persistent PCG of the block-sparse solver, ROW-SHARDED over the
-// GPUs of one node, with the exchange fused into the kernel over NVLink peer memory.
+// ba_kernels_dist.cuh -- the persistent PCG of the block-sparse solver with the PRODUCT row-sharded
+// over the GPUs of one node and the exchange fused into the kernel over NVLink peer memory.
 //
 // One process per GPU; S, b, M^-1 are complete and identical on every rank (S is all-reduced once
-// per LM iteration).  Each rank owns the camera blocks wb = rank, rank + N, ... (32 consecutive
-// cameras each, the granularity of the single-GPU partial sums) and runs the same persistent loop
-// as k_pcg_sparse_persistent on ITS rows only.  What the others need is written straight into
-// their memory (cudaIpc-mapped exchange buffers, plain st.global over NVLink), by the thread that
-// produced it:
-//     phase I   q_r, p.q of the row           -> row_pq[row]         on every rank
-//     phase II  z_c, partials of r.z, x.(b+r) -> z[c], wb_rho/wb_Q   on every rank
-//               (x_c as well on residual-reset iterations and at the end)
-// followed by a cross-GPU barrier: the local grid barrier, then the last CTA to arrive publishes
-// an epoch number into every peer's flag slot (st.release.sys) and every CTA waits for all slots.
-// No NCCL call, no host round trip inside the solve: two NVLink barriers per PCG iteration.
-// Every rank sums the same complete arrays in the same order, so the PCG scalars -- and with them
-// every iterate -- are BIT-IDENTICAL to the single-GPU solve and identical across ranks.
-// Spin waits carry a time-out (a rank that died must not hang the others' GPUs).
+// per LM iteration).  Per PCG iteration the block-CSR product q = S p + D^2 p is the only heavy
+// phase (87 MB of L2 traffic at config 5), so that is what is sharded: rank k owns the camera blocks
+// wb = k, k + N, ... (32 consecutive cameras each) and computes q and p.q for ITS rows only.  The lane
+// that holds a result stores it straight into every rank's memory (cudaIpc-mapped exchange buffers)
+// as a 16-byte FLAG-IN-DATA slot {value, epoch} (one st.v2.u64, delivered atomically over NVLink):
+// the consumer polls the slot until it carries the current epoch.  No fence, no separate flag, no
+// cross-GPU barrier -- measured on 2 x B200 (profiles/r01_nvlink_latency.txt): 1.14 us one way for a
+// flag-in-data store against 4.4-6.2 us for "stores + fence.sys + flag" (a first version of this kernel
+// with two fence + flag barriers per iteration ran at 48 us per PCG iteration against 29 us on one GPU).
+// The vector phase (alpha, x, r, z = M^-1 r, controller) is cheap and runs REPLICATED on every rank from
+// the complete q, so one exchange per PCG iteration suffices.
 //
-// STATUS (round 1, 2 x B200, cfg 5): correct (tests/test_gpu_multi.py) but NOT faster -- per PCG iteration
-// product 12.2 us (18.7 on one GPU) + 2 x 12.5 us NVLink barrier (fence.sys drain + flag round trip) against
-// 2 x 1.7 us for the local grid barrier: 48 us vs 29 us.  Selected only by persistent_pcg = 2; the default
-// multi-GPU mode runs the PCG replicated.  Next step: flag-in-data (LL-style) slots instead of fence + flag.
+//   phase I    own rows: q_r, p.q_r  -> slots on every rank        (p_new kept complete locally)
+//   sum        64-row slices of p.q (fixed granularity), then the slice partials: alpha
+//   phase II   ALL camera blocks (replicated): poll q, x += alpha p, r -= alpha q, z = M^-1 r, partials
+//   grid barrier (local), controller (every CTA of every rank: same numbers, same order)
+//
+// Slots are double-buffered by the exchange round (epoch & 1): a rank can run at most one round ahead of
+// the slowest one, because finishing a round needs everybody's data of that round.  Epochs increase
+// monotonically over the life of the context, so stale slots never match.  Every rank computes the same
+// sums in the same order: all ranks hold bit-identical iterates.  Polls time out (4 s) into an abort
+// flag, so a dead peer cannot hang the other GPUs.
 #pragma once
 #include "ba_kernels_sparse.cuh"
 
 #define BA_MAX_RANKS 8
+#define BA_PQ_SLICE 64
+
+struct __align__(16) LLSlot {
+  double v;
+  unsigned long long e;
+};
 struct PcgFan {
   int n_ranks, rank;
-  double *z[BA_MAX_RANKS], *x[BA_MAX_RANKS], *row_pq[BA_MAX_RANKS], *wb_rho[BA_MAX_RANKS], *wb_Q[BA_MAX_RANKS];
-  unsigned long long *flags[BA_MAX_RANKS];  // flags[k]: rank k's slots; this rank writes flags[k][rank]
-  unsigned long long *epoch;                // own running epoch counter (survives launches)
+  LLSlot *q[BA_MAX_RANKS];    // [2][6 n_cam]  q of every camera, written by the row owners
+  LLSlot *pq[BA_MAX_RANKS];   // [2][n_cam]    p.q of every row
+  LLSlot *slice;              // [2][n_slices] local: 64-row partial sums of p.q
+  unsigned long long *epoch;  // own running round counter (survives launches)
+  int *abort_flag;            // set on a poll time-out
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void ll_store(LLSlot *p, double v, unsigned long long e) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(e) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// local grid barrier + cross-GPU epoch exchange.  Returns false on time-out.
-__device__ __forceinline__ bool cross_barrier(const PcgFan &f, unsigned int *bar, unsigned int &local_epoch,
-                                              unsigned long long &epoch) {
-  __shared__ int ok_s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int ok = 1;
-    local_epoch += gridDim.x;
-    epoch += 1;
-    __threadfence_system();  // this CTA's peer stores are visible system-wide before it arrives
-    const unsigned int old = atomicAdd(bar, 1u);
-    if (old == local_epoch - 1u) {  // last local CTA: tell every rank (this one included)
-      __threadfence_system();
-      for (int k = 0; k < f.n_ranks; ++k) st_release_sys(f.flags[k] + f.rank, epoch);
-    }
+// spins until the slot carries epoch e; on time-out / abort returns 0.0
+__device__ __forceinline__ double ll_wait(const LLSlot *p, unsigned long long e, int *abort_flag) {
+  unsigned long long a, b;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  if (b != e) {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-    for (int k = 0; k < f.n_ranks && ok; ++k) {
-      while (ld_acquire_sys(f.flags[f.rank] + k) < epoch) {
+    for (int spin = 0;; ++spin) {
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+      if (b == e) break;
+      if ((spin & 63) == 63) {
+        if (*((volatile int *)abort_flag)) return 0.0;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) {  // 4 s: a peer is gone
-          ok = 0;
-          break;
+        if (t1 - t0 > 4000000000ull) {
+          *((volatile int *)abort_flag) = 1;
+          return 0.0;
         }
       }
     }
-    __threadfence_system();
-    ok_s = ok;
+  }
+  return __longlong_as_double(a);
+}
+// local grid barrier that gives up when the abort flag is raised
+__device__ __forceinline__ void grid_barrier_abortable(unsigned int *bar, unsigned int &epoch, int *abort_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    int spin = 0;
+    while (*((volatile unsigned int *)bar) < epoch) {
+      if ((++spin & 255) == 0 && *((volatile int *)abort_flag)) break;
+    }
+    __threadfence();
   }
   __syncthreads();
-  return ok_s != 0;
 }
 
-// rows order[gw], order[gw + nw], ... (< n_rows) of out = S v + dsq .* v, v = za (+ beta pb);
-// MODE 0: p_new for the row, p.q of the row to every rank.  MODE 1 (residual reset): out only.
-template <int MODE>
-__device__ __forceinline__ void dist_rows(const PcgFan &f, int n_rows, int gw, int nw, int lane,
+// rows order[gw], order[gw + nw], ... (< n_rows) of q = S v + dsq .* v, v = za (+ beta pb): the six
+// components and (WITH_PQ) v.q of the row go to every rank's slots of round e
+template <int WITH_PQ>
+__device__ __forceinline__ void dist_rows(const PcgFan &f, unsigned long long e, int n_cam, int n_rows, int gw, int nw, int lane,
                                           const int32_t *__restrict__ order, const int32_t *__restrict__ ent_ptr,
                                           const int2 *__restrict__ ent, const double *__restrict__ S,
                                           const double *__restrict__ dsq, const double *za, const double *pb, double beta,
-                                          bool use_pb, double *pnew, double *out) {
+                                          bool use_pb) {
   const int2 none = make_int2(0, 0);
+  const size_t qoff = (size_t)(e & 1) * 6 * n_cam, pqoff = (size_t)(e & 1) * n_cam;
   int idx = gw;
   if (idx >= n_rows) return;
   int row = __ldg(order + idx);
@@ -113,21 +124,19 @@ __device__ __forceinline__ void dist_rows(const PcgFan &f, int n_rows, int gw, i
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (b0 + lane < e0) bsr_entry(en0, S, za, pb, beta, use_pb, acc);
     if (b0 + lane + 32 < e0) bsr_entry(en0b, S, za, pb, beta, use_pb, acc);
-    for (int e = b0 + lane + 64; e < e0; e += 32) bsr_entry(__ldg(ent + e), S, za, pb, beta, use_pb, acc);
+    for (int en = b0 + lane + 64; en < e0; en += 32) bsr_entry(__ldg(ent + en), S, za, pb, beta, use_pb, acc);
 #pragma unroll
     for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
     const double pv = use_pb ? zk + beta * pk : zk;
     const double qv = pick6(acc, lane) + dk * pv;
-    if (lane < 6) {
-      if (MODE == 0) pnew[6 * (size_t)row + lane] = pv;
-      out[6 * (size_t)row + lane] = qv;
-    }
-    if (MODE == 0) {
+    if (lane < 6)
+      for (int k = 0; k < f.n_ranks; ++k) ll_store(f.q[k] + qoff + 6 * (size_t)row + lane, qv, e);
+    if (WITH_PQ) {
       const double t = pv * qv;
       double s = __shfl_sync(BA_FULL, t, 0);
 #pragma unroll
       for (int k = 1; k < 6; ++k) s += __shfl_sync(BA_FULL, t, k);
-      if (lane < f.n_ranks) f.row_pq[lane][row] = s;  // lane k writes rank k's copy
+      if (lane < f.n_ranks) ll_store(f.pq[lane] + pqoff + row, s, e);  // lane k serves rank k
     }
     row = row1; row1 = row2;
     b0 = b1; e0 = e1; en0 = en1; en0b = en1b;
@@ -135,15 +144,46 @@ __device__ __forceinline__ void dist_rows(const PcgFan &f, int n_rows, int gw, i
   }
 }
 
-// phase II for the owned warp-block wb (lane = camera); z and the two partials go to every rank,
-// x too when push_x (residual-reset iterations need the complete x for the product S x).
-template <int RESET>
-__device__ __forceinline__ void dist_update(const PcgFan &f, int n_cam, int wb, int lane, double alpha, bool skip_r, bool push_x,
-                                            const double *__restrict__ b, const double *__restrict__ Minv, double *r,
-                                            const double *pnew, const double *q) {
+// sum of p.q over all rows (every CTA gets it): 64-row slices by the CTAs of this GPU, then the slices
+__device__ __forceinline__ double ll_sum_pq(const PcgFan &f, unsigned long long e, int n_cam, double *red) {
+  const int tid = threadIdx.x, n_slices = (n_cam + BA_PQ_SLICE - 1) / BA_PQ_SLICE;
+  const LLSlot *pq = f.pq[f.rank] + (size_t)(e & 1) * n_cam;
+  LLSlot *sl = f.slice + (size_t)(e & 1) * n_slices;
+  // stage 1: four slices per CTA pass (64 threads each), fixed order inside a slice
+  for (int s0 = blockIdx.x * 4; s0 < n_slices; s0 += gridDim.x * 4) {
+    const int s = s0 + (tid >> 6), row = s * BA_PQ_SLICE + (tid & 63);
+    double v = 0.0;
+    if (s < n_slices && row < n_cam) v = ll_wait(pq + row, e, f.abort_flag);
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if ((tid & 63) == 0 && s < n_slices) ll_store(sl + s, red[tid >> 5] + red[(tid >> 5) + 1], e);
+  }
+  // stage 2: every CTA adds all the slice partials
+  double v = 0.0;
+  for (int i = tid; i < n_slices; i += BA_THREADS) v += ll_wait(sl + i, e, f.abort_flag);
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int k = 0; k < BA_WARPS; ++k) s += red[k];
+    red[BA_WARPS] = s;
+  }
+  __syncthreads();
+  return red[BA_WARPS];
+}
+
+// phase II for camera block wb (lane = camera), replicated on every rank; q comes from the slots
+template <int RESET, int CACHED>
+__device__ __forceinline__ void ll_update_warp(const PcgFan &f, unsigned long long e, int n_cam, int wb, int lane, double alpha,
+                                               bool skip_r, const double *__restrict__ b, const double *__restrict__ Minv,
+                                               const double *minv_s, const double breg[6], double *x, double *r, double *z,
+                                               const double *pnew, double *part_rho, double *part_Q) {
   const int c = wb * 32 + lane;
   double rz = 0.0, xq = 0.0;
-  double *x = f.x[f.rank];
   if (c < n_cam) {
     double xv[6], rv[6], qv[6], bv[6], zv[6];
     load6cg(x + 6 * (size_t)c, xv);
@@ -153,13 +193,16 @@ __device__ __forceinline__ void dist_update(const PcgFan &f, int n_cam, int wb, 
 #pragma unroll
       for (int k = 0; k < 6; ++k) xv[k] = xv[k] + alpha * pv[k];
       store6(x + 6 * (size_t)c, xv);
-      if (push_x)
-        for (int k = 0; k < f.n_ranks; ++k)
-          if (k != f.rank) store6(f.x[k] + 6 * (size_t)c, xv);
     }
     if (!skip_r) {
-      load6cg(q + 6 * (size_t)c, qv);
-      load6(b + 6 * (size_t)c, bv);
+      const LLSlot *qs = f.q[f.rank] + (size_t)(e & 1) * 6 * n_cam + 6 * (size_t)c;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) qv[k] = ll_wait(qs + k, e, f.abort_flag);
+      if (CACHED) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bv[k] = breg[k];
+      } else
+        load6(b + 6 * (size_t)c, bv);
       if (RESET) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) rv[k] = bv[k] - qv[k];
@@ -169,8 +212,17 @@ __device__ __forceinline__ void dist_update(const PcgFan &f, int n_cam, int wb, 
         for (int k = 0; k < 6; ++k) rv[k] = rv[k] - alpha * qv[k];
       }
       store6(r + 6 * (size_t)c, rv);
-      minv_mul(Minv, c, rv, zv);
-      for (int k = 0; k < f.n_ranks; ++k) store6(f.z[k] + 6 * (size_t)c, zv);
+      if (CACHED) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sacc += minv_s[(a * 6 + k) * 32 + lane] * rv[k];
+          zv[a] = sacc;
+        }
+      } else
+        minv_mul(Minv, c, rv, zv);
+      store6(z + 6 * (size_t)c, zv);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         rz += rv[k] * zv[k];
@@ -181,9 +233,9 @@ __device__ __forceinline__ void dist_update(const PcgFan &f, int n_cam, int wb, 
   if (!skip_r) {
     rz = warp_sum(rz);
     xq = warp_sum(xq);
-    if (lane < f.n_ranks) {
-      f.wb_rho[lane][wb] = rz;
-      f.wb_Q[lane][wb] = xq;
+    if (lane == 0) {
+      part_rho[wb] = rz;
+      part_Q[wb] = xq;
     }
   }
 }
@@ -191,21 +243,32 @@ __device__ __forceinline__ void dist_update(const PcgFan &f, int n_cam, int wb, 
 __global__ void __launch_bounds__(BA_THREADS, 1)
 k_pcg_sparse_dist(PcgFan f, int n_cam, int n_my_rows, const int32_t *__restrict__ my_rows, const int32_t *__restrict__ ent_ptr,
                   const int2 *__restrict__ ent, const double *__restrict__ S, const double *__restrict__ dsq,
-                  const double *__restrict__ b, const double *__restrict__ Minv, double *r, double *pbuf0, double *pbuf1, double *q,
-                  unsigned int *bar, LmOptions lo, LmState *st, int *comm_fail, unsigned long long *prof) {
+                  const double *__restrict__ b, const double *__restrict__ Minv, double *x, double *r, double *z, double *pbuf0,
+                  double *pbuf1, double *part_rho, double *part_Q, unsigned int *bar, LmOptions lo, LmState *st,
+                  unsigned long long *prof) {
   if (st->done || st->pcg_done) return;  // identical on every CTA and every rank
   __shared__ double red[2 * BA_WARPS + 4];
+  extern __shared__ double minv_all[];  // per warp: M^-1 [36][32] of its first camera block
   const int tid = threadIdx.x, lane = tid & 31;
   const int gtid = blockIdx.x * BA_THREADS + tid, nthreads = gridDim.x * BA_THREADS;
   const int gw = gtid >> 5, nw = nthreads >> 5;
   const int n_wb = (n_cam + 31) / 32;
-  const int N = f.n_ranks, me = f.rank;
-  double *z = f.z[me], *x = f.x[me], *row_pq = f.row_pq[me], *part_rho = f.wb_rho[me], *part_Q = f.wb_Q[me];
+  double *minv_s = minv_all + (size_t)(tid >> 5) * 36 * 32;
+  double breg[6] = {0, 0, 0, 0, 0, 0};
+  if (gw < n_wb) {
+    const int c = gw * 32 + lane;
+    if (c < n_cam) {
+#pragma unroll
+      for (int k = 0; k < 36; ++k) minv_s[k * 32 + lane] = Minv[36 * (size_t)c + k];
+      load6(b + 6 * (size_t)c, breg);
+    }
+  }
+  __syncwarp();
   int it = st->pcg_it;
   double rho = st->pcg_rho, beta = st->pcg_beta, Q0 = st->pcg_Q0;
-  int fail = 0, brk = 0, iters_last = 0, dead = 0;
+  int fail = 0, brk = 0, iters_last = 0;
   unsigned int local_epoch = 0;
-  unsigned long long epoch = *f.epoch;  // same value on every CTA: written back only after the last barrier
+  unsigned long long e = *f.epoch;  // same on every CTA and rank: written back only at the very end
   double *pold = pbuf0, *pnew = pbuf1;
   unsigned long long t0 = 0, tacc[6] = {0, 0, 0, 0, 0, 0};
 #define DPROF_TICK(slot)                                            \
@@ -218,22 +281,22 @@ k_pcg_sparse_dist(PcgFan f, int n_cam, int n_my_rows, const int32_t *__restrict_
   if (prof && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
 
   for (;;) {
-    // ---- phase I: own rows of q = S p + D^2 p (p = z + beta p_old on the fly), p.q per row to every rank;
-    //      p itself is kept complete locally (every rank updates all of it)
-    dist_rows<0>(f, n_my_rows, gw, nw, lane, my_rows, ent_ptr, ent, S, dsq, z, pold, beta, it > 1, pnew, q);
+    // ---- phase I: own rows of q = S p + D^2 p (p = z + beta p_old on the fly) -> slots of round e on every rank;
+    //      p is kept complete locally (every rank updates all of it)
+    ++e;
+    dist_rows<1>(f, e, n_cam, n_my_rows, gw, nw, lane, my_rows, ent_ptr, ent, S, dsq, z, pold, beta, it > 1);
     for (int i = gtid; i < 6 * n_cam; i += nthreads) {
       const double zv = __ldcg(z + i);
       pnew[i] = it > 1 ? zv + beta * __ldcg(pold + i) : zv;
     }
     DPROF_TICK(0)
-    if (!cross_barrier(f, bar, local_epoch, epoch)) {
-      dead = 1;
+    const double pq = ll_sum_pq(f, e, n_cam, red);
+    DPROF_TICK(1)
+    if (*((volatile int *)f.abort_flag)) {
+      fail = 1;
+      iters_last = it;
       break;
     }
-    DPROF_TICK(1)
-
-    // ---- phase II on the owned camera blocks
-    const double pq = block_sum_wide_cg(row_pq, n_cam, red);
     if (pq <= 0.0 || isinf(pq) || isnan(pq)) {
       iters_last = it;
       brk = 1;
@@ -246,30 +309,23 @@ k_pcg_sparse_dist(PcgFan f, int n_cam, int n_my_rows, const int32_t *__restrict_
       break;
     }
     const bool reset = lo.reset_period > 0 && (it % lo.reset_period) == 0;
+    // ---- phase II, replicated: all camera blocks
+    if (gw < n_wb) ll_update_warp<0, 1>(f, e, n_cam, gw, lane, alpha, reset, b, Minv, minv_s, breg, x, r, z, pnew, part_rho, part_Q);
+    for (int wb = gw + nw; wb < n_wb; wb += nw)
+      ll_update_warp<0, 0>(f, e, n_cam, wb, lane, alpha, reset, b, Minv, minv_s, breg, x, r, z, pnew, part_rho, part_Q);
     DPROF_TICK(2)
-    for (int w = gw; me + N * w < n_wb; w += nw)
-      dist_update<0>(f, n_cam, me + N * w, lane, alpha, reset, reset, b, Minv, r, pnew, q);
+    grid_barrier_abortable(bar, local_epoch, f.abort_flag);
     DPROF_TICK(3)
-    if (!cross_barrier(f, bar, local_epoch, epoch)) {
-      dead = 1;
-      break;
+    if (reset) {
+      // ---- residual reset: own rows of q = S x + D^2 x -> slots of the next round; r = b - q, z = M^-1 r everywhere
+      ++e;
+      dist_rows<0>(f, e, n_cam, n_my_rows, gw, nw, lane, my_rows, ent_ptr, ent, S, dsq, x, x, 0.0, false);
+      if (gw < n_wb) ll_update_warp<1, 1>(f, e, n_cam, gw, lane, 0.0, false, b, Minv, minv_s, breg, x, r, z, pnew, part_rho, part_Q);
+      for (int wb = gw + nw; wb < n_wb; wb += nw)
+        ll_update_warp<1, 0>(f, e, n_cam, wb, lane, 0.0, false, b, Minv, minv_s, breg, x, r, z, pnew, part_rho, part_Q);
+      grid_barrier_abortable(bar, local_epoch, f.abort_flag);
     }
     DPROF_TICK(4)
-    if (reset) {
-      dist_rows<1>(f, n_my_rows, gw, nw, lane, my_rows, ent_ptr, ent, S, dsq, x, x, 0.0, false, nullptr, q);
-      // q of the owned rows is consumed by the owner only: a local grid barrier would do, the cross barrier
-      // keeps one code path (reset iterations are 1 in 10)
-      if (!cross_barrier(f, bar, local_epoch, epoch)) {
-        dead = 1;
-        break;
-      }
-      for (int w = gw; me + N * w < n_wb; w += nw)
-        dist_update<1>(f, n_cam, me + N * w, lane, 0.0, false, false, b, Minv, r, pnew, q);
-      if (!cross_barrier(f, bar, local_epoch, epoch)) {
-        dead = 1;
-        break;
-      }
-    }
 
     // ---- controller: every CTA of every rank, same arrays, same order
     double rho_new, xq;
@@ -296,29 +352,16 @@ k_pcg_sparse_dist(PcgFan f, int n_cam, int n_my_rows, const int32_t *__restrict_
   }
   if (prof && blockIdx.x == 0 && tid == 0)
     for (int k = 0; k < 6; ++k) prof[k] += tacc[k];
-  // ---- the solution: every rank needs all of x (back-substitution is per point shard)
-  if (!dead) {
-    for (int w = gw; me + N * w < n_wb; w += nw) {
-      const int c = (me + N * w) * 32 + lane;
-      if (c < n_cam) {
-        double xv[6];
-        load6cg(x + 6 * (size_t)c, xv);
-        for (int k = 0; k < N; ++k)
-          if (k != me) store6(f.x[k] + 6 * (size_t)c, xv);
-      }
-    }
-    if (!cross_barrier(f, bar, local_epoch, epoch)) dead = 1;
-  }
+  // all CTAs of this GPU read *f.epoch at their start, before their first grid barrier; nobody gets here earlier
   if (blockIdx.x == 0 && tid == 0) {
-    *f.epoch = epoch;
+    *f.epoch = e;
     st->pcg_it = it;
     st->pcg_rho = rho;
     st->pcg_beta = beta;
     st->pcg_Q0 = Q0;
     st->pcg_iters_last = iters_last;
     st->pcg_break = brk;
-    if (fail || dead) st->lin_fail = 1;
-    if (dead) *comm_fail = 1;
+    if (fail || *((volatile int *)f.abort_flag)) st->lin_fail = 1;
     st->pcg_done = 1;
   }
 }

@@ -355,7 +355,9 @@ def main():
                    "pcg_iterations_per_lm": pcg_counts, "tolerances": "disabled (fixed iteration count)",
                    "parallelism": ("single GPU" if world == 1 else
                                    ("points sharded x%d: linearisation, point blocks and S formation per shard, NCCL all-reduce of the "
-                                    "block-sparse S (once per LM iteration), PCG replicated" % world) if solver_used == 3 else
+                                    "block-sparse S (once per LM iteration); persistent PCG with the block-CSR product row-sharded, "
+                                    "exchange through flag-in-data slots in NVLink peer memory inside the kernel" % world)
+                                   if solver_used == 3 else
                                    ("points sharded x%d, NCCL all-reduce of camera-sized vectors (one per PCG iteration)" % world)),
                    "l2": ("block-sparse S is L2-resident by design (the product is timed warm, as it runs inside PCG); "
                           if solver_used == 3 else "") +

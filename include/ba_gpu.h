@@ -108,10 +108,10 @@ typedef struct ba_gpu_options {
   int32_t poll_interval;   /* host polls the device-side LM / PCG termination
                               flag every this many iterations (>=1) */
   int32_t persistent_pcg;  /* block-sparse solver: 0 = one launch per PCG step; 1 = the whole PCG solve of an
-                              LM iteration in one persistent cooperative kernel (replicated on every rank when
-                              several GPUs take part: no exchange inside PCG); 2 = persistent and ROW-SHARDED over
-                              the ranks, exchange over NVLink peer memory inside the kernel (experimental: the
-                              two NVLink barriers per PCG iteration cost more than the sharded product saves) */
+                              LM iteration in one persistent cooperative kernel; with several GPUs (peer access,
+                              <= 8 ranks) the block-CSR product is ROW-SHARDED over the ranks and exchanged
+                              through flag-in-data slots in NVLink peer memory inside the kernel;
+                              2 = persistent, replicated on every rank (no exchange inside PCG) */
   int32_t jacobian_store;  /* BA_JAC_AUTO / _PLANES / _FACTORED / _TILED */
   int32_t sparse_max_pairs_per_obs; /* BA_SOLVER_AUTO on a large NS-mode problem (one GPU) picks the
                               block-sparse Schur solver when the number of same-point observation

@@ -14,7 +14,7 @@ def _n_gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("solver,persistent", [(2, 1), (3, 1), (3, 2)], ids=["implicit", "block-sparse", "block-sparse-row-sharded-pcg"])
+@pytest.mark.parametrize("solver,persistent", [(2, 1), (3, 1), (3, 2)], ids=["implicit", "block-sparse-row-sharded-pcg", "block-sparse-replicated-pcg"])
 @pytest.mark.parametrize("cfg", [3, 4])
 @pytest.mark.parametrize("world", [2])
 def test_sharded_solve_matches_single_gpu(world, cfg, solver, persistent):
