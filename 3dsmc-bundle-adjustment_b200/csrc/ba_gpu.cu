@@ -760,8 +760,8 @@ static int setup_dist_pcg(ba_gpu_ctx *ctx) {
   ctx->n_my_rows = n_my;
   {
     int per_sm = 0;
-    CK(cudaFuncSetAttribute(k_pcg_sparse_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_WARPS * 36 * 32 * 8));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_sparse_dist, BA_THREADS, (size_t)BA_WARPS * 36 * 32 * 8));
+    CK(cudaFuncSetAttribute(k_pcg_sparse_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_WARPS * BA_PCG_SMEM_PER_WARP));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_sparse_dist, BA_THREADS, (size_t)BA_WARPS * BA_PCG_SMEM_PER_WARP));
     ctx->dist_grid = per_sm > 0 ? ctx->n_sm : 0;
   }
   ctx->dist_pcg = ctx->dist_grid > 0;
@@ -1381,7 +1381,7 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
     void *args[] = {&fan, &n_cam, &n_my, &my_rows, &ent_ptr, &ent, &Sb, &dsq, &bb, &Minv, &x, &r, &z, &p0, &p1, &prho, &pQ, &bar, &lo, &st,
                     &prof};
     CK(cudaLaunchCooperativeKernel((const void *)k_pcg_sparse_dist, dim3(ctx->dist_grid), dim3(BA_THREADS), args,
-                                   (size_t)BA_WARPS * 36 * 32 * 8, ctx->stream));
+                                   (size_t)BA_WARPS * BA_PCG_SMEM_PER_WARP, ctx->stream));
     ctx->launches++;
     LAUNCH(k_pcg_finish, cdiv(6 * ctx->n_cam, BA_THREADS), BA_THREADS, 0, 6 * ctx->n_cam, P<double>(ctx->x), P<double>(ctx->yc), st,
            GATE_RUN);

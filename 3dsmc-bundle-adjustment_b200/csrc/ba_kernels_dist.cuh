@@ -84,6 +84,50 @@ __device__ __forceinline__ void grid_barrier_abortable(unsigned int *bar, unsign
   __syncthreads();
 }
 
+// q of one row (lanes 0..5 hold a component each after the butterfly) and v.q -> the slots of every rank
+template <int WITH_PQ>
+__device__ __forceinline__ void dist_row_publish(const PcgFan &f, unsigned long long e, size_t qoff, size_t pqoff, int row, int lane,
+                                                 const double acc[6], double pv, double dk) {
+  const double qv = pick6(acc, lane) + dk * pv;
+  if (lane < 6)
+    for (int k = 0; k < f.n_ranks; ++k) ll_store(f.q[k] + qoff + 6 * (size_t)row + lane, qv, e);
+  if (WITH_PQ) {
+    const double t = pv * qv;
+    double s = __shfl_sync(BA_FULL, t, 0);
+#pragma unroll
+    for (int k = 1; k < 6; ++k) s += __shfl_sync(BA_FULL, t, k);
+    if (lane < f.n_ranks) ll_store(f.pq[lane] + pqoff + row, s, e);  // lane k serves rank k
+  }
+}
+
+// the warp's first rows from its shared-memory entry cache (as bsr_rows_cached): one dependent L2 round trip per row
+template <int WITH_PQ>
+__device__ __forceinline__ void dist_rows_cached(const PcgFan &f, unsigned long long e, int n_cam, int lane, int n_cached,
+                                                 const int4 *rowinfo, const int2 *ecache, const double *__restrict__ S,
+                                                 const double *__restrict__ dsq, const double *za, const double *pb, double beta,
+                                                 bool use_pb) {
+  const size_t qoff = (size_t)(e & 1) * 6 * n_cam, pqoff = (size_t)(e & 1) * n_cam;
+  int slot = 0;
+  for (int i = 0; i < n_cached; ++i) {
+    const int4 be = rowinfo[i];  // (first entry, end, row, -)
+    const int row = be.z;
+    double zk = 0.0, pk = 0.0, dk = 0.0;
+    if (lane < 6) {
+      zk = __ldcg(za + 6 * (size_t)row + lane);
+      if (use_pb) pk = __ldcg(pb + 6 * (size_t)row + lane);
+      dk = __ldg(dsq + 6 * (size_t)row + lane);
+    }
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int en = be.x; en < be.y; en += 32, ++slot) {
+      const int2 ent = ecache[slot * 32 + lane];
+      if (en + lane < be.y) bsr_entry(ent, S, za, pb, beta, use_pb, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+    dist_row_publish<WITH_PQ>(f, e, qoff, pqoff, row, lane, acc, use_pb ? zk + beta * pk : zk, dk);
+  }
+}
+
 // rows order[gw], order[gw + nw], ... (< n_rows) of q = S v + dsq .* v, v = za (+ beta pb): the six
 // components and (WITH_PQ) v.q of the row go to every rank's slots of round e
 template <int WITH_PQ>
@@ -127,17 +171,7 @@ __device__ __forceinline__ void dist_rows(const PcgFan &f, unsigned long long e,
     for (int en = b0 + lane + 64; en < e0; en += 32) bsr_entry(__ldg(ent + en), S, za, pb, beta, use_pb, acc);
 #pragma unroll
     for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
-    const double pv = use_pb ? zk + beta * pk : zk;
-    const double qv = pick6(acc, lane) + dk * pv;
-    if (lane < 6)
-      for (int k = 0; k < f.n_ranks; ++k) ll_store(f.q[k] + qoff + 6 * (size_t)row + lane, qv, e);
-    if (WITH_PQ) {
-      const double t = pv * qv;
-      double s = __shfl_sync(BA_FULL, t, 0);
-#pragma unroll
-      for (int k = 1; k < 6; ++k) s += __shfl_sync(BA_FULL, t, k);
-      if (lane < f.n_ranks) ll_store(f.pq[lane] + pqoff + row, s, e);  // lane k serves rank k
-    }
+    dist_row_publish<WITH_PQ>(f, e, qoff, pqoff, row, lane, acc, use_pb ? zk + beta * pk : zk, dk);
     row = row1; row1 = row2;
     b0 = b1; e0 = e1; en0 = en1; en0b = en1b;
     b1 = b2; e1 = e2;
@@ -248,12 +282,28 @@ k_pcg_sparse_dist(PcgFan f, int n_cam, int n_my_rows, const int32_t *__restrict_
                   unsigned long long *prof) {
   if (st->done || st->pcg_done) return;  // identical on every CTA and every rank
   __shared__ double red[2 * BA_WARPS + 4];
-  extern __shared__ double minv_all[];  // per warp: M^-1 [36][32] of its first camera block
+  extern __shared__ double minv_all[];  // per warp: M^-1 [36][32] of its first camera block, entry cache, row records
   const int tid = threadIdx.x, lane = tid & 31;
   const int gtid = blockIdx.x * BA_THREADS + tid, nthreads = gridDim.x * BA_THREADS;
   const int gw = gtid >> 5, nw = nthreads >> 5;
   const int n_wb = (n_cam + 31) / 32;
-  double *minv_s = minv_all + (size_t)(tid >> 5) * 36 * 32;
+  char *wsm = reinterpret_cast<char *>(minv_all) + (size_t)(tid >> 5) * BA_PCG_SMEM_PER_WARP;
+  double *minv_s = reinterpret_cast<double *>(wsm);
+  int2 *ecache = reinterpret_cast<int2 *>(wsm + 36 * 32 * 8);
+  int4 *rowinfo = reinterpret_cast<int4 *>(ecache + BA_PCG_ENT_SLOTS * 32);
+  int n_cached = 0;
+  {
+    int slot = 0;
+    for (int idx = gw; idx < n_my_rows && n_cached < BA_PCG_ROWS; idx += nw) {
+      const int row = my_rows[idx];
+      const int b0 = ent_ptr[row], e0 = ent_ptr[row + 1];
+      const int trips = (e0 - b0 + 31) >> 5;
+      if (slot + trips > BA_PCG_ENT_SLOTS) break;
+      if (lane == 0) rowinfo[n_cached] = make_int4(b0, e0, row, 0);
+      for (int en = b0; en < e0; en += 32, ++slot) ecache[slot * 32 + lane] = en + lane < e0 ? ent[en + lane] : make_int2(0, 0);
+      ++n_cached;
+    }
+  }
   double breg[6] = {0, 0, 0, 0, 0, 0};
   if (gw < n_wb) {
     const int c = gw * 32 + lane;
@@ -284,7 +334,8 @@ k_pcg_sparse_dist(PcgFan f, int n_cam, int n_my_rows, const int32_t *__restrict_
     // ---- phase I: own rows of q = S p + D^2 p (p = z + beta p_old on the fly) -> slots of round e on every rank;
     //      p is kept complete locally (every rank updates all of it)
     ++e;
-    dist_rows<1>(f, e, n_cam, n_my_rows, gw, nw, lane, my_rows, ent_ptr, ent, S, dsq, z, pold, beta, it > 1);
+    dist_rows_cached<1>(f, e, n_cam, lane, n_cached, rowinfo, ecache, S, dsq, z, pold, beta, it > 1);
+    dist_rows<1>(f, e, n_cam, n_my_rows, gw + n_cached * nw, nw, lane, my_rows, ent_ptr, ent, S, dsq, z, pold, beta, it > 1);
     for (int i = gtid; i < 6 * n_cam; i += nthreads) {
       const double zv = __ldcg(z + i);
       pnew[i] = it > 1 ? zv + beta * __ldcg(pold + i) : zv;
@@ -319,7 +370,8 @@ k_pcg_sparse_dist(PcgFan f, int n_cam, int n_my_rows, const int32_t *__restrict_
     if (reset) {
       // ---- residual reset: own rows of q = S x + D^2 x -> slots of the next round; r = b - q, z = M^-1 r everywhere
       ++e;
-      dist_rows<0>(f, e, n_cam, n_my_rows, gw, nw, lane, my_rows, ent_ptr, ent, S, dsq, x, x, 0.0, false);
+      dist_rows_cached<0>(f, e, n_cam, lane, n_cached, rowinfo, ecache, S, dsq, x, x, 0.0, false);
+      dist_rows<0>(f, e, n_cam, n_my_rows, gw + n_cached * nw, nw, lane, my_rows, ent_ptr, ent, S, dsq, x, x, 0.0, false);
       if (gw < n_wb) ll_update_warp<1, 1>(f, e, n_cam, gw, lane, 0.0, false, b, Minv, minv_s, breg, x, r, z, pnew, part_rho, part_Q);
       for (int wb = gw + nw; wb < n_wb; wb += nw)
         ll_update_warp<1, 0>(f, e, n_cam, wb, lane, 0.0, false, b, Minv, minv_s, breg, x, r, z, pnew, part_rho, part_Q);
