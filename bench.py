@@ -65,6 +65,25 @@ def pcg_counts_for(workload, k):
     return (c + [500] * k)[:k]
 
 
+# DRAM traffic per launch from the committed `ncu --set full` captures (dram__bytes_read.sum + dram__bytes_write.sum),
+# cfg5 only; (substring of the roofline kernel name) -> (bytes per launch, source)
+NCU_TRAFFIC_CFG5 = {
+    "block-CSR product": (1.34e6, "profiles/r01_ncu_full_sparse_cfg5.csv: k_pcg_sparse_persistent moved 52.8 MB read + 0.9 MB written "
+                                  "over 40 PCG iterations: S (45 MB) is L2-resident (L2 hit rate 95.8 %)"),
+    "linearize": (567.3e6, "profiles/r01_ncu_full_linearize_cfg5.csv: 240.6 MB read + 326.7 MB written (the 24 B/obs point gathers hit L2)"),
+    "kt_schur_fused": (None, "not captured with --set full after the last change"),
+}
+
+
+def ncu_traffic(workload, kernel_name):
+    if workload != "cfg5":
+        return None, None
+    for key, (b, src) in NCU_TRAFFIC_CFG5.items():
+        if key in kernel_name:
+            return b, src
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -372,7 +391,8 @@ def main():
                 "note": "upload (pinned host -> HBM, index build) + solve + download through ba_gpu_* with host buffers"},
         "gpu_launches": int(summ.kernel_launches),
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                     "frac": kernels[dom]["frac"], "traffic": ncu_traffic(args.workload, dom)[0],
+                     "traffic_source": ncu_traffic(args.workload, dom)[1], "peak_source": peak_src,
                      "timing": "CUDA events on the solver stream, mean of 20 launches after 3 warm-ups",
                      "bytes": kernels[dom]["bytes"]},
         "roofline_kernels": kernels,
