@@ -115,7 +115,8 @@ struct ba_gpu_ctx {
   // explicit block-sparse Schur complement (ba_kernels_sparse.cuh)
   Buf sp_cnt, sp_off, sp_keys, sp_vals, sp_keys2, sp_pairs, sp_ukeys, sp_ucnt, sp_nruns, sb_ptr, sb_i, sb_j, row_ucnt, row_tcnt,
       row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
-  int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0;
+  int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0, sp_ctas_per_sm = 1;
+  Buf sp_pair_pt;
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
   Buf my_rows, row_flag, row_pos, ipc_stage;
@@ -568,6 +569,14 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   while (bits < 64 && ((u64)1 << bits) < (u64)n_cam * (u64)n_cam) ++bits;
   CUBCALL(cub::DeviceRadixSort::SortPairs, P<u64>(ctx->sp_keys), P<u64>(ctx->sp_keys2), P<u64>(ctx->sp_vals), P<u64>(ctx->sp_pairs),
           (int)n_pairs, 0, bits);
+  RES(sp_pair_pt, ((size_t)n_pairs + 1) * 4);
+  LAUNCH(k_sp_pair_points, (int)((n_pairs + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, n_pairs, P<u64>(ctx->sp_pairs),
+         P<int32_t>(ctx->pm_pt), P<int32_t>(ctx->sp_pair_pt));
+  {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sp_schur, BA_THREADS, 0));
+    ctx->sp_ctas_per_sm = std::max(1, per_sm);
+  }
   RES(sp_ukeys, np8);
   RES(sp_ucnt, ((size_t)n_pairs + 2) * 4);
   RES(sp_nruns, 16);
@@ -1298,9 +1307,12 @@ static void enqueue_sparse_values(ba_gpu_ctx *ctx, int gate) {
   if (ctx->solver != BA_SOLVER_SPARSE_SCHUR_PCG) return;
   LmState *st = P<LmState>(ctx->st);
   if (ctx->n_ranks > 1) cudaMemsetAsync(ctx->Sblk.p, 0, (size_t)ctx->n_sblk * 288, ctx->stream);
-  LAUNCH(k_sp_schur, cdiv(ctx->n_sblk_local * 32, BA_THREADS), BA_THREADS, 0, ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr),
-         P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid), P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->pm_pt),
-         ctx->Fp_, P<double>(ctx->geo), P<double>(ctx->intr), P<double>(ctx->Vs), P<double>(ctx->Sblk), st, gate);
+  int *ticket = reinterpret_cast<int *>(P<char>(ctx->pcg_bar) + 16);
+  cudaMemsetAsync(ticket, 0, 4, ctx->stream);
+  LAUNCH(k_sp_schur, std::min(cdiv(ctx->n_sblk_local * 32, BA_THREADS), ctx->n_sm * ctx->sp_ctas_per_sm), BA_THREADS, 0,
+         ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid),
+         P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->sp_pair_pt), ctx->Fp_, P<double>(ctx->geo), P<double>(ctx->intr),
+         P<double>(ctx->Vs), P<double>(ctx->Sblk), ticket, st, gate);
   if (ctx->n_ranks > 1 && nccl_allreduce(ctx, P<double>(ctx->Sblk), (size_t)ctx->n_sblk * 36, false)) ctx->comm_error = true;
   LAUNCH(k_sp_add_diag, cdiv(ctx->n_cam * 36, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->sp_diag), P<double>(ctx->U),
          P<double>(ctx->Sblk), st, gate);

@@ -171,57 +171,74 @@ k_sp_add_diag(int n_cam, const int32_t *__restrict__ diag, const double *__restr
   if (b >= 0) S[36 * (size_t)b + k] += U[36 * (size_t)c + k];
 }
 
+// point of every pair (gathered once per upload: one level less in the dependent-load chain of k_sp_schur)
+__global__ void __launch_bounds__(BA_THREADS)
+k_sp_pair_points(long long n_pairs, const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ pm_pt,
+                 int32_t *__restrict__ pair_pt) {
+  const long long e = (long long)blockIdx.x * BA_THREADS + threadIdx.x;
+  if (e < n_pairs) pair_pt[e] = pm_pt[(int)(pairs[e] >> 32)];
+}
+
+// Persistent warps fetch blocks from a shared ticket counter (integer atomic): block sizes range from a
+// handful of pairs to ~800 (diagonal blocks), a static block -> warp map leaves most warps of a CTA idle
+// behind its largest block.  The order in which blocks are PROCESSED does not touch the result: every
+// block is summed by one warp in its fixed pair order.
 __global__ void __launch_bounds__(BA_THREADS)
 k_sp_schur(int n_blk, int n_cam, const int32_t *__restrict__ blk_ptr, const unsigned long long *__restrict__ lkeys,
-           const int32_t *__restrict__ gid, const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ pm_pt,
+           const int32_t *__restrict__ gid, const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ pair_pt,
            FPlanes F, const double *__restrict__ geo, const double *__restrict__ intr, const double *__restrict__ Vs,
-           double *__restrict__ S, const LmState *st, int gate) {
+           double *__restrict__ S, int *ticket, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  const int b = (blockIdx.x * BA_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (b >= n_blk) return;
-  const unsigned long long key = lkeys[b];
-  const int ci = (int)(key / (unsigned long long)n_cam), cj = (int)(key % (unsigned long long)n_cam);
+  const int lane = threadIdx.x & 31;
   const double fx = ldg1(intr), fy = ldg1(intr + 1);
-  CamRec ri, rj;
-  load_camrec(geo, ci, ri);
-  load_camrec(geo, cj, rj);
-  double acc[36];
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(ticket, 1);
+    b = __shfl_sync(BA_FULL, b, 0);
+    if (b >= n_blk) return;
+    const unsigned long long key = lkeys[b];
+    const int ci = (int)(key / (unsigned long long)n_cam), cj = (int)(key % (unsigned long long)n_cam);
+    CamRec ri, rj;
+    load_camrec(geo, ci, ri);
+    load_camrec(geo, cj, rj);
+    double acc[36];
 #pragma unroll
-  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-  for (int e = blk_ptr[b] + lane; e < blk_ptr[b + 1]; e += 32) {
-    const unsigned long long pr = pairs[e];
-    const int oa = (int)(pr >> 32), ob = (int)(pr & 0xffffffffu);
-    const int p = __ldg(pm_pt + oa);
-    double vs[6];
+    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+    for (int e = blk_ptr[b] + lane; e < blk_ptr[b + 1]; e += 32) {
+      const unsigned long long pr = pairs[e];
+      const int p = __ldg(pair_pt + e);
+      const int oa = (int)(pr >> 32), ob = (int)(pr & 0xffffffffu);
+      double vs[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) vs[k] = ldg1(Vs + 6 * (size_t)p + k);
-    const ObsGeo ga = load_geo(F, oa, fx, fy), gb = load_geo(F, ob, fx, fy);
-    double a0[6], a1[6], pa0[3], pa1[3], b0[6], b1[6], pb0[3], pb1[3];
-    sp_rows(ga, ri.R, a0, a1, pa0, pa1);
-    sp_rows(gb, rj.R, b0, b1, pb0, pb1);
-    double v0[3], v1[3];
-    sym3_mul(vs, pa0, v0);
-    sym3_mul(vs, pa1, v1);
-    const double m00 = v0[0] * pb0[0] + v0[1] * pb0[1] + v0[2] * pb0[2];
-    const double m01 = v0[0] * pb1[0] + v0[1] * pb1[1] + v0[2] * pb1[2];
-    const double m10 = v1[0] * pb0[0] + v1[1] * pb0[1] + v1[2] * pb0[2];
-    const double m11 = v1[0] * pb1[0] + v1[1] * pb1[1] + v1[2] * pb1[2];
+      for (int k = 0; k < 6; ++k) vs[k] = ldg1(Vs + 6 * (size_t)p + k);
+      const ObsGeo ga = load_geo(F, oa, fx, fy), gb = load_geo(F, ob, fx, fy);
+      double a0[6], a1[6], pa0[3], pa1[3], b0[6], b1[6], pb0[3], pb1[3];
+      sp_rows(ga, ri.R, a0, a1, pa0, pa1);
+      sp_rows(gb, rj.R, b0, b1, pb0, pb1);
+      double v0[3], v1[3];
+      sym3_mul(vs, pa0, v0);
+      sym3_mul(vs, pa1, v1);
+      const double m00 = v0[0] * pb0[0] + v0[1] * pb0[1] + v0[2] * pb0[2];
+      const double m01 = v0[0] * pb1[0] + v0[1] * pb1[1] + v0[2] * pb1[2];
+      const double m10 = v1[0] * pb0[0] + v1[1] * pb0[1] + v1[2] * pb0[2];
+      const double m11 = v1[0] * pb1[0] + v1[1] * pb1[1] + v1[2] * pb1[2];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      const double h0 = m00 * b0[c] + m01 * b1[c], h1 = m10 * b0[c] + m11 * b1[c];
+      for (int c = 0; c < 6; ++c) {
+        const double h0 = m00 * b0[c] + m01 * b1[c], h1 = m10 * b0[c] + m11 * b1[c];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) acc[r * 6 + c] += a0[r] * h0 + a1[r] * h1;
+        for (int r = 0; r < 6; ++r) acc[r * 6 + c] += a0[r] * h0 + a1[r] * h1;
+      }
     }
-  }
 #pragma unroll
-  for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
-  // lanes 0..35 -> lane k writes entry k (two rounds)
-  double *Sb = S + 36 * (size_t)gid[b];
+    for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
+    // lanes 0..35 -> lane k writes entry k (two rounds)
+    double *Sb = S + 36 * (size_t)gid[b];
 #pragma unroll
-  for (int k = 0; k < 36; ++k) {
-    if (lane == (k & 31)) {
-      const int r = k / 6, c = k - 6 * (k / 6);
-      Sb[k] = -(acc[k] * (ri.s[r] * rj.s[c]));  // k_sp_add_diag puts U on the diagonal blocks
+    for (int k = 0; k < 36; ++k) {
+      if (lane == (k & 31)) {
+        const int r = k / 6, c = k - 6 * (k / 6);
+        Sb[k] = -(acc[k] * (ri.s[r] * rj.s[c]));  // k_sp_add_diag puts U on the diagonal blocks
+      }
     }
   }
 }
