@@ -1356,6 +1356,7 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
     const double *intr = P<double>(ctx->intr);
     LAUNCH(kf_schur_pass2, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Fc_,
            P<double>(ctx->geo), intr, P<double>(ctx->gc), P<double>(ctx->tgs), 0.0, P<double>(ctx->part6), st, GATE_RUN);
+    if (ctx->solver != BA_SOLVER_SPARSE_SCHUR_PCG)  // the block-sparse solver reads the diagonal blocks of S itself
     LAUNCH(kf_schur_diag, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Fc_,
            P<double>(ctx->geo), intr, P<double>(ctx->Vs), P<double>(ctx->part21), st, GATE_RUN);
   } else
@@ -1368,9 +1369,14 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
   });
   enqueue_sparse_values(ctx, GATE_RUN);
   sync_flags(ctx);
-  ItemRef i21 = reduce_items<21>(ctx, P<double>(ctx->part21), ctx->red21, GATE_RUN);
-  LAUNCH(k_schur_diag_fin, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i21.ptr, i21.part, P<double>(ctx->U), P<double>(ctx->dc),
-         P<double>(ctx->Minv), ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG ? P<double>(ctx->dsq) : (double *)nullptr, st, GATE_RUN);
+  if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG) {
+    LAUNCH(k_sp_minv, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->sp_diag), P<double>(ctx->Sblk), P<double>(ctx->dc),
+           P<double>(ctx->Minv), P<double>(ctx->dsq), st, GATE_RUN);
+  } else {
+    ItemRef i21 = reduce_items<21>(ctx, P<double>(ctx->part21), ctx->red21, GATE_RUN);
+    LAUNCH(k_schur_diag_fin, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i21.ptr, i21.part, P<double>(ctx->U), P<double>(ctx->dc),
+           P<double>(ctx->Minv), (double *)nullptr, st, GATE_RUN);
+  }
   ItemRef i6 = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_RUN);
   LAUNCH(k_pcg_init, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i6.ptr, i6.part, P<double>(ctx->gc), P<double>(ctx->Minv),
          P<double>(ctx->b), P<double>(ctx->x), P<double>(ctx->r), P<double>(ctx->z), P<double>(ctx->pcam_rho),

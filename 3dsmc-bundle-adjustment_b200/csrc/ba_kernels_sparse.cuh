@@ -183,6 +183,43 @@ k_sp_pair_points(long long n_pairs, const unsigned long long *__restrict__ pairs
 // handful of pairs to ~800 (diagonal blocks), a static block -> warp map leaves most warps of a CTA idle
 // behind its largest block.  The order in which blocks are PROCESSED does not touch the result: every
 // block is summed by one warp in its fixed pair order.
+// SCHUR_JACOBI preconditioner straight from the explicit matrix: M_c^-1 = (S_cc + D_c^2)^-1 (the diagonal
+// block already holds U_c - sum W V^-1 W^T), and the damping D^2 the product adds per column.
+__global__ void __launch_bounds__(BA_THREADS)
+k_sp_minv(int n_cam, const int32_t *__restrict__ diag, const double *__restrict__ S, const double *__restrict__ dc,
+          double *__restrict__ Minv, double *__restrict__ dsq, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  const int c = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (c >= n_cam) return;
+  const double radius = st->radius;
+  const int b = diag[c];
+  double B[36], Bi[36];
+  if (b >= 0) {
+    const double *Sb = S + 36 * (size_t)b;
+    // symmetrise from the upper triangle, as the packed partial sums of k_schur_diag_fin do
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int k = a; k < 6; ++k) {
+        const double v = Sb[a * 6 + k];
+        B[a * 6 + k] = v;
+        B[k * 6 + a] = v;
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) B[k] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double D = sqrt(dc[6 * (size_t)c + k] / radius);
+    B[k * 6 + k] += D * D;
+    dsq[6 * (size_t)c + k] = D * D;
+  }
+  if (!spd6_inverse(B, Bi)) st->lin_fail = 1;
+#pragma unroll
+  for (int k = 0; k < 36; ++k) Minv[36 * (size_t)c + k] = Bi[k];
+}
+
 __global__ void __launch_bounds__(BA_THREADS)
 k_sp_schur(int n_blk, int n_cam, const int32_t *__restrict__ blk_ptr, const unsigned long long *__restrict__ lkeys,
            const int32_t *__restrict__ gid, const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ pair_pt,
