@@ -77,24 +77,28 @@ def test_ragged_problem_matches_oracle(solver):
 
 
 def test_single_camera_window():
-    """One keyframe, fixed: nothing to optimise on the camera side; points still move (REF cost)."""
+    """One keyframe, fixed: nothing to optimise on the camera side; the (perturbed) points are pulled
+    back onto their single observation (REF cost, intrinsics free with a prior)."""
     p = syn.make_config(1)
     keep = p.cam_idx == 0
     q = p.copy()
     q.pose7 = p.pose7[:1].copy()
     q.cam_idx, q.pt_idx, q.uv2, q.depth = p.cam_idx[keep].copy(), p.pt_idx[keep].copy(), p.uv2[keep].copy(), p.depth[keep].copy()
-    s = _solver(max_num_iterations=5)
+    seen = np.unique(q.pt_idx)
+    q.pt3 = q.pt3.copy()
+    q.pt3[seen] += np.random.default_rng(0).normal(size=(seen.size, 3)) * 0.01
+    s = _solver(max_num_iterations=8)
     try:
         s.upload(q)
         summ = s.solve()
         pose, pt, intr = s.download()
         assert np.array_equal(pose, q.pose7)
-        assert summ.final_cost <= summ.initial_cost
+        assert summ.initial_cost > 1e-8 and summ.final_cost < 1e-3 * summ.initial_cost
         op = to_oracle(q)
-        rc, osum, _ = ora.solve(op, ora.default_options(max_num_iterations=5))
-        # every point is seen once: the cost goes to rounding-level zero on both sides
-        assert rc == 0 and abs(summ.final_cost - osum.final_cost) <= 1e-8 * osum.initial_cost
-        assert abs(summ.initial_cost - osum.initial_cost) <= 1e-12 * osum.initial_cost
+        rc, osum, _ = ora.solve(op, ora.default_options(max_num_iterations=8))
+        assert rc == 0 and summ.num_iterations == osum.num_iterations
+        assert abs(summ.final_cost - osum.final_cost) <= 1e-8 * summ.initial_cost
+        assert np.max(np.abs(pt - op.pt3)) < 1e-6 and np.max(np.abs(intr - op.intr)) < 1e-5
     finally:
         s.close()
 
