@@ -12,6 +12,7 @@
 #include "ba_kernels_tile.cuh"
 #include "ba_kernels_sparse.cuh"
 #include "ba_kernels_dist.cuh"
+#include "ba_kernels_chol.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -116,7 +117,7 @@ struct ba_gpu_ctx {
   Buf sp_cnt, sp_off, sp_keys, sp_vals, sp_keys2, sp_pairs, sp_ukeys, sp_ucnt, sp_nruns, sb_ptr, sb_i, sb_j, row_ucnt, row_tcnt,
       row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
   int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0, sp_ctas_per_sm = 1;
-  Buf sp_pair_pt;
+  Buf sp_pair_pt, chol_v;
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
   Buf my_rows, row_flag, row_pos, ipc_stage;
@@ -202,6 +203,8 @@ static T *P(const Buf &b) {
   return reinterpret_cast<T *>(b.p);
 }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// dense explicit Schur complement: n^2 doubles (2 GiB at the limit), blocked Cholesky above 1024
+#define BA_EXPLICIT_MAX_DIM 16384
 static size_t tile_smem_bytes(int npt) {
   return ((size_t)6 * (npt * BA_THREADS + 8) + 3 * BA_TILE_PTS + BA_TILE_MAXSPAN * BA_TILE_QREC + BA_TILE_MAXSPAN * 6) * 8;
 }
@@ -327,6 +330,8 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMallocHost((void **)&ctx->h_st, sizeof(LmState))) != cudaSuccess) return bail("cudaMallocHost", e);
   cudaFuncSetAttribute(k_cholesky_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
+  cudaFuncSetAttribute(k_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
   cudaFuncSetAttribute(kt_schur_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2));
   cudaFuncSetAttribute(kt_schur_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(3));
   cudaFuncSetAttribute(kt_schur_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(4));
@@ -806,8 +811,9 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     return fail(ctx, BA_ERR_UNSUPPORTED, "optimize_intrinsics needs the explicit solver (as ITERATIVE_SCHUR needs points only)");
   if (solver == BA_SOLVER_SPARSE_SCHUR_PCG && o.use_depth_prior)
     return fail(ctx, BA_ERR_UNSUPPORTED, "the block-sparse Schur solver needs NS mode (no depth prior, fixed intrinsics)");
-  if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_red > 1024)
-    return fail(ctx, BA_ERR_UNSUPPORTED, "explicit Cholesky supports reduced dimension <= 1024 (got %d)", ctx->n_red);
+  if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_red > BA_EXPLICIT_MAX_DIM)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "dense explicit Cholesky supports reduced dimension <= %d (got %d)", BA_EXPLICIT_MAX_DIM,
+                ctx->n_red);
   if (solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks > 1)
     return fail(ctx, BA_ERR_UNSUPPORTED, "the explicit solver is single-GPU (windowed problems stay on one GPU)");
   ctx->solver = solver;
@@ -1091,6 +1097,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     RES(WV, (no + 1) * 144);
     RES(S, (size_t)ctx->n_red * ctx->n_red * 8 + 64);
     RES(rhs, (size_t)ctx->n_red * 8 + 64);
+    RES(chol_v, (size_t)ctx->n_red * 8 + 64);
     int rc = build_pair_list(ctx, cam_idx, pt_idx);
     if (rc) return rc;
   }
@@ -1479,8 +1486,20 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
     const size_t smem = ((size_t)n * n + n + 8) * 8;
     LAUNCH((k_cholesky_solve<1>), 1, 256, smem, n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
            P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
-  } else {
+  } else if (n <= 1024) {
     LAUNCH((k_cholesky_solve<0>), 1, 1024, 0, n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
+           P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
+  } else {
+    // blocked right-looking Cholesky (ba_kernels_chol.cuh): the reference's global BA with free intrinsics
+    const int nt = cdiv(n, CH_NB);
+    double *S = P<double>(ctx->S);
+    for (int k = 0; k < nt; ++k) {
+      LAUNCH(k_chol_potrf, 1, CH_NB, 0, n, S, k, st, GATE_RUN);
+      const int below = nt - k - 1;
+      LAUNCH(k_chol_trsm, below, CH_NB, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
+      LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
+    }
+    LAUNCH(k_chol_solve, 1, 1024, 0, n, S, P<double>(ctx->rhs), P<double>(ctx->chol_v), ctx->n_cam, ctx->n_free,
            P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
   }
   return 0;

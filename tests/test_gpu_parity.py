@@ -211,6 +211,17 @@ def test_solve_explicit_window20_ref(solver_cache):
     assert summ.reduced_dim == 6 * 19 + 4 and summ.solver_used == ba_b200.capi.BA_SOLVER_EXPLICIT_CHOLESKY
 
 
+def test_solve_explicit_blocked_cholesky_ref(solver_cache):
+    """The reference's global optimisation (windowOptimize over ALL keyframes, REF cost with free intrinsics,
+    src/main.cpp:179-182) beyond the single-CTA Cholesky: reduced dimension 6 * 199 + 4 = 1198 -> the blocked
+    dense Cholesky (ba_kernels_chol.cuh).  Exact step: lock step with the oracle's dense Schur."""
+    seq = syn.make_tum_sequence(200, 6000, 36000, seed=21)
+    p = syn.window_problem(seq, 0, 199).problem
+    summ, _ = _compare_solve(p, "REF", 0, 6, solver_cache, trace_tol=1e-7, cost_tol=1e-7)
+    assert summ.solver_used == ba_b200.capi.BA_SOLVER_EXPLICIT_CHOLESKY and summ.reduced_dim == 1198
+    assert summ.final_cost < 0.5 * summ.initial_cost
+
+
 def test_solve_to_convergence_ref(solver_cache):
     """Reference settings (75 iterations, tolerances on): same termination."""
     _compare_solve(_problem("cfg1"), "REF", 1, 75, solver_cache)
