@@ -1097,7 +1097,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     RES(WV, (no + 1) * 144);
     RES(S, (size_t)ctx->n_red * ctx->n_red * 8 + 64);
     RES(rhs, (size_t)ctx->n_red * 8 + 64);
-    RES(chol_v, (size_t)ctx->n_red * 8 + 64);
+    RES(chol_v, (size_t)(ctx->n_red + 64 + 8) * 8);
     int rc = build_pair_list(ctx, cam_idx, pt_idx);
     if (rc) return rc;
   }
@@ -1499,8 +1499,17 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
       LAUNCH(k_chol_trsm, below, CH_NB, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
       LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
     }
-    LAUNCH(k_chol_solve, 1, 1024, 0, n, S, P<double>(ctx->rhs), P<double>(ctx->chol_v), ctx->n_cam, ctx->n_free,
-           P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
+    {
+      CK(cudaMemsetAsync(P<char>(ctx->chol_v) + (size_t)(n + 64) * 8, 0, 16, ctx->stream));
+      int nn = n, n_cam = ctx->n_cam, n_free = ctx->n_free, nk = ctx->nk, gate = GATE_RUN;
+      const double *Sc = S, *rhs = P<double>(ctx->rhs);
+      double *v = P<double>(ctx->chol_v), *ztg = v + n, *yc = P<double>(ctx->yc), *yk = P<double>(ctx->yk);
+      unsigned int *bar = reinterpret_cast<unsigned int *>(v + n + 64);
+      const int32_t *cam_slot = P<int32_t>(ctx->cam_slot);
+      void *args[] = {&nn, &Sc, &rhs, &v, &ztg, &bar, &n_cam, &n_free, &cam_slot, &nk, &yc, &yk, &st, &gate};
+      CK(cudaLaunchCooperativeKernel((const void *)k_chol_solve, dim3(ctx->n_sm), dim3(256), args, 0, ctx->stream));
+      ctx->launches++;
+    }
   }
   return 0;
 }

@@ -31,6 +31,8 @@ WORKLOADS = {
     "cfg1": dict(cfg=1, mode=(1, 1), desc="7-keyframe TUM-shaped window, 500 landmarks, 3000 obs, REF cost, explicit Schur + Cholesky"),
     "cfg2": dict(cfg=2, mode=(1, 1), desc="sliding 20-keyframe windows over 800 keyframes, REF cost, explicit Schur + Cholesky"),
     "cfg3": dict(cfg=3, mode=(0, 0), desc="global BA 800 keyframes, 60k landmarks, 400k obs, NS cost, implicit-Schur PCG"),
+    "cfg3ref": dict(cfg=3, mode=(1, 1), desc="the reference's global optimisation: 800 keyframes, 60k landmarks, 400k obs, REF cost (depth prior + "
+                                             "free intrinsics), dense explicit Schur + blocked Cholesky (exact LM step)"),
     "cfg4": dict(cfg=4, mode=(0, 0), desc="BAL-shaped loop 1723 cameras, 156k points, 680k obs, NS cost, implicit-Schur PCG"),
     "cfg5": dict(cfg=5, mode=(0, 0), desc="large synthetic 10k cameras, 2M points, 8M obs, NS cost, implicit-Schur PCG"),
 }
@@ -240,6 +242,8 @@ def main():
         # the reference's CPU implementation of the path = the oracle port (Ceres itself cannot be built here)
         if rank != 0:
             return 0
+        if args.workload == "cfg3ref":
+            raise SystemExit("cfg3ref has no bounded CPU sample (a dense 4798^2 Schur solve per iteration); use cfg3")
         problem = syn.make_config(wl["cfg"], scale=args.scale)
         if wl["cfg"] == 2:
             problem = syn.window_problem(problem, 0, 19).problem
@@ -265,9 +269,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t_gen = time.time()
-    full = syn.make_config(wl["cfg"], scale=args.scale)
-    if wl["cfg"] == 2:
-        full = syn.window_problem(full, 0, 19).problem
+    if args.workload == "cfg3ref":
+        c3 = syn.CONFIGS[3]
+        n_kf = max(4, int(round(c3["n_kf"] * args.scale)))
+        seq = syn.make_tum_sequence(n_kf, max(8, int(round(c3["n_lm"] * args.scale))), max(24, int(round(c3["n_obs"] * args.scale))),
+                                    syn.SEED_BASE + 3)
+        full = syn.window_problem(seq, 0, n_kf - 1).problem
+    else:
+        full = syn.make_config(wl["cfg"], scale=args.scale)
+        if wl["cfg"] == 2:
+            full = syn.window_problem(full, 0, 19).problem
     t_gen = time.time() - t_gen
     if world > 1 and wl["mode"] != (0, 0):
         raise SystemExit("windowed (explicit) workloads are single-GPU; use --workload cfg4/cfg5 with --gpus > 1")
