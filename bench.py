@@ -411,7 +411,9 @@ def main():
     }
     if implicit_path is not None:
         line["implicit_path"] = implicit_path
-    if not args.no_cpu_baseline and world == 1:
+    if args.workload == "cfg3ref":
+        line["cpu_baseline"] = None  # a dense 4798^2 Schur solve per LM iteration: no bounded CPU sample
+    elif not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_sample(full, wl["mode"], pcg_counts, os.cpu_count() or 1)
     print(json.dumps(line))
     if dist is not None:
