@@ -1486,9 +1486,6 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
     const size_t smem = ((size_t)n * n + n + 8) * 8;
     LAUNCH((k_cholesky_solve<1>), 1, 256, smem, n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
            P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
-  } else if (n <= 1024) {
-    LAUNCH((k_cholesky_solve<0>), 1, 1024, 0, n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
-           P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
   } else {
     // blocked right-looking Cholesky (ba_kernels_chol.cuh): the reference's global BA with free intrinsics
     const int nt = cdiv(n, CH_NB);

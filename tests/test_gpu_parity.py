@@ -211,14 +211,16 @@ def test_solve_explicit_window20_ref(solver_cache):
     assert summ.reduced_dim == 6 * 19 + 4 and summ.solver_used == ba_b200.capi.BA_SOLVER_EXPLICIT_CHOLESKY
 
 
-def test_solve_explicit_blocked_cholesky_ref(solver_cache):
+@pytest.mark.parametrize("n_kf", [60, 200])
+def test_solve_explicit_blocked_cholesky_ref(n_kf, solver_cache):
     """The reference's global optimisation (windowOptimize over ALL keyframes, REF cost with free intrinsics,
-    src/main.cpp:179-182) beyond the single-CTA Cholesky: reduced dimension 6 * 199 + 4 = 1198 -> the blocked
-    dense Cholesky (ba_kernels_chol.cuh).  Exact step: lock step with the oracle's dense Schur."""
-    seq = syn.make_tum_sequence(200, 6000, 36000, seed=21)
-    p = syn.window_problem(seq, 0, 199).problem
+    src/main.cpp:179-182) beyond the shared-memory Cholesky (n > 160): reduced dimension 6 (n_kf - 1) + 4 = 358 /
+    1198 (ragged last tile) -> the blocked dense Cholesky (ba_kernels_chol.cuh).  Exact step: lock step with
+    the oracle's dense Schur."""
+    seq = syn.make_tum_sequence(n_kf, 30 * n_kf, 180 * n_kf, seed=21)
+    p = syn.window_problem(seq, 0, n_kf - 1).problem
     summ, _ = _compare_solve(p, "REF", 0, 6, solver_cache, trace_tol=1e-7, cost_tol=1e-7)
-    assert summ.solver_used == ba_b200.capi.BA_SOLVER_EXPLICIT_CHOLESKY and summ.reduced_dim == 1198
+    assert summ.solver_used == ba_b200.capi.BA_SOLVER_EXPLICIT_CHOLESKY and summ.reduced_dim == 6 * (n_kf - 1) + 4
     assert summ.final_cost < 0.5 * summ.initial_cost
 
 
