@@ -40,10 +40,12 @@ def test_host_library_exports_and_count():
 
 
 @pytest.mark.gpu
-def test_window_optimize_cpp_dropin():
+@pytest.mark.parametrize("n_kf,kf_i,kf_f,iters", [(30, 8, 27, 10), (60, 0, 59, 6)], ids=["window", "global-blocked-cholesky"])
+def test_window_optimize_cpp_dropin(n_kf, kf_i, kf_f, iters):
+    """windowOptimize through the compiled C++ drop-in: a sliding window, and the reference's global optimisation
+    over all keyframes (src/main.cpp:179-182; reduced dimension 358 -> blocked Cholesky)."""
     L = _lib()
-    n_kf, kf_i, kf_f, iters = 30, 8, 27, 10
-    seq = syn.make_tum_sequence(n_kf, 3000, 18000, seed=13)
+    seq = syn.make_tum_sequence(n_kf, 100 * n_kf, 600 * n_kf, seed=13)
     seq.depth[5::97] = 0.0  # a few inadmissible observations
     pose = seq.pose.copy()
     lm_pt = seq.pt.copy()
@@ -82,7 +84,7 @@ def test_window_optimize_cpp_dropin():
     rc, osum, _ = ora.solve(op, ora.default_options(max_num_iterations=iters))
     assert rc == 0
     assert abs(costs[0] - osum.initial_cost) <= 1e-12 * osum.initial_cost
-    assert abs(costs[1] - osum.final_cost) <= 1e-8 * osum.final_cost
+    assert abs(costs[1] - osum.final_cost) <= (1e-8 if n_kf <= 30 else 1e-7) * osum.final_cost
     want_pose = se3.mul(np.broadcast_to(T0, op.pose7.shape), op.pose7)
     dt, dr = pose_err(pose[kf_i:kf_f + 1], want_pose)
     assert dt < 1e-6 and dr < 1e-6
