@@ -369,6 +369,18 @@ def main():
                          "gpu_launches": int(sm2.kernel_launches), "dominant_kernel": d2, "roofline_kernels": k2}
         s2.close()
 
+    # the MATERIALISED Jacobian evaluation (r + Jc 2x6 + Jp 2x3 written per observation: SURVEY 8d's "Jacobian-eval"
+    # kernel) and the planes-store Schur passes beside the factored / tiled / block-sparse kernels
+    planes_kernels = None
+    if wl["mode"] == (0, 0) and world == 1:
+        s3 = ba_b200.GpuSolver(max_num_iterations=1, **dict(opts, solver=2, jacobian_store=1))
+        s3.upload(hp)
+        planes_kernels, _, _, ms_lin_planes = kernel_rooflines(ba_b200, s3, problem, wl, 2, flush, peak)
+        s3.close()
+        jac_obs_s_factored, jac_obs_s = jac_obs_s, full.n_obs / (ms_lin_planes * 1e-3)
+    else:
+        jac_obs_s_factored = None
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -395,6 +407,9 @@ def main():
                           else "L2 flushed (512 MiB write) between timed kernel launches"),
                    "generate_s": round(t_gen, 2)},
         "jacobian_eval_obs_per_s": jac_obs_s,
+        "jacobian_eval_note": ("materialised r + Jc (2x6) + Jp (2x3), 208 B/obs (k_linearize, planes store)" if planes_kernels is not None
+                               else "kernel of the store in force (see roofline_kernels)"),
+        "jacobian_eval_factored_obs_per_s": jac_obs_s_factored,
         "final_cost": summ.final_cost, "initial_cost": summ.initial_cost,
         "solve_wall_ms": wall_solve * 1e3,
         "e2e": {"value": summ2.num_iterations / e2e_s, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d // max(K, 1),
@@ -411,6 +426,8 @@ def main():
     }
     if implicit_path is not None:
         line["implicit_path"] = implicit_path
+    if planes_kernels is not None:
+        line["planes_store_kernels"] = planes_kernels
     if args.workload == "cfg3ref":
         line["cpu_baseline"] = None  # a dense 4798^2 Schur solve per LM iteration: no bounded CPU sample
     elif not args.no_cpu_baseline and world == 1:
