@@ -70,10 +70,16 @@ def pcg_counts_for(workload, k):
 # DRAM traffic per launch from the committed `ncu --set full` captures (dram__bytes_read.sum + dram__bytes_write.sum),
 # cfg5 only; (substring of the roofline kernel name) -> (bytes per launch, source)
 NCU_TRAFFIC_CFG5 = {
-    "block-CSR product": (1.34e6, "profiles/r01_ncu_full_sparse_cfg5.csv: k_pcg_sparse_persistent moved 52.8 MB read + 0.9 MB written "
-                                  "over 40 PCG iterations: S (45 MB) is L2-resident (L2 hit rate 95.8 %)"),
-    "linearize": (567.3e6, "profiles/r01_ncu_full_linearize_cfg5.csv: 240.6 MB read + 326.7 MB written (the 24 B/obs point gathers hit L2)"),
-    "kt_schur_fused": (None, "not captured with --set full after the last change"),
+    "block-CSR product": (1.36e6, "profiles/r01_ncu_full_kernels_cfg5.csv: k_pcg_sparse_persistent moved 52.8 MB read + 1.4 MB written "
+                                  "over 40 PCG iterations: S (45 MB) is L2-resident (L2 hit rate 96.0 %)"),
+    "linearize (factored": (567.3e6, "profiles/r01_ncu_full_linearize_cfg5.csv: 240.6 MB read + 326.7 MB written (the 24 B/obs point "
+                                     "gathers hit L2)"),
+    "linearize (tiled": (567.3e6, "profiles/r01_ncu_full_linearize_cfg5.csv (same kernel as the factored store)"),
+    "kt_schur_fused": (408.3e6, "profiles/r01_ncu_full_kernels_cfg5.csv: 398.7 MB read + 9.6 MB written (algorithmic 392 MB)"),
+    "schur_pass1 (two-pass, factored": (492.4e6, "profiles/r01_ncu_full_kernels_cfg5.csv: 444.1 MB read + 48.3 MB written"),
+    "schur_pass2 (two-pass, factored": (366.6e6, "profiles/r01_ncu_full_kernels_cfg5.csv: 361.8 MB read + 4.8 MB written (the t_p gather hits L2)"),
+    "schur_pass1 (two-pass, planes": (1347e6, "profiles/r01_ncu_full_schur_cfg5.csv"),
+    "schur_pass2 (two-pass, planes": (1313e6, "profiles/r01_ncu_full_schur_cfg5.csv"),
 }
 
 
@@ -203,6 +209,9 @@ def kernel_rooflines(ba_b200, s, problem, wl, solver_used, flush, peak):
         if store != "tiled":
             dom = max((k for k in roof if k.startswith("schur_pass")), key=lambda k: roof[k][1])
     kernels = {k: {"bytes": b, "ms": ms, "achieved_gbs": b / ms / 1e6, "frac": b / ms / 1e6 / peak} for k, (b, ms) in roof.items()}
+    if n_o == 8000000:  # the ncu captures are of cfg5 on one GPU
+        for k in kernels:
+            kernels[k]["ncu_dram_bytes"] = ncu_traffic("cfg5", k)[0]
     return kernels, dom, store, ms_lin
 
 
