@@ -257,7 +257,7 @@ kt_schur_fused(int n_pt, const int32_t *__restrict__ pt_rowptr, const TileMeta *
       o[j].wfx = w.y * fx;
       o[j].wfy = w.y * fy;
     } else {
-      a[j] = 0;
+      a[j] = (uint32_t)CAP;  // rank CAP = the padding of the staging columns: a harmless dummy slot
       o[j].xz = o[j].yz = o[j].iz = o[j].wfx = o[j].wfy = 0.0;
     }
   }
@@ -286,11 +286,13 @@ kt_schur_fused(int n_pt, const int32_t *__restrict__ pt_rowptr, const TileMeta *
   __syncthreads();
 
   // ---- phase 1: v = Jpu^T (Jcu (s.*x)) into the point-major slot
+  // Whole warps beyond the tile's observations skip a round (warp-uniform branch); inside a partially filled
+  // warp the idle lanes compute on zero weights into the dummy slot -- no per-lane divergence.
   double a0[NPT], a1[NPT];
 #pragma unroll
   for (int j = 0; j < NPT; ++j) {
     a0[j] = a1[j] = 0.0;
-    if (tid + j * BA_THREADS < m.n) {
+    if ((tid & ~31) + j * BA_THREADS < m.n) {
       const int slot = a[j] >> 24, rank = a[j] & 0xffff;
       const double2 *cx = reinterpret_cast<const double2 *>(rec + slot * BA_TILE_QREC);
       const double2 c0 = cx[0], c1 = cx[1], c2 = cx[2], c3 = cx[3], c4 = cx[4];
@@ -328,7 +330,7 @@ kt_schur_fused(int n_pt, const int32_t *__restrict__ pt_rowptr, const TileMeta *
 #pragma unroll
   for (int j = 0; j < NPT; ++j) {
     const int l = tid + j * BA_THREADS;
-    if (l < m.n) {
+    if ((tid & ~31) + j * BA_THREADS < m.n) {
       const int slot = a[j] >> 24, lp = (a[j] >> 16) & 0xff;
       const double2 *cx = reinterpret_cast<const double2 *>(rec + slot * BA_TILE_QREC);
       const double2 c3 = cx[3], c4 = cx[4];
@@ -338,10 +340,14 @@ kt_schur_fused(int n_pt, const int32_t *__restrict__ pt_rowptr, const TileMeta *
       quat_rot_t(q, tt, u);
       const double b0 = (o[j].wfx * o[j].iz) * (u[0] - o[j].xz * u[2]);
       const double b1 = (o[j].wfy * o[j].iz) * (u[1] - o[j].yz * u[2]);
-      double c[6] = {0, 0, 0, 0, 0, 0};
-      jc_tacc(o[j], a0[j] - b0, a1[j] - b1, c);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) buf[k * CS + l] = c[k];
+      // c = Jcu^T (e0, e1), written out (no accumulator to clear)
+      const double e0 = o[j].wfx * (a0[j] - b0), e1 = o[j].wfy * (a1[j] - b1);
+      buf[l] = -(o[j].iz * e0);
+      buf[CS + l] = -(o[j].iz * e1);
+      buf[2 * CS + l] = o[j].iz * (o[j].xz * e0 + o[j].yz * e1);
+      buf[3 * CS + l] = (o[j].xz * o[j].yz) * e0 + (1.0 + o[j].yz * o[j].yz) * e1;
+      buf[4 * CS + l] = -((1.0 + o[j].xz * o[j].xz) * e0 + (o[j].xz * o[j].yz) * e1);
+      buf[5 * CS + l] = o[j].yz * e0 - o[j].xz * e1;
     }
   }
   __syncthreads();

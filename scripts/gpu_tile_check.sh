@@ -1,4 +1,4 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "matvec or implicit or tiled" > gpurun_out/gputests.log 2>&1; echo rc=$? >> gpurun_out/gputests.log
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py -m gpu -x -q -k "matvec or implicit or tiled or full_size" > gpurun_out/gputests.log 2>&1; echo rc=$? >> gpurun_out/gputests.log
 python - > gpurun_out/tile_time.log 2>&1 <<'PY'
 import sys, time
 sys.path.insert(0,'.')
