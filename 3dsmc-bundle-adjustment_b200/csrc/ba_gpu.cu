@@ -81,6 +81,11 @@ struct ba_gpu_ctx {
   ba_gpu_options opt;
   int device = 0, n_sm = 148;
   cudaStream_t stream = nullptr;
+  // second stream for the independent branches of an LM iteration (fork / join by events): the windowed
+  // problems are chains of ~25 latency-bound small kernels, several of which do not depend on each other
+  cudaStream_t stream2 = nullptr, cur = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool forking = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int64_t launches = 0;
@@ -212,7 +217,7 @@ static size_t tile_smem_bytes(int npt) {
 #define LAUNCH(kern, grid, block, smem, ...)                              \
   do {                                                                    \
     if ((grid) > 0) {                                                     \
-      kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);        \
+      kern<<<(grid), (block), (smem), ctx->cur>>>(__VA_ARGS__);           \
       ctx->launches++;                                                    \
     }                                                                     \
   } while (0)
@@ -326,6 +331,10 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
     return BA_ERR_CUDA;
   }
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  ctx->cur = ctx->stream;
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMallocHost((void **)&ctx->h_st, sizeof(LmState))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -352,6 +361,10 @@ extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
   for (Buf *b : ctx->bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_st) cudaFreeHost(ctx->h_st);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1102,6 +1115,8 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     if (rc) return rc;
   }
   CK(cudaGetLastError());
+  ctx->forking = ctx->n_ranks == 1 && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && getenv("BA_NO_FORK") == nullptr;
+  ctx->cur = ctx->stream;
   ctx->uploaded = true;
   return BA_OK;
 }
@@ -1153,6 +1168,24 @@ static void sync_flags(ba_gpu_ctx *ctx) {
   ctx->launches += 2;
 }
 
+// ------------------------------------------------------------------ fork / join of independent branches
+// fork_side(): what follows runs on the side stream, after everything enqueued so far on the main one;
+// fork_main(): back on the main stream (concurrently with the side branch); join(): the main stream waits
+// for the side branch.  No-ops unless ctx->forking (single GPU, windowed explicit solver).
+static void fork_side(ba_gpu_ctx *ctx) {
+  if (!ctx->forking) return;
+  cudaEventRecord(ctx->ev_fork, ctx->stream);
+  cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
+  ctx->cur = ctx->stream2;
+}
+static void fork_main(ba_gpu_ctx *ctx) { ctx->cur = ctx->stream; }
+static void join(ba_gpu_ctx *ctx) {
+  ctx->cur = ctx->stream;
+  if (!ctx->forking) return;
+  cudaEventRecord(ctx->ev_join, ctx->stream2);
+  cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+}
+
 // ------------------------------------------------------------------ pipeline pieces
 // linearise at the current point in both orders + normal-equation blocks
 static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk,
@@ -1182,25 +1215,30 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
     return;
   }
   DISPATCH_DK(D, K, {
-    LAUNCH((k_linearize<DD, KK, 1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
-           P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc, sp,
-           sk, ctx->cp, ctx->Jc_, P<double>(ctx->pc_lin), st, gate);
+    // point-major branch (side stream): linearise + point blocks
+    fork_side(ctx);
     LAUNCH((k_linearize<DD, KK, 0>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt),
            P<double2>(ctx->pm_uv), P<double>(ctx->pm_depth), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc,
            sp, sk, ctx->cp, ctx->Jp_, (double *)nullptr, st, gate);
+    LAUNCH((k_pt_blocks<DD, KK>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), ctx->Jp_, P<double>(ctx->V),
+           P<double>(ctx->gp), P<double>(ctx->Wk), P<double>(ctx->dp), ctx->lo, st, gate);
+    // camera-major branch (main stream): linearise + camera blocks
+    fork_main(ctx);
+    LAUNCH((k_linearize<DD, KK, 1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+           P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc, sp,
+           sk, ctx->cp, ctx->Jc_, P<double>(ctx->pc_lin), st, gate);
     LAUNCH((k_cam_blocks<DD, KK>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), ctx->Jc_,
            P<double>(ctx->part_blk), st, gate);
     ItemRef ir = ItemRef{P<int32_t>(ctx->item_ptr), P<double>(ctx->part_blk)};
     if (KK == 0) ir = reduce_items<27>(ctx, P<double>(ctx->part_blk), ctx->red_blk, gate);
     LAUNCH((k_cam_blocks_fin<KK>), ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part,
            P<double>(ctx->U), P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
-    LAUNCH((k_pt_blocks<DD, KK>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), ctx->Jp_, P<double>(ctx->V),
-           P<double>(ctx->gp), P<double>(ctx->Wk), P<double>(ctx->dp), ctx->lo, st, gate);
   });
   if (K)
     LAUNCH(k_kk_fin, 1, BA_THREADS, 0, ctx->n_items, P<double>(ctx->part_blk), P<double>(ctx->intr), P<double>(ctx->intr_prior),
            sk, ctx->cp, ctx->lo, P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->rk),
            P<double>(ctx->Jkk), st, gate);
+  join(ctx);
 }
 static void enqueue_state_norms(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk) {
   LAUNCH(k_state_norms, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, ctx->nk, ctx->fixed_cam, P<double>(ctx->pose),
@@ -1462,6 +1500,8 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
     LAUNCH((k_obs_W<DD>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pt_idx), ctx->Jc_, P<double>(ctx->Vinv),
            P<double>(ctx->W), P<double>(ctx->WV), st, GATE_RUN);
   });
+  // borders + right-hand side on the side stream, the camera-camera blocks on the main one (disjoint parts of S)
+  fork_side(ctx);
   if (ctx->nk) {
     LAUNCH((k_explicit_cam<4>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
            P<double>(ctx->W), P<double>(ctx->WV), P<double>(ctx->tg), P<double>(ctx->Wk), P<double>(ctx->part_ex), st, GATE_RUN);
@@ -1479,9 +1519,11 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
            P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->S),
            P<double>(ctx->rhs), st, GATE_RUN);
   }
+  fork_main(ctx);
   LAUNCH(k_schur_pairs, ctx->n_blk, BA_THREADS, 0, n, P<int32_t>(ctx->blk_i), P<int32_t>(ctx->blk_j), P<int32_t>(ctx->blk_cam),
          P<int32_t>(ctx->pair_ptr), P<int32_t>(ctx->pair_a), P<int32_t>(ctx->pair_b), P<double>(ctx->W), P<double>(ctx->WV),
          P<double>(ctx->U), P<double>(ctx->dc), P<double>(ctx->S), st, GATE_RUN);
+  join(ctx);
   if (n <= 160) {
     const size_t smem = ((size_t)n * n + n + 8) * 8;
     LAUNCH((k_cholesky_solve<1>), 1, 256, smem, n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
@@ -1534,8 +1576,10 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
     LAUNCH((k_schur_pass1<DD, KK, 1>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
            ctx->Jp_, P<double>(ctx->yc), P<double>(ctx->yk), P<double>(ctx->Vinv), P<double>(ctx->gp), P<double>(ctx->yp), st,
            GATE_RUN, 0);
+    fork_side(ctx);  // the model cost change does not depend on the candidate point
     LAUNCH((k_model_cost<DD, KK>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
            ctx->Jc_, P<double>(ctx->yc), P<double>(ctx->yp), P<double>(ctx->yk), P<double>(ctx->pc_mcc), st, GATE_RUN);
+    fork_main(ctx);
   });
   LAUNCH(k_candidate, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, K, ctx->fixed_cam, P<double>(ctx->pose), P<double>(ctx->pt),
          P<double>(ctx->intr), P<double>(ctx->yc), P<double>(ctx->yp), P<double>(ctx->yk), P<double>(ctx->sc), P<double>(ctx->sp),
@@ -1546,6 +1590,7 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
            P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c),
            ctx->cp, P<double>(ctx->pc_cand), st, GATE_RUN);
   });
+  join(ctx);
   sync_flags(ctx);
   {
     const PartRef rm = reduce_scalar(ctx, P<double>(ctx->pc_mcc), ctx->nblk_obs, 3, false, GATE_RUN);

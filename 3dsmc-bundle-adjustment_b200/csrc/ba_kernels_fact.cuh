@@ -420,6 +420,7 @@ kf_schur_pass1(int n_pt, const int32_t *__restrict__ pt_rowptr, const int32_t *_
 __device__ __forceinline__ void ldg256(const double *p, double &a, double &b, double &c) {
   double d;
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+  (void)d;  // padding lane of the 32-byte record
 }
 
 // ------------------------------------------------------------------ pass 2 (camera-major items)
