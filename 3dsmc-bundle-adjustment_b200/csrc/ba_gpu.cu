@@ -1115,7 +1115,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     if (rc) return rc;
   }
   CK(cudaGetLastError());
-  ctx->forking = ctx->n_ranks == 1 && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && getenv("BA_NO_FORK") == nullptr;
+  ctx->forking = ctx->n_ranks == 1 && getenv("BA_NO_FORK") == nullptr;
   ctx->cur = ctx->stream;
   ctx->uploaded = true;
   return BA_OK;
@@ -1196,22 +1196,26 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
     const double *intr = P<double>(ctx->intr);
     LAUNCH(k_cam_geo, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->fixed_cam, P<double>(ctx->pose), sc, P<double>(ctx->geo), st,
            gate);
-    LAUNCH((kf_linearize<1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
-           P<double2>(ctx->uv), P<double>(ctx->pose), P<double>(ctx->pt), intr, ctx->cp, ctx->Fc_, P<double>(ctx->pc_lin), st,
-           gate);
+    // point-major branch on the side stream, camera-major branch on the main one (both need geo)
+    fork_side(ctx);
     LAUNCH((kf_linearize<0>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt),
            P<double2>(ctx->pm_uv), P<double>(ctx->pose), P<double>(ctx->pt), intr, ctx->cp, ctx->Fp_, (double *)nullptr, st,
            gate);
+    LAUNCH(kf_pt_blocks, ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam), ctx->Fp_,
+           P<double>(ctx->geo), intr, sp, P<double>(ctx->V), P<double>(ctx->gp), P<double>(ctx->dp), ctx->lo, st, gate);
     if (ctx->tiled)
       LAUNCH(kt_linearize, ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->tm_cam), P<int32_t>(ctx->tm_pt),
              P<double2>(ctx->tm_uv), P<double>(ctx->pose), P<double>(ctx->pt), intr, ctx->cp, ctx->Tg0, ctx->Tg1, st, gate);
+    fork_main(ctx);
+    LAUNCH((kf_linearize<1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+           P<double2>(ctx->uv), P<double>(ctx->pose), P<double>(ctx->pt), intr, ctx->cp, ctx->Fc_, P<double>(ctx->pc_lin), st,
+           gate);
     LAUNCH(kf_cam_blocks, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), ctx->Fc_, P<double>(ctx->geo), intr,
            P<double>(ctx->part_blk), st, gate);
     ItemRef ir = reduce_items<27>(ctx, P<double>(ctx->part_blk), ctx->red_blk, gate);
     LAUNCH((k_cam_blocks_fin<0>), ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->U), P<double>(ctx->gc),
            P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
-    LAUNCH(kf_pt_blocks, ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam), ctx->Fp_,
-           P<double>(ctx->geo), intr, sp, P<double>(ctx->V), P<double>(ctx->gp), P<double>(ctx->dp), ctx->lo, st, gate);
+    join(ctx);
     return;
   }
   DISPATCH_DK(D, K, {
