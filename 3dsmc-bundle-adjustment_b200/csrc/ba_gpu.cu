@@ -123,6 +123,12 @@ struct ba_gpu_ctx {
       row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
   int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0, sp_ctas_per_sm = 1;
   Buf sp_pair_pt, chol_v;
+  // one LM iteration of the windowed explicit solver as an instantiated CUDA graph (every decision is taken on the
+  // device, so the node parameters never change between iterations); dropped by upload / set_options
+  cudaGraphExec_t lm_graph = nullptr;
+  int64_t lm_graph_launches = 0;
+  bool lm_graph_off = false;
+  bool legacy_chol = false;  // BA_LEGACY_CHOL=1: the round-1 left-looking single-CTA Cholesky (A/B timing only)
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
   Buf my_rows, row_flag, row_pos, ipc_stage;
@@ -338,7 +344,10 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMallocHost((void **)&ctx->h_st, sizeof(LmState))) != cudaSuccess) return bail("cudaMallocHost", e);
+  ctx->legacy_chol = getenv("BA_LEGACY_CHOL") != nullptr;
+  ctx->lm_graph_off = getenv("BA_NO_LM_GRAPH") != nullptr;
   cudaFuncSetAttribute(k_cholesky_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  cudaFuncSetAttribute(k_ldlt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(BA_LDLT_MAX_N));
   cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
   cudaFuncSetAttribute(k_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
   cudaFuncSetAttribute(kt_schur_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2));
@@ -350,10 +359,16 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   return BA_OK;
 }
 
+static void drop_lm_graph(ba_gpu_ctx *ctx) {
+  if (ctx->lm_graph) cudaGraphExecDestroy(ctx->lm_graph);
+  ctx->lm_graph = nullptr;
+}
+
 extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  drop_lm_graph(ctx);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   for (int k = 0; k < 8; ++k)
     if (ctx->xch_peer[k] && k != ctx->rank) cudaIpcCloseMemHandle(ctx->xch_peer[k]);
@@ -381,6 +396,7 @@ extern "C" int ba_gpu_set_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
   ctx->opt = *o;
   ctx->opt.device = dev;
   ctx->uploaded = false;
+  drop_lm_graph(ctx);
   return BA_OK;
 }
 
@@ -800,6 +816,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
                              const double *uv2, const double *depth, const double intr4[4], const double intr_prior4[4]) {
   if (!ctx) return BA_ERR_INVALID;
   ctx->uploaded = false;
+  drop_lm_graph(ctx);
   ctx->linearized = false;
   const ba_gpu_options &o = ctx->opt;
   if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !pose7 || !intr4 || (n_pt > 0 && !pt3) ||
@@ -1002,7 +1019,11 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   LAUNCH(k_index_gather, ctx->nblk_pt, BA_THREADS, 0, n_pt, n_obs, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->perm),
          P<int32_t>(ctx->cam_idx), P<double2>(ctx->uv), depth ? P<double>(ctx->depthv) : (double *)nullptr,
          P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt), P<double2>(ctx->pm_uv), P<double>(ctx->pm_depth));
-  LAUNCH(k_item_count, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->item_cnt));
+  // work-item length: 256 observations for streaming-sized problems, down to one observation per lane when the whole
+  // problem has fewer items than twice the SM count (windows)
+  int item_obs = BA_ITEM_OBS;
+  while (item_obs > 32 && cdiv(n_obs, item_obs) < 2 * ctx->n_sm) item_obs >>= 1;
+  LAUNCH(k_item_count, ctx->nblk_cam, BA_THREADS, 0, n_cam, item_obs, P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->item_cnt));
   LAUNCH(k_exclusive_scan, 1, 1024, 0, n_cam, P<int32_t>(ctx->item_cnt), P<int32_t>(ctx->item_ptr));
   LAUNCH(k_slots, ctx->nblk_cam, BA_THREADS, 0, n_cam, ctx->fixed_cam, P<int32_t>(ctx->cam_slot));
   LAUNCH(k_iota, cdiv(n_cam + 1, 256), 256, 0, n_cam + 1, P<int32_t>(ctx->ident));
@@ -1014,7 +1035,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   ctx->n_items = h_items;
   ctx->nblk_item = cdiv(h_items * 32, BA_THREADS);
   RES(items, (size_t)(h_items + 1) * sizeof(BaItem));
-  LAUNCH(k_item_fill, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->item_ptr),
+  LAUNCH(k_item_fill, ctx->nblk_cam, BA_THREADS, 0, n_cam, item_obs, P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->item_ptr),
          P<BaItem>(ctx->items));
   if (ctx->fact) {
     // camera span of every point tile -> shared-memory staging of pass 1
@@ -1213,7 +1234,7 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
     LAUNCH(kf_cam_blocks, ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), ctx->Fc_, P<double>(ctx->geo), intr,
            P<double>(ctx->part_blk), st, gate);
     ItemRef ir = reduce_items<27>(ctx, P<double>(ctx->part_blk), ctx->red_blk, gate);
-    LAUNCH((k_cam_blocks_fin<0>), ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->U), P<double>(ctx->gc),
+    LAUNCH((k_cam_blocks_fin<0>), cdiv(ctx->n_cam * 27, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->U), P<double>(ctx->gc),
            P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
     join(ctx);
     return;
@@ -1235,7 +1256,7 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
            P<double>(ctx->part_blk), st, gate);
     ItemRef ir = ItemRef{P<int32_t>(ctx->item_ptr), P<double>(ctx->part_blk)};
     if (KK == 0) ir = reduce_items<27>(ctx, P<double>(ctx->part_blk), ctx->red_blk, gate);
-    LAUNCH((k_cam_blocks_fin<KK>), ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part,
+    LAUNCH((k_cam_blocks_fin<KK>), cdiv(ctx->n_cam * (27 + (KK ? 24 : 0)), BA_THREADS), BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part,
            P<double>(ctx->U), P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
   });
   if (K)
@@ -1511,24 +1532,33 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
            P<double>(ctx->W), P<double>(ctx->WV), P<double>(ctx->tg), P<double>(ctx->Wk), P<double>(ctx->part_ex), st, GATE_RUN);
     LAUNCH(k_explicit_kk, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->Wk), P<double>(ctx->Vinv), P<double>(ctx->tg),
            P<double>(ctx->part_kk), st, GATE_RUN);
-    LAUNCH((k_explicit_assemble<4>), cdiv(ctx->n_cam + 1, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ctx->n_free, n,
+    LAUNCH((k_explicit_assemble<4>), cdiv(ctx->n_cam * 30 + 14, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ctx->n_free, n,
            P<int32_t>(ctx->cam_slot), P<int32_t>(ctx->item_ptr), P<double>(ctx->part_ex), ctx->nblk_pt, P<double>(ctx->part_kk),
            P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->S),
            P<double>(ctx->rhs), st, GATE_RUN);
   } else {
     LAUNCH((k_explicit_cam<0>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
            P<double>(ctx->W), P<double>(ctx->WV), P<double>(ctx->tg), P<double>(ctx->Wk), P<double>(ctx->part_ex), st, GATE_RUN);
-    LAUNCH((k_explicit_assemble<0>), cdiv(ctx->n_cam + 1, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ctx->n_free, n,
+    LAUNCH((k_explicit_assemble<0>), cdiv(ctx->n_cam * 6, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ctx->n_free, n,
            P<int32_t>(ctx->cam_slot), P<int32_t>(ctx->item_ptr), P<double>(ctx->part_ex), ctx->nblk_pt, P<double>(ctx->part_kk),
            P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->S),
            P<double>(ctx->rhs), st, GATE_RUN);
   }
   fork_main(ctx);
-  LAUNCH(k_schur_pairs, ctx->n_blk, BA_THREADS, 0, n, P<int32_t>(ctx->blk_i), P<int32_t>(ctx->blk_j), P<int32_t>(ctx->blk_cam),
+  if (ctx->n_blk <= 4 * ctx->n_sm)
+    LAUNCH(k_schur_pairs<28>, ctx->n_blk, 28 * 36, 0, n, P<int32_t>(ctx->blk_i), P<int32_t>(ctx->blk_j), P<int32_t>(ctx->blk_cam),
+         P<int32_t>(ctx->pair_ptr), P<int32_t>(ctx->pair_a), P<int32_t>(ctx->pair_b), P<double>(ctx->W), P<double>(ctx->WV),
+         P<double>(ctx->U), P<double>(ctx->dc), P<double>(ctx->S), st, GATE_RUN);
+  else
+    LAUNCH(k_schur_pairs<7>, ctx->n_blk, 7 * 36, 0, n, P<int32_t>(ctx->blk_i), P<int32_t>(ctx->blk_j), P<int32_t>(ctx->blk_cam),
          P<int32_t>(ctx->pair_ptr), P<int32_t>(ctx->pair_a), P<int32_t>(ctx->pair_b), P<double>(ctx->W), P<double>(ctx->WV),
          P<double>(ctx->U), P<double>(ctx->dc), P<double>(ctx->S), st, GATE_RUN);
   join(ctx);
-  if (n <= 160) {
+  if (n <= BA_LDLT_MAX_N && !ctx->legacy_chol) {
+    // single CTA, matrix in shared memory, L D L^T with the right-hand side as an extra row (ba_kernels_chol.cuh)
+    LAUNCH(k_ldlt_solve, 1, 1024, ldlt_smem_bytes(n), n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
+           P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
+  } else if (n <= 160) {
     const size_t smem = ((size_t)n * n + n + 8) * 8;
     LAUNCH((k_cholesky_solve<1>), 1, 256, smem, n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
            P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
@@ -1629,9 +1659,32 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   enqueue_iteration_zero(ctx);
   const int poll = std::max(1, ctx->opt.poll_interval);
   int rc = 0;
+  // windowed explicit solver on one GPU: the ~26 small kernels of an LM iteration (two streams, fork / join) are
+  // captured once per upload and replayed
+  const bool graphed = !ctx->lm_graph_off && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks == 1 &&
+                       ctx->n_red > 0 && ctx->n_red <= BA_LDLT_MAX_N;
   for (int it = 1;; ++it) {
-    rc = enqueue_lm_iteration(ctx);
-    if (rc) return rc;
+    if (graphed) {
+      if (!ctx->lm_graph) {
+        const int64_t lb = ctx->launches;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_lm_iteration(ctx);
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        ctx->lm_graph_launches = ctx->launches - lb;
+        ctx->launches = lb;
+        if (rc) return rc;
+        if (ce != cudaSuccess || !g) return fail(ctx, BA_ERR_CUDA, "LM iteration graph capture: %s", cudaGetErrorString(ce));
+        const cudaError_t ie = cudaGraphInstantiate(&ctx->lm_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) return fail(ctx, BA_ERR_CUDA, "LM iteration graph instantiate: %s", cudaGetErrorString(ie));
+      }
+      CK(cudaGraphLaunch(ctx->lm_graph, ctx->stream));
+      ctx->launches += ctx->lm_graph_launches;
+    } else {
+      rc = enqueue_lm_iteration(ctx);
+      if (rc) return rc;
+    }
     const bool implicit = ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY;
     if (!implicit && (it % poll) != 0 && it <= ctx->lo.max_num_iterations) continue;
     rc = poll_state(ctx);

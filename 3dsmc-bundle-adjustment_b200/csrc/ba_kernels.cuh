@@ -124,24 +124,25 @@ __global__ void __launch_bounds__(BA_THREADS) k_index_gather(int n_pt, int n_obs
     if (depth) pm_depth[s] = depth[i];
   }
 }
-// camera-major work items: runs of <= BA_ITEM_OBS observations of one camera
-__global__ void __launch_bounds__(BA_THREADS) k_item_count(int n_cam, const int32_t *__restrict__ cam_rowptr, int32_t *item_cnt) {
+// camera-major work items: runs of <= item_obs (<= BA_ITEM_OBS) observations of one camera; small problems get
+// shorter runs so that the warp-per-item kernels still fill the GPU (chosen at upload)
+__global__ void __launch_bounds__(BA_THREADS) k_item_count(int n_cam, int item_obs, const int32_t *__restrict__ cam_rowptr, int32_t *item_cnt) {
   const int c = blockIdx.x * BA_THREADS + threadIdx.x;
   if (c >= n_cam) return;
   const int n = cam_rowptr[c + 1] - cam_rowptr[c];
-  item_cnt[c] = (n + BA_ITEM_OBS - 1) / BA_ITEM_OBS;
+  item_cnt[c] = (n + item_obs - 1) / item_obs;
 }
-__global__ void __launch_bounds__(BA_THREADS) k_item_fill(int n_cam, const int32_t *__restrict__ cam_rowptr,
+__global__ void __launch_bounds__(BA_THREADS) k_item_fill(int n_cam, int item_obs, const int32_t *__restrict__ cam_rowptr,
                                                          const int32_t *__restrict__ item_ptr, BaItem *items) {
   const int c = blockIdx.x * BA_THREADS + threadIdx.x;
   if (c >= n_cam) return;
   const int b = cam_rowptr[c], e = cam_rowptr[c + 1];
   int k = item_ptr[c];
-  for (int s = b; s < e; s += BA_ITEM_OBS, ++k) {
+  for (int s = b; s < e; s += item_obs, ++k) {
     BaItem it;
     it.cam = c;
     it.begin = s;
-    it.end = min(e, s + BA_ITEM_OBS);
+    it.end = min(e, s + item_obs);
     it.pad = 0;
     items[k] = it;
   }
@@ -376,34 +377,29 @@ k_cam_blocks_fin(int n_cam, const int32_t *__restrict__ item_ptr, const double *
                  double *__restrict__ gc, double *__restrict__ Uck, double *__restrict__ dc, LmOptions lo,
                  const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  const int c = blockIdx.x * BA_THREADS + threadIdx.x;
-  if (c >= n_cam) return;
+  // one thread per (camera, value): a camera's item partials are added in item order (coalesced across values)
   constexpr int NV = CamBlk<NK>::NV;
   constexpr int NL = 27 + (NK ? 24 : 0);
-  double acc[NL];
-#pragma unroll
-  for (int k = 0; k < NL; ++k) acc[k] = 0.0;
-  for (int it = item_ptr[c]; it < item_ptr[c + 1]; ++it) {
-    const double *o = part + (size_t)it * NV;
-#pragma unroll
-    for (int k = 0; k < NL; ++k) acc[k] += o[k];
-  }
-  double *Uc = U + 36 * (size_t)c;
-  int u = 0;
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int b = a; b < 6; ++b) {
-      Uc[a * 6 + b] = acc[u];
-      Uc[b * 6 + a] = acc[u];
-      if (a == b) dc[6 * (size_t)c + a] = fmin(fmax(acc[u], lo.min_lm_diagonal), lo.max_lm_diagonal);
-      ++u;
+  const int idx = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (idx >= n_cam * NL) return;
+  const int c = idx / NL, k = idx - c * NL;
+  double acc = 0.0;
+  for (int it = item_ptr[c]; it < item_ptr[c + 1]; ++it) acc += part[(size_t)it * NV + k];
+  if (k < 21) {
+    int a = 0, r = k;  // k-th entry of the row-major upper triangle -> (a, b)
+    while (r >= 6 - a) {
+      r -= 6 - a;
+      ++a;
     }
-#pragma unroll
-  for (int a = 0; a < 6; ++a) gc[6 * (size_t)c + a] = acc[21 + a];
-  if (NK) {
-#pragma unroll
-    for (int k = 0; k < 24; ++k) Uck[24 * (size_t)c + k] = acc[27 + k];
+    const int b2 = a + r;
+    double *Uc = U + 36 * (size_t)c;
+    Uc[a * 6 + b2] = acc;
+    Uc[b2 * 6 + a] = acc;
+    if (a == b2) dc[6 * (size_t)c + a] = fmin(fmax(acc, lo.min_lm_diagonal), lo.max_lm_diagonal);
+  } else if (k < 27) {
+    gc[6 * (size_t)c + k - 21] = acc;
+  } else if (NK) {
+    Uck[24 * (size_t)c + k - 27] = acc;
   }
 }
 
@@ -1735,32 +1731,43 @@ k_explicit_kk(int n_pt, const double *__restrict__ Wk, const double *__restrict_
 // thread = (entry of the 6x6 block, slice of the pair run); fixed-order
 // reduction over the slices in shared memory.
 //   S_ij = [i==j] (U_i + D_i^2) - sum_{(a,b)} WV_a W_b^T
-#define BA_PAIR_SLICES 7
-__global__ void __launch_bounds__(BA_THREADS)
+// SLICES = 28 (1008 threads) when the blocks are few and their pair runs long (windows), 7 otherwise
+template <int SLICES>
+__global__ void __launch_bounds__(SLICES * 36)
 k_schur_pairs(int n, const int32_t *__restrict__ blk_i, const int32_t *__restrict__ blk_j,
               const int32_t *__restrict__ blk_cam_i, const int32_t *__restrict__ pair_ptr,
               const int32_t *__restrict__ pair_a, const int32_t *__restrict__ pair_b, const double *__restrict__ W,
               const double *__restrict__ WV, const double *__restrict__ U, const double *__restrict__ dc,
               double *__restrict__ S, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  __shared__ double sm[BA_PAIR_SLICES * 36];
+  __shared__ double sm[SLICES * 36];
   const int blk = blockIdx.x;
   const int e = threadIdx.x % 36, sl = threadIdx.x / 36;
   const int row = e / 6, col = e % 6;
-  double acc = 0.0;
-  if (sl < BA_PAIR_SLICES) {
-    for (int k = pair_ptr[blk] + sl; k < pair_ptr[blk + 1]; k += BA_PAIR_SLICES) {
-      const double *wv = WV + 18 * (size_t)pair_a[k] + 3 * row;
-      const double *w = W + 18 * (size_t)pair_b[k] + 3 * col;
-      acc += wv[0] * w[0] + wv[1] * w[1] + wv[2] * w[2];
-    }
-    sm[sl * 36 + e] = acc;
+  // two independent gather chains per thread (the loop is bound by the index -> block load latency);
+  // the slice's partial is (even pairs) + (odd pairs), a fixed order
+  double acc0 = 0.0, acc1 = 0.0;
+  const int k1 = pair_ptr[blk + 1];
+  int k = pair_ptr[blk] + sl;
+  for (; k + SLICES < k1; k += 2 * SLICES) {
+    const double *wv0 = WV + 18 * (size_t)pair_a[k] + 3 * row;
+    const double *w0 = W + 18 * (size_t)pair_b[k] + 3 * col;
+    const double *wv1 = WV + 18 * (size_t)pair_a[k + SLICES] + 3 * row;
+    const double *w1 = W + 18 * (size_t)pair_b[k + SLICES] + 3 * col;
+    acc0 += wv0[0] * w0[0] + wv0[1] * w0[1] + wv0[2] * w0[2];
+    acc1 += wv1[0] * w1[0] + wv1[1] * w1[1] + wv1[2] * w1[2];
   }
+  if (k < k1) {
+    const double *wv = WV + 18 * (size_t)pair_a[k] + 3 * row;
+    const double *w = W + 18 * (size_t)pair_b[k] + 3 * col;
+    acc0 += wv[0] * w[0] + wv[1] * w[1] + wv[2] * w[2];
+  }
+  sm[sl * 36 + e] = acc0 + acc1;
   __syncthreads();
   if (threadIdx.x < 36) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < BA_PAIR_SLICES; ++k) s += sm[k * 36 + e];
+    for (int q = 0; q < SLICES; ++q) s += sm[q * 36 + e];
     const int i = blk_i[blk], j = blk_j[blk];
     double v = -s;
     if (i == j) {
@@ -1776,8 +1783,10 @@ k_schur_pairs(int n, const int32_t *__restrict__ blk_i, const int32_t *__restric
   }
 }
 
-// borders + right-hand side.  One thread per free camera, thread (n_free) for
-// the intrinsics block.  rhs = -g + W V^-1 g_p
+// borders + right-hand side.  One thread per (camera, value): 6 right-hand-side entries and (REF mode) the 6 x 4
+// border block of a free camera, item partials added in item order; 14 more threads own the intrinsics corner
+// (10 upper entries of the 4 x 4 block + 4 right-hand-side entries, point-tile partials added in tile order).
+//   rhs = -g + W V^-1 g_p
 template <int NK>
 __global__ void __launch_bounds__(BA_THREADS)
 k_explicit_assemble(int n_cam, int n_free, int n, const int32_t *__restrict__ cam_slot, const int32_t *__restrict__ item_ptr,
@@ -1786,49 +1795,44 @@ k_explicit_assemble(int n_cam, int n_free, int n, const int32_t *__restrict__ ca
                     const double *__restrict__ gk, const double *__restrict__ dk, double *__restrict__ S,
                     double *__restrict__ rhs, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  const int c = blockIdx.x * BA_THREADS + threadIdx.x;
   constexpr int NV = 6 + (NK ? 24 : 0);
+  const int idx = blockIdx.x * BA_THREADS + threadIdx.x;
   const int koff = 6 * n_free;
-  if (c < n_cam) {
+  if (idx < n_cam * NV) {
+    const int c = idx / NV, k = idx - c * NV;
     const int slot = cam_slot[c];
     if (slot < 0) return;
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    for (int it = item_ptr[c]; it < item_ptr[c + 1]; ++it)
-#pragma unroll
-      for (int k = 0; k < NV; ++k) acc[k] += part_cam[(size_t)it * NV + k];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) rhs[6 * slot + a] = -gc[6 * (size_t)c + a] + acc[a];
-    if (NK) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const double v = Uck[24 * (size_t)c + a * 4 + b] - acc[6 + a * 4 + b];
-          S[(size_t)(6 * slot + a) * n + koff + b] = v;
-          S[(size_t)(koff + b) * n + 6 * slot + a] = v;
-        }
+    double acc = 0.0;
+    for (int it = item_ptr[c]; it < item_ptr[c + 1]; ++it) acc += part_cam[(size_t)it * NV + k];
+    if (k < 6) {
+      rhs[6 * slot + k] = -gc[6 * (size_t)c + k] + acc;
+    } else if (NK) {
+      const int a = (k - 6) >> 2, b = (k - 6) & 3;
+      const double v = Uck[24 * (size_t)c + k - 6] - acc;
+      S[(size_t)(6 * slot + a) * n + koff + b] = v;
+      S[(size_t)(koff + b) * n + 6 * slot + a] = v;
     }
-  } else if (c == n_cam && NK) {
-    double v[14];
-    for (int k = 0; k < 14; ++k) {
-      double s = 0.0;
-      for (int b = 0; b < nblk_pt; ++b) s += part_kk[14 * (size_t)b + k];
-      v[k] = s;
-    }
-    int u = 0;
-    for (int a = 0; a < 4; ++a)
-      for (int b = a; b < 4; ++b) {
-        double x = Ukk[a * 4 + b] - v[u++];
-        if (a == b) {
-          const double D = sqrt(dk[a] / st->radius);
-          x += D * D;
-        }
-        S[(size_t)(koff + a) * n + koff + b] = x;
-        S[(size_t)(koff + b) * n + koff + a] = x;
+  } else if (NK && idx < n_cam * NV + 14) {
+    const int k = idx - n_cam * NV;
+    double v = 0.0;
+    for (int b = 0; b < nblk_pt; ++b) v += part_kk[14 * (size_t)b + k];
+    if (k < 10) {
+      int a = 0, r = k;  // k-th entry of the row-major upper triangle of the 4 x 4 block -> (a, b)
+      while (r >= 4 - a) {
+        r -= 4 - a;
+        ++a;
       }
-    for (int a = 0; a < 4; ++a) rhs[koff + a] = -gk[a] + v[10 + a];
+      const int b = a + r;
+      double x = Ukk[a * 4 + b] - v;
+      if (a == b) {
+        const double D = sqrt(dk[a] / st->radius);
+        x += D * D;
+      }
+      S[(size_t)(koff + a) * n + koff + b] = x;
+      S[(size_t)(koff + b) * n + koff + a] = x;
+    } else {
+      rhs[koff + k - 10] = -gk[k - 10] + v;
+    }
   }
 }
 

@@ -231,3 +231,148 @@ k_chol_solve(int n, const double *__restrict__ A, const double *__restrict__ rhs
   }
   if (gtid < 4) yk[gtid] = nk ? __ldcg(v + 6 * n_free + gtid) : 0.0;
 }
+
+// =====================================================================
+// Windowed problems (n <= BA_LDLT_MAX_N): the whole reduced-system solve in ONE CTA with the matrix in
+// shared memory.  A = L D L^T, right-looking, no square roots:
+//   * the right-hand side rides along as row n of the matrix, so the forward substitution L w = b is
+//     part of the elimination (row n ends up holding w);
+//   * column j is only READ during step j (trailing entries take  A_ik -= (A_ij / d_j) A_kj), so one
+//     barrier per column suffices; every thread forms 1/d_j itself from the shared pivot;
+//   * leading dimension odd: the strided column reads A_kj are bank-conflict free for 8-byte words;
+//   * the back substitution L^T y = D^-1 w runs in warp 0 with register-resident w (lane l owns rows
+//     l, l+32, ...) and one shuffle broadcast per unknown instead of a CTA barrier.
+// The critical path per column is barrier + 1/d + one fused multiply-add (about 250 cycles) instead of a
+// j-long dependent FMA chain, a square root and two barriers (k_cholesky_solve: 135 us at n = 118).
+// Every sum has a fixed order.  == the exact step of Ceres DENSE_SCHUR / SPARSE_SCHUR.
+// =====================================================================
+#define BA_LDLT_MAX_N 160
+#define BA_LDLT_SLOTS (BA_LDLT_MAX_N / 32)
+static_assert(BA_LDLT_MAX_N <= 160, "k_ldlt_solve: phases cover at most 5 row tiles");
+__host__ __device__ inline int ldlt_ld(int n) { return n | 1; }
+__host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)(n + 1) * ldlt_ld(n) + 2 * (size_t)(n + 8)) * 8; }
+
+// One elimination step with NT = ceil((n - j) / 32) row tiles (compile-time: the j loop is split into phases).
+// The trailing update is a grid of 32 x 32 tiles, row = warp, column = lane: tile (ti, tk) holds entry
+// (i, k) = (j + 1 + warp + 32 ti, j + 1 + lane + 32 tk); tk < ti, and tk == ti for lane <= warp, lie in the lower
+// triangle.  Only the last tile row / column can leave the matrix: its loads go to a clamped (valid) address and
+// its stores are predicated.  All loads of a step are issued before the first multiply-add (the compiler cannot
+// move the column reads across the trailing stores itself: same array).
+template <int NT>
+__device__ __forceinline__ void ldlt_step(double *__restrict__ A, double *__restrict__ invd, int ld, int n, int j, int warp,
+                                          int lane, double rd) {
+  const int i0 = j + 1 + warp, k0 = j + 1 + lane;
+  const int base = i0 * ld + k0;                 // entry (i0, k0)
+  const int cbi = base - lane - 1;               // (i0, j)
+  const int cbk = k0 * ld + j;                   // (k0, j)
+  const int ld32 = 32 * ld;
+  const bool row_ok = i0 + 32 * (NT - 1) <= n;   // last tile row inside the matrix (rows .. n)
+  const bool col_ok = k0 + 32 * (NT - 1) < n;    // last tile column inside the matrix (columns .. n-1)
+  double li[NT], ck[NT], a[NT * (NT + 1) / 2];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    li[t] = (t < NT - 1 || row_ok) ? A[cbi + t * ld32] : 0.0;
+    ck[t] = (t < NT - 1 || col_ok) ? A[cbk + t * ld32] : 0.0;
+  }
+#pragma unroll
+  for (int ti = 0, u = 0; ti < NT; ++ti)
+#pragma unroll
+    for (int tk = 0; tk <= ti; ++tk, ++u)
+      a[u] = ((ti < NT - 1 || row_ok) && (tk < NT - 1 || col_ok)) ? A[base + ti * ld32 + tk * 32] : 0.0;
+#pragma unroll
+  for (int ti = 0, u = 0; ti < NT; ++ti) {
+    const double l = li[ti] * rd;
+#pragma unroll
+    for (int tk = 0; tk <= ti; ++tk, ++u) {
+      const double v = a[u] - l * ck[tk];
+      bool ok = true;
+      if (ti == NT - 1) ok = ok && row_ok;
+      if (tk == NT - 1) ok = ok && col_ok;
+      if (tk == ti) ok = ok && lane <= warp;
+      if (ok) A[base + ti * ld32 + tk * 32] = v;
+      // the owner of the next pivot (entry (j+1, j+1)) publishes its reciprocal: nobody else needs to form it.
+      // -1 marks a non-positive pivot; +inf gives 0 and NaN stays NaN, both fail the "> 0" test of the next step
+      if (ti == 0 && tk == 0 && (warp | lane) == 0 && j + 1 < n) invd[j + 1] = v > 0.0 ? __drcp_rn(v) : -1.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+k_ldlt_solve(int n, const double *__restrict__ Sg, const double *__restrict__ rhs, int n_cam, int n_free,
+             const int32_t *__restrict__ cam_slot, int nk, double *__restrict__ yc, double *__restrict__ yk, LmState *st,
+             int gate) {
+  if (!gate_open(st, gate)) return;
+  if (st->lin_fail) return;
+  extern __shared__ double smd[];
+  const int ld = ldlt_ld(n);
+  double *A = smd;                           // (n + 1) x ld, lower triangle; row n = right-hand side
+  double *invd = smd + (size_t)(n + 1) * ld;  // n + 8
+  double *ysh = invd + n + 8;                 // n + 8
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // launched with exactly 32 warps
+  for (int i = warp; i < n; i += 32)
+    for (int k = lane; k <= i; k += 32) A[i * ld + k] = Sg[(size_t)i * n + k];
+  for (int k = tid; k < n; k += 1024) A[n * ld + k] = rhs[k];
+  if (tid == 0) {
+    const double d = A[0];  // written by this thread
+    invd[0] = d > 0.0 ? __drcp_rn(d) : -1.0;
+  }
+  bool bad = false;
+  int j = 0;
+#define BA_LDLT_PHASE(NT)                                                  \
+  for (; !bad && j < n && ((n - j + 31) >> 5) == NT; ++j) {                \
+    __syncthreads();                                                       \
+    const double rd = invd[j];                                             \
+    if (!(rd > 0.0)) { /* same value in every thread: uniform exit */      \
+      bad = true;                                                          \
+      break;                                                               \
+    }                                                                      \
+    ldlt_step<NT>(A, invd, ld, n, j, warp, lane, rd);                      \
+  }
+  BA_LDLT_PHASE(5)
+  BA_LDLT_PHASE(4)
+  BA_LDLT_PHASE(3)
+  BA_LDLT_PHASE(2)
+  BA_LDLT_PHASE(1)
+#undef BA_LDLT_PHASE
+  if (bad) {
+    if (tid == 0) st->lin_fail = 1;
+    return;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double w[BA_LDLT_SLOTS], iv[BA_LDLT_SLOTS];
+#pragma unroll
+    for (int s = 0; s < BA_LDLT_SLOTS; ++s) {
+      const int i = lane + 32 * s;
+      w[s] = i < n ? A[n * ld + i] : 0.0;
+      iv[s] = i < n ? invd[i] : 0.0;
+    }
+#pragma unroll
+    for (int s = BA_LDLT_SLOTS - 1; s >= 0; --s) {
+      if (32 * s >= n) continue;
+#pragma unroll 4
+      for (int kk = 31; kk >= 0; --kk) {
+        const int k = 32 * s + kk;
+        if (k >= n) continue;
+        const double y = __shfl_sync(0xffffffffu, w[s] * iv[s], kk);
+        const double *Ak = A + k * ld;
+        if (lane == kk) ysh[k] = y;
+        if (lane < kk) w[s] -= Ak[32 * s + lane] * y;
+#pragma unroll
+        for (int s2 = 0; s2 < BA_LDLT_SLOTS; ++s2)
+          if (s2 < s) w[s2] -= Ak[32 * s2 + lane] * y;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < n_cam; c += blockDim.x) {
+    const int slot = cam_slot[c];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double v = slot >= 0 ? ysh[6 * slot + k] : 0.0;
+      if (!isfinite(v)) st->lin_fail = 1;
+      yc[6 * (size_t)c + k] = v;
+    }
+  }
+  if (tid < 4) yk[tid] = nk ? ysh[6 * n_free + tid] : 0.0;
+}
