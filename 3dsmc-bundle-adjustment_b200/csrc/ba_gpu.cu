@@ -96,7 +96,7 @@ struct ba_gpu_ctx {
   int n_cam = 0, n_pt = 0, n_obs = 0, fixed_cam = -1, n_free = 0, n_items = 0;
   int depth = 0, nk = 0;  // cost-model switches in force
   int solver = 0, n_red = 0;
-  int nblk_obs = 0, nblk_ent = 0, nblk_cam = 0, nblk_pt = 0, n_tiles = 0, nblk_item = 0;
+  int nblk_obs = 0, nblk_ent = 0, nblk_cam = 0, nblk_pt = 0, n_tiles = 0, nblk_item = 0, pl_tile_pts = BA_TILE_PTS, pl_tiles = 0;
   CostParams cp;
   LmOptions lo;
 
@@ -128,7 +128,7 @@ struct ba_gpu_ctx {
   cudaGraphExec_t lm_graph = nullptr;
   int64_t lm_graph_launches = 0;
   bool lm_graph_off = false;
-  bool legacy_chol = false;  // BA_LEGACY_CHOL=1: the round-1 left-looking single-CTA Cholesky (A/B timing only)
+  int legacy_chol = 0;  // BA_LEGACY_CHOL=1: left-looking single-CTA Cholesky, =2: shared-memory L D L^T (A/B timing only)
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
   Buf my_rows, row_flag, row_pos, ipc_stage;
@@ -344,10 +344,15 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMallocHost((void **)&ctx->h_st, sizeof(LmState))) != cudaSuccess) return bail("cudaMallocHost", e);
-  ctx->legacy_chol = getenv("BA_LEGACY_CHOL") != nullptr;
+  ctx->legacy_chol = getenv("BA_LEGACY_CHOL") ? atoi(getenv("BA_LEGACY_CHOL")) : 0;
   ctx->lm_graph_off = getenv("BA_NO_LM_GRAPH") != nullptr;
   cudaFuncSetAttribute(k_cholesky_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
   cudaFuncSetAttribute(k_ldlt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(BA_LDLT_MAX_N));
+  cudaFuncSetAttribute(k_ldlt2_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(31));
+  cudaFuncSetAttribute(k_ldlt2_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(63));
+  cudaFuncSetAttribute(k_ldlt2_solve<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(95));
+  cudaFuncSetAttribute(k_ldlt2_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(127));
+  cudaFuncSetAttribute(k_ldlt2_solve<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(BA_LDLT2_MAX_N));
   cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
   cudaFuncSetAttribute(k_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
   cudaFuncSetAttribute(kt_schur_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2));
@@ -893,6 +898,10 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   ctx->nblk_cam = cdiv(n_cam, BA_THREADS);
   ctx->nblk_pt = cdiv(n_pt, BA_THREADS);
   ctx->n_tiles = cdiv(n_pt, BA_TILE_PTS);
+  // planes-store point-major kernels: shorter tiles while the problem has fewer tiles than twice the SM count
+  ctx->pl_tile_pts = BA_TILE_PTS;
+  while (ctx->pl_tile_pts > 8 && cdiv(n_pt, ctx->pl_tile_pts) < 2 * ctx->n_sm) ctx->pl_tile_pts >>= 1;
+  ctx->pl_tiles = cdiv(n_pt, ctx->pl_tile_pts);
 
   RES(pose, nc * 56);
   RES(pose_c, nc * 56);
@@ -1245,7 +1254,7 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
     LAUNCH((k_linearize<DD, KK, 0>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt),
            P<double2>(ctx->pm_uv), P<double>(ctx->pm_depth), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc,
            sp, sk, ctx->cp, ctx->Jp_, (double *)nullptr, st, gate);
-    LAUNCH((k_pt_blocks<DD, KK>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), ctx->Jp_, P<double>(ctx->V),
+    LAUNCH((k_pt_blocks<DD, KK>), ctx->pl_tiles, BA_THREADS, 0, ctx->n_pt, ctx->pl_tile_pts, P<int32_t>(ctx->pt_rowptr), ctx->Jp_, P<double>(ctx->V),
            P<double>(ctx->gp), P<double>(ctx->Wk), P<double>(ctx->dp), ctx->lo, st, gate);
     // camera-major branch (main stream): linearise + camera blocks
     fork_main(ctx);
@@ -1361,7 +1370,7 @@ static ItemRef enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int pa
   }
   DISPATCH_D(ctx->depth, {
     if (passes & 1)
-    LAUNCH((k_schur_pass1<DD, 0, 0>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+    LAUNCH((k_schur_pass1<DD, 0, 0>), ctx->pl_tiles, BA_THREADS, 0, ctx->n_pt, ctx->pl_tile_pts, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
            ctx->Jp_, v, (const double *)nullptr, P<double>(ctx->Vinv), (const double *)nullptr, P<double>(ctx->t), st, gate, rp);
     if (passes & 2)
     LAUNCH((k_schur_pass2<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
@@ -1554,7 +1563,20 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
          P<int32_t>(ctx->pair_ptr), P<int32_t>(ctx->pair_a), P<int32_t>(ctx->pair_b), P<double>(ctx->W), P<double>(ctx->WV),
          P<double>(ctx->U), P<double>(ctx->dc), P<double>(ctx->S), st, GATE_RUN);
   join(ctx);
-  if (n <= BA_LDLT_MAX_N && !ctx->legacy_chol) {
+  if (n <= BA_LDLT2_MAX_N && !ctx->legacy_chol) {
+    // single CTA, L D L^T with the trailing matrix in registers and the right-hand side as an extra row (ba_kernels_chol.cuh)
+#define LDLT2_LAUNCH(NT)                                                                                                  \
+  LAUNCH(k_ldlt2_solve<NT>, 1, 1024, ldlt2_smem_bytes(n), n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free, \
+         P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN)
+    switch (ldlt2_tiles(n)) {
+      case 1: LDLT2_LAUNCH(1); break;
+      case 2: LDLT2_LAUNCH(2); break;
+      case 3: LDLT2_LAUNCH(3); break;
+      case 4: LDLT2_LAUNCH(4); break;
+      default: LDLT2_LAUNCH(5); break;
+    }
+#undef LDLT2_LAUNCH
+  } else if (n <= BA_LDLT_MAX_N && ctx->legacy_chol != 1) {
     // single CTA, matrix in shared memory, L D L^T with the right-hand side as an extra row (ba_kernels_chol.cuh)
     LAUNCH(k_ldlt_solve, 1, 1024, ldlt_smem_bytes(n), n, P<double>(ctx->S), P<double>(ctx->rhs), ctx->n_cam, ctx->n_free,
            P<int32_t>(ctx->cam_slot), ctx->nk, P<double>(ctx->yc), P<double>(ctx->yk), st, GATE_RUN);
@@ -1607,7 +1629,7 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
   } else
   DISPATCH_DK(D, K, {
     // back-substitution y_p = V^-1 (-g_p - W^T y_c)
-    LAUNCH((k_schur_pass1<DD, KK, 1>), ctx->n_tiles, BA_THREADS, 0, ctx->n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+    LAUNCH((k_schur_pass1<DD, KK, 1>), ctx->pl_tiles, BA_THREADS, 0, ctx->n_pt, ctx->pl_tile_pts, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
            ctx->Jp_, P<double>(ctx->yc), P<double>(ctx->yk), P<double>(ctx->Vinv), P<double>(ctx->gp), P<double>(ctx->yp), st,
            GATE_RUN, 0);
     fork_side(ctx);  // the model cost change does not depend on the candidate point

@@ -411,14 +411,19 @@ k_kk_fin(int n_items, const double *__restrict__ part, const double *__restrict_
          const double *__restrict__ sk, CostParams cp, LmOptions lo, double *__restrict__ Ukk, double *__restrict__ gk,
          double *__restrict__ dk, double *__restrict__ rk, double *__restrict__ Jkk, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  __shared__ double red[BA_WARPS + 2];
-  double v[10];
-  for (int k = 0; k < 10; ++k) {
+  // one warp per value (lanes stride the items, butterfly sum): one pass instead of ten CTA-wide reductions
+  __shared__ double vs[10];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < 10; k += BA_WARPS) {
     double s = 0.0;
-    for (int i = threadIdx.x; i < n_items; i += BA_THREADS) s += part[(size_t)i * CamBlk<4>::NV + 51 + k];
-    v[k] = block_sum(s, red);
+    for (int i = lane; i < n_items; i += 32) s += part[(size_t)i * CamBlk<4>::NV + 51 + k];
+    s = warp_sum(s);
+    if (lane == 0) vs[k] = s;
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    double v[10];
+    for (int k = 0; k < 10; ++k) v[k] = vs[k];
     double K[16];
     for (int k = 0; k < 16; ++k) K[k] = 0.0;
     K[0] = v[0];
@@ -454,12 +459,13 @@ k_kk_fin(int n_items, const double *__restrict__ part, const double *__restrict_
 // over the stable point-major permutation, with no atomics.
 template <int NV, int TOBS, class Contrib, class Finish>
 __device__ __forceinline__ void tile_point_reduce(int n_pt, const int32_t *__restrict__ pt_rowptr, double *sm /*[NV*TOBS]*/,
-                                                  Contrib contrib, Finish finish) {
-  const int p0 = blockIdx.x * BA_TILE_PTS;
-  const int p1 = min(n_pt, p0 + BA_TILE_PTS);
+                                                  Contrib contrib, Finish finish, int tile_pts = BA_TILE_PTS) {
+  // tile_pts <= BA_TILE_PTS: the planes-store kernels of small problems run with shorter tiles (more CTAs)
+  const int p0 = blockIdx.x * tile_pts;
+  const int p1 = min(n_pt, p0 + tile_pts);
   const int o0 = pt_rowptr[p0], o1 = pt_rowptr[p1];
   const int p = p0 + threadIdx.x;
-  const bool own = threadIdx.x < BA_TILE_PTS && p < p1;
+  const bool own = p < p1;
   int pb = 0, pe = 0;
   if (own) {
     pb = pt_rowptr[p];
@@ -496,8 +502,8 @@ __device__ __forceinline__ void tile_point_reduce(int n_pt, const int32_t *__res
 // clamped LM diagonal of the point columns
 template <int DEPTH, int NK>
 __global__ void __launch_bounds__(BA_THREADS)
-k_pt_blocks(int n_pt, const int32_t *__restrict__ pt_rowptr, JPlanes J, double *__restrict__ V, double *__restrict__ gp,
-            double *__restrict__ Wk, double *__restrict__ dp, LmOptions lo, const LmState *st, int gate) {
+k_pt_blocks(int n_pt, int tile_pts, const int32_t *__restrict__ pt_rowptr, JPlanes J, double *__restrict__ V,
+            double *__restrict__ gp, double *__restrict__ Wk, double *__restrict__ dp, LmOptions lo, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
   constexpr int NV = 9 + (NK ? 12 : 0);
   constexpr int TOBS = NK ? 256 : 512;
@@ -554,7 +560,8 @@ k_pt_blocks(int n_pt, const int32_t *__restrict__ pt_rowptr, JPlanes J, double *
 #pragma unroll
           for (int k = 0; k < 12; ++k) Wk[12 * (size_t)p + k] = sum[9 + k];
         }
-      });
+      },
+      tile_pts);
 }
 
 // V_p + D_p^2 -> V_p^-1 (in-register 3x3 Cholesky inverse), tg_p = V_p^-1 g_p
@@ -597,7 +604,7 @@ k_point_inverse(int n_pt, const double *__restrict__ V, const double *__restrict
 // =====================================================================
 template <int DEPTH, int NK, int MODE>
 __global__ void __launch_bounds__(BA_THREADS)
-k_schur_pass1(int n_pt, const int32_t *__restrict__ pt_rowptr, const int32_t *__restrict__ pm_cam, JPlanes J,
+k_schur_pass1(int n_pt, int tile_pts, const int32_t *__restrict__ pt_rowptr, const int32_t *__restrict__ pm_cam, JPlanes J,
               const double *__restrict__ x, const double *__restrict__ yk, const double *__restrict__ Vinv,
               const double *__restrict__ gp, double *__restrict__ out, const LmState *st, int gate, int reset_period) {
   if (!gate_open(st, gate, reset_period)) return;
@@ -654,7 +661,8 @@ k_schur_pass1(int n_pt, const int32_t *__restrict__ pt_rowptr, const int32_t *__
         out[3 * (size_t)p] = t[0];
         out[3 * (size_t)p + 1] = t[1];
         out[3 * (size_t)p + 2] = t[2];
-      });
+      },
+      tile_pts);
 }
 
 // =====================================================================
@@ -1744,23 +1752,32 @@ k_schur_pairs(int n, const int32_t *__restrict__ blk_i, const int32_t *__restric
   const int blk = blockIdx.x;
   const int e = threadIdx.x % 36, sl = threadIdx.x / 36;
   const int row = e / 6, col = e % 6;
-  // two independent gather chains per thread (the loop is bound by the index -> block load latency);
-  // the slice's partial is (even pairs) + (odd pairs), a fixed order
+  // the loop is bound by the index -> block gather latency: four pairs per round, all index loads issued before
+  // the first block load; the slice's partial is (even pairs) + (odd pairs), a fixed order
   double acc0 = 0.0, acc1 = 0.0;
   const int k1 = pair_ptr[blk + 1];
-  int k = pair_ptr[blk] + sl;
-  for (; k + SLICES < k1; k += 2 * SLICES) {
-    const double *wv0 = WV + 18 * (size_t)pair_a[k] + 3 * row;
-    const double *w0 = W + 18 * (size_t)pair_b[k] + 3 * col;
-    const double *wv1 = WV + 18 * (size_t)pair_a[k + SLICES] + 3 * row;
-    const double *w1 = W + 18 * (size_t)pair_b[k + SLICES] + 3 * col;
-    acc0 += wv0[0] * w0[0] + wv0[1] * w0[1] + wv0[2] * w0[2];
-    acc1 += wv1[0] * w1[0] + wv1[1] * w1[1] + wv1[2] * w1[2];
-  }
-  if (k < k1) {
-    const double *wv = WV + 18 * (size_t)pair_a[k] + 3 * row;
-    const double *w = W + 18 * (size_t)pair_b[k] + 3 * col;
-    acc0 += wv[0] * w[0] + wv[1] * w[1] + wv[2] * w[2];
+  for (int k = pair_ptr[blk] + sl; k < k1; k += 4 * SLICES) {
+    int ia[4], ib[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kk = k + u * SLICES;
+      ia[u] = kk < k1 ? pair_a[kk] : -1;
+      ib[u] = kk < k1 ? pair_b[kk] : 0;
+    }
+    double t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      t[u] = 0.0;
+      if (ia[u] >= 0) {
+        const double *wv = WV + 18 * (size_t)ia[u] + 3 * row;
+        const double *w = W + 18 * (size_t)ib[u] + 3 * col;
+        t[u] = wv[0] * w[0] + wv[1] * w[1] + wv[2] * w[2];
+      }
+    }
+    acc0 += t[0];
+    acc1 += t[1];
+    acc0 += t[2];
+    acc1 += t[3];
   }
   sm[sl * 36 + e] = acc0 + acc1;
   __syncthreads();

@@ -376,3 +376,150 @@ k_ldlt_solve(int n, const double *__restrict__ Sg, const double *__restrict__ rh
   }
   if (tid < 4) yk[tid] = nk ? ysh[6 * n_free + tid] : 0.0;
 }
+
+// =====================================================================
+// Register-resident variant (the one in force).  k_ldlt_solve above keeps the trailing matrix in shared memory
+// and is bound by shared-memory bandwidth (n^3/6 entries loaded and stored once each: 58 of its 67 us at n = 118).
+// Here every thread OWNS the entries (i, k) = (warp + 32 ti, lane + 32 tk), tk <= ti, in registers for the whole
+// factorisation (NT (NT + 1) / 2 <= 15 doubles); only the pivot column travels through shared memory:
+//   step j:  barrier; read column j (c_k by lane, c_i by warp: broadcast) and 1 / d_j; a_ik -= (c_i / d_j) c_k on
+//            the live tiles (tile columns >= j / 32: compile-time phases); the owners of column j + 1 (lane ==
+//            (j + 1) % 32) store it to its permanent slot C[(j + 1) ldc + i], the owner of the next pivot also
+//            stores its reciprocal.
+// No predicates in the update: entries of finished rows / columns and of the upper halves of the diagonal tiles
+// keep being "updated" with whatever the finished part of the column slot holds -- they are never read again.
+// The stored columns C are L D (column-major, ldc odd: the row-wise reads of the back substitution are
+// bank-conflict free); row n carries the right-hand side, so C[j ldc + n] = w_j (L w = b) at the end.
+// =====================================================================
+#define BA_LDLT2_MAX_N 159
+__host__ __device__ inline int ldlt2_ldc(int n) { return (n + 1) | 1; }
+__host__ __device__ inline int ldlt2_tiles(int n) { return (n + 1 + 31) / 32; }
+__host__ __device__ inline size_t ldlt2_smem_bytes(int n) {
+  return ((size_t)n * ldlt2_ldc(n) + 32 * ldlt2_tiles(n) + 2 * (size_t)(n + 8)) * 8;
+}
+#define LDLT2_IDX(ti, tk) ((ti) * ((ti) + 1) / 2 + (tk))
+
+template <int NT, int P, int PUB>
+__device__ __forceinline__ bool ldlt2_step(double (&a)[NT * (NT + 1) / 2], double *__restrict__ C, double *__restrict__ invd,
+                                           int ldc, int n, int j, int warp, int lane) {
+  __syncthreads();
+  const double *cj = C + j * ldc;
+  const double rd = invd[j];
+  if (!(rd > 0.0)) return false;  // -1: non-positive pivot, 0: infinite pivot, NaN; the same value in every thread
+  double ck[NT];
+#pragma unroll
+  for (int t = P; t < NT; ++t) ck[t] = cj[lane + 32 * t];
+#pragma unroll
+  for (int ti = P; ti < NT; ++ti) {
+    const double l = cj[warp + 32 * ti] * rd;
+#pragma unroll
+    for (int tk = P; tk <= ti; ++tk) a[LDLT2_IDX(ti, tk)] -= l * ck[tk];
+  }
+  const int jn = j + 1;
+  if (jn < n && lane == (jn & 31)) {  // this lane owns column jn in every warp
+    double *cn = C + jn * ldc;
+#pragma unroll
+    for (int ti = PUB; ti < NT; ++ti) {
+      const int i = warp + 32 * ti;
+      if (i >= jn && i <= n) cn[i] = a[LDLT2_IDX(ti, PUB)];
+    }
+    if (warp == lane) {
+      const double d = a[LDLT2_IDX(PUB, PUB)];
+      invd[jn] = d > 0.0 ? __drcp_rn(d) : -1.0;
+    }
+  }
+  return true;
+}
+
+template <int NT, int P>
+__device__ __forceinline__ bool ldlt2_phase(double (&a)[NT * (NT + 1) / 2], double *__restrict__ C, double *__restrict__ invd,
+                                            int ldc, int n, int warp, int lane) {
+  if constexpr (P < NT) {
+    const int jend = min(32 * P + 31, n);
+    for (int j = 32 * P; j < jend; ++j)
+      if (!ldlt2_step<NT, P, P>(a, C, invd, ldc, n, j, warp, lane)) return false;
+    if (32 * P + 31 < n)  // the last column of the tile column publishes into the next one
+      if (!ldlt2_step<NT, P, (P + 1 < NT ? P + 1 : P)>(a, C, invd, ldc, n, 32 * P + 31, warp, lane)) return false;
+    return ldlt2_phase<NT, P + 1>(a, C, invd, ldc, n, warp, lane);
+  } else {
+    return true;
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(1024)
+k_ldlt2_solve(int n, const double *__restrict__ Sg, const double *__restrict__ rhs, int n_cam, int n_free,
+              const int32_t *__restrict__ cam_slot, int nk, double *__restrict__ yc, double *__restrict__ yk, LmState *st,
+              int gate) {
+  if (!gate_open(st, gate)) return;
+  if (st->lin_fail) return;
+  extern __shared__ double smd[];
+  const int ldc = ldlt2_ldc(n);
+  double *C = smd;                                      // n columns of ldc (+ 32 NT: reads of the last tile row)
+  double *invd = smd + (size_t)n * ldc + 32 * NT;       // n + 8
+  double *ysh = invd + n + 8;                           // n + 8
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // launched with exactly 32 warps
+  double a[NT * (NT + 1) / 2];
+#pragma unroll
+  for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+    for (int tk = 0; tk <= ti; ++tk) {
+      const int i = warp + 32 * ti, k = lane + 32 * tk;
+      double v = 0.0;
+      if (k < n) {
+        if (i < n) v = Sg[(size_t)i * n + k];
+        else if (i == n) v = rhs[k];
+      }
+      a[LDLT2_IDX(ti, tk)] = v;
+    }
+  if (lane == 0) {  // column 0
+#pragma unroll
+    for (int ti = 0; ti < NT; ++ti) {
+      const int i = warp + 32 * ti;
+      if (i <= n) C[i] = a[LDLT2_IDX(ti, 0)];
+    }
+    if (warp == 0) invd[0] = a[0] > 0.0 ? __drcp_rn(a[0]) : -1.0;
+  }
+  const bool ok = ldlt2_phase<NT, 0>(a, C, invd, ldc, n, warp, lane);
+  if (!ok) {
+    if (tid == 0) st->lin_fail = 1;
+    return;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // L^T y = D^-1 w: lane l owns rows l + 32 s; y_k broadcast by shuffle, c_ki = C[i ldc + k]
+    double w[NT], iv[NT];
+#pragma unroll
+    for (int s = 0; s < NT; ++s) {
+      const int i = lane + 32 * s;
+      w[s] = i < n ? C[i * ldc + n] : 0.0;
+      iv[s] = i < n ? invd[i] : 0.0;
+    }
+#pragma unroll
+    for (int s = NT - 1; s >= 0; --s) {
+      if (32 * s >= n) continue;
+#pragma unroll 4
+      for (int kk = 31; kk >= 0; --kk) {
+        const int k = 32 * s + kk;
+        if (k >= n) continue;
+        const double y = __shfl_sync(0xffffffffu, w[s] * iv[s], kk);
+        if (lane == kk) ysh[k] = y;
+        if (lane < kk) w[s] -= C[(32 * s + lane) * ldc + k] * y;
+#pragma unroll
+        for (int s2 = 0; s2 < NT; ++s2)
+          if (s2 < s) w[s2] -= C[(32 * s2 + lane) * ldc + k] * y;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < n_cam; c += 1024) {
+    const int slot = cam_slot[c];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double v = slot >= 0 ? ysh[6 * slot + k] : 0.0;
+      if (!isfinite(v)) st->lin_fail = 1;
+      yc[6 * (size_t)c + k] = v;
+    }
+  }
+  if (tid < 4) yk[tid] = nk ? ysh[6 * n_free + tid] : 0.0;
+}
