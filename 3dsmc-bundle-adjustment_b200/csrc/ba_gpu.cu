@@ -84,7 +84,7 @@ struct ba_gpu_ctx {
   // second stream for the independent branches of an LM iteration (fork / join by events): the windowed
   // problems are chains of ~25 latency-bound small kernels, several of which do not depend on each other
   cudaStream_t stream2 = nullptr, cur = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
   bool forking = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -341,6 +341,7 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   ctx->cur = ctx->stream;
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMallocHost((void **)&ctx->h_st, sizeof(LmState))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -384,6 +385,7 @@ extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1209,6 +1211,14 @@ static void fork_side(ba_gpu_ctx *ctx) {
   ctx->cur = ctx->stream2;
 }
 static void fork_main(ba_gpu_ctx *ctx) { ctx->cur = ctx->stream; }
+// inside a fork: the side branch continues after what the main branch has enqueued so far
+static void side_after_main(ba_gpu_ctx *ctx) {
+  if (ctx->forking) {
+    cudaEventRecord(ctx->ev_mid, ctx->stream);
+    cudaStreamWaitEvent(ctx->stream2, ctx->ev_mid, 0);
+    ctx->cur = ctx->stream2;
+  }
+}
 static void join(ba_gpu_ctx *ctx) {
   ctx->cur = ctx->stream;
   if (!ctx->forking) return;
@@ -1265,13 +1275,17 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
            P<double>(ctx->part_blk), st, gate);
     ItemRef ir = ItemRef{P<int32_t>(ctx->item_ptr), P<double>(ctx->part_blk)};
     if (KK == 0) ir = reduce_items<27>(ctx, P<double>(ctx->part_blk), ctx->red_blk, gate);
-    LAUNCH((k_cam_blocks_fin<KK>), cdiv(ctx->n_cam * (27 + (KK ? 24 : 0)), BA_THREADS), BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part,
-           P<double>(ctx->U), P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
+    if (KK) {
+      // camera blocks and the intrinsics block finish in one launch
+      const int nb = cdiv(ctx->n_cam * 51, BA_THREADS);
+      LAUNCH(k_cam_kk_fin, nb + 1, BA_THREADS, 0, nb, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->U), P<double>(ctx->gc),
+             P<double>(ctx->Uck), P<double>(ctx->dc), ctx->n_items, P<double>(ctx->intr), P<double>(ctx->intr_prior), sk, ctx->cp,
+             ctx->lo, P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->rk), P<double>(ctx->Jkk), st, gate);
+    } else {
+      LAUNCH((k_cam_blocks_fin<0>), cdiv(ctx->n_cam * 27, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part,
+             P<double>(ctx->U), P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->dc), ctx->lo, st, gate);
+    }
   });
-  if (K)
-    LAUNCH(k_kk_fin, 1, BA_THREADS, 0, ctx->n_items, P<double>(ctx->part_blk), P<double>(ctx->intr), P<double>(ctx->intr_prior),
-           sk, ctx->cp, ctx->lo, P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->rk),
-           P<double>(ctx->Jkk), st, gate);
   join(ctx);
 }
 static void enqueue_state_norms(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk) {
@@ -1281,7 +1295,7 @@ static void enqueue_state_norms(ba_gpu_ctx *ctx, int gate, const double *sc, con
 }
 
 // IterationZero of the trust-region minimizer
-static void enqueue_iteration_zero(ba_gpu_ctx *ctx) {
+static void enqueue_iteration_zero(ba_gpu_ctx *ctx, bool begin_loop = true) {
   LmState *st = P<LmState>(ctx->st);
   LAUNCH(k_lm_init, 1, 1, 0, st, ctx->opt.initial_trust_region_radius);
   const bool js = ctx->opt.jacobi_scaling != 0;
@@ -1304,6 +1318,7 @@ static void enqueue_iteration_zero(ba_gpu_ctx *ctx) {
   const PartRef rx_ = reduce_scalar(ctx, P<double>(ctx->pe_xn), ctx->nblk_ent, 2, false, GATE_RUN);
   LAUNCH(k_lm_iter0, 1, BA_THREADS, 0, rc_.n, rg_.n, ctx->nk, rc_.p, rg_.p, rx_.p, P<double>(ctx->rk), ctx->lo, st,
          P<BaIterRec>(ctx->trace));
+  if (begin_loop) LAUNCH(k_lm_begin, 1, 1, 0, ctx->lo, st);  // top-of-loop checks of iteration 1; later ones ride on k_lm_control / k_lm_post
   ctx->linearized = true;
 }
 
@@ -1530,17 +1545,20 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
   const int n = ctx->n_red;
   if (n == 0) return 0;
   cudaMemsetAsync(ctx->S.p, 0, (size_t)n * n * 8, ctx->stream);
-  DISPATCH_D(ctx->depth, {
-    LAUNCH((k_obs_W<DD>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pt_idx), ctx->Jc_, P<double>(ctx->Vinv),
-           P<double>(ctx->W), P<double>(ctx->WV), st, GATE_RUN);
-  });
-  // borders + right-hand side on the side stream, the camera-camera blocks on the main one (disjoint parts of S)
+  // side stream: point-block inverses (k_obs_W re-derives the inverse it needs), then -- once W is there -- borders +
+  // right-hand side; main stream: W, then the camera-camera blocks (disjoint parts of S)
   fork_side(ctx);
+  enqueue_point_inverse(ctx, GATE_RUN);
+  fork_main(ctx);
+  DISPATCH_D(ctx->depth, {
+    LAUNCH((k_obs_W<DD>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pt_idx), ctx->Jc_, P<double>(ctx->V),
+           P<double>(ctx->dp), P<double>(ctx->W), P<double>(ctx->WV), st, GATE_RUN);
+  });
+  side_after_main(ctx);
   if (ctx->nk) {
-    LAUNCH((k_explicit_cam<4>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx),
-           P<double>(ctx->W), P<double>(ctx->WV), P<double>(ctx->tg), P<double>(ctx->Wk), P<double>(ctx->part_ex), st, GATE_RUN);
-    LAUNCH(k_explicit_kk, ctx->nblk_pt, BA_THREADS, 0, ctx->n_pt, P<double>(ctx->Wk), P<double>(ctx->Vinv), P<double>(ctx->tg),
-           P<double>(ctx->part_kk), st, GATE_RUN);
+    LAUNCH(k_explicit_cam_kk, ctx->nblk_item + ctx->nblk_pt, BA_THREADS, 0, ctx->nblk_item, ctx->n_items, P<BaItem>(ctx->items),
+           P<int32_t>(ctx->pt_idx), P<double>(ctx->W), P<double>(ctx->WV), P<double>(ctx->tg), P<double>(ctx->Wk),
+           P<double>(ctx->part_ex), ctx->n_pt, P<double>(ctx->Vinv), P<double>(ctx->part_kk), st, GATE_RUN);
     LAUNCH((k_explicit_assemble<4>), cdiv(ctx->n_cam * 30 + 14, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ctx->n_free, n,
            P<int32_t>(ctx->cam_slot), P<int32_t>(ctx->item_ptr), P<double>(ctx->part_ex), ctx->nblk_pt, P<double>(ctx->part_kk),
            P<double>(ctx->gc), P<double>(ctx->Uck), P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->S),
@@ -1612,8 +1630,7 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
 static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
   LmState *st = P<LmState>(ctx->st);
   const int D = ctx->depth, K = ctx->nk;
-  LAUNCH(k_lm_begin, 1, 1, 0, ctx->lo, st);
-  enqueue_point_inverse(ctx, GATE_RUN);
+  if (ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY) enqueue_point_inverse(ctx, GATE_RUN);  // (explicit: inside solve_explicit)
   int rc = ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY ? solve_implicit(ctx) : solve_explicit(ctx);
   if (rc) return rc;
   if (ctx->fact) {
@@ -1890,7 +1907,7 @@ __global__ void k_set_radius(LmState *st, double radius) { st->radius = radius; 
 // brings the device to "linearised at the current point" with a given radius:
 // iteration zero (scaling included) + damped point-block inverses
 static int prepare_linear_system(ba_gpu_ctx *ctx, double radius) {
-  enqueue_iteration_zero(ctx);
+  enqueue_iteration_zero(ctx, false);
   LmState *st = P<LmState>(ctx->st);
   LAUNCH(k_set_radius, 1, 1, 0, st, radius);
   enqueue_point_inverse(ctx, GATE_RUN);

@@ -372,15 +372,14 @@ k_cam_blocks(int n_items, const BaItem *__restrict__ items, JPlanes J, double *_
 
 // per camera: add item partials in order; U (full 6x6), g_c, U_ck, clamped LM diagonal
 template <int NK>
-__global__ void __launch_bounds__(BA_THREADS)
-k_cam_blocks_fin(int n_cam, const int32_t *__restrict__ item_ptr, const double *__restrict__ part, double *__restrict__ U,
+__device__ __forceinline__ void d_k_cam_blocks_fin(int bid, int n_cam, const int32_t *__restrict__ item_ptr, const double *__restrict__ part, double *__restrict__ U,
                  double *__restrict__ gc, double *__restrict__ Uck, double *__restrict__ dc, LmOptions lo,
                  const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
   // one thread per (camera, value): a camera's item partials are added in item order (coalesced across values)
   constexpr int NV = CamBlk<NK>::NV;
   constexpr int NL = 27 + (NK ? 24 : 0);
-  const int idx = blockIdx.x * BA_THREADS + threadIdx.x;
+  const int idx = bid * BA_THREADS + threadIdx.x;
   if (idx >= n_cam * NL) return;
   const int c = idx / NL, k = idx - c * NL;
   double acc = 0.0;
@@ -402,12 +401,18 @@ k_cam_blocks_fin(int n_cam, const int32_t *__restrict__ item_ptr, const double *
     Uck[24 * (size_t)c + k - 27] = acc;
   }
 }
+template <int NK>
+__global__ void __launch_bounds__(BA_THREADS)
+k_cam_blocks_fin(int n_cam, const int32_t *__restrict__ item_ptr, const double *__restrict__ part, double *__restrict__ U,
+                 double *__restrict__ gc, double *__restrict__ Uck, double *__restrict__ dc, LmOptions lo,
+                 const LmState *st, int gate) {
+  d_k_cam_blocks_fin<NK>(blockIdx.x, n_cam, item_ptr, part, U, gc, Uck, dc, lo, st, gate);
+}
 
 // intrinsics block: U_kk (4x4), g_k, LM diagonal; single CTA, fixed order.
 // Adds the IntrinsicsPrior (:116-125) residual r_k = sqrt(w)(prior - intr) with
 // Jacobian -sqrt(w) I (column-scaled by sk).
-__global__ void __launch_bounds__(BA_THREADS)
-k_kk_fin(int n_items, const double *__restrict__ part, const double *__restrict__ intr, const double *__restrict__ intr_prior,
+__device__ __forceinline__ void d_k_kk_fin(int bid, int n_items, const double *__restrict__ part, const double *__restrict__ intr, const double *__restrict__ intr_prior,
          const double *__restrict__ sk, CostParams cp, LmOptions lo, double *__restrict__ Ukk, double *__restrict__ gk,
          double *__restrict__ dk, double *__restrict__ rk, double *__restrict__ Jkk, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
@@ -447,6 +452,26 @@ k_kk_fin(int n_items, const double *__restrict__ part, const double *__restrict_
       dk[k] = fmin(fmax(K[k * 5], lo.min_lm_diagonal), lo.max_lm_diagonal);
     }
   }
+}
+__global__ void __launch_bounds__(BA_THREADS)
+k_kk_fin(int n_items, const double *__restrict__ part, const double *__restrict__ intr, const double *__restrict__ intr_prior,
+         const double *__restrict__ sk, CostParams cp, LmOptions lo, double *__restrict__ Ukk, double *__restrict__ gk,
+         double *__restrict__ dk, double *__restrict__ rk, double *__restrict__ Jkk, const LmState *st, int gate) {
+  d_k_kk_fin(blockIdx.x, n_items, part, intr, intr_prior, sk, cp, lo, Ukk, gk, dk, rk, Jkk, st, gate);
+}
+
+// REF mode: the two finishing kernels above are independent -> one launch (CTAs [0, nb_cam) finish the camera
+// blocks, the last CTA the intrinsics block); one launch less on the critical path of the windowed LM iteration
+__global__ void __launch_bounds__(BA_THREADS)
+k_cam_kk_fin(int nb_cam, int n_cam, const int32_t *__restrict__ item_ptr, const double *__restrict__ part, double *__restrict__ U,
+             double *__restrict__ gc, double *__restrict__ Uck, double *__restrict__ dc, int n_items,
+             const double *__restrict__ intr, const double *__restrict__ intr_prior, const double *__restrict__ sk, CostParams cp,
+             LmOptions lo, double *__restrict__ Ukk, double *__restrict__ gk, double *__restrict__ dk, double *__restrict__ rk,
+             double *__restrict__ Jkk, const LmState *st, int gate) {
+  if ((int)blockIdx.x < nb_cam)
+    d_k_cam_blocks_fin<4>(blockIdx.x, n_cam, item_ptr, part, U, gc, Uck, dc, lo, st, gate);
+  else
+    d_k_kk_fin(0, n_items, part, intr, intr_prior, sk, cp, lo, Ukk, gk, dk, rk, Jkk, st, gate);
 }
 
 // =====================================================================
@@ -1462,8 +1487,11 @@ k_lm_iter0(int nblk_obs, int nblk_ent, int nk, const double *__restrict__ part_c
   }
 }
 
-// top of the minimizer loop (FinalizeIterationAndCheckIfMinimizerCanContinue)
-__global__ void k_lm_begin(LmOptions lo, LmState *st) {
+// top of the minimizer loop (FinalizeIterationAndCheckIfMinimizerCanContinue).  Evaluated by the thread that ENDS
+// the previous iteration (k_lm_control when the step is not accepted, k_lm_post when it is; k_lm_begin after
+// iteration zero): one launch less per iteration, and the termination flag is already set when the host polls
+// after the last iteration (no trailing gated-off iteration).
+__device__ __forceinline__ void lm_begin(const LmOptions &lo, LmState *st) {
   if (st->done) return;
   if (st->iter - 1 >= lo.max_num_iterations) {
     st->done = 1;
@@ -1484,20 +1512,14 @@ __global__ void k_lm_begin(LmOptions lo, LmState *st) {
   st->lin_fail = 0;
   st->pcg_iters_last = 0;
 }
+__global__ void k_lm_begin(LmOptions lo, LmState *st) { lm_begin(lo, st); }
 
 // step evaluation: model cost change, tolerances, relative decrease, radius
 // update (LevenbergMarquardtStrategy::StepAccepted / StepRejected)
-__global__ void __launch_bounds__(BA_THREADS)
-k_lm_control(int nblk_obs, int nblk_ent, int nk, const double *__restrict__ part_mcc, const double *__restrict__ part_step,
-             const double *__restrict__ part_cost, const double *__restrict__ rk, const double *__restrict__ Jkk,
-             const double *__restrict__ yk, const double *__restrict__ intr_c, const double *__restrict__ intr_prior,
-             double sw_intr, LmOptions lo, LmState *st, BaIterRec *trace) {
-  if (st->done) return;
-  __shared__ double red[BA_WARPS + 2];
-  double msum = block_sum_array(part_mcc, nblk_obs, red);
-  const double step2 = block_sum_array(part_step, nblk_ent, red);
-  double cand = block_sum_array(part_cost, nblk_obs, red);
-  if (threadIdx.x != 0) return;
+__device__ __forceinline__ void lm_control_thread0(double msum, double step2, double cand, int nk, const double *__restrict__ rk,
+                                                   const double *__restrict__ Jkk, const double *__restrict__ yk,
+                                                   const double *__restrict__ intr_c, const double *__restrict__ intr_prior,
+                                                   double sw_intr, const LmOptions &lo, LmState *st, BaIterRec *trace) {
   BaIterRec r;
   memset(&r, 0, sizeof(r));
   r.iteration = st->iter;
@@ -1578,6 +1600,20 @@ k_lm_control(int nblk_obs, int nblk_ent, int nk, const double *__restrict__ part
   }
   st->iter++;
 }
+__global__ void __launch_bounds__(BA_THREADS)
+k_lm_control(int nblk_obs, int nblk_ent, int nk, const double *__restrict__ part_mcc, const double *__restrict__ part_step,
+             const double *__restrict__ part_cost, const double *__restrict__ rk, const double *__restrict__ Jkk,
+             const double *__restrict__ yk, const double *__restrict__ intr_c, const double *__restrict__ intr_prior,
+             double sw_intr, LmOptions lo, LmState *st, BaIterRec *trace) {
+  if (st->done) return;
+  __shared__ double red[BA_WARPS + 2];
+  const double msum = block_sum_array(part_mcc, nblk_obs, red);
+  const double step2 = block_sum_array(part_step, nblk_ent, red);
+  const double cand = block_sum_array(part_cost, nblk_obs, red);
+  if (threadIdx.x != 0) return;
+  lm_control_thread0(msum, step2, cand, nk, rk, Jkk, yk, intr_c, intr_prior, sw_intr, lo, st, trace);
+  if (!st->accepted) lm_begin(lo, st);  // not accepted (or finished): the iteration ends here
+}
 
 // after the relinearisation of an accepted step
 __global__ void __launch_bounds__(BA_THREADS)
@@ -1607,6 +1643,7 @@ k_lm_post(int nblk_obs, int nblk_ent, int nk, const double *__restrict__ part_co
     st->done = 1;
     st->termination = 5;
   }
+  lm_begin(lo, st);  // an accepted iteration ends here
 }
 
 // =====================================================================
@@ -1617,20 +1654,35 @@ k_lm_post(int nblk_obs, int nblk_ent, int nk, const double *__restrict__ part_co
 // per observation (camera-major): W = Jc^T Jp (6x3) and WV = W V_p^-1
 template <int DEPTH>
 __global__ void __launch_bounds__(BA_THREADS)
-k_obs_W(int n_obs, const int32_t *__restrict__ pt_idx, JPlanes J, const double *__restrict__ Vinv,
+k_obs_W(int n_obs, const int32_t *__restrict__ pt_idx, JPlanes J, const double *__restrict__ V, const double *__restrict__ dp,
         double *__restrict__ W, double *__restrict__ WV, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
   const int i = blockIdx.x * BA_THREADS + threadIdx.x;
   if (i >= n_obs) return;
   const int p = pt_idx[i];
+  // V_p^-1 is re-derived here from V_p and the LM diagonal with k_point_inverse's arithmetic (identical bits), so that
+  // kernel runs beside this one on the side stream instead of in front of it
+  double vi[6];
+  {
+    const double radius = st->radius;
+    double v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = V[6 * (size_t)p + k];
+    const double D0 = sqrt(dp[3 * (size_t)p] / radius), D1 = sqrt(dp[3 * (size_t)p + 1] / radius),
+                 D2 = sqrt(dp[3 * (size_t)p + 2] / radius);
+    v[0] += D0 * D0;
+    v[3] += D1 * D1;
+    v[5] += D2 * D2;
+    if (!spd3_inverse(v, vi)) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) vi[k] = 0.0;
+    }
+  }
   double2 jc[6], jp[3];
 #pragma unroll
   for (int k = 0; k < 6; ++k) jc[k] = lds2(J.Jc[k] + i);
 #pragma unroll
   for (int k = 0; k < 3; ++k) jp[k] = lds2(J.Jp[k] + i);
-  double vi[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) vi[k] = Vinv[6 * (size_t)p + k];
   double w[6][3];
 #pragma unroll
   for (int a = 0; a < 6; ++a)
@@ -1660,12 +1712,11 @@ k_obs_W(int n_obs, const int32_t *__restrict__ pt_idx, JPlanes J, const double *
 //   rhs_c += W_o (V^-1 g_p)          (6)
 //   S_ck  += WV_o Wk_p^T             (6x4, REF mode)
 template <int NK>
-__global__ void __launch_bounds__(BA_THREADS)
-k_explicit_cam(int n_items, const BaItem *__restrict__ items, const int32_t *__restrict__ pt_idx,
+__device__ __forceinline__ void d_k_explicit_cam(int bid, int n_items, const BaItem *__restrict__ items, const int32_t *__restrict__ pt_idx,
                const double *__restrict__ W, const double *__restrict__ WV, const double *__restrict__ tg,
                const double *__restrict__ Wk, double *__restrict__ part, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  const int wid = (blockIdx.x * BA_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int wid = (bid * BA_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= n_items) return;
   const BaItem it = items[wid];
   constexpr int NV = 6 + (NK ? 24 : 0);
@@ -1697,15 +1748,21 @@ k_explicit_cam(int n_items, const BaItem *__restrict__ items, const int32_t *__r
     for (int k = 0; k < NV; ++k) part[(size_t)wid * NV + k] = acc[k];
   }
 }
+template <int NK>
+__global__ void __launch_bounds__(BA_THREADS)
+k_explicit_cam(int n_items, const BaItem *__restrict__ items, const int32_t *__restrict__ pt_idx,
+               const double *__restrict__ W, const double *__restrict__ WV, const double *__restrict__ tg,
+               const double *__restrict__ Wk, double *__restrict__ part, const LmState *st, int gate) {
+  d_k_explicit_cam<NK>(blockIdx.x, n_items, items, pt_idx, W, WV, tg, Wk, part, st, gate);
+}
 
 // intrinsics corner: per-CTA partials over points of Wk V^-1 Wk^T (10 upper
 // entries) and Wk (V^-1 g_p) (4)
-__global__ void __launch_bounds__(BA_THREADS)
-k_explicit_kk(int n_pt, const double *__restrict__ Wk, const double *__restrict__ Vinv, const double *__restrict__ tg,
+__device__ __forceinline__ void d_k_explicit_kk(int bid, int n_pt, const double *__restrict__ Wk, const double *__restrict__ Vinv, const double *__restrict__ tg,
               double *__restrict__ part, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
   __shared__ double red[BA_WARPS + 1];
-  const int p = blockIdx.x * BA_THREADS + threadIdx.x;
+  const int p = bid * BA_THREADS + threadIdx.x;
   double v[14];
 #pragma unroll
   for (int k = 0; k < 14; ++k) v[k] = 0.0;
@@ -1731,8 +1788,25 @@ k_explicit_kk(int n_pt, const double *__restrict__ Wk, const double *__restrict_
 #pragma unroll
   for (int k = 0; k < 14; ++k) {
     const double s = block_sum(v[k], red);
-    if (threadIdx.x == 0) part[14 * (size_t)blockIdx.x + k] = s;
+    if (threadIdx.x == 0) part[14 * (size_t)bid + k] = s;
   }
+}
+__global__ void __launch_bounds__(BA_THREADS)
+k_explicit_kk(int n_pt, const double *__restrict__ Wk, const double *__restrict__ Vinv, const double *__restrict__ tg,
+              double *__restrict__ part, const LmState *st, int gate) {
+  d_k_explicit_kk(blockIdx.x, n_pt, Wk, Vinv, tg, part, st, gate);
+}
+
+// REF mode: camera-side vectors and the intrinsics corner in one launch (CTAs [0, nb_item) / [nb_item, ..))
+__global__ void __launch_bounds__(BA_THREADS)
+k_explicit_cam_kk(int nb_item, int n_items, const BaItem *__restrict__ items, const int32_t *__restrict__ pt_idx,
+                  const double *__restrict__ W, const double *__restrict__ WV, const double *__restrict__ tg,
+                  const double *__restrict__ Wk, double *__restrict__ part, int n_pt, const double *__restrict__ Vinv,
+                  double *__restrict__ part_kk, const LmState *st, int gate) {
+  if ((int)blockIdx.x < nb_item)
+    d_k_explicit_cam<4>(blockIdx.x, n_items, items, pt_idx, W, WV, tg, Wk, part, st, gate);
+  else
+    d_k_explicit_kk(blockIdx.x - nb_item, n_pt, Wk, Vinv, tg, part_kk, st, gate);
 }
 
 // camera-camera blocks: one CTA per block pair (i <= j) of the pair list;
