@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -124,10 +125,12 @@ struct ba_gpu_ctx {
   int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0, sp_ctas_per_sm = 1;
   Buf sp_pair_pt, chol_v;
   // one LM iteration of the windowed explicit solver as an instantiated CUDA graph (every decision is taken on the
-  // device, so the node parameters never change between iterations); dropped by upload / set_options
+  // device, so the node parameters never change between iterations); upload / set_options mark it stale and the next
+  // solve re-captures and updates the executable in place (cudaGraphExecUpdate: destroying and re-instantiating it cost
+  // 0.2 + 0.1 ms per window)
   cudaGraphExec_t lm_graph = nullptr;
   int64_t lm_graph_launches = 0;
-  bool lm_graph_off = false;
+  bool lm_graph_off = false, lm_graph_stale = true;
   int legacy_chol = 0;  // BA_LEGACY_CHOL=1: left-looking single-CTA Cholesky, =2: shared-memory L D L^T (A/B timing only)
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
@@ -153,6 +156,7 @@ struct ba_gpu_ctx {
   Buf red_blk, red6, red21, scal, ident;
   // explicit solver
   Buf W, WV, S, rhs, blk_i, blk_j, blk_cam, pair_ptr, pair_a, pair_b;
+  Buf ex_keys, ex_keys2, ex_vals, ex_vals2, blk_cnt;  // device-built pair list (windows)
   int n_blk = 0;
   // controller
   Buf st, trace;
@@ -403,7 +407,7 @@ extern "C" int ba_gpu_set_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
   ctx->opt = *o;
   ctx->opt.device = dev;
   ctx->uploaded = false;
-  drop_lm_graph(ctx);
+  ctx->lm_graph_stale = true;
   return BA_OK;
 }
 
@@ -573,6 +577,52 @@ static int allreduce_host_scalar(ba_gpu_ctx *ctx, double *v, bool is_max) {
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+// pair list of the dense explicit solver, device-built (windowed problems: the host loop of build_pair_list()
+// plus its six host->device copies were the largest part of ba_gpu_upload).  Every block of the upper triangle is
+// listed; k_schur_pairs skips the empty off-diagonal ones.
+static int build_pair_list_device(ba_gpu_ctx *ctx) {
+  const int n_pt = ctx->n_pt, nf = ctx->n_free;
+  const int nb_all = nf * (nf + 1) / 2;
+  cudaStream_t s = ctx->stream;
+  RES(sp_cnt, ((size_t)n_pt + 2) * 8);
+  RES(sp_off, ((size_t)n_pt + 2) * 8);
+  LAUNCH(k_sp_count, cdiv(n_pt + 1, BA_THREADS), BA_THREADS, 0, n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam),
+         ctx->fixed_cam, P<long long>(ctx->sp_cnt));
+  CUBCALL(cub::DeviceScan::ExclusiveSum, P<long long>(ctx->sp_cnt), P<long long>(ctx->sp_off), n_pt + 1);
+  long long n_pairs = 0;
+  CK(cudaMemcpyAsync(&n_pairs, P<long long>(ctx->sp_off) + n_pt, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (n_pairs > 0x7fffffffLL) return fail(ctx, BA_ERR_UNSUPPORTED, "explicit Schur pair list too large");
+  const size_t np1 = (size_t)n_pairs + 1;
+  RES(ex_keys, np1 * 4);
+  RES(ex_keys2, np1 * 4);
+  RES(ex_vals, np1 * 8);
+  RES(ex_vals2, np1 * 8);
+  RES(blk_cnt, ((size_t)nb_all + 2) * 4);
+  RES(blk_i, ((size_t)nb_all + 1) * 4);
+  RES(blk_j, ((size_t)nb_all + 1) * 4);
+  RES(blk_cam, ((size_t)nb_all + 1) * 4);
+  RES(pair_ptr, ((size_t)nb_all + 2) * 4);
+  RES(pair_a, np1 * 4);
+  RES(pair_b, np1 * 4);
+  CK(cudaMemsetAsync(ctx->blk_cnt.p, 0, ((size_t)nb_all + 2) * 4, s));
+  LAUNCH(k_ex_emit, ctx->nblk_pt, BA_THREADS, 0, n_pt, nf, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->perm),
+         ctx->fixed_cam, P<long long>(ctx->sp_off), P<uint32_t>(ctx->ex_keys), P<unsigned long long>(ctx->ex_vals),
+         P<int32_t>(ctx->blk_cnt));
+  if (n_pairs > 0) {
+    int bits = 1;
+    while (bits < 31 && (1 << bits) < nb_all) ++bits;
+    CUBCALL(cub::DeviceRadixSort::SortPairs, P<uint32_t>(ctx->ex_keys), P<uint32_t>(ctx->ex_keys2),
+            P<unsigned long long>(ctx->ex_vals), P<unsigned long long>(ctx->ex_vals2), (int)n_pairs, 0, bits);
+  }
+  LAUNCH(k_exclusive_scan, 1, 1024, 0, nb_all, P<int32_t>(ctx->blk_cnt), P<int32_t>(ctx->pair_ptr));
+  LAUNCH(k_ex_finish, cdiv(std::max((int)n_pairs, nf * nf), BA_THREADS), BA_THREADS, 0, (int)n_pairs,
+         P<unsigned long long>(ctx->ex_vals2), P<int32_t>(ctx->pair_a), P<int32_t>(ctx->pair_b), nf, ctx->fixed_cam,
+         P<int32_t>(ctx->blk_i), P<int32_t>(ctx->blk_j), P<int32_t>(ctx->blk_cam));
+  ctx->n_blk = nb_all;
+  return 0;
+}
+
 static int sparse_count_pairs(ba_gpu_ctx *ctx, long long *n_pairs_out) {
   const int n_pt = ctx->n_pt;
   cudaStream_t s = ctx->stream;
@@ -818,12 +868,30 @@ static int setup_dist_pcg(ba_gpu_ctx *ctx) {
   return 0;
 }
 
+// BA_UPLOAD_PROF=1: host wall-clock stamps of the upload phases on stderr (measurement aid)
+struct UploadProf {
+  bool on = getenv("BA_UPLOAD_PROF") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  char line[512];
+  int len = 0;
+  void stamp(const char *what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    len += snprintf(line + len, sizeof(line) - len, " %s %.0f us |", what, std::chrono::duration<double, std::micro>(n - t).count());
+    t = n;
+  }
+  void flush() {
+    if (on) fprintf(stderr, "[BA_UPLOAD_PROF]%s\n", line);
+  }
+};
+
 extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7, int32_t fixed_cam, int32_t n_pt,
                              const double *pt3, int32_t n_obs, const int32_t *cam_idx, const int32_t *pt_idx,
                              const double *uv2, const double *depth, const double intr4[4], const double intr_prior4[4]) {
   if (!ctx) return BA_ERR_INVALID;
+  UploadProf prof;
   ctx->uploaded = false;
-  drop_lm_graph(ctx);
+  ctx->lm_graph_stale = true;
   ctx->linearized = false;
   const ba_gpu_options &o = ctx->opt;
   if (n_cam <= 0 || n_pt < 0 || n_obs < 0 || !pose7 || !intr4 || (n_pt > 0 && !pt3) ||
@@ -1004,6 +1072,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   RES(st, sizeof(LmState));
   RES(trace, (size_t)lo.trace_cap * sizeof(BaIterRec));
 
+  prof.stamp("reserve");
   cudaStream_t s = ctx->stream;
   CK(cudaMemcpyAsync(ctx->pose.p, pose7, nc * 56, cudaMemcpyHostToDevice, s));
   if (np) CK(cudaMemcpyAsync(ctx->pt.p, pt3, np * 24, cudaMemcpyHostToDevice, s));
@@ -1015,6 +1084,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     CK(cudaMemcpyAsync(ctx->uv.p, uv2, no * 16, cudaMemcpyHostToDevice, s));
     if (depth) CK(cudaMemcpyAsync(ctx->depthv.p, depth, no * 8, cudaMemcpyHostToDevice, s));
   }
+  prof.stamp("h2d");
   // ---- device-built indices
   CK(cudaMemsetAsync(ctx->pt_cnt.p, 0, (np + 1) * 4, s));
   CK(cudaMemsetAsync(ctx->cam_cnt.p, 0, (nc + 1) * 4, s));
@@ -1043,6 +1113,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   CK(cudaMemcpyAsync(&h_err, ctx->err_flag.p, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (h_err) return fail(ctx, BA_ERR_INVALID, "observation indices out of range or cam_idx not non-decreasing");
+  prof.stamp("index build + sync");
   ctx->n_items = h_items;
   ctx->nblk_item = cdiv(h_items * 32, BA_THREADS);
   RES(items, (size_t)(h_items + 1) * sizeof(BaItem));
@@ -1143,9 +1214,15 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     RES(S, (size_t)ctx->n_red * ctx->n_red * 8 + 64);
     RES(rhs, (size_t)ctx->n_red * 8 + 64);
     RES(chol_v, (size_t)(ctx->n_red + 64 + 8) * 8);
-    int rc = build_pair_list(ctx, cam_idx, pt_idx);
+    prof.stamp("rest");
+    // windows: device-built pair list; the global REF problem keeps the host-built list of NON-EMPTY blocks
+    // (320 k mostly empty blocks at 800 keyframes)
+    const bool dev_pairs = ctx->n_free <= 64 && getenv("BA_HOST_PAIRS") == nullptr;
+    int rc = dev_pairs ? build_pair_list_device(ctx) : build_pair_list(ctx, cam_idx, pt_idx);
     if (rc) return rc;
+    prof.stamp("pair list");
   }
+  prof.flush();
   CK(cudaGetLastError());
   ctx->forking = ctx->n_ranks == 1 && getenv("BA_NO_FORK") == nullptr;
   ctx->cur = ctx->stream;
@@ -1704,7 +1781,7 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
                        ctx->n_red > 0 && ctx->n_red <= BA_LDLT_MAX_N;
   for (int it = 1;; ++it) {
     if (graphed) {
-      if (!ctx->lm_graph) {
+      if (!ctx->lm_graph || ctx->lm_graph_stale) {
         const int64_t lb = ctx->launches;
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -1714,9 +1791,18 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
         ctx->launches = lb;
         if (rc) return rc;
         if (ce != cudaSuccess || !g) return fail(ctx, BA_ERR_CUDA, "LM iteration graph capture: %s", cudaGetErrorString(ce));
-        const cudaError_t ie = cudaGraphInstantiate(&ctx->lm_graph, g, 0);
+        if (ctx->lm_graph) {  // same topology, new sizes / pointers: update in place
+          cudaGraphExecUpdateResultInfo info;
+          if (cudaGraphExecUpdate(ctx->lm_graph, g, &info) != cudaSuccess) {
+            cudaGetLastError();  // topology changed (e.g. another cost model): rebuild
+            drop_lm_graph(ctx);
+          }
+        }
+        cudaError_t ie = cudaSuccess;
+        if (!ctx->lm_graph) ie = cudaGraphInstantiate(&ctx->lm_graph, g, 0);
         cudaGraphDestroy(g);
         if (ie != cudaSuccess) return fail(ctx, BA_ERR_CUDA, "LM iteration graph instantiate: %s", cudaGetErrorString(ie));
+        ctx->lm_graph_stale = false;
       }
       CK(cudaGraphLaunch(ctx->lm_graph, ctx->stream));
       ctx->launches += ctx->lm_graph_launches;

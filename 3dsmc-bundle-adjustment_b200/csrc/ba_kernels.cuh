@@ -1824,6 +1824,8 @@ k_schur_pairs(int n, const int32_t *__restrict__ blk_i, const int32_t *__restric
   if (!gate_open(st, gate)) return;
   __shared__ double sm[SLICES * 36];
   const int blk = blockIdx.x;
+  // device-built block table lists the whole upper triangle: an off-diagonal block without pairs stays zero
+  if (pair_ptr[blk] == pair_ptr[blk + 1] && blk_i[blk] != blk_j[blk]) return;
   const int e = threadIdx.x % 36, sl = threadIdx.x / 36;
   const int row = e / 6, col = e % 6;
   // the loop is bound by the index -> block gather latency: four pairs per round, all index loads issued before
