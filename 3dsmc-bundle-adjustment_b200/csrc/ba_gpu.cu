@@ -1306,9 +1306,12 @@ static void join(ba_gpu_ctx *ctx) {
 // ------------------------------------------------------------------ pipeline pieces
 // linearise at the current point in both orders + normal-equation blocks
 static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk,
-                              bool force_planes = false) {
+                              bool force_planes = false, bool from_candidate = false) {
   const int D = ctx->depth, K = ctx->nk;
   LmState *st = P<LmState>(ctx->st);
+  // from_candidate (planes path): read the accepted candidate x+ directly while k_accept copies it into x on the side stream
+  const double *xpose = P<double>(from_candidate ? ctx->pose_c : ctx->pose), *xpt = P<double>(from_candidate ? ctx->pt_c : ctx->pt),
+               *xintr = P<double>(from_candidate ? ctx->intr_c : ctx->intr);
   if (ctx->fact && !force_planes) {
     const double *intr = P<double>(ctx->intr);
     LAUNCH(k_cam_geo, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, ctx->fixed_cam, P<double>(ctx->pose), sc, P<double>(ctx->geo), st,
@@ -1339,14 +1342,14 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
     // point-major branch (side stream): linearise + point blocks
     fork_side(ctx);
     LAUNCH((k_linearize<DD, KK, 0>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->pm_pt),
-           P<double2>(ctx->pm_uv), P<double>(ctx->pm_depth), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc,
+           P<double2>(ctx->pm_uv), P<double>(ctx->pm_depth), xpose, xpt, xintr, sc,
            sp, sk, ctx->cp, ctx->Jp_, (double *)nullptr, st, gate);
     LAUNCH((k_pt_blocks<DD, KK>), ctx->pl_tiles, BA_THREADS, 0, ctx->n_pt, ctx->pl_tile_pts, P<int32_t>(ctx->pt_rowptr), ctx->Jp_, P<double>(ctx->V),
            P<double>(ctx->gp), P<double>(ctx->Wk), P<double>(ctx->dp), ctx->lo, st, gate);
     // camera-major branch (main stream): linearise + camera blocks
     fork_main(ctx);
     LAUNCH((k_linearize<DD, KK, 1>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
-           P<double2>(ctx->uv), P<double>(ctx->depthv), P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr), sc, sp,
+           P<double2>(ctx->uv), P<double>(ctx->depthv), xpose, xpt, xintr, sc, sp,
            sk, ctx->cp, ctx->Jc_, P<double>(ctx->pc_lin), st, gate);
     LAUNCH((k_cam_blocks<DD, KK>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), ctx->Jc_,
            P<double>(ctx->part_blk), st, gate);
@@ -1356,7 +1359,7 @@ static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const
       // camera blocks and the intrinsics block finish in one launch
       const int nb = cdiv(ctx->n_cam * 51, BA_THREADS);
       LAUNCH(k_cam_kk_fin, nb + 1, BA_THREADS, 0, nb, ctx->n_cam, ir.ptr, ir.part, P<double>(ctx->U), P<double>(ctx->gc),
-             P<double>(ctx->Uck), P<double>(ctx->dc), ctx->n_items, P<double>(ctx->intr), P<double>(ctx->intr_prior), sk, ctx->cp,
+             P<double>(ctx->Uck), P<double>(ctx->dc), ctx->n_items, xintr, P<double>(ctx->intr_prior), sk, ctx->cp,
              ctx->lo, P<double>(ctx->Ukk), P<double>(ctx->gk), P<double>(ctx->dk), P<double>(ctx->rk), P<double>(ctx->Jkk), st, gate);
     } else {
       LAUNCH((k_cam_blocks_fin<0>), cdiv(ctx->n_cam * 27, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ir.ptr, ir.part,
@@ -1627,8 +1630,9 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
   fork_side(ctx);
   enqueue_point_inverse(ctx, GATE_RUN);
   fork_main(ctx);
+  const int obs_w_threads = ctx->n_obs <= 64 * 2 * ctx->n_sm ? 64 : BA_THREADS;  // latency-bound on windows: spread over the SMs
   DISPATCH_D(ctx->depth, {
-    LAUNCH((k_obs_W<DD>), ctx->nblk_obs, BA_THREADS, 0, ctx->n_obs, P<int32_t>(ctx->pt_idx), ctx->Jc_, P<double>(ctx->V),
+    LAUNCH((k_obs_W<DD>), cdiv(ctx->n_obs, obs_w_threads), obs_w_threads, 0, ctx->n_obs, P<int32_t>(ctx->pt_idx), ctx->Jc_, P<double>(ctx->V),
            P<double>(ctx->dp), P<double>(ctx->W), P<double>(ctx->WV), st, GATE_RUN);
   });
   side_after_main(ctx);
@@ -1751,9 +1755,13 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
            P<BaIterRec>(ctx->trace));
   }
   // accepted: x <- x+, relinearise (all gated on the device-side decision)
+  const bool overlap_accept = ctx->forking && !ctx->fact;  // windowed explicit path
+  if (overlap_accept) fork_side(ctx);
   LAUNCH(k_accept, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, P<double>(ctx->pose), P<double>(ctx->pt), P<double>(ctx->intr),
          P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c), st, GATE_ACCEPTED);
-  enqueue_linearize(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk));
+  if (overlap_accept) fork_main(ctx);
+  // (the side stream runs k_accept, then the point-major branch of the relinearisation; enqueue_linearize joins both)
+  enqueue_linearize(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk), false, overlap_accept);
   enqueue_state_norms(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk));
   sync_flags(ctx);
   {

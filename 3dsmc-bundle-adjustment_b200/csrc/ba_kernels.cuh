@@ -1657,7 +1657,7 @@ __global__ void __launch_bounds__(BA_THREADS)
 k_obs_W(int n_obs, const int32_t *__restrict__ pt_idx, JPlanes J, const double *__restrict__ V, const double *__restrict__ dp,
         double *__restrict__ W, double *__restrict__ WV, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  const int i = blockIdx.x * BA_THREADS + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (64-thread CTAs on windows: one CTA per SM)
   if (i >= n_obs) return;
   const int p = pt_idx[i];
   // V_p^-1 is re-derived here from V_p and the LM diagonal with k_point_inverse's arithmetic (identical bits), so that

@@ -446,3 +446,90 @@ def test_eval_hook_with_factored_store(solver_cache):
     assert rel_err(out["Jc"][free], ref["Jc"][free]) < 1e-12 and rel_err(out["Jp"], ref["Jp"]) < 1e-12
     summ = s.solve()
     assert summ.final_cost < summ.initial_cost
+
+
+# ---------------------------------------------------------------- windowed explicit path: variants of the same solve
+def _explicit_run(p, env=None, iters=8, **kw):
+    """One REF-mode explicit solve in a fresh context under temporary environment switches (A/B aids of the library)."""
+    env = env or {}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        g, _ = mode_opts("REF", solver=1, max_num_iterations=iters, **kw)
+        s = ba_b200.GpuSolver(**g)
+        try:
+            s.upload(p)
+            summ = s.solve()
+            pose, pt, intr = s.download()
+            tr = s.trace()
+        finally:
+            s.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return summ, pose, pt, intr, tr
+
+
+@pytest.mark.parametrize("name", ["cfg1", "window20"])
+def test_window_graph_and_device_pairs_are_bit_identical(name):
+    """The CUDA-graph replay of the LM iteration and the device-built pair list change HOW the work is enqueued /
+    indexed, not the arithmetic: results must equal the direct-enqueue / host-built-list run bit for bit."""
+    p = _problem(name)
+    base = _explicit_run(p)
+    for env in ({"BA_NO_LM_GRAPH": "1"}, {"BA_HOST_PAIRS": "1"}, {"BA_NO_FORK": "1"}):
+        other = _explicit_run(p, env)
+        assert other[0].num_iterations == base[0].num_iterations
+        assert other[0].final_cost == base[0].final_cost, env
+        assert np.array_equal(other[1], base[1]) and np.array_equal(other[2], base[2]) and np.array_equal(other[3], base[3]), env
+        assert [t["cost"] for t in other[4]] == [t["cost"] for t in base[4]], env
+
+
+@pytest.mark.parametrize("name", ["cfg1", "window20"])
+def test_window_solver_variants_agree(name):
+    """Register-resident L D L^T (in force) vs the shared-memory L D L^T vs the left-looking Cholesky: three exact
+    solves of the same reduced system; LM traces agree to round-off amplified by the conditioning."""
+    p = _problem(name)
+    base = _explicit_run(p)
+    for mode in ("1", "2"):
+        other = _explicit_run(p, {"BA_LEGACY_CHOL": mode})
+        assert other[0].num_iterations == base[0].num_iterations
+        assert other[0].num_successful == base[0].num_successful
+        assert abs(other[0].final_cost - base[0].final_cost) <= 1e-9 * base[0].final_cost, mode
+        dt, dr = pose_err(other[1], base[1])
+        assert dt < 1e-7 and dr < 1e-7, (mode, dt, dr)
+
+
+def test_window_reupload_updates_graph():
+    """Sliding windows through ONE context: every upload re-captures the LM iteration and updates the graph executable
+    in place; each window must equal its solve in a fresh context."""
+    seq = syn.make_tum_sequence(60, 6000, 36000, seed=9)
+    g, _ = mode_opts("REF", solver=1, max_num_iterations=6)
+    s = ba_b200.GpuSolver(**g)
+    try:
+        for a in (0, 10, 25, 40, 3):  # different sizes, last one smaller again
+            p = syn.window_problem(seq, a, min(a + 19, 59) if a != 3 else 9).problem
+            s.upload(p)
+            summ = s.solve()
+            pose, pt, intr = s.download()
+            ref = _explicit_run(p, iters=6)
+            assert summ.final_cost == ref[0].final_cost
+            assert np.array_equal(pose, ref[1]) and np.array_equal(pt, ref[2])
+    finally:
+        s.close()
+
+
+def test_explicit_duplicate_camera_observations(solver_cache):
+    """A camera that observes the same landmark twice, through the dense explicit path (device-built pair list):
+    lock step with the oracle."""
+    p = _problem("cfg1")
+    idx = np.flatnonzero(p.cam_idx == 3)[:40]
+    ins = idx[-1] + 1
+    p.cam_idx = np.insert(p.cam_idx, ins, p.cam_idx[idx])
+    p.pt_idx = np.insert(p.pt_idx, ins, p.pt_idx[idx])
+    p.uv2 = np.insert(p.uv2, ins, p.uv2[idx] + 0.25, axis=0)
+    if p.depth is not None:
+        p.depth = np.insert(p.depth, ins, p.depth[idx])
+    _compare_solve(p, "REF", 1, 6, solver_cache)
