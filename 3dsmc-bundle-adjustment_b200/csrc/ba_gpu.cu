@@ -123,7 +123,7 @@ struct ba_gpu_ctx {
   Buf sp_cnt, sp_off, sp_keys, sp_vals, sp_keys2, sp_pairs, sp_ukeys, sp_ucnt, sp_nruns, sb_ptr, sb_i, sb_j, row_ucnt, row_tcnt,
       row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
   int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0, sp_ctas_per_sm = 1;
-  Buf sp_pair_pt, chol_v;
+  Buf sp_pair_pt, chol_v, chol_linv;
   // one LM iteration of the windowed explicit solver as an instantiated CUDA graph (every decision is taken on the
   // device, so the node parameters never change between iterations); upload / set_options mark it stale and the next
   // solve re-captures and updates the executable in place (cudaGraphExecUpdate: destroying and re-instantiating it cost
@@ -360,6 +360,8 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   cudaFuncSetAttribute(k_ldlt2_solve<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(BA_LDLT2_MAX_N));
   cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
   cudaFuncSetAttribute(k_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
+  cudaFuncSetAttribute(k_chol_trsm2, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
+  cudaFuncSetAttribute(k_chol_potrf2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_potrf2_smem_bytes());
   cudaFuncSetAttribute(kt_schur_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2));
   cudaFuncSetAttribute(kt_schur_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(3));
   cudaFuncSetAttribute(kt_schur_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(4));
@@ -1214,6 +1216,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     RES(S, (size_t)ctx->n_red * ctx->n_red * 8 + 64);
     RES(rhs, (size_t)ctx->n_red * 8 + 64);
     RES(chol_v, (size_t)(ctx->n_red + 64 + 8) * 8);
+    RES(chol_linv, (size_t)CH_NB * CH_NB * 8);
     prof.stamp("rest");
     // windows: device-built pair list; the global REF problem keeps the host-built list of NON-EMPTY blocks
     // (320 k mostly empty blocks at 800 keyframes)
@@ -1687,10 +1690,17 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
     // blocked right-looking Cholesky (ba_kernels_chol.cuh): the reference's global BA with free intrinsics
     const int nt = cdiv(n, CH_NB);
     double *S = P<double>(ctx->S);
+    double *Linv = P<double>(ctx->chol_linv);
     for (int k = 0; k < nt; ++k) {
-      LAUNCH(k_chol_potrf, 1, CH_NB, 0, n, S, k, st, GATE_RUN);
       const int below = nt - k - 1;
-      LAUNCH(k_chol_trsm, below, CH_NB, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
+      if (ctx->legacy_chol == 1) {
+        LAUNCH(k_chol_potrf, 1, CH_NB, 0, n, S, k, st, GATE_RUN);
+        LAUNCH(k_chol_trsm, below, CH_NB, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
+      } else {
+        // diagonal tile: register-resident L D L^T that also yields L^-1; panel: product with L^-1
+        LAUNCH(k_chol_potrf2, 1, 1024, chol_potrf2_smem_bytes(), n, S, Linv, k, st, GATE_RUN);
+        LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv, k, st, GATE_RUN);
+      }
       LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
     }
     {

@@ -115,7 +115,7 @@ k_chol_update(int n, double *__restrict__ A, int k, const LmState *st, int gate)
 #pragma unroll
     for (int r = 0; r < 4; ++r) a[r] = As[(ty * 4 + r) * CH_LD + q];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) bb[c] = Bs[(tx * 4 + c) * CH_LD + q];
+    for (int c = 0; c < 4; ++c) bb[c] = Bs[(tx + 16 * c) * CH_LD + q];  // columns tx, tx+16, ..: 16 distinct banks (CH_LD odd)
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -127,7 +127,7 @@ k_chol_update(int n, double *__restrict__ A, int k, const LmState *st, int gate)
     if (row >= n) continue;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int col = c0 + tx * 4 + c;
+      const int col = c0 + tx + 16 * c;
       if (col < n && col <= row) A[(size_t)row * n + col] -= acc[r][c];
     }
   }
@@ -401,7 +401,7 @@ __host__ __device__ inline size_t ldlt2_smem_bytes(int n) {
 
 template <int NT, int P, int PUB>
 __device__ __forceinline__ bool ldlt2_step(double (&a)[NT * (NT + 1) / 2], double *__restrict__ C, double *__restrict__ invd,
-                                           int ldc, int n, int j, int warp, int lane) {
+                                           int ldc, int n, int nrows, int j, int warp, int lane) {
   __syncthreads();
   const double *cj = C + j * ldc;
   const double rd = invd[j];
@@ -421,7 +421,7 @@ __device__ __forceinline__ bool ldlt2_step(double (&a)[NT * (NT + 1) / 2], doubl
 #pragma unroll
     for (int ti = PUB; ti < NT; ++ti) {
       const int i = warp + 32 * ti;
-      if (i >= jn && i <= n) cn[i] = a[LDLT2_IDX(ti, PUB)];
+      if (i >= jn && i < nrows) cn[i] = a[LDLT2_IDX(ti, PUB)];  // nrows = n + 1 (solve) or n + m (potrf: identity rows)
     }
     if (warp == lane) {
       const double d = a[LDLT2_IDX(PUB, PUB)];
@@ -433,14 +433,14 @@ __device__ __forceinline__ bool ldlt2_step(double (&a)[NT * (NT + 1) / 2], doubl
 
 template <int NT, int P>
 __device__ __forceinline__ bool ldlt2_phase(double (&a)[NT * (NT + 1) / 2], double *__restrict__ C, double *__restrict__ invd,
-                                            int ldc, int n, int warp, int lane) {
+                                            int ldc, int n, int nrows, int warp, int lane) {
   if constexpr (P < NT) {
     const int jend = min(32 * P + 31, n);
     for (int j = 32 * P; j < jend; ++j)
-      if (!ldlt2_step<NT, P, P>(a, C, invd, ldc, n, j, warp, lane)) return false;
+      if (!ldlt2_step<NT, P, P>(a, C, invd, ldc, n, nrows, j, warp, lane)) return false;
     if (32 * P + 31 < n)  // the last column of the tile column publishes into the next one
-      if (!ldlt2_step<NT, P, (P + 1 < NT ? P + 1 : P)>(a, C, invd, ldc, n, 32 * P + 31, warp, lane)) return false;
-    return ldlt2_phase<NT, P + 1>(a, C, invd, ldc, n, warp, lane);
+      if (!ldlt2_step<NT, P, (P + 1 < NT ? P + 1 : P)>(a, C, invd, ldc, n, nrows, 32 * P + 31, warp, lane)) return false;
+    return ldlt2_phase<NT, P + 1>(a, C, invd, ldc, n, nrows, warp, lane);
   } else {
     return true;
   }
@@ -480,7 +480,7 @@ k_ldlt2_solve(int n, const double *__restrict__ Sg, const double *__restrict__ r
     }
     if (warp == 0) invd[0] = a[0] > 0.0 ? __drcp_rn(a[0]) : -1.0;
   }
-  const bool ok = ldlt2_phase<NT, 0>(a, C, invd, ldc, n, warp, lane);
+  const bool ok = ldlt2_phase<NT, 0>(a, C, invd, ldc, n, n + 1, warp, lane);
   if (!ok) {
     if (tid == 0) st->lin_fail = 1;
     return;
@@ -522,4 +522,108 @@ k_ldlt2_solve(int n, const double *__restrict__ Sg, const double *__restrict__ r
     }
   }
   if (tid < 4) yk[tid] = nk ? ysh[6 * n_free + tid] : 0.0;
+}
+
+
+// =====================================================================
+// Diagonal tile and panel of the blocked factorisation, second version (in force):
+//  * k_chol_potrf2: the register-resident L D L^T above applied to the m x m diagonal tile (m <= 64) with m extra
+//    rows holding the identity: row m + r ends up as column r of the unit factor's inverse, so the kernel writes
+//    both the Cholesky factor L = Lu D^1/2 (back into A) and L^-1 = D^-1/2 Lu^-1 (into Linv, dense 64 x 64, zeros above
+//    the diagonal) in ~64 barrier steps.  k_chol_potrf (left-looking, one thread per row): 45 us per tile.
+//  * k_chol_trsm2: the panel X = A_ik L^-T as a 64 x 64 x 64 product with L^-1 (256 threads, 4 x 4 outputs each)
+//    instead of one thread per row walking a 64-step substitution with j-long dependent chains (63 us per launch).
+// =====================================================================
+#define CH_P2_LDC 129
+__host__ __device__ inline size_t chol_potrf2_smem_bytes() { return ((size_t)CH_NB * CH_P2_LDC + 128 + 2 * (CH_NB + 8)) * 8; }
+
+__global__ void __launch_bounds__(1024)
+k_chol_potrf2(int n, double *__restrict__ A, double *__restrict__ Linv, int k, LmState *st, int gate) {
+  if (!gate_open(st, gate) || st->lin_fail) return;
+  constexpr int NT = 4;
+  extern __shared__ double smd[];
+  double *C = smd;                                   // m columns of CH_P2_LDC (+ 128: reads of the last tile rows)
+  double *invd = smd + (size_t)CH_NB * CH_P2_LDC + 128;
+  const int j0 = k * CH_NB, m = min(CH_NB, n - j0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a[NT * (NT + 1) / 2];
+#pragma unroll
+  for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+    for (int tk = 0; tk <= ti; ++tk) {
+      const int i = warp + 32 * ti, c = lane + 32 * tk;
+      double v = 0.0;
+      if (c < m) {
+        if (i < m) v = c <= i ? A[(size_t)(j0 + i) * n + j0 + c] : A[(size_t)(j0 + c) * n + j0 + i];  // the lower triangle is current
+        else if (i - m == c) v = 1.0;
+      }
+      a[LDLT2_IDX(ti, tk)] = v;
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int ti = 0; ti < NT; ++ti) {
+      const int i = warp + 32 * ti;
+      if (i < 2 * m) C[i] = a[LDLT2_IDX(ti, 0)];
+    }
+    if (warp == 0) invd[0] = a[0] > 0.0 ? __drcp_rn(a[0]) : -1.0;
+  }
+  const bool ok = ldlt2_phase<NT, 0>(a, C, invd, CH_P2_LDC, m, 2 * m, warp, lane);
+  if (!ok) {
+    if (tid == 0) st->lin_fail = 1;
+    return;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < CH_NB * CH_NB; idx += 1024) {
+    const int i = idx >> 6, j = idx & 63;  // (row, column) of L resp. L^-1
+    double li = 0.0;
+    if (i < m && j < m && j <= i) {
+      const double sj = sqrt(invd[j]);
+      A[(size_t)(j0 + i) * n + j0 + j] = i == j ? 1.0 / sj : C[j * CH_P2_LDC + i] * sj;  // L_ij = c_ij / sqrt(d_j), L_jj = sqrt(d_j)
+      li = C[i * CH_P2_LDC + m + j] * sqrt(invd[i]);  // (L^-1)_ij = (Lu^-1)_ij / sqrt(d_i); identity row m + j, column i
+    }
+    Linv[idx] = li;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_chol_trsm2(int n, double *__restrict__ A, const double *__restrict__ Linv, int k, const LmState *st, int gate) {
+  if (!gate_open(st, gate) || st->lin_fail) return;
+  extern __shared__ double sh[];
+  double *As = sh, *Bs = sh + CH_NB * CH_LD;
+  const int j0 = k * CH_NB, kk = min(CH_NB, n - j0);
+  const int i0 = (k + 1 + blockIdx.x) * CH_NB;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    As[r * CH_LD + c] = (i0 + r < n && c < kk) ? A[(size_t)(i0 + r) * n + j0 + c] : 0.0;
+    Bs[r * CH_LD + c] = Linv[idx];  // row r of L^-1 (zero beyond the tile and above the diagonal)
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+  for (int q = 0; q < CH_NB; ++q) {  // X[r][c] = sum_q A[r][q] Linv[c][q]
+    double av[4], bb[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) av[r] = As[(ty * 4 + r) * CH_LD + q];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bb[c] = Bs[(tx + 16 * c) * CH_LD + q];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * bb[c];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = i0 + ty * 4 + r;
+    if (row >= n) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = tx + 16 * c;
+      if (col < kk) A[(size_t)row * n + j0 + col] = acc[r][c];
+    }
+  }
 }
