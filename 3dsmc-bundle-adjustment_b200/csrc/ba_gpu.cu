@@ -123,7 +123,7 @@ struct ba_gpu_ctx {
   Buf sp_cnt, sp_off, sp_keys, sp_vals, sp_keys2, sp_pairs, sp_ukeys, sp_ucnt, sp_nruns, sb_ptr, sb_i, sb_j, row_ucnt, row_tcnt,
       row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
   int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0, sp_ctas_per_sm = 1;
-  Buf sp_pair_pt, chol_v, chol_linv;
+  Buf sp_pair_pt, chol_v, chol_linv, chol_slots;
   // one LM iteration of the windowed explicit solver as an instantiated CUDA graph (every decision is taken on the
   // device, so the node parameters never change between iterations); upload / set_options mark it stale and the next
   // solve re-captures and updates the executable in place (cudaGraphExecUpdate: destroying and re-instantiating it cost
@@ -131,7 +131,7 @@ struct ba_gpu_ctx {
   cudaGraphExec_t lm_graph = nullptr;
   int64_t lm_graph_launches = 0;
   bool lm_graph_off = false, lm_graph_stale = true;
-  int legacy_chol = 0;  // BA_LEGACY_CHOL=1: left-looking single-CTA Cholesky, =2: shared-memory L D L^T (A/B timing only)
+  int legacy_chol = 0;  // BA_LEGACY_CHOL=1: left-looking single-CTA Cholesky, =2: shared-memory L D L^T, =3: grid-barrier blocked substitution (A/B timing only)
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
   Buf my_rows, row_flag, row_pos, ipc_stage;
@@ -1216,7 +1216,9 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     RES(S, (size_t)ctx->n_red * ctx->n_red * 8 + 64);
     RES(rhs, (size_t)ctx->n_red * 8 + 64);
     RES(chol_v, (size_t)(ctx->n_red + 64 + 8) * 8);
-    RES(chol_linv, (size_t)CH_NB * CH_NB * 8);
+    // blocked Cholesky: L^-1 of every diagonal tile (kept for the substitution) and the flag-in-data slots of k_chol_solve2
+    RES(chol_linv, (size_t)cdiv(ctx->n_red, CH_NB) * CH_NB * CH_NB * 8);
+    RES(chol_slots, (size_t)2 * cdiv(ctx->n_red, CH_NB) * CH_NB * sizeof(ChSlot));
     prof.stamp("rest");
     // windows: device-built pair list; the global REF problem keeps the host-built list of NON-EMPTY blocks
     // (320 k mostly empty blocks at 800 keyframes)
@@ -1698,18 +1700,27 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
         LAUNCH(k_chol_trsm, below, CH_NB, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
       } else {
         // diagonal tile: register-resident L D L^T that also yields L^-1; panel: product with L^-1
-        LAUNCH(k_chol_potrf2, 1, 1024, chol_potrf2_smem_bytes(), n, S, Linv, k, st, GATE_RUN);
-        LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv, k, st, GATE_RUN);
+        LAUNCH(k_chol_potrf2, 1, 1024, chol_potrf2_smem_bytes(), n, S, Linv + (size_t)k * CH_NB * CH_NB, k, st, GATE_RUN);
+        LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv + (size_t)k * CH_NB * CH_NB, k, st, GATE_RUN);
       }
       LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
     }
-    {
+    int nn = n, n_cam = ctx->n_cam, n_free = ctx->n_free, nk = ctx->nk, gate = GATE_RUN;
+    const double *Sc = S, *rhs = P<double>(ctx->rhs);
+    double *yc = P<double>(ctx->yc), *yk = P<double>(ctx->yk);
+    const int32_t *cam_slot = P<int32_t>(ctx->cam_slot);
+    if (ctx->legacy_chol == 0 && nt <= CH_S2_OWN * ctx->n_sm) {
+      // substitution through the stored L_kk^-1 tiles, solved values exchanged as flag-in-data slots (k_chol_solve2)
+      ChSlot *fwd = P<ChSlot>(ctx->chol_slots), *bwd = fwd + (size_t)nt * CH_NB;
+      CK(cudaMemsetAsync(fwd, 0, (size_t)2 * nt * CH_NB * sizeof(ChSlot), ctx->stream));
+      const double *Li = Linv;
+      void *args[] = {&nn, &Sc, &Li, &rhs, &fwd, &bwd, &n_cam, &n_free, &cam_slot, &nk, &yc, &yk, &st, &gate};
+      CK(cudaLaunchCooperativeKernel((const void *)k_chol_solve2, dim3(ctx->n_sm), dim3(256), args, 0, ctx->stream));
+      ctx->launches++;
+    } else {
       CK(cudaMemsetAsync(P<char>(ctx->chol_v) + (size_t)(n + 64) * 8, 0, 16, ctx->stream));
-      int nn = n, n_cam = ctx->n_cam, n_free = ctx->n_free, nk = ctx->nk, gate = GATE_RUN;
-      const double *Sc = S, *rhs = P<double>(ctx->rhs);
-      double *v = P<double>(ctx->chol_v), *ztg = v + n, *yc = P<double>(ctx->yc), *yk = P<double>(ctx->yk);
+      double *v = P<double>(ctx->chol_v), *ztg = v + n;
       unsigned int *bar = reinterpret_cast<unsigned int *>(v + n + 64);
-      const int32_t *cam_slot = P<int32_t>(ctx->cam_slot);
       void *args[] = {&nn, &Sc, &rhs, &v, &ztg, &bar, &n_cam, &n_free, &cam_slot, &nk, &yc, &yk, &st, &gate};
       CK(cudaLaunchCooperativeKernel((const void *)k_chol_solve, dim3(ctx->n_sm), dim3(256), args, 0, ctx->stream));
       ctx->launches++;

@@ -627,3 +627,200 @@ k_chol_trsm2(int n, double *__restrict__ A, const double *__restrict__ Linv, int
     }
   }
 }
+
+// =====================================================================
+// Blocked substitution, second version (in force): L z = b, L^T y = z over the 64 x 64 tiles WITHOUT grid barriers
+// and without a sequential triangular solve per diagonal tile.
+//  * k_chol_potrf2 leaves L_kk^-1 of every diagonal tile (Linv + 4096 k), so a diagonal step is a 64 x 64 product:
+//    z_k = L_kk^-1 v_k (forward), y_k = L_kk^-T v_k (backward).
+//  * tile row (forward) / tile column (backward) t belongs to CTA t % gridDim.x for the whole pass; its running
+//    right-hand side v_t never leaves that CTA's shared memory, so only the 64 solved values of a step travel:
+//    published as 16-byte FLAG-IN-DATA slots {value, tag} with one vector store each and polled by the consumers
+//    (no fence, no separate flag, no barrier: one L2 round trip per step).
+//  * the owner of the NEXT diagonal tile applies the step to that tile first and publishes the next 64 values
+//    before touching its other tiles; the tile it needs (and L^-1 of its diagonal tile) is already in registers
+//    when the awaited values arrive (the loads are issued before the wait).
+// Critical path per step: poll -> 64 x 64 product -> 64 x 64 product -> publish (about 3 us) instead of a tile load,
+// 64 two-barrier substitution steps in one CTA and two grid barriers (33 us: 5.0 of the 13.2 ms of an exact LM step
+// at n = 4798).  Every sum has a fixed order (per thread 16 products in two chains, then a fixed tree).
+// Cooperative launch only for co-residency (consumers spin on producers); gridDim.x * CH_S2_OWN >= tile count.
+// =====================================================================
+#define CH_S2_OWN 4
+struct __align__(16) ChSlot {
+  double v;
+  unsigned long long tag;
+};
+__device__ __forceinline__ void ch_publish(ChSlot *p, double v) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(1ull) : "memory");
+}
+__device__ __forceinline__ double ch_wait(const ChSlot *p) {
+  unsigned long long a, b;
+  do {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  } while (b != 1ull);
+  return __longlong_as_double((long long)a);
+}
+// row layout: thread (r = tid >> 2, part = tid & 3) holds A[r0 + r][c0 + 4 q + part], q = 0..15 (a quarter-warp reads
+// whole 32-byte sectors); column layout: thread (c = tid & 63, g = tid >> 6) holds A[r0 + g + 4 q][c0 + c]
+__device__ __forceinline__ void ch_load_rows(const double *__restrict__ A, int ld, int nr, int nc, int r0, int c0, int tid,
+                                             double (&reg)[16]) {
+  const int r = r0 + (tid >> 2), part = tid & 3;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int c = c0 + 4 * q + part;
+    reg[q] = (r < nr && c < nc) ? A[(size_t)r * ld + c] : 0.0;
+  }
+}
+__device__ __forceinline__ void ch_load_cols(const double *__restrict__ A, int ld, int nr, int nc, int r0, int c0, int tid,
+                                             double (&reg)[16]) {
+  const int c = c0 + (tid & 63), g = tid >> 6;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int r = r0 + g + 4 * q;
+    reg[q] = (r < nr && c < nc) ? A[(size_t)r * ld + c] : 0.0;
+  }
+}
+// sum_c A[r][c] x[c] for the thread's row; identical in the four threads of a row
+__device__ __forceinline__ double ch_dot_rows(const double (&reg)[16], const double *__restrict__ x, int tid) {
+  const int part = tid & 3;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int q = 0; q < 16; q += 2) {
+    s0 += reg[q] * x[4 * q + part];
+    s1 += reg[q + 1] * x[4 * q + 4 + part];
+  }
+  double s = s0 + s1;
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  return s;
+}
+// partial of sum_r A[r][c] x[r] over the thread's 16 rows -> red[g][c]; the caller adds the four groups in order
+__device__ __forceinline__ void ch_dot_cols(const double (&reg)[16], const double *__restrict__ x, int tid, double *red) {
+  const int g = tid >> 6;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int q = 0; q < 16; q += 2) {
+    s0 += reg[q] * x[g + 4 * q];
+    s1 += reg[q + 1] * x[g + 4 * q + 4];
+  }
+  red[g * CH_NB + (tid & 63)] = s0 + s1;
+}
+
+__global__ void __launch_bounds__(256)
+k_chol_solve2(int n, const double *__restrict__ A, const double *__restrict__ Linv, const double *__restrict__ rhs,
+              ChSlot *fwd, ChSlot *bwd /* [nt * 64] each, zeroed before the launch */, int n_cam, int n_free,
+              const int32_t *__restrict__ cam_slot, int nk, double *__restrict__ yc, double *__restrict__ yk, LmState *st,
+              int gate) {
+  if (!gate_open(st, gate) || st->lin_fail) return;  // identical on every CTA
+  __shared__ double vs[CH_S2_OWN][CH_NB];  // running right-hand side of the owned tiles, then their solved values
+  __shared__ double xb[2][CH_NB];          // the solved values of step k (buffer k & 1)
+  __shared__ double red[4 * CH_NB];
+  const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
+  const int nt = (n + CH_NB - 1) / CH_NB;
+  double Lr[16], Ir[16];
+  if (b < nt) {
+    for (int idx = tid; idx < CH_S2_OWN * CH_NB; idx += 256) {
+      const int t = b + (idx >> 6) * G, i = t * CH_NB + (idx & 63);
+      vs[idx >> 6][idx & 63] = (t < nt && i < n) ? rhs[i] : 0.0;
+    }
+    __syncthreads();
+    // ---------------- forward: L z = b
+    if (b == 0) {  // z_0 = L_00^-1 v_0
+      ch_load_rows(Linv, CH_NB, CH_NB, CH_NB, 0, 0, tid, Ir);
+      const double z = ch_dot_rows(Ir, vs[0], tid);
+      __syncthreads();
+      if ((tid & 3) == 0) {
+        vs[0][tid >> 2] = z;
+        xb[0][tid >> 2] = z;
+        ch_publish(fwd + (tid >> 2), z);
+      }
+      __syncthreads();
+    }
+    for (int k = 0; k + 1 < nt; ++k) {
+      // first owned tile row below k
+      int i = k + 1 <= b ? b : b + ((k + 1 - b + G - 1) / G) * G;
+      if (i >= nt) break;  // no tile rows left below k: this CTA's part of the pass is done
+      const bool diag_next = i == k + 1;
+      ch_load_rows(A, n, n, n, i * CH_NB, k * CH_NB, tid, Lr);
+      if (diag_next) ch_load_rows(Linv + (size_t)i * CH_NB * CH_NB, CH_NB, CH_NB, CH_NB, 0, 0, tid, Ir);
+      double *x = xb[k & 1];
+      if (k % G != b && tid < CH_NB) x[tid] = ch_wait(fwd + k * CH_NB + tid);
+      __syncthreads();
+      for (; i < nt; i += G) {
+        const int slot = (i - b) / G;
+        const double s = ch_dot_rows(Lr, x, tid);
+        if ((tid & 3) == 0) vs[slot][tid >> 2] -= s;
+        if (i == k + 1) {  // the next diagonal tile is mine: solve it and publish before anything else
+          __syncthreads();
+          const double z = ch_dot_rows(Ir, vs[slot], tid);
+          __syncthreads();
+          if ((tid & 3) == 0) {
+            vs[slot][tid >> 2] = z;
+            xb[(k + 1) & 1][tid >> 2] = z;
+            ch_publish(fwd + (k + 1) * CH_NB + (tid >> 2), z);
+          }
+        }
+        if (i + G < nt) ch_load_rows(A, n, n, n, (i + G) * CH_NB, k * CH_NB, tid, Lr);
+      }
+      __syncthreads();
+    }
+    // ---------------- backward: L^T y = z (vs holds z of the owned tiles)
+    if ((nt - 1) % G == b) {
+      const int slot = (nt - 1 - b) / G;
+      ch_load_cols(Linv + (size_t)(nt - 1) * CH_NB * CH_NB, CH_NB, CH_NB, CH_NB, 0, 0, tid, Ir);
+      ch_dot_cols(Ir, vs[slot], tid, red);
+      __syncthreads();
+      if (tid < CH_NB) {
+        const double y = ((red[tid] + red[CH_NB + tid]) + red[2 * CH_NB + tid]) + red[3 * CH_NB + tid];
+        vs[slot][tid] = y;
+        xb[(nt - 1) & 1][tid] = y;
+        ch_publish(bwd + (nt - 1) * CH_NB + tid, y);
+      }
+      __syncthreads();
+    }
+    for (int i = nt - 1; i >= 1; --i) {
+      // last owned tile column left of i
+      int k = -1;
+      if (b <= i - 1) k = b + ((i - 1 - b) / G) * G;
+      if (k < 0) break;  // no tile columns left of i
+      const bool diag_next = k == i - 1;
+      ch_load_cols(A, n, n, n, i * CH_NB, k * CH_NB, tid, Lr);
+      if (diag_next) ch_load_cols(Linv + (size_t)k * CH_NB * CH_NB, CH_NB, CH_NB, CH_NB, 0, 0, tid, Ir);
+      double *x = xb[i & 1];
+      if (i % G != b && tid < CH_NB) x[tid] = ch_wait(bwd + i * CH_NB + tid);
+      __syncthreads();
+      for (; k >= 0; k -= G) {
+        const int slot = (k - b) / G;
+        ch_dot_cols(Lr, x, tid, red);
+        __syncthreads();
+        if (tid < CH_NB) vs[slot][tid] -= ((red[tid] + red[CH_NB + tid]) + red[2 * CH_NB + tid]) + red[3 * CH_NB + tid];
+        __syncthreads();
+        if (k == i - 1) {
+          ch_dot_cols(Ir, vs[slot], tid, red);
+          __syncthreads();
+          if (tid < CH_NB) {
+            const double y = ((red[tid] + red[CH_NB + tid]) + red[2 * CH_NB + tid]) + red[3 * CH_NB + tid];
+            vs[slot][tid] = y;
+            xb[(i - 1) & 1][tid] = y;
+            ch_publish(bwd + (i - 1) * CH_NB + tid, y);
+          }
+          __syncthreads();
+        }
+        if (k - G >= 0) ch_load_cols(A, n, n, n, i * CH_NB, (k - G) * CH_NB, tid, Lr);
+      }
+      __syncthreads();
+    }
+  }
+  // ---------------- scatter (every CTA; a value is read when its tag has arrived)
+  const int gtid = b * 256 + tid, nthr = G * 256;
+  for (int c = gtid; c < n_cam; c += nthr) {
+    const int slot = cam_slot[c];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double x = slot >= 0 ? ch_wait(bwd + 6 * slot + q) : 0.0;
+      if (!isfinite(x)) st->lin_fail = 1;
+      yc[6 * (size_t)c + q] = x;
+    }
+  }
+  if (gtid < 4) yk[gtid] = nk ? ch_wait(bwd + 6 * n_free + gtid) : 0.0;
+}

@@ -13,8 +13,8 @@
 #include "compat/reference_types.h"
 #endif
 
+#include <chrono>
 #include <cstdio>
-#include <set>
 #include <vector>
 
 #include "../../include/ba_gpu.h"
@@ -33,9 +33,14 @@ struct Ctx {
 };
 thread_local Ctx g_ctx;
 thread_local BaHostLastProblem g_last;
+thread_local bool g_fixed_iterations = false;
+inline double ms_since(const std::chrono::steady_clock::time_point &t0) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
 }  // namespace
 
 const BaHostLastProblem &ba_host_last_problem() { return g_last; }
+void ba_host_fixed_iterations(bool on) { g_fixed_iterations = on; }
 
 int countConstraints(const Map3D &map, const vector<KeyFrame> &keyframes, int kf_i, int kf_f) {
   (void)map;
@@ -71,6 +76,9 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   opt.use_depth_prior = 1;       // DepthPrior residual per observation (:288-294)
   opt.optimize_intrinsics = 1;   // intrinsics are a free block with a prior (:236-241)
   opt.solver = BA_SOLVER_AUTO;   // SPARSE_SCHUR == exact Schur step
+  if (g_fixed_iterations)        // measurement only (ba_host_debug.h): exactly max_num_iterations LM iterations
+    opt.function_tolerance = opt.parameter_tolerance = opt.gradient_tolerance = 0.0;
+  const auto t_begin = std::chrono::steady_clock::now();
 
   // ---- snapshot for the error path: inputs stay untouched on failure
   vector<Sophus::SE3d> pose_backup(n_cam);
@@ -81,16 +89,20 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   const Sophus::SE3d initialPoseInv = keyframes[kf_i].T_w_c.inverse();  // :232
   const int admissible_obs = countConstraints(map, keyframes, kf_i, kf_f);  // :242
 
-  // ---- canonical enumeration (:244-294): container order, first-appearance point ids
-  std::set<int> already_observed_pts;
+  // ---- canonical enumeration (:244-294): container order, first-appearance point ids.
+  // One hash lookup per observation (landmark id -> point index, inserted on first appearance) and one map
+  // lookup per DISTINCT landmark; the Landmark addresses are kept (unordered_map nodes do not move), so the
+  // gather of the points, the error path and the write-back never search the map again.
   std::unordered_map<int, int> pt_of_landmark;
   vector<int> landmark_of_pt;
+  vector<Landmark *> landmark_ptr;
   vector<int32_t> cam_idx, pt_idx;
   vector<double> uv2, depthv, pose7((size_t)n_cam * 7), pt3;
   cam_idx.reserve(admissible_obs);
   pt_idx.reserve(admissible_obs);
   uv2.reserve((size_t)admissible_obs * 2);
   depthv.reserve(admissible_obs);
+  pt_of_landmark.reserve((size_t)admissible_obs / 2 + 16);
   bool missing_landmark = false;
   for (int kf_n = kf_i; kf_n <= kf_f && !missing_landmark; kf_n++) {
     KeyFrame &curr_kf = keyframes[kf_n];
@@ -100,21 +112,21 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
       const int localId = index_pair.first;
       const double depth = curr_kf.points3d_local[localId](2);
       if (depth <= 1e-15) continue;  // :265-268
-      auto found = map.find(landmarkId);
-      if (found == map.end()) {  // the reference would throw from map.at (:270)
-        missing_landmark = true;
-        break;
-      }
-      Landmark &map_point = found->second;
-      if (already_observed_pts.find(landmarkId) == already_observed_pts.end()) {
-        already_observed_pts.insert(landmarkId);
+      const auto ins = pt_of_landmark.try_emplace(landmarkId, (int)landmark_of_pt.size());
+      if (ins.second) {  // first appearance in the window (:271)
+        auto found = map.find(landmarkId);
+        if (found == map.end()) {  // the reference would throw from map.at (:270)
+          missing_landmark = true;
+          break;
+        }
+        Landmark &map_point = found->second;
         point_backup.emplace_back(landmarkId, map_point.point);
         map_point.point = initialPoseInv * map_point.point;  // :274, in place
-        pt_of_landmark[landmarkId] = (int)landmark_of_pt.size();
         landmark_of_pt.push_back(landmarkId);
+        landmark_ptr.push_back(&map_point);
       }
       cam_idx.push_back(kf_n - kf_i);
-      pt_idx.push_back(pt_of_landmark[landmarkId]);
+      pt_idx.push_back(ins.first->second);
       uv2.push_back((double)curr_kf.keypoints[localId].pt.x);  // float -> double (:262)
       uv2.push_back((double)curr_kf.keypoints[localId].pt.y);
       depthv.push_back(depth);
@@ -122,7 +134,7 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   }
   auto restore = [&]() {
     for (int k = 0; k < n_cam; ++k) keyframes[kf_i + k].T_w_c = pose_backup[k];
-    for (auto &pb : point_backup) map.at(pb.first).point = pb.second;
+    for (size_t p = 0; p < landmark_ptr.size(); ++p) landmark_ptr[p]->point = point_backup[p].second;
   };
   if (missing_landmark) {
     std::fprintf(stderr, "windowOptimize: keyframe references a landmark that is not in the map\n");
@@ -134,16 +146,14 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
     for (int j = 0; j < 7; ++j) pose7[(size_t)k * 7 + j] = keyframes[kf_i + k].T_w_c.data()[j];
   pt3.resize((size_t)n_pt * 3);
   for (int p = 0; p < n_pt; ++p)
-    for (int j = 0; j < 3; ++j) pt3[(size_t)p * 3 + j] = map.at(landmark_of_pt[p]).point(j);
+    for (int j = 0; j < 3; ++j) pt3[(size_t)p * 3 + j] = landmark_ptr[p]->point(j);
   double intr[4], prior[4];
   for (int j = 0; j < 4; ++j) {
     intr[j] = intrinsics_optimized(j);
     prior[j] = intrinsics_initial(j);
   }
-  g_last.cam_idx = cam_idx;
-  g_last.pt_idx = pt_idx;
-  g_last.landmark_of_pt = landmark_of_pt;
   g_last.admissible_obs = admissible_obs;
+  g_last.ms_extract = ms_since(t_begin);
 
   // ---- ceres::Solve (:300) -> GPU
   int rc = BA_OK;
@@ -152,22 +162,32 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   else
     rc = ba_gpu_set_options(g_ctx.ctx, &opt);
   ba_gpu_summary summary;
+  auto t_phase = std::chrono::steady_clock::now();
   if (rc == BA_OK)
     rc = ba_gpu_upload(g_ctx.ctx, n_cam, pose7.data(), /*fixed_cam=*/0 /* :299 */, n_pt, pt3.data(), n_obs, cam_idx.data(),
                        pt_idx.data(), uv2.data(), depthv.data(), intr, prior);
+  g_last.ms_upload = ms_since(t_phase);
+  t_phase = std::chrono::steady_clock::now();
   if (rc == BA_OK) rc = ba_gpu_solve(g_ctx.ctx, &summary);
+  g_last.ms_solve = ms_since(t_phase);
+  t_phase = std::chrono::steady_clock::now();
   if (rc == BA_OK) rc = ba_gpu_download(g_ctx.ctx, pose7.data(), pt3.data(), intr);
+  g_last.ms_download = ms_since(t_phase);
+  t_phase = std::chrono::steady_clock::now();
   if (rc != BA_OK) {
     std::fprintf(stderr, "windowOptimize: GPU solve failed (%d): %s\n", rc, ba_gpu_last_error(g_ctx.ctx));
     restore();
     return false;
   }
   g_last.summary = summary;
+  g_last.cam_idx.swap(cam_idx);
+  g_last.pt_idx.swap(pt_idx);
+  g_last.landmark_of_pt = landmark_of_pt;
 
   // ---- Ceres wrote the optimum into the caller-owned blocks: do the same
   for (int k = 0; k < n_cam; ++k) keyframes[kf_i + k].T_w_c = Sophus::SE3d(pose7.data() + (size_t)k * 7);
   for (int p = 0; p < n_pt; ++p) {
-    Vector3d &x = map.at(landmark_of_pt[p]).point;
+    Vector3d &x = landmark_ptr[p]->point;
     for (int j = 0; j < 3; ++j) x(j) = pt3[(size_t)p * 3 + j];
   }
   for (int j = 0; j < 4; ++j) intrinsics_optimized(j) = intr[j];
@@ -177,6 +197,7 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
     KeyFrame &curr_kf = keyframes[kf_n];
     curr_kf.T_w_c = Sophus::SE3d(initialPose * curr_kf.T_w_c);
   }
-  for (int lId : already_observed_pts) map.at(lId).point = initialPose * map.at(lId).point;
+  for (Landmark *lm : landmark_ptr) lm->point = initialPose * lm->point;
+  g_last.ms_writeback = ms_since(t_phase);
   return true;
 }

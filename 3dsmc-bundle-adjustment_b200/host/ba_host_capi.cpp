@@ -5,6 +5,7 @@
 #include "compat/reference_types.h"
 #include "ba_host_debug.h"
 
+#include <chrono>
 #include <cstring>
 
 extern "C" {
@@ -71,6 +72,79 @@ int ba_host_window_optimize(int n_kf, double *pose7, const int32_t *kf_ptr, cons
     for (int j = 0; j < 3; ++j) lm_pt[3 * (size_t)l + j] = map.at(lm_id[l]).point(j);
   for (int j = 0; j < 4; ++j) intr[j] = io(j);
   return ok ? 0 : -1;
+}
+
+// The reference's optimisation schedule (src/main.cpp:161-182) over a whole recorded sequence through the compiled
+// drop-in: a window over the last `window_size` keyframes whenever the keyframe count is a multiple of
+// `frame_frequency` (:162-166), the leftover window at the end of tracking (:169-175), and, if do_global != 0, the
+// global optimisation over all keyframes instead (:178-182).  Containers are built once (as the tracking front end
+// would have left them); every window is warm-started by the previous ones.  fixed_iterations != 0 switches the
+// tolerances off, so that every call runs exactly max_num_iterations LM iterations (throughput measurement).
+// out_ms[6]: accumulated host wall clock -- total, container walk + frame change, ba_gpu_upload, ba_gpu_solve,
+// ba_gpu_download, write-back.  Returns the number of windowOptimize calls, or -1 if one failed.
+int ba_host_sliding_sequence(int n_kf, double *pose7, const int32_t *kf_ptr, const int32_t *lm, const float *uv,
+                             const double *depth, int n_lm, const int32_t *lm_id, double *lm_pt, int window_size,
+                             int frame_frequency, int do_global, int max_num_iterations, int fixed_iterations,
+                             const double *intr0, double *intr, double *out_ms, int64_t *out_lm_iterations) {
+  if (n_kf <= 0 || frame_frequency <= 0 || window_size <= 0 || window_size > n_kf) return -1;
+  std::vector<KeyFrame> keyframes(n_kf);
+  Map3D map;
+  for (int k = 0; k < n_kf; ++k) {
+    KeyFrame &kf = keyframes[k];
+    kf.frame_id = (uint)k;
+    kf.T_w_c = Sophus::SE3d(pose7 + (size_t)k * 7);
+    const int a = kf_ptr[k], b = kf_ptr[k + 1];
+    kf.keypoints.resize(b - a);
+    kf.points3d_local.resize(b - a);
+    for (int i = a; i < b; ++i) {
+      const int local = i - a;
+      kf.keypoints[local].pt.x = uv[2 * (size_t)i];
+      kf.keypoints[local].pt.y = uv[2 * (size_t)i + 1];
+      kf.points3d_local[local] = Vector3d(0.0, 0.0, depth[i]);
+      kf.global_points_map.insert({local, lm[i]});
+    }
+  }
+  for (int l = 0; l < n_lm; ++l) {
+    Landmark L;
+    L.point = Vector3d(lm_pt[3 * (size_t)l], lm_pt[3 * (size_t)l + 1], lm_pt[3 * (size_t)l + 2]);
+    map.insert({lm_id[l], L});
+  }
+  ceresGlobalProblem gp;
+  gp.options.max_num_iterations = max_num_iterations;
+  Vector4d i0(intr0[0], intr0[1], intr0[2], intr0[3]), io(intr[0], intr[1], intr[2], intr[3]);
+  double ms[6] = {0, 0, 0, 0, 0, 0};
+  int64_t lm_iterations = 0;
+  int calls = 0;
+  bool ok = true;
+  ba_host_fixed_iterations(fixed_iterations != 0);
+  auto run = [&](int kf_i, int kf_f) {
+    const auto t0 = std::chrono::steady_clock::now();
+    ok = ok && windowOptimize(gp, kf_i, kf_f, keyframes, map, i0, io);
+    ms[0] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const BaHostLastProblem &last = ba_host_last_problem();
+    ms[1] += last.ms_extract;
+    ms[2] += last.ms_upload;
+    ms[3] += last.ms_solve;
+    ms[4] += last.ms_download;
+    ms[5] += last.ms_writeback;
+    lm_iterations += last.summary.num_iterations;
+    ++calls;
+  };
+  if (do_global) {
+    run(0, n_kf - 1);
+  } else {
+    for (int size = 1; size <= n_kf && ok; ++size)  // keyframes.size() after every tracking step
+      if (size % frame_frequency == 0 && size >= window_size) run(size - window_size, size - 1);
+    if (ok && n_kf % frame_frequency != 0) run(n_kf - window_size, n_kf - 1);  // leftovers
+  }
+  ba_host_fixed_iterations(false);
+  if (out_ms) std::memcpy(out_ms, ms, sizeof(ms));
+  if (out_lm_iterations) *out_lm_iterations = lm_iterations;
+  for (int k = 0; k < n_kf; ++k) std::memcpy(pose7 + (size_t)k * 7, keyframes[k].T_w_c.data(), 7 * sizeof(double));
+  for (int l = 0; l < n_lm; ++l)
+    for (int j = 0; j < 3; ++j) lm_pt[3 * (size_t)l + j] = map.at(lm_id[l]).point(j);
+  for (int j = 0; j < 4; ++j) intr[j] = io(j);
+  return ok ? calls : -1;
 }
 
 int ba_host_count_constraints(int n_kf, const int32_t *kf_ptr, const double *depth, int kf_i, int kf_f) {

@@ -461,6 +461,16 @@ def main():
                                                   "Python stand-ins for the C++ wrapper's container walk",
                                     "note": "second pass over 79 warm-started 20-keyframe windows of the 800-keyframe sequence through window_optimize "
                                             "(Python mirror of windowOptimize: container walk, upload, K LM iterations, download, write-back)"}
+        # the same schedule through the COMPILED drop-in (host/OptimizationUtils_gpu.cpp: windowOptimize with the reference's
+        # signature over std::vector<KeyFrame> / Map3D, hash-map walk included) -- what main.cpp would call
+        for rep in range(2):
+            seq3 = syn.make_config(2, scale=args.scale)
+            cpp = ba_b200.hostlib.sliding_sequence(seq3, 20, gp.frame_frequency, max_num_iterations=K, fixed_iterations=True)
+        line["sliding_sequence"]["cpp_dropin"] = {
+            "windows": cpp["windows"], "lm_iterations": cpp["lm_iterations"],
+            "windows_per_s": 1e3 * cpp["windows"] / cpp["ms"]["total"], "lm_iterations_per_s": 1e3 * cpp["lm_iterations"] / cpp["ms"]["total"],
+            "ms_per_window": {k: v / max(cpp["windows"], 1) for k, v in cpp["ms"].items()},
+            "note": "windowOptimize of the compiled C++ drop-in over the reference's containers (second pass; host wall clock)"}
     if implicit_path is not None:
         line["implicit_path"] = implicit_path
     if planes_kernels is not None:

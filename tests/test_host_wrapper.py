@@ -29,6 +29,10 @@ def _ptr(a, t):
 def test_host_library_exports_and_count():
     L = _lib()
     assert hasattr(L, "ba_host_window_optimize") and hasattr(L, "ba_host_count_constraints")
+    assert hasattr(ba_b200.hostlib.load(), "ba_host_sliding_sequence")
+    # a schedule that cannot run is refused before any GPU call (window larger than the sequence)
+    with pytest.raises(RuntimeError):
+        ba_b200.hostlib.sliding_sequence(syn.make_tum_sequence(4, 40, 160, seed=1), window_size=8)
     seq = syn.make_tum_sequence(12, 200, 1200, seed=4)
     seq.depth[::7] = 0.0          # inadmissible observations (depth <= 1e-15 are skipped, :265)
     seq.depth[3::11] = -1.0
@@ -94,3 +98,31 @@ def test_window_optimize_cpp_dropin(n_kf, kf_i, kf_f, iters):
     assert np.array_equal(pose[:kf_i], seq.pose[:kf_i]) and np.array_equal(pose[kf_f + 1:], seq.pose[kf_f + 1:])
     others = np.setdiff1d(lm_id, lm_order)
     assert np.array_equal(lm_pt[others], seq.pt[others])
+
+
+@pytest.mark.gpu
+def test_sliding_sequence_cpp_dropin_matches_python_mirror():
+    """The reference's schedule (src/main.cpp:161-175: a window over the last 20 keyframes every 10 keyframes, plus
+    the leftover window) through the compiled windowOptimize == the same schedule through the Python mirror.  The two
+    enumerate the observations in different orders (std::unordered_map iteration vs array order), so the sums differ
+    in the last bits: poses agree to 1e-6 m / 1e-6 rad after 6 warm-started windows."""
+    n_kf, W, F, iters = 65, 20, 10, 8
+    a = syn.make_tum_sequence(n_kf, 100 * n_kf, 600 * n_kf, seed=21)
+    b = syn.make_tum_sequence(n_kf, 100 * n_kf, 600 * n_kf, seed=21)
+    ia = a.K.copy()
+    res = ba_b200.hostlib.sliding_sequence(a, W, F, max_num_iterations=iters, fixed_iterations=True, intrinsics_optimized=ia)
+    assert res["windows"] == 6 and res["lm_iterations"] == 6 * iters   # sizes 20, 30, ..., 60 and the leftover (45..64)
+    assert res["ms"]["total"] >= res["ms"]["upload"] + res["ms"]["solve"] + res["ms"]["download"] > 0.0
+    gp = ba_b200.CeresGlobalProblem(max_num_iterations=iters, window_size=W, frame_frequency=F)
+    sw = ba_b200.GpuSolver(gp.gpu_options(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0))
+    ib = b.K.copy()
+    ends = [s for s in range(1, n_kf + 1) if s % F == 0 and s >= W] + ([n_kf] if n_kf % F else [])
+    for s_ in ends:
+        assert ba_b200.window_optimize(gp, s_ - W, s_ - 1, b, b.K, ib, solver=sw)
+    sw.close()
+    dt, dr = pose_err(a.pose, b.pose)
+    assert dt < 1e-6 and dr < 1e-6
+    assert np.max(np.abs(a.pt - b.pt)) < 1e-5
+    assert np.max(np.abs(ia - ib)) < 1e-5
+    moved = np.max(np.abs(a.pose[:, 4:] - syn.make_tum_sequence(n_kf, 100 * n_kf, 600 * n_kf, seed=21).pose[:, 4:]))
+    assert moved > 1e-4   # the windows did change the trajectory
