@@ -85,6 +85,8 @@ struct ba_gpu_ctx {
   // second stream for the independent branches of an LM iteration (fork / join by events): the windowed
   // problems are chains of ~25 latency-bound small kernels, several of which do not depend on each other
   cudaStream_t stream2 = nullptr, cur = nullptr;
+  cudaStream_t stream3 = nullptr;  // blocked Cholesky look-ahead: bulk of the trailing update
+  cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
   bool forking = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -340,8 +342,15 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
     delete ctx;
     return BA_ERR_CUDA;
   }
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  // main / side stream at the highest priority, a third one at the lowest for the bulk of the blocked Cholesky's trailing
+  // update: the CTAs of the critical chain (next column, diagonal tile, panel) are dispatched ahead of the queued bulk
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_least)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_panel, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_bulk, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   ctx->cur = ctx->stream;
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -389,6 +398,12 @@ extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
     if (b->p) cudaFree(b->p);
   if (ctx->h_st) cudaFreeHost(ctx->h_st);
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+  if (ctx->stream3) {
+    cudaStreamSynchronize(ctx->stream3);
+    cudaStreamDestroy(ctx->stream3);
+  }
+  if (ctx->ev_panel) cudaEventDestroy(ctx->ev_panel);
+  if (ctx->ev_bulk) cudaEventDestroy(ctx->ev_bulk);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
@@ -1693,6 +1708,8 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
     const int nt = cdiv(n, CH_NB);
     double *S = P<double>(ctx->S);
     double *Linv = P<double>(ctx->chol_linv);
+    const bool lookahead = ctx->forking && ctx->cur == ctx->stream && ctx->legacy_chol == 0 && getenv("BA_NO_LOOKAHEAD") == nullptr;
+    bool bulk_pending = false;
     for (int k = 0; k < nt; ++k) {
       const int below = nt - k - 1;
       if (ctx->legacy_chol == 1) {
@@ -1703,8 +1720,27 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
         LAUNCH(k_chol_potrf2, 1, 1024, chol_potrf2_smem_bytes(), n, S, Linv + (size_t)k * CH_NB * CH_NB, k, st, GATE_RUN);
         LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv + (size_t)k * CH_NB * CH_NB, k, st, GATE_RUN);
       }
-      LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
+      if (!lookahead) {
+        LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, k, 0, st, GATE_RUN);
+        continue;
+      }
+      // look-ahead: the tiles of column k + 1 on the main stream (the next diagonal tile and panel follow at once), the
+      // rest of the trailing matrix on the low-priority stream, concurrently with them.  Column k + 1 was last written by
+      // the bulk update of step k - 1, the bulk of step k reads the panel of step k.
+      if (below > 1) CK(cudaEventRecord(ctx->ev_panel, ctx->stream));
+      if (bulk_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0));
+      bulk_pending = false;
+      LAUNCH(k_chol_update, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, k, 1, st, GATE_RUN);
+      if (below > 1) {
+        CK(cudaStreamWaitEvent(ctx->stream3, ctx->ev_panel, 0));
+        ctx->cur = ctx->stream3;
+        LAUNCH(k_chol_update, (below - 1) * below / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, k + 1, 0, st, GATE_RUN);
+        ctx->cur = ctx->stream;
+        CK(cudaEventRecord(ctx->ev_bulk, ctx->stream3));
+        bulk_pending = true;
+      }
     }
+    if (bulk_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0));
     int nn = n, n_cam = ctx->n_cam, n_free = ctx->n_free, nk = ctx->nk, gate = GATE_RUN;
     const double *Sc = S, *rhs = P<double>(ctx->rhs);
     double *yc = P<double>(ctx->yc), *yk = P<double>(ctx->yk);

@@ -83,19 +83,24 @@ k_chol_trsm(int n, double *__restrict__ A, int k, const LmState *st, int gate) {
     if (r0 + r < n && t < m) A[(size_t)(r0 + r) * n + j0 + t] = X[r * CH_LD + t];
 }
 
-// trailing update of the lower triangle: linear CTA index -> tile (i, j), j <= i, both > k
+// trailing update with panel k, A_ij -= L_ik L_jk^T, of the lower-triangle tiles (i, j), kmap < j <= i (linear CTA index ->
+// tile), or, with single_col, of the tiles (i, kmap + 1) only.  kmap = k: the whole trailing matrix; the look-ahead
+// schedule splits it into the next column (single_col) and the rest (kmap = k + 1).
 __global__ void __launch_bounds__(256)
-k_chol_update(int n, double *__restrict__ A, int k, const LmState *st, int gate) {
+k_chol_update(int n, double *__restrict__ A, int k, int kmap, int single_col, const LmState *st, int gate) {
   if (!gate_open(st, gate) || st->lin_fail) return;
   extern __shared__ double sh[];
   double *As = sh, *Bs = sh + CH_NB * CH_LD;
   // triangular decode: b = ti (ti + 1) / 2 + tj
   const int b = blockIdx.x;
-  int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
-  while (ti * (ti + 1) / 2 > b) --ti;
-  const int tj = b - ti * (ti + 1) / 2;
-  const int i0 = (k + 1 + ti) * CH_NB, c0 = (k + 1 + tj) * CH_NB, j0 = k * CH_NB;
+  int ti = b, tj = 0;
+  if (!single_col) {
+    ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
+    while (ti * (ti + 1) / 2 > b) --ti;
+    tj = b - ti * (ti + 1) / 2;
+  }
+  const int i0 = (kmap + 1 + ti) * CH_NB, c0 = (kmap + 1 + tj) * CH_NB, j0 = k * CH_NB;
   const int kk = min(CH_NB, n - j0);
   const int tid = threadIdx.x;
   for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {

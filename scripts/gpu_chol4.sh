@@ -1,0 +1,10 @@
+# look-ahead schedule of the blocked Cholesky: parity tests, then cfg3ref with / without it
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_host_wrapper.py -m gpu -x -q -k "blocked or cpp_dropin" > gpurun_out/c4_tests.log 2>&1; echo rc=$? >> gpurun_out/c4_tests.log
+tail -4 gpurun_out/c4_tests.log
+timeout 200 python bench.py --workload cfg3ref --no-cpu-baseline > gpurun_out/c4_new.log 2>&1; echo rc=$?
+BA_NO_LOOKAHEAD=1 timeout 200 python bench.py --workload cfg3ref --no-cpu-baseline > gpurun_out/c4_old.log 2>&1
+grep -h '"value"' gpurun_out/c4_new.log gpurun_out/c4_old.log | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['value'], d['ms_per_step'], d['final_cost'], d['e2e']['value'])
+"
