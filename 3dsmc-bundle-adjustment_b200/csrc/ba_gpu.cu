@@ -133,6 +133,7 @@ struct ba_gpu_ctx {
   cudaGraphExec_t lm_graph = nullptr;
   int64_t lm_graph_launches = 0;
   bool lm_graph_off = false, lm_graph_stale = true;
+  bool pdl = false, pdl_off = false;  // programmatic dependent launches inside the windowed LM iteration (BA_NO_PDL=1: off)
   int legacy_chol = 0;  // BA_LEGACY_CHOL=1: left-looking single-CTA Cholesky, =2: shared-memory L D L^T, =3: grid-barrier blocked substitution (A/B timing only)
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
@@ -226,12 +227,29 @@ static size_t tile_smem_bytes(int npt) {
   return ((size_t)6 * (npt * BA_THREADS + 8) + 3 * BA_TILE_PTS + BA_TILE_MAXSPAN * BA_TILE_QREC + BA_TILE_MAXSPAN * 6) * 8;
 }
 
-#define LAUNCH(kern, grid, block, smem, ...)                              \
-  do {                                                                    \
-    if ((grid) > 0) {                                                     \
-      kern<<<(grid), (block), (smem), ctx->cur>>>(__VA_ARGS__);           \
-      ctx->launches++;                                                    \
-    }                                                                     \
+// ctx->pdl (windowed explicit LM iteration only): programmatic stream serialisation -- the kernel's CTAs may be made
+// resident before the previous kernel of the stream has finished; every kernel launched in that region starts with
+// pdl_wait() (ba_kernels.cuh; tests/test_cabi_cpu.py audits the sources)
+#define LAUNCH(kern, grid, block, smem, ...)                                          \
+  do {                                                                                \
+    if ((grid) > 0) {                                                                 \
+      if (ctx->pdl) {                                                                 \
+        cudaLaunchConfig_t cfg_ = {};                                                 \
+        cfg_.gridDim = dim3(grid);                                                    \
+        cfg_.blockDim = dim3(block);                                                  \
+        cfg_.dynamicSmemBytes = (smem);                                               \
+        cfg_.stream = ctx->cur;                                                       \
+        cudaLaunchAttribute at_[1];                                                   \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;               \
+        at_[0].val.programmaticStreamSerializationAllowed = 1;                        \
+        cfg_.attrs = at_;                                                             \
+        cfg_.numAttrs = 1;                                                            \
+        cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__);                                 \
+      } else {                                                                        \
+        kern<<<(grid), (block), (smem), ctx->cur>>>(__VA_ARGS__);                     \
+      }                                                                               \
+      ctx->launches++;                                                                \
+    }                                                                                 \
   } while (0)
 
 // dispatch on the cost-model switches (template parameters of the kernels)
@@ -360,6 +378,7 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if ((e = cudaMallocHost((void **)&ctx->h_st, sizeof(LmState))) != cudaSuccess) return bail("cudaMallocHost", e);
   ctx->legacy_chol = getenv("BA_LEGACY_CHOL") ? atoi(getenv("BA_LEGACY_CHOL")) : 0;
   ctx->lm_graph_off = getenv("BA_NO_LM_GRAPH") != nullptr;
+  ctx->pdl_off = getenv("BA_NO_PDL") != nullptr;
   cudaFuncSetAttribute(k_cholesky_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
   cudaFuncSetAttribute(k_ldlt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(BA_LDLT_MAX_N));
   cudaFuncSetAttribute(k_ldlt2_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(31));
@@ -1844,13 +1863,18 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   // captured once per upload and replayed
   const bool graphed = !ctx->lm_graph_off && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks == 1 &&
                        ctx->n_red > 0 && ctx->n_red <= BA_LDLT_MAX_N;
+  // the same problems (single-CTA solve: every kernel of the iteration is a small gated kernel) launch with PDL
+  const bool pdl = !ctx->pdl_off && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks == 1 && ctx->n_red > 0 &&
+                   ctx->n_red <= BA_LDLT_MAX_N;
   for (int it = 1;; ++it) {
     if (graphed) {
       if (!ctx->lm_graph || ctx->lm_graph_stale) {
         const int64_t lb = ctx->launches;
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        ctx->pdl = pdl;
         rc = enqueue_lm_iteration(ctx);
+        ctx->pdl = false;
         const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
         ctx->lm_graph_launches = ctx->launches - lb;
         ctx->launches = lb;
@@ -1872,7 +1896,9 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
       CK(cudaGraphLaunch(ctx->lm_graph, ctx->stream));
       ctx->launches += ctx->lm_graph_launches;
     } else {
+      ctx->pdl = pdl;
       rc = enqueue_lm_iteration(ctx);
+      ctx->pdl = false;
       if (rc) return rc;
     }
     const bool implicit = ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY;

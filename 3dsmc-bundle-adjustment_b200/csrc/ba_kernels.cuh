@@ -16,7 +16,18 @@
 
 enum { GATE_RUN = 0, GATE_ACCEPTED = 1, GATE_PCG = 2, GATE_PCG_RESET = 3, GATE_SCALE = 4 };
 
+// Programmatic dependent launch: the windowed LM iteration is a chain of ~20 small dependent kernels, so every kernel of
+// the iteration is launched with programmatic stream serialisation (ba_gpu.cu: LAUNCH with ctx->pdl).  Its CTAs may become
+// resident while the previous kernel still runs; nothing is read or written before this wait returns (= the previous
+// grid has completed and its writes are visible), and the kernel's own dependents are released at once, so their launch
+// latency overlaps this kernel's execution.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ bool gate_open(const LmState *st, int gate, int reset_period = 0) {
+  pdl_wait();
   if (st->done) return false;
   switch (gate) {
     case GATE_ACCEPTED: return st->accepted != 0;
@@ -1292,6 +1303,7 @@ k_make_scale(int n_cam, int n_pt, int nk, const double *__restrict__ U, const do
   }
 }
 __global__ void k_set_have_scale(LmState *st) {
+  pdl_wait();
   if (st->done) return;
   st->have_scale = 1;
 }
@@ -1440,6 +1452,7 @@ __device__ __forceinline__ double block_max_array(const double *part, int n, dou
 }
 
 __global__ void k_lm_init(LmState *st, double initial_radius) {
+  pdl_wait();
   LmState s;
   memset(&s, 0, sizeof(s));
   s.radius = initial_radius;
@@ -1453,6 +1466,7 @@ __global__ void __launch_bounds__(BA_THREADS)
 k_lm_iter0(int nblk_obs, int nblk_ent, int nk, const double *__restrict__ part_cost, const double *__restrict__ part_gmax,
            const double *__restrict__ part_xn, const double *__restrict__ rk, LmOptions lo, LmState *st,
            BaIterRec *trace) {
+  pdl_wait();
   __shared__ double red[BA_WARPS + 2];
   double cost = block_sum_array(part_cost, nblk_obs, red);
   const double gmax = block_max_array(part_gmax, nblk_ent, red);
@@ -1512,7 +1526,10 @@ __device__ __forceinline__ void lm_begin(const LmOptions &lo, LmState *st) {
   st->lin_fail = 0;
   st->pcg_iters_last = 0;
 }
-__global__ void k_lm_begin(LmOptions lo, LmState *st) { lm_begin(lo, st); }
+__global__ void k_lm_begin(LmOptions lo, LmState *st) {
+  pdl_wait();
+  lm_begin(lo, st);
+}
 
 // step evaluation: model cost change, tolerances, relative decrease, radius
 // update (LevenbergMarquardtStrategy::StepAccepted / StepRejected)
@@ -1605,6 +1622,7 @@ k_lm_control(int nblk_obs, int nblk_ent, int nk, const double *__restrict__ part
              const double *__restrict__ part_cost, const double *__restrict__ rk, const double *__restrict__ Jkk,
              const double *__restrict__ yk, const double *__restrict__ intr_c, const double *__restrict__ intr_prior,
              double sw_intr, LmOptions lo, LmState *st, BaIterRec *trace) {
+  pdl_wait();
   if (st->done) return;
   __shared__ double red[BA_WARPS + 2];
   const double msum = block_sum_array(part_mcc, nblk_obs, red);
@@ -2028,10 +2046,12 @@ k_reduce_partials(int n, const double *__restrict__ part, double *__restrict__ o
   if (threadIdx.x == 0) out[0] = v;
 }
 __global__ void k_flags_pack(const LmState *st, double *out) {
+  pdl_wait();
   out[0] = (double)st->eval_fail;
   out[1] = (double)st->lin_fail;
 }
 __global__ void k_flags_unpack(LmState *st, const double *in) {
+  pdl_wait();
   if (in[0] != 0.0) st->eval_fail = 1;
   if (in[1] != 0.0) st->lin_fail = 1;
 }

@@ -2,6 +2,7 @@
 symbol include/ba_gpu.h declares; create fails loudly without a GPU (no CPU
 fallback); host-side SE3 mirror agrees with the oracle's Sophus restatement."""
 import ctypes as C
+import os
 import re
 
 import numpy as np
@@ -98,3 +99,31 @@ def test_shard_points_partition():
         assert q.n_cam == p.n_cam and np.all(np.diff(q.cam_idx) >= 0)
         assert np.allclose(q.pt3, p.pt3[ids])
     assert tot == p.n_obs
+
+
+def test_pdl_kernels_wait_before_touching_memory():
+    """Kernels of the windowed LM iteration are launched with programmatic stream serialisation (ba_gpu.cu: LAUNCH with
+    ctx->pdl), which is only correct if every one of them executes griddepcontrol.wait before its first memory access:
+    the first statement of each kernel in ba_kernels.cuh / ba_kernels_chol.cuh must be gate_open() / pdl_wait() (or a
+    d_k_* helper that starts with gate_open).  Upload-time index kernels are exempt: they are never launched with PDL."""
+    import re
+    src_dir = os.path.join(os.path.dirname(ba_b200.capi.LIB_PATH), "csrc")
+    exempt = {"k_index_count", "k_exclusive_scan", "k_index_fill", "k_index_sort", "k_index_gather", "k_item_count",
+              "k_item_fill", "k_iota", "k_fill", "k_fill_i32"}
+    helpers_ok = True
+    bad = []
+    for f in ("ba_kernels.cuh", "ba_kernels_chol.cuh"):
+        s = open(os.path.join(src_dir, f)).read()
+        for m in re.finditer(r"__global__[^{;]*?\b(k\w+)\s*\(([^{;]*?)\)\s*\{", s, re.S):
+            first = s[m.end():m.end() + 600].split(";")[0]
+            if m.group(1) in exempt:
+                continue
+            if not ("gate_open" in first or "pdl_wait" in first or "d_k_" in first):
+                bad.append((f, m.group(1)))
+        for m in re.finditer(r"void (d_k_\w+)\s*\(([^{;]*?)\)\s*\{", s, re.S):
+            helpers_ok &= "gate_open" in s[m.end():m.end() + 300].split(";")[0]
+    assert not bad, bad
+    assert helpers_ok
+    k = open(os.path.join(src_dir, "ba_kernels.cuh")).read()
+    body = k[k.index("bool gate_open("):]
+    assert body.index("pdl_wait()") < body.index("st->done")
