@@ -925,6 +925,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
                              const double *pt3, int32_t n_obs, const int32_t *cam_idx, const int32_t *pt_idx,
                              const double *uv2, const double *depth, const double intr4[4], const double intr_prior4[4]) {
   if (!ctx) return BA_ERR_INVALID;
+  ctx->pdl = false;
   UploadProf prof;
   ctx->uploaded = false;
   ctx->lm_graph_stale = true;
@@ -1729,6 +1730,7 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
     double *Linv = P<double>(ctx->chol_linv);
     const bool lookahead = ctx->forking && ctx->cur == ctx->stream && ctx->legacy_chol == 0 && getenv("BA_NO_LOOKAHEAD") == nullptr;
     bool bulk_pending = false;
+    ctx->pdl = lookahead && !ctx->pdl_off;  // potrf2 -> trsm2 -> next-column update: a chain of ~225 short dependent kernels
     for (int k = 0; k < nt; ++k) {
       const int below = nt - k - 1;
       if (ctx->legacy_chol == 1) {
@@ -1759,6 +1761,7 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
         bulk_pending = true;
       }
     }
+    ctx->pdl = false;
     if (bulk_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0));
     int nn = n, n_cam = ctx->n_cam, n_free = ctx->n_free, nk = ctx->nk, gate = GATE_RUN;
     const double *Sc = S, *rhs = P<double>(ctx->rhs);
@@ -1854,6 +1857,8 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   if (!ctx) return BA_ERR_INVALID;
   if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_solve before ba_gpu_upload");
   CK(cudaSetDevice(ctx->device));
+  ctx->pdl = false;  // (an error return may have left the LM-iteration launch mode on)
+  ctx->cur = ctx->stream;
   const int64_t l0 = ctx->launches;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   enqueue_iteration_zero(ctx);

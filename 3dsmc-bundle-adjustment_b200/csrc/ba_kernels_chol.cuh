@@ -138,6 +138,10 @@ k_chol_update(int n, double *__restrict__ A, int k, int kmap, int single_col, co
   }
 }
 
+// (Measured and rejected: a 128 x 128 super-tile version of this kernel -- 512 threads, 8 x 4 outputs each, every panel
+// tile loaded half as often, 12 instead of 16 shared-memory loads per 32 multiply-adds.  Alone it is faster per tile, but
+// its 133 KB CTAs fill an SM for their whole run, so the CTAs of the look-ahead chain (diagonal tile, panel, next column)
+// wait for one to drain: 800-keyframe REF step 7.23 ms against 6.43 ms with the 64 x 64 tiles, three CTAs per SM.)
 // L z = b, L^T y = z, then the scatter of k_cholesky_solve.  Cooperative kernel (one CTA per SM): CTA 0 solves
 // the 64 x 64 diagonal tile in shared memory (column-oriented), a grid barrier publishes the 64 values, all CTAs
 // update the remaining right-hand side (92 MB of L per pass at n = 4798, spread over the grid).  The single-CTA

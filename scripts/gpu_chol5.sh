@@ -1,0 +1,11 @@
+# 128 x 128 bulk update + PDL in the blocked Cholesky chain: parity tests, then cfg3ref A/B
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_host_wrapper.py -m gpu -x -q -k "blocked or cpp_dropin" > gpurun_out/c5_tests.log 2>&1; echo rc=$? >> gpurun_out/c5_tests.log
+tail -4 gpurun_out/c5_tests.log
+timeout 200 python bench.py --workload cfg3ref --no-cpu-baseline > gpurun_out/c5_new.log 2>&1; echo rc=$?
+BA_CHOL_SMALL_TILES=1 timeout 200 python bench.py --workload cfg3ref --no-cpu-baseline > gpurun_out/c5_small.log 2>&1
+BA_NO_PDL=1 timeout 200 python bench.py --workload cfg3ref --no-cpu-baseline > gpurun_out/c5_nopdl.log 2>&1
+grep -h '"value"' gpurun_out/c5_new.log gpurun_out/c5_small.log gpurun_out/c5_nopdl.log | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['value'], d['ms_per_step'], d['final_cost'], d['e2e']['value'])
+"
