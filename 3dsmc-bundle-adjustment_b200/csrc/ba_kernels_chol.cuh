@@ -400,6 +400,10 @@ k_ldlt_solve(int n, const double *__restrict__ Sg, const double *__restrict__ rh
 // The stored columns C are L D (column-major, ldc odd: the row-wise reads of the back substitution are
 // bank-conflict free); row n carries the right-hand side, so C[j ldc + n] = w_j (L w = b) at the end.
 // =====================================================================
+// (Measured and rejected: replacing the CTA barrier of a step by a split arrive / wait on a shared-memory mbarrier, so that
+// column j + 1 is published before the bulk of the update with column j -- bit-identical factor, but slower: cfg 2
+// 8,003 -> 7,695 LM it/s with 1,024 pollers, 4,723 with one poller per warp + __syncwarp; bar.sync is cheaper than the
+// mbarrier round trip it would hide.)
 #define BA_LDLT2_MAX_N 159
 __host__ __device__ inline int ldlt2_ldc(int n) { return (n + 1) | 1; }
 __host__ __device__ inline int ldlt2_tiles(int n) { return (n + 1 + 31) / 32; }
