@@ -86,7 +86,7 @@ struct ba_gpu_ctx {
   // problems are chains of ~25 latency-bound small kernels, several of which do not depend on each other
   cudaStream_t stream2 = nullptr, cur = nullptr;
   cudaStream_t stream3 = nullptr;  // blocked Cholesky look-ahead: bulk of the trailing update
-  cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr, ev_trsm = nullptr, ev_col[2] = {nullptr, nullptr}, ev_bulk2[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
   bool forking = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -125,7 +125,7 @@ struct ba_gpu_ctx {
   Buf sp_cnt, sp_off, sp_keys, sp_vals, sp_keys2, sp_pairs, sp_ukeys, sp_ucnt, sp_nruns, sb_ptr, sb_i, sb_j, row_ucnt, row_tcnt,
       row_ustart, row_tstart, sp_tkeys, sp_tvals, sp_tkeys2, sp_tvals2, ent_ptr, ent, Sblk, ysp, cub_tmp, dsq, row_pq;
   int n_sblk = 0, n_sblk_local = 0, n_ent = 0, pcg_grid = 0, sp_ctas_per_sm = 1;
-  Buf sp_pair_pt, chol_v, chol_linv, chol_slots;
+  Buf sp_pair_pt, chol_v, chol_linv, chol_lsub, chol_slots;
   // one LM iteration of the windowed explicit solver as an instantiated CUDA graph (every decision is taken on the
   // device, so the node parameters never change between iterations); upload / set_options mark it stale and the next
   // solve re-captures and updates the executable in place (cudaGraphExecUpdate: destroying and re-instantiating it cost
@@ -369,6 +369,11 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if ((e = cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_least)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_panel, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_bulk, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_trsm, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_col[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_bulk2[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  }
   ctx->cur = ctx->stream;
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -423,6 +428,11 @@ extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
   }
   if (ctx->ev_panel) cudaEventDestroy(ctx->ev_panel);
   if (ctx->ev_bulk) cudaEventDestroy(ctx->ev_bulk);
+  if (ctx->ev_trsm) cudaEventDestroy(ctx->ev_trsm);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_col[i]) cudaEventDestroy(ctx->ev_col[i]);
+    if (ctx->ev_bulk2[i]) cudaEventDestroy(ctx->ev_bulk2[i]);
+  }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
@@ -1253,6 +1263,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     RES(chol_v, (size_t)(ctx->n_red + 64 + 8) * 8);
     // blocked Cholesky: L^-1 of every diagonal tile (kept for the substitution) and the flag-in-data slots of k_chol_solve2
     RES(chol_linv, (size_t)cdiv(ctx->n_red, CH_NB) * CH_NB * CH_NB * 8);
+    RES(chol_lsub, (size_t)(cdiv(ctx->n_red, CH_NB) + 1) * CH_NB * CH_NB * 8);  // panel tiles right below the diagonal (look-ahead)
     RES(chol_slots, (size_t)2 * cdiv(ctx->n_red, CH_NB) * CH_NB * sizeof(ChSlot));
     prof.stamp("rest");
     // windows: device-built pair list; the global REF problem keeps the host-built list of NON-EMPTY blocks
@@ -1660,6 +1671,59 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
 }
 
 // reduced system by explicit Schur complement + dense Cholesky (windowed problems)
+// Blocked Cholesky, look-ahead schedule 2 (in force): three streams.
+//   main  (high priority): k_chol_potrf2 with the fused prologue -- diagonal tile k brought up to date inside the kernel, so the
+//         critical chain is one kernel per tile column
+//   side  (high priority): k_chol_trsm2 (panel k; the tile right below the diagonal goes to the side buffer), then the update
+//         of the tiles (i, k + 1), i >= k + 2
+//   bulk  (low priority) : the rest of the trailing update with panel k
+// Dependencies (events; [k & 1] ping-pong where a wait refers to two steps back):
+//   potrf2(k) <- potrf2(k-1) [stream order], column(k-2) = the next-column update of step k - 2, bulk(k-2)
+//   trsm2(k)  <- potrf2(k), column(k-1) [stream order]
+//   column(k) <- trsm2(k) [stream order], bulk(k-1)
+//   bulk(k)   <- trsm2(k), bulk(k-1) [stream order]
+static int factor_blocked_lookahead2(ba_gpu_ctx *ctx, int n, int nt, double *S, double *Linv, double *Lsub, LmState *st) {
+  const size_t tile = (size_t)CH_NB * CH_NB, sm2 = (size_t)2 * CH_NB * CH_LD * 8;
+  cudaStream_t A = ctx->stream, B = ctx->stream2, C = ctx->stream3;
+  bool col_rec[2] = {false, false}, bulk_rec[2] = {false, false};
+  ctx->pdl = !ctx->pdl_off;
+  for (int k = 0; k < nt; ++k) {
+    const int below = nt - k - 1, e = k & 1;
+    if (col_rec[e]) CK(cudaStreamWaitEvent(A, ctx->ev_col[e], 0));    // column(k - 2)
+    if (bulk_rec[e]) CK(cudaStreamWaitEvent(A, ctx->ev_bulk2[e], 0));  // bulk(k - 2)
+    ctx->cur = A;
+    LAUNCH(k_chol_potrf2, 1, 1024, chol_potrf2_smem_bytes(), n, S, Linv + k * tile, k, 1, st, GATE_RUN);
+    if (below == 0) break;
+    CK(cudaEventRecord(ctx->ev_panel, A));
+    CK(cudaStreamWaitEvent(B, ctx->ev_panel, 0));
+    ctx->cur = B;
+    LAUNCH(k_chol_trsm2, below, 256, sm2, n, S, Linv + k * tile, Lsub + (size_t)(k + 1) * tile, k, st, GATE_RUN);
+    if (below > 1) {
+      CK(cudaEventRecord(ctx->ev_trsm, B));
+      if (bulk_rec[e ^ 1]) CK(cudaStreamWaitEvent(B, ctx->ev_bulk2[e ^ 1], 0));  // bulk(k - 1)
+      LAUNCH(k_chol_update, below - 1, 256, sm2, n, S, (const double *)(Lsub + (size_t)(k + 1) * tile), k, k, 1, st, GATE_RUN);
+      CK(cudaEventRecord(ctx->ev_col[e], B));
+      col_rec[e] = true;
+      CK(cudaStreamWaitEvent(C, ctx->ev_trsm, 0));
+      ctx->cur = C;
+      LAUNCH(k_chol_update, (below - 1) * below / 2, 256, sm2, n, S, (const double *)nullptr, k, k + 1, 0, st, GATE_RUN);
+      CK(cudaEventRecord(ctx->ev_bulk2[e], C));
+      bulk_rec[e] = true;
+    } else {
+      CK(cudaEventRecord(ctx->ev_col[e], B));  // the last panel: nothing left to update, the main stream waits for the panel
+      col_rec[e] = true;
+    }
+  }
+  ctx->cur = A;
+  for (int e = 0; e < 2; ++e) {
+    if (col_rec[e]) CK(cudaStreamWaitEvent(A, ctx->ev_col[e], 0));
+    if (bulk_rec[e]) CK(cudaStreamWaitEvent(A, ctx->ev_bulk2[e], 0));
+  }
+  LAUNCH(k_chol_fixup, nt - 1, 256, 0, n, S, Lsub, st, GATE_RUN);
+  ctx->pdl = false;
+  return 0;
+}
+
 static int solve_explicit(ba_gpu_ctx *ctx) {
   LmState *st = P<LmState>(ctx->st);
   const int n = ctx->n_red;
@@ -1730,19 +1794,28 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
     double *Linv = P<double>(ctx->chol_linv);
     const bool lookahead = ctx->forking && ctx->cur == ctx->stream && ctx->legacy_chol == 0 && getenv("BA_NO_LOOKAHEAD") == nullptr;
     bool bulk_pending = false;
-    ctx->pdl = lookahead && !ctx->pdl_off;  // potrf2 -> trsm2 -> next-column update: a chain of ~225 short dependent kernels
-    for (int k = 0; k < nt; ++k) {
+    const bool sched2 = lookahead && ctx->stream2 && getenv("BA_LOOKAHEAD1") == nullptr;
+    if (sched2) {
+      int rcf = factor_blocked_lookahead2(ctx, n, nt, S, Linv, P<double>(ctx->chol_lsub), st);
+      ctx->cur = ctx->stream;
+      ctx->pdl = false;
+      if (rcf) return rcf;
+    }
+    ctx->pdl = lookahead && !sched2 && !ctx->pdl_off;  // potrf2 -> trsm2 -> next-column update: a chain of ~225 short dependent kernels
+    for (int k = 0; k < nt && !sched2; ++k) {
       const int below = nt - k - 1;
       if (ctx->legacy_chol == 1) {
         LAUNCH(k_chol_potrf, 1, CH_NB, 0, n, S, k, st, GATE_RUN);
         LAUNCH(k_chol_trsm, below, CH_NB, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, st, GATE_RUN);
       } else {
         // diagonal tile: register-resident L D L^T that also yields L^-1; panel: product with L^-1
-        LAUNCH(k_chol_potrf2, 1, 1024, chol_potrf2_smem_bytes(), n, S, Linv + (size_t)k * CH_NB * CH_NB, k, st, GATE_RUN);
-        LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv + (size_t)k * CH_NB * CH_NB, k, st, GATE_RUN);
+        LAUNCH(k_chol_potrf2, 1, 1024, chol_potrf2_smem_bytes(), n, S, Linv + (size_t)k * CH_NB * CH_NB, k, 0, st, GATE_RUN);
+        LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv + (size_t)k * CH_NB * CH_NB, (double *)nullptr, k, st,
+               GATE_RUN);
       }
       if (!lookahead) {
-        LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, k, 0, st, GATE_RUN);
+        LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, (const double *)nullptr, k, k, 0, st,
+               GATE_RUN);
         continue;
       }
       // look-ahead: the tiles of column k + 1 on the main stream (the next diagonal tile and panel follow at once), the
@@ -1751,11 +1824,12 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
       if (below > 1) CK(cudaEventRecord(ctx->ev_panel, ctx->stream));
       if (bulk_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0));
       bulk_pending = false;
-      LAUNCH(k_chol_update, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, k, 1, st, GATE_RUN);
+      LAUNCH(k_chol_update, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, (const double *)nullptr, k, k, 1, st, GATE_RUN);
       if (below > 1) {
         CK(cudaStreamWaitEvent(ctx->stream3, ctx->ev_panel, 0));
         ctx->cur = ctx->stream3;
-        LAUNCH(k_chol_update, (below - 1) * below / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, k, k + 1, 0, st, GATE_RUN);
+        LAUNCH(k_chol_update, (below - 1) * below / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, (const double *)nullptr, k, k + 1, 0, st,
+               GATE_RUN);
         ctx->cur = ctx->stream;
         CK(cudaEventRecord(ctx->ev_bulk, ctx->stream3));
         bulk_pending = true;

@@ -86,14 +86,17 @@ k_chol_trsm(int n, double *__restrict__ A, int k, const LmState *st, int gate) {
 // trailing update with panel k, A_ij -= L_ik L_jk^T, of the lower-triangle tiles (i, j), kmap < j <= i (linear CTA index ->
 // tile), or, with single_col, of the tiles (i, kmap + 1) only.  kmap = k: the whole trailing matrix; the look-ahead
 // schedule splits it into the next column (single_col) and the rest (kmap = k + 1).
+// Bsub != nullptr (single_col only, look-ahead schedule): the column operand L_{k+1,k} comes from the side buffer and the
+// diagonal tile (k + 1, k + 1) is left to the fused k_chol_potrf2: tiles (i, k + 1), i >= k + 2.
 __global__ void __launch_bounds__(256)
-k_chol_update(int n, double *__restrict__ A, int k, int kmap, int single_col, const LmState *st, int gate) {
+k_chol_update(int n, double *__restrict__ A, const double *__restrict__ Bsub, int k, int kmap, int single_col, const LmState *st,
+              int gate) {
   if (!gate_open(st, gate) || st->lin_fail) return;
   extern __shared__ double sh[];
   double *As = sh, *Bs = sh + CH_NB * CH_LD;
   // triangular decode: b = ti (ti + 1) / 2 + tj
   const int b = blockIdx.x;
-  int ti = b, tj = 0;
+  int ti = Bsub ? b + 1 : b, tj = 0;
   if (!single_col) {
     ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
     while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
@@ -106,7 +109,7 @@ k_chol_update(int n, double *__restrict__ A, int k, int kmap, int single_col, co
   for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
     const int r = idx >> 6, c = idx & 63;
     As[r * CH_LD + c] = (i0 + r < n && c < kk) ? A[(size_t)(i0 + r) * n + j0 + c] : 0.0;
-    Bs[r * CH_LD + c] = (c0 + r < n && c < kk) ? A[(size_t)(c0 + r) * n + j0 + c] : 0.0;
+    Bs[r * CH_LD + c] = Bsub ? Bsub[idx] : ((c0 + r < n && c < kk) ? A[(size_t)(c0 + r) * n + j0 + c] : 0.0);
   }
   __syncthreads();
   const int ty = tid >> 4, tx = tid & 15;
@@ -548,17 +551,67 @@ k_ldlt2_solve(int n, const double *__restrict__ Sg, const double *__restrict__ r
 //    instead of one thread per row walking a 64-step substitution with j-long dependent chains (63 us per launch).
 // =====================================================================
 #define CH_P2_LDC 129
-__host__ __device__ inline size_t chol_potrf2_smem_bytes() { return ((size_t)CH_NB * CH_P2_LDC + 128 + 2 * (CH_NB + 8)) * 8; }
+// fuse != 0 (look-ahead schedule, k > 0): the kernel first brings its own diagonal tile up to date, so that the chain
+// diagonal tile k - 1 -> diagonal tile k has no other kernel in it:
+//   L_{k,k-1} = A_{k,k-1} L_{k-1,k-1}^-T   (A_{k,k-1} is still the un-solved tile: k_chol_trsm2 writes this panel tile to a side
+//                                          buffer, never in place, so nothing overwrites what this kernel reads)
+//   D = A_kk - L_{k,k-1} L_{k,k-1}^T       (the update k_chol_update would have applied)
+// with the same operation order per entry as k_chol_trsm2 / k_chol_update (sums over q ascending from zero), i.e. the same bits.
+__host__ __device__ inline size_t chol_potrf2_smem_bytes() {
+  return ((size_t)CH_NB * CH_P2_LDC + 128 + 2 * (CH_NB + 8) + 2 * CH_NB * CH_LD) * 8;
+}
 
 __global__ void __launch_bounds__(1024)
-k_chol_potrf2(int n, double *__restrict__ A, double *__restrict__ Linv, int k, LmState *st, int gate) {
+k_chol_potrf2(int n, double *__restrict__ A, double *__restrict__ Linv, int k, int fuse, LmState *st, int gate) {
   if (!gate_open(st, gate) || st->lin_fail) return;
   constexpr int NT = 4;
   extern __shared__ double smd[];
   double *C = smd;                                   // m columns of CH_P2_LDC (+ 128: reads of the last tile rows)
   double *invd = smd + (size_t)CH_NB * CH_P2_LDC + 128;
+  double *Xs = invd + 2 * (CH_NB + 8);               // fused prologue: A_{k,k-1}, then L_{k,k-1}
+  double *Ds = Xs + CH_NB * CH_LD;                   // fused prologue: L_{k-1,k-1}^-1, then the updated diagonal tile
   const int j0 = k * CH_NB, m = min(CH_NB, n - j0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool fused = fuse && k > 0;
+  if (fused) {
+    const int jp = j0 - CH_NB;
+    const double *Lp = Linv - (size_t)CH_NB * CH_NB;  // L^-1 of the previous diagonal tile (Linv points at this tile's slot)
+    for (int idx = tid; idx < CH_NB * CH_NB; idx += 1024) {
+      const int r = idx >> 6, c = idx & 63;
+      Xs[r * CH_LD + c] = r < m ? A[(size_t)(j0 + r) * n + jp + c] : 0.0;
+      Ds[r * CH_LD + c] = Lp[idx];
+    }
+    __syncthreads();
+    const int r = tid >> 4, cg = tid & 15;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int q = 0; q < CH_NB; ++q) {
+      const double x = Xs[r * CH_LD + q];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) acc[cc] += x * Ds[(cg + 16 * cc) * CH_LD + q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) Xs[r * CH_LD + cg + 16 * cc] = acc[cc];
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) acc[cc] = 0.0;
+    for (int q = 0; q < CH_NB; ++q) {
+      const double x = Xs[r * CH_LD + q];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) acc[cc] += x * Xs[(cg + 16 * cc) * CH_LD + q];
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = cg + 16 * cc;
+      double d = 0.0;
+      if (r < m && c <= r) {
+        d = A[(size_t)(j0 + r) * n + j0 + c];
+        d -= acc[cc];
+      }
+      Ds[r * CH_LD + c] = d;
+    }
+    __syncthreads();
+  }
   double a[NT * (NT + 1) / 2];
 #pragma unroll
   for (int ti = 0; ti < NT; ++ti)
@@ -567,8 +620,10 @@ k_chol_potrf2(int n, double *__restrict__ A, double *__restrict__ Linv, int k, L
       const int i = warp + 32 * ti, c = lane + 32 * tk;
       double v = 0.0;
       if (c < m) {
-        if (i < m) v = c <= i ? A[(size_t)(j0 + i) * n + j0 + c] : A[(size_t)(j0 + c) * n + j0 + i];  // the lower triangle is current
-        else if (i - m == c) v = 1.0;
+        if (i < m) {  // the lower triangle is current
+          if (fused) v = c <= i ? Ds[i * CH_LD + c] : Ds[c * CH_LD + i];
+          else v = c <= i ? A[(size_t)(j0 + i) * n + j0 + c] : A[(size_t)(j0 + c) * n + j0 + i];
+        } else if (i - m == c) v = 1.0;
       }
       a[LDLT2_IDX(ti, tk)] = v;
     }
@@ -598,8 +653,11 @@ k_chol_potrf2(int n, double *__restrict__ A, double *__restrict__ Linv, int k, L
   }
 }
 
+// Lsub != nullptr (look-ahead schedule): the tile right below the diagonal, (k + 1, k), goes to Lsub (dense 64 x 64) instead
+// of in place -- the fused k_chol_potrf2 of step k + 1 reads the un-solved tile concurrently; k_chol_fixup stores it at the end.
 __global__ void __launch_bounds__(256)
-k_chol_trsm2(int n, double *__restrict__ A, const double *__restrict__ Linv, int k, const LmState *st, int gate) {
+k_chol_trsm2(int n, double *__restrict__ A, const double *__restrict__ Linv, double *__restrict__ Lsub, int k, const LmState *st,
+             int gate) {
   if (!gate_open(st, gate) || st->lin_fail) return;
   extern __shared__ double sh[];
   double *As = sh, *Bs = sh + CH_NB * CH_LD;
@@ -629,6 +687,13 @@ k_chol_trsm2(int n, double *__restrict__ A, const double *__restrict__ Linv, int
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * bb[c];
   }
+  if (Lsub && blockIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Lsub[(ty * 4 + r) * CH_NB + tx + 16 * c] = acc[r][c];  // zero beyond the matrix
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int row = i0 + ty * 4 + r;
@@ -638,6 +703,18 @@ k_chol_trsm2(int n, double *__restrict__ A, const double *__restrict__ Linv, int
       const int col = tx + 16 * c;
       if (col < kk) A[(size_t)row * n + j0 + col] = acc[r][c];
     }
+  }
+}
+
+// look-ahead schedule: the panel tiles right below the diagonal, kept aside during the factorisation, into the matrix
+__global__ void __launch_bounds__(256)
+k_chol_fixup(int n, double *__restrict__ A, const double *__restrict__ Lsub, const LmState *st, int gate) {
+  if (!gate_open(st, gate) || st->lin_fail) return;
+  const int k = blockIdx.x + 1, j0 = k * CH_NB, jp = j0 - CH_NB;
+  const double *L = Lsub + (size_t)k * CH_NB * CH_NB;
+  for (int idx = threadIdx.x; idx < CH_NB * CH_NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    if (j0 + r < n) A[(size_t)(j0 + r) * n + jp + c] = L[idx];
   }
 }
 
