@@ -144,7 +144,10 @@ k_chol_update(int n, double *__restrict__ A, const double *__restrict__ Bsub, in
 // (Measured and rejected: a 128 x 128 super-tile version of this kernel -- 512 threads, 8 x 4 outputs each, every panel
 // tile loaded half as often, 12 instead of 16 shared-memory loads per 32 multiply-adds.  Alone it is faster per tile, but
 // its 133 KB CTAs fill an SM for their whole run, so the CTAs of the look-ahead chain (diagonal tile, panel, next column)
-// wait for one to drain: 800-keyframe REF step 7.23 ms against 6.43 ms with the 64 x 64 tiles, three CTAs per SM.)
+// wait for one to drain: 800-keyframe REF step 7.23 ms against 6.43 ms with the 64 x 64 tiles, three CTAs per SM.
+// Also rejected: 128 threads with 8 x 4 outputs and both operand tiles transposed in shared memory (LDS.128 operands, 5 instead
+// of 8 shared-memory wavefronts per warp and inner-product step): 7.10 ms against 6.18 ms -- with 12 instead of 24 warps per
+// SM the kernel is bound by latency, not by the LSU / fp64 pipes.)
 // L z = b, L^T y = z, then the scatter of k_cholesky_solve.  Cooperative kernel (one CTA per SM): CTA 0 solves
 // the 64 x 64 diagonal tile in shared memory (column-oriented), a grid barrier publishes the 64 values, all CTAs
 // update the remaining right-hand side (92 MB of L per pass at n = 4798, spread over the grid).  The single-CTA
