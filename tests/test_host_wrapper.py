@@ -126,3 +126,26 @@ def test_sliding_sequence_cpp_dropin_matches_python_mirror():
     assert np.max(np.abs(ia - ib)) < 1e-5
     moved = np.max(np.abs(a.pose[:, 4:] - syn.make_tum_sequence(n_kf, 100 * n_kf, 600 * n_kf, seed=21).pose[:, 4:]))
     assert moved > 1e-4   # the windows did change the trajectory
+
+
+def test_window_optimize_missing_landmark_leaves_inputs_untouched():
+    """A keyframe that references a landmark id absent from the map made the reference throw (map.at,
+    src/OptimizationUtils.cpp:270); the drop-in returns false BEFORE any GPU call and undoes the in-place frame change
+    (:248, :274): poses and landmarks are bit-identical afterwards.  Runs without a GPU."""
+    L = _lib()
+    seq = syn.make_tum_sequence(12, 240, 1440, seed=9)
+    pose = seq.pose.copy()
+    kf_ptr = seq.kf_ptr.astype(np.int32)
+    uv = seq.uv.astype(np.float32)
+    # the map lacks the landmark of an observation in the middle of the window
+    victim = int(seq.lm[kf_ptr[5] + 3])
+    lm_id = np.array([l for l in range(seq.pt.shape[0]) if l != victim], dtype=np.int32)
+    lm_pt = seq.pt[lm_id].copy()
+    lm_pt0 = lm_pt.copy()
+    intr0 = seq.K.copy(); intr = seq.K.copy()
+    rc = L.ba_host_window_optimize(12, _ptr(pose, C.c_double), _ptr(kf_ptr, C.c_int32), _ptr(seq.lm, C.c_int32),
+                                   _ptr(uv, C.c_float), _ptr(seq.depth, C.c_double), lm_id.shape[0], _ptr(lm_id, C.c_int32),
+                                   _ptr(lm_pt, C.c_double), 2, 9, 5, _ptr(intr0, C.c_double), _ptr(intr, C.c_double),
+                                   None, None, None, None, None, None, None)
+    assert rc == -1
+    assert np.array_equal(pose, seq.pose) and np.array_equal(lm_pt, lm_pt0) and np.array_equal(intr, seq.K)
