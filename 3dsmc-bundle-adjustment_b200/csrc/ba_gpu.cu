@@ -86,7 +86,7 @@ struct ba_gpu_ctx {
   // problems are chains of ~25 latency-bound small kernels, several of which do not depend on each other
   cudaStream_t stream2 = nullptr, cur = nullptr;
   cudaStream_t stream3 = nullptr;  // blocked Cholesky look-ahead: bulk of the trailing update
-  cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr, ev_trsm = nullptr, ev_col[2] = {nullptr, nullptr}, ev_bulk2[2] = {nullptr, nullptr};
+  cudaEvent_t ev_panel = nullptr, ev_trsm = nullptr, ev_col[2] = {nullptr, nullptr}, ev_bulk2[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
   bool forking = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -368,7 +368,6 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_least)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_panel, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-  if ((e = cudaEventCreateWithFlags(&ctx->ev_bulk, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_trsm, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (int i = 0; i < 2; ++i) {
     if ((e = cudaEventCreateWithFlags(&ctx->ev_col[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -427,7 +426,6 @@ extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
     cudaStreamDestroy(ctx->stream3);
   }
   if (ctx->ev_panel) cudaEventDestroy(ctx->ev_panel);
-  if (ctx->ev_bulk) cudaEventDestroy(ctx->ev_bulk);
   if (ctx->ev_trsm) cudaEventDestroy(ctx->ev_trsm);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_col[i]) cudaEventDestroy(ctx->ev_col[i]);
@@ -1792,17 +1790,17 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
     const int nt = cdiv(n, CH_NB);
     double *S = P<double>(ctx->S);
     double *Linv = P<double>(ctx->chol_linv);
-    const bool lookahead = ctx->forking && ctx->cur == ctx->stream && ctx->legacy_chol == 0 && getenv("BA_NO_LOOKAHEAD") == nullptr;
-    bool bulk_pending = false;
-    const bool sched2 = lookahead && ctx->stream2 && getenv("BA_LOOKAHEAD1") == nullptr;
-    if (sched2) {
+    // one GPU: three-stream look-ahead schedule (factor_blocked_lookahead2); otherwise (sharded run, BA_NO_LOOKAHEAD=1, legacy
+    // kernels) the plain right-looking sequence on the solver stream
+    const bool lookahead = ctx->forking && ctx->stream2 && ctx->cur == ctx->stream && ctx->legacy_chol == 0 &&
+                           getenv("BA_NO_LOOKAHEAD") == nullptr;
+    if (lookahead) {
       int rcf = factor_blocked_lookahead2(ctx, n, nt, S, Linv, P<double>(ctx->chol_lsub), st);
       ctx->cur = ctx->stream;
       ctx->pdl = false;
       if (rcf) return rcf;
     }
-    ctx->pdl = lookahead && !sched2 && !ctx->pdl_off;  // potrf2 -> trsm2 -> next-column update: a chain of ~225 short dependent kernels
-    for (int k = 0; k < nt && !sched2; ++k) {
+    for (int k = 0; k < nt && !lookahead; ++k) {
       const int below = nt - k - 1;
       if (ctx->legacy_chol == 1) {
         LAUNCH(k_chol_potrf, 1, CH_NB, 0, n, S, k, st, GATE_RUN);
@@ -1813,30 +1811,9 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
         LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv + (size_t)k * CH_NB * CH_NB, (double *)nullptr, k, st,
                GATE_RUN);
       }
-      if (!lookahead) {
-        LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, (const double *)nullptr, k, k, 0, st,
-               GATE_RUN);
-        continue;
-      }
-      // look-ahead: the tiles of column k + 1 on the main stream (the next diagonal tile and panel follow at once), the
-      // rest of the trailing matrix on the low-priority stream, concurrently with them.  Column k + 1 was last written by
-      // the bulk update of step k - 1, the bulk of step k reads the panel of step k.
-      if (below > 1) CK(cudaEventRecord(ctx->ev_panel, ctx->stream));
-      if (bulk_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0));
-      bulk_pending = false;
-      LAUNCH(k_chol_update, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, (const double *)nullptr, k, k, 1, st, GATE_RUN);
-      if (below > 1) {
-        CK(cudaStreamWaitEvent(ctx->stream3, ctx->ev_panel, 0));
-        ctx->cur = ctx->stream3;
-        LAUNCH(k_chol_update, (below - 1) * below / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, (const double *)nullptr, k, k + 1, 0, st,
-               GATE_RUN);
-        ctx->cur = ctx->stream;
-        CK(cudaEventRecord(ctx->ev_bulk, ctx->stream3));
-        bulk_pending = true;
-      }
+      LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, (const double *)nullptr, k, k, 0, st,
+             GATE_RUN);
     }
-    ctx->pdl = false;
-    if (bulk_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0));
     int nn = n, n_cam = ctx->n_cam, n_free = ctx->n_free, nk = ctx->nk, gate = GATE_RUN;
     const double *Sc = S, *rhs = P<double>(ctx->rhs);
     double *yc = P<double>(ctx->yc), *yk = P<double>(ctx->yk);

@@ -4,11 +4,14 @@
 // -- needs an exact dense solve beyond the single-CTA kernel's 1024 unknowns).
 //
 // Right-looking, 64 x 64 fp64 tiles, lower triangle of the row-major n x n matrix, in place:
-//   for k = 0 .. nt-1:   k_chol_potrf   diagonal tile (one CTA, shared memory, column Cholesky)
-//                        k_chol_trsm    tiles (i, k), i > k:  X L_kk^T = A_ik   (one thread per row)
+//   for k = 0 .. nt-1:   k_chol_potrf2  diagonal tile (one CTA: register-resident L D L^T, yields L_kk and L_kk^-1)
+//                        k_chol_trsm2   tiles (i, k), i > k:  L_ik = A_ik L_kk^-T   (a product with L_kk^-1)
 //                        k_chol_update  tiles (i, j), k < j <= i:  A_ij -= L_ik L_jk^T
 //                                       (256 threads, 4 x 4 outputs each, both operand tiles in shared memory)
-// then k_chol_solve: blocked forward / backward substitution and the scatter into y_c / y_k.
+// then k_chol_solve2: blocked forward / backward substitution through the stored L_kk^-1 tiles and the scatter into y_c / y_k.
+// On one GPU the steps are software-pipelined over three streams (ba_gpu.cu: factor_blocked_lookahead2): the diagonal kernel
+// brings its own tile up to date (fused prologue), so it is the only kernel on the critical chain.
+// k_chol_potrf / k_chol_trsm / k_chol_solve are the first versions (BA_LEGACY_CHOL, A/B timing only).
 // Every sum has a fixed order (no atomics).  == the exact step of Ceres DENSE_SCHUR / SPARSE_SCHUR.
 #pragma once
 #include "ba_kernels.cuh"

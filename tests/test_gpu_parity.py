@@ -225,6 +225,38 @@ def test_solve_explicit_blocked_cholesky_ref(n_kf, solver_cache):
     assert summ.final_cost < 0.5 * summ.initial_cost
 
 
+def test_blocked_cholesky_schedules_are_bit_identical(monkeypatch, solver_cache):
+    """The three-stream look-ahead schedule (fused diagonal kernel, side buffer for the panel tile below the diagonal,
+    flag-in-data substitution) performs the same operations per matrix entry in the same order as the plain right-looking
+    sequence on one stream (BA_NO_LOOKAHEAD=1): every LM iteration's cost and the final state agree bit for bit.
+    Also exercises the first-version kernels (BA_LEGACY_CHOL: left-looking diagonal tile, grid-barrier substitution)
+    against them within round-off."""
+    n_kf = 50
+    seq = syn.make_tum_sequence(n_kf, 30 * n_kf, 180 * n_kf, seed=5)
+    p = syn.window_problem(seq, 0, n_kf - 1).problem   # n = 298: five tiles, ragged last one
+    g, _ = mode_opts("REF", solver=0, max_num_iterations=5)
+
+    def run():
+        s = ba_b200.GpuSolver(**g)   # the schedule switches are read when the context is created / at every solve
+        s.upload(p)
+        summ = s.solve()
+        pose, pt, intr = s.download()
+        costs = [t["cost"] for t in s.trace()]
+        s.close()
+        return summ, pose, pt, intr, costs
+
+    a = run()
+    monkeypatch.setenv("BA_NO_LOOKAHEAD", "1")
+    b = run()
+    assert a[0].reduced_dim == 6 * (n_kf - 1) + 4 and a[0].num_iterations == b[0].num_iterations >= 3
+    assert a[4] == b[4] and a[0].final_cost == b[0].final_cost
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    monkeypatch.setenv("BA_LEGACY_CHOL", "1")
+    c = run()
+    assert abs(c[0].final_cost - a[0].final_cost) <= 1e-9 * a[0].final_cost
+    assert np.max(np.abs(c[1] - a[1])) < 1e-8
+
+
 def test_solve_to_convergence_ref(solver_cache):
     """Reference settings (75 iterations, tolerances on): same termination."""
     _compare_solve(_problem("cfg1"), "REF", 1, 75, solver_cache)
