@@ -390,7 +390,7 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   cudaFuncSetAttribute(k_ldlt2_solve<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(95));
   cudaFuncSetAttribute(k_ldlt2_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(127));
   cudaFuncSetAttribute(k_ldlt2_solve<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(BA_LDLT2_MAX_N));
-  cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
+  cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_UPD_SMEM);
   cudaFuncSetAttribute(k_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
   cudaFuncSetAttribute(k_chol_trsm2, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH_NB * CH_LD * 8);
   cudaFuncSetAttribute(k_chol_potrf2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_potrf2_smem_bytes());
@@ -1699,12 +1699,12 @@ static int factor_blocked_lookahead2(ba_gpu_ctx *ctx, int n, int nt, double *S, 
     if (below > 1) {
       CK(cudaEventRecord(ctx->ev_trsm, B));
       if (bulk_rec[e ^ 1]) CK(cudaStreamWaitEvent(B, ctx->ev_bulk2[e ^ 1], 0));  // bulk(k - 1)
-      LAUNCH(k_chol_update, below - 1, 256, sm2, n, S, (const double *)(Lsub + (size_t)(k + 1) * tile), k, k, 1, st, GATE_RUN);
+      LAUNCH(k_chol_update, below - 1, 256, CH_UPD_SMEM, n, S, (const double *)(Lsub + (size_t)(k + 1) * tile), k, k, 1, st, GATE_RUN);
       CK(cudaEventRecord(ctx->ev_col[e], B));
       col_rec[e] = true;
       CK(cudaStreamWaitEvent(C, ctx->ev_trsm, 0));
       ctx->cur = C;
-      LAUNCH(k_chol_update, (below - 1) * below / 2, 256, sm2, n, S, (const double *)nullptr, k, k + 1, 0, st, GATE_RUN);
+      LAUNCH(k_chol_update, (below - 1) * below / 2, 256, CH_UPD_SMEM, n, S, (const double *)nullptr, k, k + 1, 0, st, GATE_RUN);
       CK(cudaEventRecord(ctx->ev_bulk2[e], C));
       bulk_rec[e] = true;
     } else {
@@ -1811,7 +1811,7 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
         LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv + (size_t)k * CH_NB * CH_NB, (double *)nullptr, k, st,
                GATE_RUN);
       }
-      LAUNCH(k_chol_update, below * (below + 1) / 2, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, (const double *)nullptr, k, k, 0, st,
+      LAUNCH(k_chol_update, below * (below + 1) / 2, 256, CH_UPD_SMEM, n, S, (const double *)nullptr, k, k, 0, st,
              GATE_RUN);
     }
     int nn = n, n_cam = ctx->n_cam, n_free = ctx->n_free, nk = ctx->nk, gate = GATE_RUN;

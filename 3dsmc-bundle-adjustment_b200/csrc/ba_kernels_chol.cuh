@@ -91,12 +91,15 @@ k_chol_trsm(int n, double *__restrict__ A, int k, const LmState *st, int gate) {
 // schedule splits it into the next column (single_col) and the rest (kmap = k + 1).
 // Bsub != nullptr (single_col only, look-ahead schedule): the column operand L_{k+1,k} comes from the side buffer and the
 // diagonal tile (k + 1, k + 1) is left to the fused k_chol_potrf2: tiles (i, k + 1), i >= k + 2.
-__global__ void __launch_bounds__(256)
+#define CH_KH 32               // the 64-deep inner product in two halves: 34 KB of shared memory per CTA instead of 67 KB
+#define CH_HLD (CH_KH + 1)
+#define CH_UPD_SMEM ((size_t)2 * CH_NB * CH_HLD * 8)
+__global__ void __launch_bounds__(256, 4)
 k_chol_update(int n, double *__restrict__ A, const double *__restrict__ Bsub, int k, int kmap, int single_col, const LmState *st,
               int gate) {
   if (!gate_open(st, gate) || st->lin_fail) return;
   extern __shared__ double sh[];
-  double *As = sh, *Bs = sh + CH_NB * CH_LD;
+  double *As = sh, *Bs = sh + CH_NB * CH_HLD;
   // triangular decode: b = ti (ti + 1) / 2 + tj
   const int b = blockIdx.x;
   int ti = Bsub ? b + 1 : b, tj = 0;
@@ -109,28 +112,31 @@ k_chol_update(int n, double *__restrict__ A, const double *__restrict__ Bsub, in
   const int i0 = (kmap + 1 + ti) * CH_NB, c0 = (kmap + 1 + tj) * CH_NB, j0 = k * CH_NB;
   const int kk = min(CH_NB, n - j0);
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    As[r * CH_LD + c] = (i0 + r < n && c < kk) ? A[(size_t)(i0 + r) * n + j0 + c] : 0.0;
-    Bs[r * CH_LD + c] = Bsub ? Bsub[idx] : ((c0 + r < n && c < kk) ? A[(size_t)(c0 + r) * n + j0 + c] : 0.0);
-  }
-  __syncthreads();
   const int ty = tid >> 4, tx = tid & 15;
   double acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-  for (int q = 0; q < CH_NB; ++q) {
-    double a[4], bb[4];
+  for (int h = 0; h < CH_NB / CH_KH; ++h) {
+    if (h) __syncthreads();
+    for (int idx = tid; idx < CH_NB * CH_KH; idx += 256) {
+      const int r = idx >> 5, c = (idx & 31) + h * CH_KH;
+      As[r * CH_HLD + (idx & 31)] = (i0 + r < n && c < kk) ? A[(size_t)(i0 + r) * n + j0 + c] : 0.0;
+      Bs[r * CH_HLD + (idx & 31)] = Bsub ? Bsub[r * CH_NB + c] : ((c0 + r < n && c < kk) ? A[(size_t)(c0 + r) * n + j0 + c] : 0.0);
+    }
+    __syncthreads();
+    for (int q = 0; q < CH_KH; ++q) {  // q ascending over both halves: the same sum per entry as one 64-deep pass
+      double a[4], bb[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) a[r] = As[(ty * 4 + r) * CH_LD + q];
+      for (int r = 0; r < 4; ++r) a[r] = As[(ty * 4 + r) * CH_HLD + q];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) bb[c] = Bs[(tx + 16 * c) * CH_LD + q];  // columns tx, tx+16, ..: 16 distinct banks (CH_LD odd)
+      for (int c = 0; c < 4; ++c) bb[c] = Bs[(tx + 16 * c) * CH_HLD + q];  // columns tx, tx+16, ..: 16 distinct banks (odd stride)
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] += a[r] * bb[c];
+        for (int c = 0; c < 4; ++c) acc[r][c] += a[r] * bb[c];
+    }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
