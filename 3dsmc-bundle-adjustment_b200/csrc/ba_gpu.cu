@@ -1912,16 +1912,18 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   ctx->cur = ctx->stream;
   const int64_t l0 = ctx->launches;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  // windowed explicit solver on one GPU (single-CTA solve: every kernel is a small gated kernel): programmatic dependent launches
+  const bool pdl = !ctx->pdl_off && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks == 1 && ctx->n_red > 0 &&
+                   ctx->n_red <= BA_LDLT_MAX_N;
+  ctx->pdl = pdl;
   enqueue_iteration_zero(ctx);
+  ctx->pdl = false;
   const int poll = std::max(1, ctx->opt.poll_interval);
   int rc = 0;
   // windowed explicit solver on one GPU: the ~26 small kernels of an LM iteration (two streams, fork / join) are
   // captured once per upload and replayed
   const bool graphed = !ctx->lm_graph_off && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks == 1 &&
                        ctx->n_red > 0 && ctx->n_red <= BA_LDLT_MAX_N;
-  // the same problems (single-CTA solve: every kernel of the iteration is a small gated kernel) launch with PDL
-  const bool pdl = !ctx->pdl_off && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks == 1 && ctx->n_red > 0 &&
-                   ctx->n_red <= BA_LDLT_MAX_N;
   for (int it = 1;; ++it) {
     if (graphed) {
       if (!ctx->lm_graph || ctx->lm_graph_stale) {

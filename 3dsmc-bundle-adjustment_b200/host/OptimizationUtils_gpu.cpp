@@ -87,7 +87,11 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
 
   const Sophus::SE3d initialPose = keyframes[kf_i].T_w_c;          // :231
   const Sophus::SE3d initialPoseInv = keyframes[kf_i].T_w_c.inverse();  // :232
-  const int admissible_obs = countConstraints(map, keyframes, kf_i, kf_f);  // :242
+  // The reference counts the admissible observations first (:242) because the count is the weight normaliser of every
+  // residual; here the normaliser is the n_obs of the upload (the same number by construction), so the extra walk over all
+  // hash maps is replaced by an upper bound for the reservations.
+  size_t obs_bound = 0;
+  for (int kf_n = kf_i; kf_n <= kf_f; kf_n++) obs_bound += keyframes[kf_n].global_points_map.size();
 
   // ---- canonical enumeration (:244-294): container order, first-appearance point ids.
   // One hash lookup per observation (landmark id -> point index, inserted on first appearance) and one map
@@ -98,11 +102,11 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   vector<Landmark *> landmark_ptr;
   vector<int32_t> cam_idx, pt_idx;
   vector<double> uv2, depthv, pose7((size_t)n_cam * 7), pt3;
-  cam_idx.reserve(admissible_obs);
-  pt_idx.reserve(admissible_obs);
-  uv2.reserve((size_t)admissible_obs * 2);
-  depthv.reserve(admissible_obs);
-  pt_of_landmark.reserve((size_t)admissible_obs / 2 + 16);
+  cam_idx.reserve(obs_bound);
+  pt_idx.reserve(obs_bound);
+  uv2.reserve(obs_bound * 2);
+  depthv.reserve(obs_bound);
+  pt_of_landmark.reserve(obs_bound / 2 + 16);
   bool missing_landmark = false;
   for (int kf_n = kf_i; kf_n <= kf_f && !missing_landmark; kf_n++) {
     KeyFrame &curr_kf = keyframes[kf_n];
@@ -152,7 +156,7 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
     intr[j] = intrinsics_optimized(j);
     prior[j] = intrinsics_initial(j);
   }
-  g_last.admissible_obs = admissible_obs;
+  g_last.admissible_obs = n_obs;  // == countConstraints(map, keyframes, kf_i, kf_f)
   g_last.ms_extract = ms_since(t_begin);
 
   // ---- ceres::Solve (:300) -> GPU
