@@ -133,6 +133,7 @@ struct ba_gpu_ctx {
   cudaGraphExec_t lm_graph = nullptr;
   int64_t lm_graph_launches = 0;
   bool lm_graph_off = false, lm_graph_stale = true;
+  bool spmv6 = false;  // BA_SPMV6=1: six-lanes-per-block product kernel in the launch-per-step PCG / product hook (experiment)
   bool pdl = false, pdl_off = false;  // programmatic dependent launches inside the windowed LM iteration (BA_NO_PDL=1: off)
   int legacy_chol = 0;  // BA_LEGACY_CHOL=1: left-looking single-CTA Cholesky, =2: shared-memory L D L^T, =3: grid-barrier blocked substitution (A/B timing only)
   Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
@@ -383,6 +384,7 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   ctx->legacy_chol = getenv("BA_LEGACY_CHOL") ? atoi(getenv("BA_LEGACY_CHOL")) : 0;
   ctx->lm_graph_off = getenv("BA_NO_LM_GRAPH") != nullptr;
   ctx->pdl_off = getenv("BA_NO_PDL") != nullptr;
+  ctx->spmv6 = getenv("BA_SPMV6") != nullptr;
   cudaFuncSetAttribute(k_cholesky_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
   cudaFuncSetAttribute(k_ldlt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(BA_LDLT_MAX_N));
   cudaFuncSetAttribute(k_ldlt2_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt2_smem_bytes(31));
@@ -1478,8 +1480,12 @@ static ItemRef enqueue_matvec(ba_gpu_ctx *ctx, const double *v, int gate, int pa
   LmState *st = P<LmState>(ctx->st);
   const int rp = ctx->lo.reset_period;
   if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && passes == 3) {
-    LAUNCH(k_bsr_spmv, cdiv(ctx->n_cam * 32, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->ent_ptr),
-           P<int2>(ctx->ent), P<double>(ctx->Sblk), v, P<double>(ctx->ysp), st, gate);
+    if (ctx->spmv6)
+      LAUNCH(k_bsr_spmv6, cdiv(ctx->n_cam * 32, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->ent_ptr),
+             P<int2>(ctx->ent), P<double>(ctx->Sblk), v, P<double>(ctx->ysp), st, gate);
+    else
+      LAUNCH(k_bsr_spmv, cdiv(ctx->n_cam * 32, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->ent_ptr),
+             P<int2>(ctx->ent), P<double>(ctx->Sblk), v, P<double>(ctx->ysp), st, gate);
     return ItemRef{P<int32_t>(ctx->ident), P<double>(ctx->ysp)};
   }
   if (ctx->tiled && passes == 3) {

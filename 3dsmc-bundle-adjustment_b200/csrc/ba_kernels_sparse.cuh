@@ -402,6 +402,46 @@ __device__ __forceinline__ double pick6(const double a[6], int k) {
   return k == 0 ? a[0] : k == 1 ? a[1] : k == 2 ? a[2] : k == 3 ? a[3] : k == 4 ? a[4] : a[5];
 }
 
+// Experimental mapping (BA_SPMV6=1; measurement for the next step of the persistent PCG): a block is shared
+// by SIX lanes -- lane a of a group forms component a of (S_ij x_j), reading one 48-byte block row (or one strided column when
+// the block is used transposed) -- and five groups walk the row's entries.  ~40 registers instead of ~230, so six times as many
+// warps per SM keep loads in flight; the lanes of the same component are added in group order (fixed).
+__global__ void __launch_bounds__(BA_THREADS)
+k_bsr_spmv6(int n_cam, const int32_t *__restrict__ ent_ptr, const int2 *__restrict__ ent, const double *__restrict__ S,
+            const double *__restrict__ x, double *__restrict__ y, const LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  const int r = (blockIdx.x * BA_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n_cam) return;
+  const int g = lane / 6, a = lane - 6 * g;
+  const int b0 = __ldg(ent_ptr + r), e0 = __ldg(ent_ptr + r + 1);
+  double acc = 0.0;
+  if (g < 5) {
+#pragma unroll 4
+    for (int e = b0 + g; e < e0; e += 5) {
+      const int2 en = __ldg(ent + e);
+      const double *B = S + 36 * (size_t)((uint32_t)en.x & 0x7fffffffu);
+      double xv[6], m[6];
+      load6(x + 6 * (size_t)en.y, xv);
+      if ((uint32_t)en.x & 0x80000000u) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) m[k] = __ldg(B + 6 * k + a);
+      } else {
+        const double2 *row = reinterpret_cast<const double2 *>(B + 6 * a);
+        const double2 m0 = __ldg(row), m1 = __ldg(row + 1), m2 = __ldg(row + 2);
+        m[0] = m0.x; m[1] = m0.y; m[2] = m1.x; m[3] = m1.y; m[4] = m2.x; m[5] = m2.y;
+      }
+      double sdot = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) sdot += m[k] * xv[k];
+      acc += sdot;
+    }
+  }
+  double sum = acc;
+#pragma unroll
+  for (int gg = 1; gg < 5; ++gg) sum += __shfl_sync(BA_FULL, acc, (lane + 6 * gg) & 31);
+  if (lane < 6) y[6 * (size_t)r + lane] = sum;
+}
+
 __global__ void __launch_bounds__(BA_THREADS)
 k_bsr_spmv(int n_cam, const int32_t *__restrict__ ent_ptr, const int2 *__restrict__ ent, const double *__restrict__ S,
            const double *__restrict__ x, double *__restrict__ y, const LmState *st, int gate) {
