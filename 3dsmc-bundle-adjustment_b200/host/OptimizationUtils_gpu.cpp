@@ -97,6 +97,19 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   // One hash lookup per observation (landmark id -> point index, inserted on first appearance) and one map
   // lookup per DISTINCT landmark; the Landmark addresses are kept (unordered_map nodes do not move), so the
   // gather of the points, the error path and the write-back never search the map again.
+  // landmark id -> point index: ids are small non-negative integers in the reference (a running counter, src/main.cpp), so
+  // the lookup is a flat epoch-stamped table that persists across calls (no clearing, no hashing); any other id falls back
+  // to a hash map
+  struct Stamp {
+    int epoch, pt;
+  };
+  static thread_local vector<Stamp> flat;
+  static thread_local int epoch = 0;
+  if (++epoch == 0x7fffffff) {
+    flat.assign(flat.size(), Stamp{0, 0});
+    epoch = 1;
+  }
+  constexpr int kFlatMax = 1 << 24;
   std::unordered_map<int, int> pt_of_landmark;
   vector<int> landmark_of_pt;
   vector<Landmark *> landmark_ptr;
@@ -106,7 +119,6 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   pt_idx.reserve(obs_bound);
   uv2.reserve(obs_bound * 2);
   depthv.reserve(obs_bound);
-  pt_of_landmark.reserve(obs_bound / 2 + 16);
   bool missing_landmark = false;
   for (int kf_n = kf_i; kf_n <= kf_f && !missing_landmark; kf_n++) {
     KeyFrame &curr_kf = keyframes[kf_n];
@@ -116,8 +128,23 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
       const int localId = index_pair.first;
       const double depth = curr_kf.points3d_local[localId](2);
       if (depth <= 1e-15) continue;  // :265-268
-      const auto ins = pt_of_landmark.try_emplace(landmarkId, (int)landmark_of_pt.size());
-      if (ins.second) {  // first appearance in the window (:271)
+      int *pt_slot;
+      bool first;
+      if (landmarkId >= 0 && landmarkId < kFlatMax) {
+        if ((size_t)landmarkId >= flat.size()) flat.resize((size_t)landmarkId + 1 + flat.size() / 2, Stamp{0, 0});
+        Stamp &st = flat[landmarkId];
+        first = st.epoch != epoch;
+        if (first) {
+          st.epoch = epoch;
+          st.pt = (int)landmark_of_pt.size();
+        }
+        pt_slot = &st.pt;
+      } else {
+        const auto ins = pt_of_landmark.try_emplace(landmarkId, (int)landmark_of_pt.size());
+        first = ins.second;
+        pt_slot = &ins.first->second;
+      }
+      if (first) {  // first appearance in the window (:271)
         auto found = map.find(landmarkId);
         if (found == map.end()) {  // the reference would throw from map.at (:270)
           missing_landmark = true;
@@ -130,7 +157,7 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
         landmark_ptr.push_back(&map_point);
       }
       cam_idx.push_back(kf_n - kf_i);
-      pt_idx.push_back(ins.first->second);
+      pt_idx.push_back(*pt_slot);
       uv2.push_back((double)curr_kf.keypoints[localId].pt.x);  // float -> double (:262)
       uv2.push_back((double)curr_kf.keypoints[localId].pt.y);
       depthv.push_back(depth);
