@@ -321,13 +321,15 @@ extern "C" void ba_gpu_default_options(ba_gpu_options *o) {
 static int check_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
   if (!(o->HUB_P_REPR > 0.0) || !(o->HUB_P_UNPR > 0.0) || !(o->WEIGHT_UNPR >= 0.0) || !(o->WEIGHT_INTRINSICS >= 0.0))
     return fail(ctx, BA_ERR_INVALID, "Huber deltas must be > 0 and weights >= 0");
-  if (o->max_num_iterations < 0 || o->poll_interval < 1) return fail(ctx, BA_ERR_INVALID, "bad iteration options");
+  if (o->max_num_iterations < 0 || o->max_num_iterations > 10000000 || o->poll_interval < 1)
+    return fail(ctx, BA_ERR_INVALID, "bad iteration options (0 <= max_num_iterations <= 10^7, poll_interval >= 1)");
   if (o->solver < BA_SOLVER_AUTO || o->solver > BA_SOLVER_SPARSE_SCHUR_PCG) return fail(ctx, BA_ERR_INVALID, "bad solver");
   if (o->jacobian_store < BA_JAC_AUTO || o->jacobian_store > BA_JAC_TILED) return fail(ctx, BA_ERR_INVALID, "bad jacobian_store");
   if (!(o->initial_trust_region_radius > 0.0)) return fail(ctx, BA_ERR_INVALID, "bad trust-region radius");
   return 0;
 }
 
+extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx);
 extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   if (!o || !out) return fail(nullptr, BA_ERR_INVALID, "null argument");
   *out = nullptr;
@@ -349,7 +351,7 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   ctx->device = dev;
   auto bail = [&](const char *what, cudaError_t ce) {
     fail(nullptr, BA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
-    delete ctx;
+    ba_gpu_destroy(ctx);  // releases whatever was created so far (streams, events, pinned state)
     return BA_ERR_CUDA;
   };
   if ((e = cudaSetDevice(dev)) != cudaSuccess) return bail("cudaSetDevice", e);
@@ -358,7 +360,7 @@ extern "C" int ba_gpu_create(const ba_gpu_options *o, ba_gpu_ctx **out) {
   ctx->n_sm = prop.multiProcessorCount;
   if (prop.major < 10) {
     fail(nullptr, BA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
-    delete ctx;
+    ba_gpu_destroy(ctx);
     return BA_ERR_CUDA;
   }
   // main / side stream at the highest priority, a third one at the lowest for the bulk of the blocked Cholesky's trailing
@@ -838,6 +840,13 @@ static int setup_dist_pcg(ba_gpu_ctx *ctx) {
       if (ctx->xch_peer[k] && k != ctx->rank) cudaIpcCloseMemHandle(ctx->xch_peer[k]);
       ctx->xch_peer[k] = nullptr;
     }
+    {
+      // every rank has closed its mappings of the peers' buffers (above) before any rank frees its exported one: the
+      // camera count is the same on all ranks, so all of them pass through here in the same upload
+      double tok = 1.0;
+      int rcb = allreduce_host_scalar(ctx, &tok, false);
+      if (rcb) return rcb;
+    }
     if (ctx->xch) cudaFree(ctx->xch);
     ctx->xch = nullptr;
     CK(cudaMalloc(&ctx->xch, bytes));
@@ -1141,8 +1150,8 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
          P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->cam_cnt), P<int32_t>(ctx->err_flag));
   LAUNCH(k_exclusive_scan, 1, 1024, 0, n_pt, P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->pt_rowptr));
   LAUNCH(k_exclusive_scan, 1, 1024, 0, n_cam, P<int32_t>(ctx->cam_cnt), P<int32_t>(ctx->cam_rowptr));
-  LAUNCH(k_index_fill, ctx->nblk_obs, BA_THREADS, 0, n_obs, P<int32_t>(ctx->pt_idx), P<int32_t>(ctx->pt_rowptr),
-         P<int32_t>(ctx->cursor), P<int32_t>(ctx->perm));
+  LAUNCH(k_index_fill, ctx->nblk_obs, BA_THREADS, 0, n_obs, n_cam, n_pt, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
+         P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->cursor), P<int32_t>(ctx->perm));
   LAUNCH(k_index_sort, ctx->nblk_pt, BA_THREADS, 0, n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->perm));
   LAUNCH(k_index_gather, ctx->nblk_pt, BA_THREADS, 0, n_pt, n_obs, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->perm),
          P<int32_t>(ctx->cam_idx), P<double2>(ctx->uv), depth ? P<double>(ctx->depthv) : (double *)nullptr,
@@ -1942,8 +1951,14 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
         const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
         ctx->lm_graph_launches = ctx->launches - lb;
         ctx->launches = lb;
-        if (rc) return rc;
-        if (ce != cudaSuccess || !g) return fail(ctx, BA_ERR_CUDA, "LM iteration graph capture: %s", cudaGetErrorString(ce));
+        if (rc) {
+          if (g) cudaGraphDestroy(g);
+          return rc;
+        }
+        if (ce != cudaSuccess || !g) {
+          if (g) cudaGraphDestroy(g);
+          return fail(ctx, BA_ERR_CUDA, "LM iteration graph capture: %s", cudaGetErrorString(ce));
+        }
         if (ctx->lm_graph) {  // same topology, new sizes / pointers: update in place
           cudaGraphExecUpdateResultInfo info;
           if (cudaGraphExecUpdate(ctx->lm_graph, g, &info) != cudaSuccess) {
@@ -2378,6 +2393,11 @@ extern "C" int ba_gpu_comm_init(ba_gpu_ctx *ctx, const char id128[128], int32_t 
   CK(cudaSetDevice(ctx->device));
   ncclUniqueId id;
   memcpy(id.internal, id128, 128);
+  if (ctx->comm && g_nccl.CommDestroy) {  // re-initialisation: release the previous communicator
+    cudaStreamSynchronize(ctx->stream);
+    g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
   ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank);
   if (r != 0) return fail(ctx, BA_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   ctx->rank = rank;

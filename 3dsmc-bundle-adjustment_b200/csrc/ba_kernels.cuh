@@ -95,12 +95,16 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(int n, const int32_t *_
 }
 
 // unordered bucket fill (integer atomics), made canonical by k_index_sort
-__global__ void __launch_bounds__(BA_THREADS) k_index_fill(int n_obs, const int32_t *__restrict__ pt_idx,
+// (same validity predicate as k_index_count: an observation that was not counted must not be filled either, or the
+// cursor would run past its bucket / index outside the arrays before the host has read the error flag)
+__global__ void __launch_bounds__(BA_THREADS) k_index_fill(int n_obs, int n_cam, int n_pt, const int32_t *__restrict__ cam_idx,
+                                                          const int32_t *__restrict__ pt_idx,
                                                           const int32_t *__restrict__ pt_rowptr, int32_t *cursor,
                                                           int32_t *perm) {
   const int i = blockIdx.x * BA_THREADS + threadIdx.x;
   if (i >= n_obs) return;
-  const int p = pt_idx[i];
+  const int c = cam_idx[i], p = pt_idx[i];
+  if (c < 0 || c >= n_cam || p < 0 || p >= n_pt || (i > 0 && c < cam_idx[i - 1])) return;
   const int pos = atomicAdd(&cursor[p], 1);
   perm[pt_rowptr[p] + pos] = i;
 }

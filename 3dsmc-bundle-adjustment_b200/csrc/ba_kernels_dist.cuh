@@ -6,8 +6,8 @@
 // phase (87 MB of L2 traffic at config 5), so that is what is sharded: rank k owns the camera blocks
 // wb = k, k + N, ... (32 consecutive cameras each) and computes q and p.q for ITS rows only.  The lane
 // that holds a result stores it straight into every rank's memory (cudaIpc-mapped exchange buffers)
-// as a 16-byte FLAG-IN-DATA slot {value, epoch} (one st.v2.u64, delivered atomically over NVLink):
-// the consumer polls the slot until it carries the current epoch.  No fence, no separate flag, no
+// as a 16-byte FLAG-IN-DATA slot of two tagged 8-byte words {32 value bits | 32-bit round tag} (one st.v2.u64; each
+// 8-byte word is single-copy atomic, the pair need not be): the consumer polls until both words carry the current tag.  No fence, no separate flag, no
 // cross-GPU barrier -- measured on 2 x B200 (profiles/r01_nvlink_latency.txt): 1.14 us one way for a
 // flag-in-data store against 4.4-6.2 us for "stores + fence.sys + flag" (a first version of this kernel
 // with two fence + flag barriers per iteration ran at 48 us per PCG iteration against 29 us on one GPU).
@@ -43,19 +43,28 @@ struct PcgFan {
   int *abort_flag;            // set on a poll time-out
 };
 
+// Slot encoding (NCCL-LL style): the 16-byte slot is TWO independent 8-byte words {32 data bits | 32-bit tag << 32}.
+// The PTX memory model only guarantees single-copy atomicity per aligned scalar of a vector access, so each 8-byte word
+// carries its own tag and the consumer accepts a slot only when BOTH words show the tag of the current round: a torn
+// delivery (one word new, one old) can never be read as a value.  tag = (round & 0x7fffffff) | 0x80000000: never zero
+// (fresh buffers are zeroed), a stale slot could only match 2^31 rounds later.
+__device__ __forceinline__ unsigned long long ll_tag(unsigned long long e) { return ((e & 0x7fffffffull) | 0x80000000ull) << 32; }
 __device__ __forceinline__ void ll_store(LLSlot *p, double v, unsigned long long e) {
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(e) : "memory");
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v), tag = ll_tag(e);
+  const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
-// spins until the slot carries epoch e; on time-out / abort returns 0.0
+// spins until both words of the slot carry the tag of round e; on time-out / abort returns 0.0
 __device__ __forceinline__ double ll_wait(const LLSlot *p, unsigned long long e, int *abort_flag) {
   unsigned long long a, b;
+  const unsigned long long tag = ll_tag(e), hi = 0xffffffff00000000ull;
   asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-  if (b != e) {
+  if ((a & hi) != tag || (b & hi) != tag) {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     for (int spin = 0;; ++spin) {
       asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-      if (b == e) break;
+      if ((a & hi) == tag && (b & hi) == tag) break;
       if ((spin & 63) == 63) {
         if (*((volatile int *)abort_flag)) return 0.0;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
@@ -66,7 +75,7 @@ __device__ __forceinline__ double ll_wait(const LLSlot *p, unsigned long long e,
       }
     }
   }
-  return __longlong_as_double(a);
+  return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
 }
 // local grid barrier that gives up when the abort flag is raised
 __device__ __forceinline__ void grid_barrier_abortable(unsigned int *bar, unsigned int &epoch, int *abort_flag) {

@@ -19,6 +19,7 @@
 
 #include "../../include/ba_gpu.h"
 #include "ba_host_debug.h"
+#include "se3_raw.h"
 
 using std::vector;
 
@@ -216,7 +217,7 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   g_last.landmark_of_pt = landmark_of_pt;
 
   // ---- Ceres wrote the optimum into the caller-owned blocks: do the same
-  for (int k = 0; k < n_cam; ++k) keyframes[kf_i + k].T_w_c = Sophus::SE3d(pose7.data() + (size_t)k * 7);
+  for (int k = 0; k < n_cam; ++k) keyframes[kf_i + k].T_w_c = se3_from_raw(pose7.data() + (size_t)k * 7);
   for (int p = 0; p < n_pt; ++p) {
     Vector3d &x = landmark_ptr[p]->point;
     for (int j = 0; j < 3; ++j) x(j) = pt3[(size_t)p * 3 + j];

@@ -14,6 +14,8 @@
 #include "compat/reference_types.h"
 #endif
 
+#include "se3_raw.h"
+
 #include <cmath>
 #include <fstream>
 #include <iostream>
@@ -68,14 +70,8 @@ Sophus::SE3d getFirstPose(const string &first_timestamp, const string &ground_tr
   }
   if (rows.empty()) return Sophus::SE3d();
   const double *r = &rows[8 * best];
-#ifdef BA_USE_REFERENCE_HEADERS
-  return Sophus::SE3d(Eigen::Quaterniond(r[7], r[4], r[5], r[6]), Sophus::SE3d::Point(r[1], r[2], r[3]));
-#else
   // SE3(quaternion, translation) normalises the quaternion (so3.hpp:203-205)
-  const double n = std::sqrt(r[4] * r[4] + r[5] * r[5] + r[6] * r[6] + r[7] * r[7]);
-  const double p7[7] = {r[4] / n, r[5] / n, r[6] / n, r[7] / n, r[1], r[2], r[3]};
-  return Sophus::SE3d(p7);
-#endif
+  return Sophus::SE3d(Eigen::Quaterniond(r[7], r[4], r[5], r[6]), Sophus::SE3d::Point(r[1], r[2], r[3]));
 }
 
 // every pose pre-multiplied by initial_pose * T_0^-1 (:377-384)

@@ -2,8 +2,13 @@
 // vector<KeyFrame> + Map3D from arrays with the SAME std::unordered_map insert
 // sequence the caller specifies, runs windowOptimize / countConstraints with the
 // reference's signatures, and flattens the mutated state back.
+#ifdef BA_USE_REFERENCE_HEADERS
+#include "OptimizationUtils.h"
+#else
 #include "compat/reference_types.h"
+#endif
 #include "ba_host_debug.h"
+#include "se3_raw.h"
 
 #include <chrono>
 #include <cstring>
@@ -24,7 +29,7 @@ int ba_host_window_optimize(int n_kf, double *pose7, const int32_t *kf_ptr, cons
   for (int k = 0; k < n_kf; ++k) {
     KeyFrame &kf = keyframes[k];
     kf.frame_id = (uint)k;
-    kf.T_w_c = Sophus::SE3d(pose7 + (size_t)k * 7);
+    kf.T_w_c = se3_from_raw(pose7 + (size_t)k * 7);
     const int a = kf_ptr[k], b = kf_ptr[k + 1];
     kf.keypoints.resize(b - a);
     kf.points3d_local.resize(b - a);
@@ -92,7 +97,7 @@ int ba_host_sliding_sequence(int n_kf, double *pose7, const int32_t *kf_ptr, con
   for (int k = 0; k < n_kf; ++k) {
     KeyFrame &kf = keyframes[k];
     kf.frame_id = (uint)k;
-    kf.T_w_c = Sophus::SE3d(pose7 + (size_t)k * 7);
+    kf.T_w_c = se3_from_raw(pose7 + (size_t)k * 7);
     const int a = kf_ptr[k], b = kf_ptr[k + 1];
     kf.keypoints.resize(b - a);
     kf.points3d_local.resize(b - a);
@@ -179,15 +184,15 @@ int ba_host_write_poses(const char *path, int n, const char *timestamps, const d
   for (int i = 0; i < n; ++i) {
     kfs[i].timestamp = t;
     t += kfs[i].timestamp.size() + 1;
-    kfs[i].T_w_c = Sophus::SE3d(pose7 + (size_t)i * 7);
+    kfs[i].T_w_c = se3_from_raw(pose7 + (size_t)i * 7);
   }
   write_keyframe_poses_to_file(path, kfs);
   return 0;
 }
 int ba_host_pose_offset(int n, double *pose7, const double *initial7) {
   std::vector<KeyFrame> kfs(n);
-  for (int i = 0; i < n; ++i) kfs[i].T_w_c = Sophus::SE3d(pose7 + (size_t)i * 7);
-  poseOffset(kfs, Sophus::SE3d(initial7));
+  for (int i = 0; i < n; ++i) kfs[i].T_w_c = se3_from_raw(pose7 + (size_t)i * 7);
+  poseOffset(kfs, se3_from_raw(initial7));
   for (int i = 0; i < n; ++i) std::memcpy(pose7 + (size_t)i * 7, kfs[i].T_w_c.data(), 7 * sizeof(double));
   return 0;
 }

@@ -44,6 +44,15 @@ struct Vector4d : VecN<4> {
   Vector4d() {}
   Vector4d(double a, double b, double c, double d) { v[0] = a; v[1] = b; v[2] = c; v[3] = d; }
 };
+// Eigen::Quaterniond(w, x, y, z): the one constructor the wrapper uses (argument order of Eigen 3.4.0)
+struct Quaterniond {
+  double w_, x_, y_, z_;
+  Quaterniond(double w, double x, double y, double z) : w_(w), x_(x), y_(y), z_(z) {}
+  double w() const { return w_; }
+  double x() const { return x_; }
+  double y() const { return y_; }
+  double z() const { return z_; }
+};
 }  // namespace Eigen
 using Eigen::Vector2d;
 using Eigen::Vector3d;
@@ -53,8 +62,15 @@ namespace Sophus {
 class SE3d {
  public:
   static const int num_parameters = 7;
+  using Point = Eigen::Vector3d;
+  // the constructors below are the ones headers/sophus/se3.hpp:407-455 has (default, copy, quaternion + translation);
+  // raw storage is reached through data() only (:469-476), as in the real class
+  SE3d(const Eigen::Quaterniond &q, const Point &t) {  // SO3(quaternion) normalises (so3.hpp:203-205)
+    const double n = std::sqrt(q.x() * q.x() + q.y() * q.y() + q.z() * q.z() + q.w() * q.w());
+    p_[0] = q.x() / n; p_[1] = q.y() / n; p_[2] = q.z() / n; p_[3] = q.w() / n;
+    p_[4] = t[0]; p_[5] = t[1]; p_[6] = t[2];
+  }
   SE3d() { p_[0] = p_[1] = p_[2] = 0.0; p_[3] = 1.0; p_[4] = p_[5] = p_[6] = 0.0; }
-  explicit SE3d(const double *p7) { std::memcpy(p_, p7, sizeof(p_)); }
   double *data() { return p_; }
   const double *data() const { return p_; }
   SE3d inverse() const {

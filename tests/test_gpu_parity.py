@@ -70,6 +70,29 @@ def test_upload_rejects_unsorted(solver_cache):
     assert e.value.code == ba_b200.capi.BA_ERR_INVALID
 
 
+@pytest.mark.parametrize("bad", ["pt_negative", "pt_large", "cam_negative", "cam_large"])
+def test_upload_rejects_out_of_range_indices(bad, solver_cache):
+    """Out-of-range indices must come back as BA_ERR_INVALID with the context still usable (the index build guards every
+    kernel that runs before the host reads the error flag: no out-of-bounds write, no poisoned context)."""
+    p = _problem("cfg1_small")
+    q = p.copy()
+    k = q.n_obs // 2
+    if bad == "pt_negative":
+        q.pt_idx[k] = -1
+    elif bad == "pt_large":
+        q.pt_idx[k] = q.n_pt + 1000
+    elif bad == "cam_negative":
+        q.cam_idx[0] = -1
+    else:
+        q.cam_idx[-1] = q.n_cam + 1000
+    s = _solver(solver_cache, **mode_opts("NS")[0])
+    with pytest.raises(ba_b200.BAError) as e:
+        s.upload(q)
+    assert e.value.code == ba_b200.capi.BA_ERR_INVALID
+    s.upload(p)   # the same context still works
+    assert s.solve().final_cost > 0.0
+
+
 # ---------------------------------------------------------------- residuals / Jacobians
 @pytest.mark.parametrize("mode", ["REF", "NS", "DEPTH", "INTR"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg4_small"])

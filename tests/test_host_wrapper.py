@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import ba_b200, ora, pose_err
+from helpers import ROOT, ba_b200, ora, pose_err
 
 HOST_LIB = os.path.join(os.path.dirname(ba_b200.capi.LIB_PATH), "libba_host.so")
 syn = ba_b200.synthetic
@@ -149,3 +149,33 @@ def test_window_optimize_missing_landmark_leaves_inputs_untouched():
                                    None, None, None, None, None, None, None)
     assert rc == -1
     assert np.array_equal(pose, seq.pose) and np.array_equal(lm_pt, lm_pt0) and np.array_equal(intr, seq.K)
+
+
+# ---------------------------------------------------------------- the build INTEGRATION.md prescribes
+HOST_DIR = os.path.join(ROOT, "3dsmc-bundle-adjustment_b200", "host")
+
+
+@pytest.mark.parametrize("src", ["OptimizationUtils_gpu.cpp", "TrajectoryIO.cpp", "ba_host_capi.cpp"])
+def test_wrapper_compiles_with_reference_headers_macro(src):
+    """-DBA_USE_REFERENCE_HEADERS (include "OptimizationUtils.h" instead of the compat types) against a shim that only
+    has the members the reference's vendored Sophus / Eigen really offer (tests/ref_header_shim): no SE3d(const double*)."""
+    import subprocess
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-DBA_USE_REFERENCE_HEADERS",
+           "-I", os.path.join(ROOT, "tests", "ref_header_shim"), os.path.join(HOST_DIR, src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_no_raw_pointer_se3_constructor_anywhere():
+    """Sophus::SE3 has no constructor from `const double*` (headers/sophus/se3.hpp:407-455): neither the compat class
+    nor the wrapper may rely on one; raw storage goes through data() (se3_raw.h)."""
+    import re
+    compat = open(os.path.join(HOST_DIR, "compat", "reference_types.h")).read()
+    assert re.search(r"SE3d\s*\(\s*const\s+double\s*\*", compat) is None
+    for f in ("OptimizationUtils_gpu.cpp", "TrajectoryIO.cpp", "ba_host_capi.cpp"):
+        s = open(os.path.join(HOST_DIR, f)).read()
+        assert re.search(r"SE3d\s*\(\s*(pose7|p7|initial7)", s) is None, f
+    ref = "/root/reference/headers/sophus/se3.hpp"
+    if os.path.exists(ref):  # (this container only; the GPU box has no /root/reference)
+        real = open(ref).read()
+        assert re.search(r"SE3\s*\(\s*(Scalar|double)\s+const\s*\*", real) is None and "Scalar* data()" in real
