@@ -1080,6 +1080,233 @@ static int solve_dense_schur(ora_ws *w, double radius) {
   return rc;
 }
 
+/* ---------- SPARSE_SCHUR-equivalent exact step: explicit S in envelope (skyline) storage + sparse Cholesky ----------
+ * What the reference configures (headers/BundleAdjustmentConfig.h:62: linear_solver_type = SPARSE_SCHUR): Ceres forms the
+ * reduced camera matrix S block-sparse (schur_eliminator_impl.h) and factorises it with a sparse Cholesky.  The sparse
+ * backend's ordering does not change the solution (exact solve); this restatement keeps the natural camera order and stores
+ * every scalar row from its first structural non-zero to the diagonal (envelope): Cholesky creates no fill outside it.
+ * Rows of the 4 intrinsics (REF mode) are a dense border at the end.  Same arithmetic as solve_dense_schur, other storage. */
+static int solve_sparse_schur(ora_ws *w, double radius) {
+  const ora_problem *p = w->p;
+  const ora_layout *L = &w->L;
+  const int R = L->R, nk = L->nk;
+  const int nf = L->n_free;
+  const int n = 6 * nf + nk;
+  const int koff = 6 * nf;
+  if (n == 0) return 0;
+  if (point_blocks(w, radius)) return -1;
+  /* envelope: first coupled camera slot of every camera slot */
+  int *first = (int *)malloc(sizeof(int) * (size_t)(nf + 1));
+  int *slot_cam = (int *)malloc(sizeof(int) * (size_t)(nf + 1));
+  for (int c = 0; c < p->n_cam; ++c)
+    if (L->cam_slot[c] >= 0) {
+      first[L->cam_slot[c]] = L->cam_slot[c];
+      slot_cam[L->cam_slot[c]] = c;
+    }
+  for (int q = 0; q < p->n_pt; ++q) {
+    int lo = -1;
+    for (int s = L->pt_rowptr[q]; s < L->pt_rowptr[q + 1]; ++s) {
+      const int sl = L->cam_slot[p->cam_idx[L->perm[s]]];
+      if (sl < 0) continue;
+      if (lo < 0 || sl < lo) lo = sl;
+    }
+    if (lo < 0) continue;
+    for (int s = L->pt_rowptr[q]; s < L->pt_rowptr[q + 1]; ++s) {
+      const int sl = L->cam_slot[p->cam_idx[L->perm[s]]];
+      if (sl >= 0 && lo < first[sl]) first[sl] = lo;
+    }
+  }
+  size_t *rowstart = (size_t *)malloc(sizeof(size_t) * (size_t)(n + 1));
+  int *rfirst = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+  size_t tot = 0;
+  for (int i = 0; i < n; ++i) {
+    rfirst[i] = i < koff ? 6 * first[i / 6] : 0;
+    rowstart[i] = tot;
+    tot += (size_t)(i - rfirst[i] + 1);
+  }
+  rowstart[n] = tot;
+  double *A = (double *)calloc(tot + 1, sizeof(double));
+  double *rhs = (double *)calloc((size_t)n + 1, sizeof(double));
+#define SKY(i, j) A[rowstart[i] + (size_t)((j) - rfirst[i])]
+  /* W_o = Jc_o^T Jp_o (6x3) of every observation */
+  double *W = (double *)malloc(sizeof(double) * ((size_t)p->n_obs + 1) * 18);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < p->n_obs; ++i) {
+    double *W6 = W + (size_t)i * 18;
+    for (int k = 0; k < 18; ++k) W6[k] = 0.0;
+    for (int row = 0; row < R; ++row) {
+      const double *e = w->J.Jp + ((size_t)i * R + row) * 3;
+      const double *jc = w->J.Jc + ((size_t)i * R + row) * 6;
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 3; ++b) W6[a * 3 + b] += jc[a] * e[b];
+    }
+  }
+  /* camera rows: every thread owns the rows of its cameras (no write conflicts, fixed summation order) */
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int sa = 0; sa < nf; ++sa) {
+    const int c = slot_cam[sa];
+    for (int i = L->cam_rowptr[c]; i < L->cam_rowptr[c + 1]; ++i) {
+      /* F^T F and -F^T r */
+      for (int row = 0; row < R; ++row) {
+        const double *jc = w->J.Jc + ((size_t)i * R + row) * 6;
+        const double r = w->J.r[(size_t)i * R + row];
+        for (int a = 0; a < 6; ++a) {
+          rhs[6 * sa + a] -= jc[a] * r;
+          for (int b = 0; b <= a; ++b) SKY(6 * sa + a, 6 * sa + b) += jc[a] * jc[b];
+        }
+      }
+      /* - W_i V^-1 W_j^T for the observations j of the same point with slot_j <= slot_a */
+      const int q = p->pt_idx[i];
+      const double *Vi = w->Vinv + 9 * (size_t)q;
+      const double *Wa = W + (size_t)i * 18;
+      double WV[18];
+      for (int x = 0; x < 6; ++x)
+        for (int y = 0; y < 3; ++y)
+          WV[x * 3 + y] = Wa[x * 3 + 0] * Vi[0 * 3 + y] + Wa[x * 3 + 1] * Vi[1 * 3 + y] + Wa[x * 3 + 2] * Vi[2 * 3 + y];
+      const double *gq = w->gp + 3 * q;
+      double Vg[3];
+      for (int a = 0; a < 3; ++a) Vg[a] = Vi[a * 3 + 0] * gq[0] + Vi[a * 3 + 1] * gq[1] + Vi[a * 3 + 2] * gq[2];
+      for (int x = 0; x < 6; ++x) rhs[6 * sa + x] += Wa[x * 3 + 0] * Vg[0] + Wa[x * 3 + 1] * Vg[1] + Wa[x * 3 + 2] * Vg[2];
+      for (int s = L->pt_rowptr[q]; s < L->pt_rowptr[q + 1]; ++s) {
+        const int j = L->perm[s];
+        const int sb = L->cam_slot[p->cam_idx[j]];
+        if (sb < 0 || sb > sa) continue;
+        const double *Wb = W + (size_t)j * 18;
+        for (int x = 0; x < 6; ++x) {
+          const int ymax = sb == sa ? x : 5;
+          for (int y = 0; y <= ymax; ++y)
+            SKY(6 * sa + x, 6 * sb + y) -= WV[x * 3 + 0] * Wb[y * 3 + 0] + WV[x * 3 + 1] * Wb[y * 3 + 1] + WV[x * 3 + 2] * Wb[y * 3 + 2];
+        }
+      }
+    }
+    for (int k = 0; k < 6; ++k) {
+      const double D = sqrt(w->dc[6 * c + k] / radius);
+      SKY(6 * sa + k, 6 * sa + k) += D * D;
+    }
+  }
+  if (nk) {
+    /* border rows of the 4 intrinsics columns (sequential: one owner) */
+    for (int i = 0; i < p->n_obs; ++i) {
+      const int sl = L->cam_slot[p->cam_idx[i]];
+      for (int row = 0; row < 2; ++row) {
+        const double *jk = w->J.Jk + ((size_t)i * 2 + row) * 4;
+        const double r = w->J.r[(size_t)i * R + row];
+        for (int a = 0; a < 4; ++a) {
+          rhs[koff + a] -= jk[a] * r;
+          for (int b = 0; b <= a; ++b) SKY(koff + a, koff + b) += jk[a] * jk[b];
+          if (sl >= 0) {
+            const double *jc = w->J.Jc + ((size_t)i * R + row) * 6;
+            for (int b = 0; b < 6; ++b) SKY(koff + a, 6 * sl + b) += jk[a] * jc[b];
+          }
+        }
+      }
+    }
+    for (int k = 0; k < 4; ++k) {
+      SKY(koff + k, koff + k) += w->J.Jkk[k] * w->J.Jkk[k];
+      rhs[koff + k] -= w->J.Jkk[k] * w->J.rk[k];
+      const double D = sqrt(w->dk[k] / radius);
+      SKY(koff + k, koff + k) += D * D;
+    }
+    for (int q = 0; q < p->n_pt; ++q) {
+      const double *Vi = w->Vinv + 9 * (size_t)q;
+      double Wk[12], WkV[12];
+      memset(Wk, 0, sizeof(Wk));
+      for (int s = L->pt_rowptr[q]; s < L->pt_rowptr[q + 1]; ++s) {
+        const int i = L->perm[s];
+        for (int row = 0; row < 2; ++row) {
+          const double *e = w->J.Jp + ((size_t)i * R + row) * 3;
+          const double *jk = w->J.Jk + ((size_t)i * 2 + row) * 4;
+          for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 3; ++b) Wk[a * 3 + b] += jk[a] * e[b];
+        }
+      }
+      for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 3; ++y)
+          WkV[x * 3 + y] = Wk[x * 3 + 0] * Vi[0 * 3 + y] + Wk[x * 3 + 1] * Vi[1 * 3 + y] + Wk[x * 3 + 2] * Vi[2 * 3 + y];
+      const double *gq = w->gp + 3 * q;
+      double Vg[3];
+      for (int a = 0; a < 3; ++a) Vg[a] = Vi[a * 3 + 0] * gq[0] + Vi[a * 3 + 1] * gq[1] + Vi[a * 3 + 2] * gq[2];
+      for (int x = 0; x < 4; ++x) {
+        rhs[koff + x] += Wk[x * 3 + 0] * Vg[0] + Wk[x * 3 + 1] * Vg[1] + Wk[x * 3 + 2] * Vg[2];
+        for (int y = 0; y <= x; ++y)
+          SKY(koff + x, koff + y) -= WkV[x * 3 + 0] * Wk[y * 3 + 0] + WkV[x * 3 + 1] * Wk[y * 3 + 1] + WkV[x * 3 + 2] * Wk[y * 3 + 2];
+      }
+      for (int s = L->pt_rowptr[q]; s < L->pt_rowptr[q + 1]; ++s) {
+        const int j = L->perm[s];
+        const int sb = L->cam_slot[p->cam_idx[j]];
+        if (sb < 0) continue;
+        const double *Wb = W + (size_t)j * 18;
+        for (int x = 0; x < 4; ++x)
+          for (int y = 0; y < 6; ++y)
+            SKY(koff + x, 6 * sb + y) -= WkV[x * 3 + 0] * Wb[y * 3 + 0] + WkV[x * 3 + 1] * Wb[y * 3 + 1] + WkV[x * 3 + 2] * Wb[y * 3 + 2];
+      }
+    }
+  }
+  free(W);
+  /* envelope Cholesky, row by row: L_ij = (A_ij - sum_{k >= max(f_i, f_j)}^{j-1} L_ik L_jk) / L_jj */
+  int rc = 0;
+  for (int i = 0; i < n && !rc; ++i) {
+    const int fi = rfirst[i];
+    double *Li = A + rowstart[i];
+    for (int j = fi; j <= i; ++j) {
+      const int fj = rfirst[j];
+      const int k0 = fi > fj ? fi : fj;
+      const double *Lj = A + rowstart[j];
+      double sacc = Li[j - fi];
+      const double *a = Li + (k0 - fi), *b = Lj + (k0 - fj);
+      const int len = j - k0;
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+      int k = 0;
+      for (; k + 3 < len; k += 4) {
+        d0 += a[k] * b[k];
+        d1 += a[k + 1] * b[k + 1];
+        d2 += a[k + 2] * b[k + 2];
+        d3 += a[k + 3] * b[k + 3];
+      }
+      for (; k < len; ++k) d0 += a[k] * b[k];
+      sacc -= (d0 + d1) + (d2 + d3);
+      if (j < i) {
+        Li[j - fi] = sacc / Lj[j - fj];
+      } else {
+        if (!(sacc > 0.0) || !isfinite(sacc)) {
+          rc = -1;
+          break;
+        }
+        Li[j - fi] = sqrt(sacc);
+      }
+    }
+  }
+  if (!rc) {
+    for (int i = 0; i < n; ++i) {
+      const int fi = rfirst[i];
+      const double *Li = A + rowstart[i];
+      double sacc = rhs[i];
+      for (int k = fi; k < i; ++k) sacc -= Li[k - fi] * rhs[k];
+      rhs[i] = sacc / Li[i - fi];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      const int fi = rfirst[i];
+      const double *Li = A + rowstart[i];
+      const double v = rhs[i] / Li[i - fi];
+      rhs[i] = v;
+      for (int k = fi; k < i; ++k) rhs[k] -= Li[k - fi] * v;
+    }
+    for (int c = 0; c < p->n_cam; ++c) {
+      const int slot = L->cam_slot[c];
+      for (int k = 0; k < 6; ++k) w->yc[6 * c + k] = slot >= 0 ? rhs[6 * slot + k] : 0.0;
+    }
+    for (int k = 0; k < 4; ++k) w->yk[k] = nk ? rhs[koff + k] : 0.0;
+  }
+#undef SKY
+  free(A);
+  free(rhs);
+  free(rowstart);
+  free(rfirst);
+  free(first);
+  free(slot_cam);
+  return rc;
+}
+
 /* back substitution: y_p = Vinv (-g_p - sum_o W_o^T y_c - Wk^T y_k) */
 static void back_substitute(ora_ws *w) {
   const ora_problem *p = w->p;
@@ -1532,6 +1759,8 @@ int ora_solve(ora_problem *p, const ora_options *o, ora_summary *sum,
     int lin_rc, lin_iters = 0;
     if (o->solver == ORA_SOLVER_DENSE_SCHUR) {
       lin_rc = solve_dense_schur(&w, radius);
+    } else if (o->solver == ORA_SOLVER_SPARSE_SCHUR) {
+      lin_rc = solve_sparse_schur(&w, radius);
     } else {
       lin_rc = solve_implicit_pcg(&w, radius, &lin_iters);
     }

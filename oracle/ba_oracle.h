@@ -49,7 +49,9 @@ typedef struct ora_problem {
   double intr_prior[4];
 } ora_problem;
 
-enum { ORA_SOLVER_DENSE_SCHUR = 0, ORA_SOLVER_IMPLICIT_PCG = 1 };
+/* DENSE_SCHUR: dense S + dense Cholesky; IMPLICIT_PCG: ITERATIVE_SCHUR-equivalent; SPARSE_SCHUR: the reference's own
+ * setting (headers/BundleAdjustmentConfig.h:62) -- explicit S in envelope storage + sparse Cholesky (exact step) */
+enum { ORA_SOLVER_DENSE_SCHUR = 0, ORA_SOLVER_IMPLICIT_PCG = 1, ORA_SOLVER_SPARSE_SCHUR = 2 };
 
 typedef struct ora_options {
   /* reference knobs, headers/BundleAdjustmentConfig.h:47-50,64-65 */
