@@ -18,6 +18,7 @@ c_int32_p = C.POINTER(C.c_int32)
 
 BA_OK, BA_ERR_INVALID, BA_ERR_CUDA, BA_ERR_STATE, BA_ERR_UNSUPPORTED, BA_ERR_NUMERIC, BA_ERR_COMM = 0, -1, -2, -3, -4, -5, -6
 BA_SOLVER_AUTO, BA_SOLVER_EXPLICIT_CHOLESKY, BA_SOLVER_IMPLICIT_PCG, BA_SOLVER_SPARSE_SCHUR_PCG = 0, 1, 2, 3
+BA_SOLVER_SPARSE_SCHUR_CHOLESKY = 4
 BA_JAC_AUTO, BA_JAC_PLANES, BA_JAC_FACTORED, BA_JAC_TILED = 0, 1, 2, 3
 BA_KERNEL_LINEARIZE, BA_KERNEL_SCHUR_MATVEC, BA_KERNEL_SCHUR_PASS1, BA_KERNEL_SCHUR_PASS2 = 0, 1, 2, 3
 TERMINATION = {0: "NO_CONVERGENCE", 1: "GRADIENT", 2: "PARAMETER", 3: "FUNCTION", 4: "MIN_RADIUS", 5: "FAILURE"}
@@ -66,6 +67,8 @@ EXPORTS = [
     "ba_gpu_upload", "ba_gpu_solve", "ba_gpu_get_trace", "ba_gpu_download", "ba_gpu_eval", "ba_gpu_get_indices",
     "ba_gpu_schur_matvec", "ba_gpu_se3_plus", "ba_gpu_time_kernel", "ba_gpu_launch_count", "ba_gpu_comm_unique_id",
     "ba_gpu_comm_init", "ba_gpu_jacobian_store_used", "ba_gpu_sparse_stats", "ba_gpu_backproject",
+    "ba_gpu_schur_solve", "ba_gpu_spchol_info",
+    "ba_sparse_symbolic_create", "ba_sparse_symbolic_info", "ba_sparse_symbolic_get", "ba_sparse_symbolic_destroy",
 ]
 
 _LIB = None
@@ -107,8 +110,16 @@ def load():
     L.ba_gpu_sparse_stats.argtypes = [vp, C.POINTER(C.c_int64), c_int32_p, c_int32_p]
     L.ba_gpu_comm_unique_id.argtypes = [C.c_char_p]
     L.ba_gpu_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
+    L.ba_gpu_schur_solve.argtypes = [vp, C.c_double, c_double_p, c_double_p]
+    L.ba_gpu_spchol_info.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.ba_sparse_symbolic_create.argtypes = [C.c_int32, C.c_int32, c_int32_p, c_int32_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.ba_sparse_symbolic_info.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.ba_sparse_symbolic_get.argtypes = [vp, C.c_int32, c_int32_p]
+    L.ba_sparse_symbolic_destroy.argtypes = [vp]
+    L.ba_sparse_symbolic_destroy.restype = None
     for name in EXPORTS:
-        if name not in ("ba_gpu_destroy", "ba_gpu_default_options", "ba_gpu_last_error", "ba_gpu_launch_count"):
+        if name not in ("ba_gpu_destroy", "ba_gpu_default_options", "ba_gpu_last_error", "ba_gpu_launch_count",
+                        "ba_sparse_symbolic_destroy"):
             getattr(L, name).restype = C.c_int
     _LIB = L
     return L

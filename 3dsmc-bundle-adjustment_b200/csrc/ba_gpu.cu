@@ -13,6 +13,7 @@
 #include "ba_kernels_sparse.cuh"
 #include "ba_kernels_dist.cuh"
 #include "ba_kernels_chol.cuh"
+#include "ba_kernels_spchol.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -147,6 +148,13 @@ struct ba_gpu_ctx {
   bool dist_pcg = false;
   int n_my_rows = 0, dist_grid = 0;
   long long n_pairs = 0;
+  // exact sparse Cholesky of S (ba_sparse_symbolic.h / ba_kernels_spchol.cuh)
+  bool spchol = false;          // the block-sparse solver factorises S instead of running PCG
+  SpSymbolic sym;               // host-side structure of the last upload
+  Buf spn_node, spn_bord, spn_children, spn_rel, spn_inv, spn_aent, spn_perm, spn_levels;
+  Buf spc_panel, spc_U, spc_ru, spc_z, spc_linv, spc_ypos;
+  size_t spc_smem_factor = 0, spc_smem_solve = 0;
+  double sym_ms = 0.0;          // host time of the symbolic phase (last upload)
   Buf p2, pcg_bar, wb_rho, wb_Q, bp_buf, err_flag_bp, row_keys, row_keys2, row_ids, row_order;
   // scaling / diag / gradient / blocks
   Buf sc, sp, sk, dc, dp, dk, gc, gp, gk, U, Uck, Ukk, V, Vinv, Wk, tg, t, yc, yp, yk, rk, Jkk;
@@ -323,7 +331,7 @@ static int check_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
     return fail(ctx, BA_ERR_INVALID, "Huber deltas must be > 0 and weights >= 0");
   if (o->max_num_iterations < 0 || o->max_num_iterations > 10000000 || o->poll_interval < 1)
     return fail(ctx, BA_ERR_INVALID, "bad iteration options (0 <= max_num_iterations <= 10^7, poll_interval >= 1)");
-  if (o->solver < BA_SOLVER_AUTO || o->solver > BA_SOLVER_SPARSE_SCHUR_PCG) return fail(ctx, BA_ERR_INVALID, "bad solver");
+  if (o->solver < BA_SOLVER_AUTO || o->solver > BA_SOLVER_SPARSE_SCHUR_CHOLESKY) return fail(ctx, BA_ERR_INVALID, "bad solver");
   if (o->jacobian_store < BA_JAC_AUTO || o->jacobian_store > BA_JAC_TILED) return fail(ctx, BA_ERR_INVALID, "bad jacobian_store");
   if (!(o->initial_trust_region_radius > 0.0)) return fail(ctx, BA_ERR_INVALID, "bad trust-region radius");
   return 0;
@@ -462,7 +470,7 @@ extern "C" int ba_gpu_set_options(ba_gpu_ctx *ctx, const ba_gpu_options *o) {
 extern "C" int64_t ba_gpu_launch_count(const ba_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int ba_gpu_sparse_stats(const ba_gpu_ctx *ctx, int64_t *n_pairs, int32_t *n_blocks, int32_t *n_entries) {
   if (!ctx || !ctx->uploaded) return BA_ERR_STATE;
-  const bool sp = ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG;
+  const bool sp = ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG;  // (also the Cholesky variant: ctx->spchol)
   if (n_pairs) *n_pairs = sp ? ctx->n_pairs : 0;
   if (n_blocks) *n_blocks = sp ? ctx->n_sblk : 0;
   if (n_entries) *n_entries = sp ? ctx->n_ent : 0;
@@ -822,6 +830,63 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   return 0;
 }
 
+// symbolic phase of the exact sparse Cholesky (host: ordering, elimination tree, supernodes, maps) from the block structure of
+// the last build_sparse_structure(); uploads the integer tables and sizes the numeric buffers.  BA_ERR_UNSUPPORTED when a front
+// cannot fit one SM's shared memory (co-visibility without a sequential structure): the caller keeps PCG then.
+static int build_spchol(ba_gpu_ctx *ctx) {
+  cudaStream_t s = ctx->stream;
+  const int n_cam = ctx->n_cam, n_blk = ctx->n_sblk;
+  std::vector<int32_t> bi((size_t)n_blk + 1), bj((size_t)n_blk + 1);
+  if (n_blk > 0) {
+    CK(cudaMemcpyAsync(bi.data(), ctx->sb_i.p, (size_t)n_blk * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(bj.data(), ctx->sb_j.p, (size_t)n_blk * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  const auto t0 = std::chrono::steady_clock::now();
+  const int leaf = getenv("BA_SPCHOL_LEAF") ? std::max(2, atoi(getenv("BA_SPCHOL_LEAF"))) : 32;
+  ctx->sym = spsym_build(n_cam, n_blk, bi.data(), bj.data(), leaf, SPC_CAP_BLOCKS, SPC_MAX_OWN);
+  ctx->sym_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  const SpSymbolic &S = ctx->sym;
+  if (S.error == 1)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "sparse Cholesky: a front of the reduced camera system does not fit shared memory "
+                                         "(co-visibility too wide); use BA_SOLVER_SPARSE_SCHUR_PCG or BA_SOLVER_IMPLICIT_PCG");
+  if (S.error) return fail(ctx, BA_ERR_STATE, "sparse Cholesky: inconsistent symbolic structure (%d)", S.error);
+  if ((double)S.panel_blocks * 288.0 + (double)S.u_blocks * 288.0 > 64e9)
+    return fail(ctx, BA_ERR_UNSUPPORTED, "sparse Cholesky: factor would need %.1f GB", ((double)S.panel_blocks + (double)S.u_blocks) * 288e-9);
+  auto up = [&](Buf &b, const std::vector<int32_t> &v) -> int {
+    int rc = buf_reserve(ctx, b, (v.size() + 1) * 4);
+    if (rc) return rc;
+    if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice, s));
+    return 0;
+  };
+  int rc;
+  if ((rc = up(ctx->spn_node, S.node)) || (rc = up(ctx->spn_bord, S.bord)) || (rc = up(ctx->spn_children, S.children)) ||
+      (rc = up(ctx->spn_rel, S.rel)) || (rc = up(ctx->spn_inv, S.inv)) || (rc = up(ctx->spn_aent, S.aent)) ||
+      (rc = up(ctx->spn_perm, S.perm)) || (rc = up(ctx->spn_levels, S.level_nodes)))
+    return rc;
+  RES(spc_panel, ((size_t)S.panel_blocks + 1) * 288);
+  RES(spc_U, ((size_t)S.u_blocks + 1) * 288);
+  RES(spc_ru, (S.bord.size() + 1) * 48);
+  RES(spc_z, ((size_t)n_cam + 1) * 48);
+  RES(spc_linv, ((size_t)n_cam + 1) * 288);
+  RES(spc_ypos, ((size_t)n_cam + 1) * 48);
+  RES(dsq, ((size_t)n_cam + 1) * 48);
+  size_t sf = 0, ss = 0;
+  for (int id = 0; id < S.n_nodes; ++id) {
+    const int32_t *N = S.node.data() + (size_t)id * SPSYM_NODE_INTS;
+    sf = std::max(sf, spc_factor_smem(N[SPN_M], N[SPN_NB]));
+    ss = std::max(ss, spc_solve_smem(N[SPN_M], N[SPN_NB]));
+  }
+  if (sf > 227 * 1024 || ss > 227 * 1024) return fail(ctx, BA_ERR_STATE, "sparse Cholesky: front exceeds shared memory (%zu / %zu bytes)", sf, ss);
+  ctx->spc_smem_factor = sf;
+  ctx->spc_smem_solve = ss;
+  CK(cudaFuncSetAttribute(k_spchol_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
+  CK(cudaFuncSetAttribute(k_spchol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
+  CK(cudaStreamSynchronize(s));  // host vectors of this call die here
+  ctx->spchol = true;
+  return 0;
+}
+
 // exchange buffers of the row-sharded PCG: one cudaMalloc per rank, handles all-gathered through NCCL,
 // peers mapped with cudaIpcOpenMemHandle (NVLink peer access)
 static int setup_dist_pcg(ba_gpu_ctx *ctx) {
@@ -966,6 +1031,10 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   ctx->nk = o.optimize_intrinsics ? 4 : 0;
   ctx->n_red = 6 * ctx->n_free + ctx->nk;
   int solver = o.solver;
+  // the exact sparse Cholesky shares the block-sparse S machinery of the PCG variant; ctx->spchol switches the linear solve
+  bool want_chol = solver == BA_SOLVER_SPARSE_SCHUR_CHOLESKY;
+  if (want_chol) solver = BA_SOLVER_SPARSE_SCHUR_PCG;
+  ctx->spchol = false;
   if (solver == BA_SOLVER_AUTO)
     solver = (ctx->n_red <= o.explicit_max_dim || ctx->nk) ? BA_SOLVER_EXPLICIT_CHOLESKY : BA_SOLVER_IMPLICIT_PCG;
   if ((solver == BA_SOLVER_IMPLICIT_PCG || solver == BA_SOLVER_SPARSE_SCHUR_PCG) && ctx->nk)
@@ -1196,14 +1265,20 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
       return rcs;
     if (tot_pairs <= (double)o.sparse_max_pairs_per_obs * tot_obs && max_pairs <= 2147483647.0) {
       sparse = true;
+      want_chol = getenv("BA_AUTO_PCG") == nullptr;  // AUTO: exact factorisation (the reference's SPARSE_SCHUR) when its fronts fit
       ctx->solver = BA_SOLVER_SPARSE_SCHUR_PCG;
     }
   }
   if (sparse) {
     int rcs = build_sparse_structure(ctx);
     if (rcs) return rcs;
+    if (want_chol) {
+      rcs = build_spchol(ctx);
+      if (rcs == BA_ERR_UNSUPPORTED && o.solver == BA_SOLVER_AUTO) rcs = 0;  // falls back to PCG on the same S
+      if (rcs) return rcs;
+    }
     ctx->dist_pcg = false;
-    if (ctx->n_ranks > 1 && o.persistent_pcg == 1 && (rcs = setup_dist_pcg(ctx))) return rcs;
+    if (!ctx->spchol && ctx->n_ranks > 1 && o.persistent_pcg == 1 && (rcs = setup_dist_pcg(ctx))) return rcs;
   }
   if (ctx->fact && !sparse && o.jacobian_store != BA_JAC_FACTORED && ctx->n_tiles > 0) {
     // tile-fused product: tile metadata, then (if the locality bounds hold) the tile-camera-major store
@@ -1556,6 +1631,40 @@ static void enqueue_sparse_values(ba_gpu_ctx *ctx, int gate) {
          P<double>(ctx->Sblk), st, gate);
 }
 
+// exact solve of the reduced camera system by the sparse Cholesky: factorisation bottom-up (one launch per tree level, forward
+// substitution fused), backward substitution top-down.  b / dsq are complete (all-reduced) on every rank: the solve is replicated.
+static SpChol spchol_args(ba_gpu_ctx *ctx) {
+  SpChol a;
+  a.node = P<int32_t>(ctx->spn_node);
+  a.bord = P<int32_t>(ctx->spn_bord);
+  a.children = P<int32_t>(ctx->spn_children);
+  a.rel = P<int32_t>(ctx->spn_rel);
+  a.inv = P<int32_t>(ctx->spn_inv);
+  a.aent = P<int32_t>(ctx->spn_aent);
+  a.perm = P<int32_t>(ctx->spn_perm);
+  a.level_nodes = P<int32_t>(ctx->spn_levels);
+  a.S = P<double>(ctx->Sblk);
+  a.dsq = P<double>(ctx->dsq);
+  a.b = P<double>(ctx->b);
+  a.panel = P<double>(ctx->spc_panel);
+  a.U = P<double>(ctx->spc_U);
+  a.ru = P<double>(ctx->spc_ru);
+  a.z = P<double>(ctx->spc_z);
+  a.linv = P<double>(ctx->spc_linv);
+  a.ypos = P<double>(ctx->spc_ypos);
+  a.yc = P<double>(ctx->yc);
+  return a;
+}
+static void enqueue_spchol(ba_gpu_ctx *ctx, int gate) {
+  LmState *st = P<LmState>(ctx->st);
+  const SpSymbolic &S = ctx->sym;
+  const SpChol a = spchol_args(ctx);
+  for (int l = 0; l < S.n_levels; ++l)
+    LAUNCH(k_spchol_factor, S.level_ptr[l + 1] - S.level_ptr[l], SPC_THREADS, ctx->spc_smem_factor, a, S.level_ptr[l], st, gate);
+  for (int l = S.n_levels - 1; l >= 0; --l)
+    LAUNCH(k_spchol_solve, S.level_ptr[l + 1] - S.level_ptr[l], SPC_THREADS, ctx->spc_smem_solve, a, S.level_ptr[l], st, gate);
+}
+
 static int poll_state(ba_gpu_ctx *ctx) {
   CK(cudaMemcpyAsync(ctx->h_st, ctx->st.p, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1607,6 +1716,14 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
   });
   enqueue_sparse_values(ctx, GATE_RUN);
   sync_flags(ctx);
+  if (ctx->spchol) {
+    // exact step: b and the damping, then the factorisation and the two substitutions (yc written by the last kernels)
+    ItemRef i6c = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_RUN);
+    LAUNCH(k_spchol_rhs, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, i6c.ptr, i6c.part, P<double>(ctx->gc), P<double>(ctx->dc),
+           P<double>(ctx->b), P<double>(ctx->dsq), st, GATE_RUN, 0);
+    enqueue_spchol(ctx, GATE_RUN);
+    return 0;
+  }
   if (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG) {
     LAUNCH(k_sp_minv, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->sp_diag), P<double>(ctx->Sblk), P<double>(ctx->dc),
            P<double>(ctx->Minv), P<double>(ctx->dsq), st, GATE_RUN);
@@ -2006,7 +2123,7 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   s.initial_cost = h.initial_cost;
   s.final_cost = h.x_cost;
   s.total_linear_iters = h.total_lin_iters;
-  s.solver_used = ctx->solver;
+  s.solver_used = ctx->spchol ? BA_SOLVER_SPARSE_SCHUR_CHOLESKY : ctx->solver;
   s.reduced_dim = ctx->n_red;
   s.solve_ms = ms;
   s.kernel_launches = ctx->launches - l0;
@@ -2201,6 +2318,44 @@ extern "C" int ba_gpu_schur_matvec(ba_gpu_ctx *ctx, double radius, const double 
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   for (size_t i = 0; i < n; ++i) y[i] = xs[i] / sc[i];
+  return BA_OK;
+}
+
+// y = (S + D^2)^-1 rhs by the sparse Cholesky of the last upload (test hook; un-scaled coordinates like ba_gpu_schur_matvec)
+extern "C" int ba_gpu_schur_solve(ba_gpu_ctx *ctx, double radius, const double *rhs, double *y) {
+  if (!ctx || !rhs || !y) return BA_ERR_INVALID;
+  if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_schur_solve before ba_gpu_upload");
+  if (!ctx->spchol) return fail(ctx, BA_ERR_UNSUPPORTED, "ba_gpu_schur_solve needs the sparse Cholesky solver");
+  CK(cudaSetDevice(ctx->device));
+  int rc = prepare_linear_system(ctx, radius);
+  if (rc) return rc;
+  LmState *st = P<LmState>(ctx->st);
+  LAUNCH(k_clear_done, 1, 1, 0, st);
+  const size_t n = (size_t)6 * ctx->n_cam;
+  std::vector<double> sc(n), bs(n);
+  CK(cudaMemcpy(sc.data(), ctx->sc.p, n * 8, cudaMemcpyDeviceToHost));
+  // S_unscaled = diag(1/sc) S_scaled diag(1/sc):  S_scaled (y / sc) = sc .* rhs
+  for (size_t i = 0; i < n; ++i) bs[i] = rhs[i] * sc[i];
+  CK(cudaMemcpyAsync(ctx->b.p, bs.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(k_spchol_rhs, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->ident), P<double>(ctx->part6), P<double>(ctx->gc),
+         P<double>(ctx->dc), P<double>(ctx->b), P<double>(ctx->dsq), st, GATE_RUN, 1);
+  enqueue_spchol(ctx, GATE_RUN);
+  CK(cudaMemcpyAsync(bs.data(), ctx->yc.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = poll_state(ctx))) return rc;
+  CK(cudaGetLastError());
+  if (ctx->h_st->lin_fail) return fail(ctx, BA_ERR_NUMERIC, "sparse Cholesky: non-positive pivot");
+  for (size_t i = 0; i < n; ++i) y[i] = bs[i] * sc[i];
+  return BA_OK;
+}
+
+extern "C" int ba_gpu_spchol_info(const ba_gpu_ctx *ctx, int64_t info[24]) {
+  if (!ctx || !info) return BA_ERR_INVALID;
+  memset(info, 0, 24 * sizeof(int64_t));
+  if (!ctx->uploaded || !ctx->spchol) return BA_OK;
+  const SpSymbolic &s = ctx->sym;
+  info[0] = s.n_cam; info[1] = s.n_nodes; info[2] = s.n_levels; info[3] = s.panel_blocks; info[4] = s.u_blocks;
+  info[5] = s.max_front_blocks; info[6] = s.max_m; info[7] = s.max_nb; info[8] = s.max_children;
+  info[9] = (int64_t)s.flops; info[10] = (int64_t)s.crit_blocks; info[11] = (int64_t)(ctx->sym_ms * 1e3);
   return BA_OK;
 }
 
@@ -2402,5 +2557,66 @@ extern "C" int ba_gpu_comm_init(ba_gpu_ctx *ctx, const char id128[128], int32_t 
   if (r != 0) return fail(ctx, BA_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   ctx->rank = rank;
   ctx->n_ranks = n_ranks;
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------ symbolic phase of the sparse Cholesky (host only; test hook)
+struct ba_spsym {
+  SpSymbolic s;
+};
+extern "C" int ba_sparse_symbolic_create(int32_t n_cam, int32_t n_blk, const int32_t *blk_i, const int32_t *blk_j, int32_t leaf_cams,
+                                         int32_t cap_blocks, int32_t max_own, ba_spsym **out) {
+  if (!out || n_cam <= 0 || n_blk < 0 || (n_blk > 0 && (!blk_i || !blk_j)) || cap_blocks < 2 || max_own < 1) return BA_ERR_INVALID;
+  for (int b = 0; b < n_blk; ++b)
+    if (blk_i[b] < 0 || blk_j[b] >= n_cam || blk_i[b] > blk_j[b]) return BA_ERR_INVALID;
+  ba_spsym *h = new ba_spsym();
+  h->s = spsym_build(n_cam, n_blk, blk_i, blk_j, leaf_cams, cap_blocks, max_own);
+  if (h->s.error) {
+    const int e = h->s.error;
+    delete h;
+    return e == 1 ? BA_ERR_UNSUPPORTED : BA_ERR_STATE;
+  }
+  *out = h;
+  return BA_OK;
+}
+extern "C" void ba_sparse_symbolic_destroy(ba_spsym *h) { delete h; }
+static const std::vector<int32_t> *spsym_array(const SpSymbolic &s, int which) {
+  switch (which) {
+    case 0: return &s.perm;
+    case 1: return &s.pos;
+    case 2: return &s.node;
+    case 3: return &s.bord;
+    case 4: return &s.children;
+    case 5: return &s.rel;
+    case 6: return &s.inv;
+    case 7: return &s.aent;
+    case 8: return &s.level_ptr;
+    case 9: return &s.level_nodes;
+    default: return nullptr;
+  }
+}
+extern "C" int ba_sparse_symbolic_info(const ba_spsym *h, int64_t info[24]) {
+  if (!h || !info) return BA_ERR_INVALID;
+  const SpSymbolic &s = h->s;
+  memset(info, 0, 24 * sizeof(int64_t));
+  info[0] = s.n_cam;
+  info[1] = s.n_nodes;
+  info[2] = s.n_levels;
+  info[3] = s.panel_blocks;
+  info[4] = s.u_blocks;
+  info[5] = s.max_front_blocks;
+  info[6] = s.max_m;
+  info[7] = s.max_nb;
+  info[8] = s.max_children;
+  info[9] = (int64_t)s.flops;
+  info[10] = (int64_t)s.crit_blocks;
+  for (int w = 0; w < 10; ++w) info[12 + w] = (int64_t)spsym_array(s, w)->size();
+  return BA_OK;
+}
+extern "C" int ba_sparse_symbolic_get(const ba_spsym *h, int32_t which, int32_t *dst) {
+  if (!h || !dst) return BA_ERR_INVALID;
+  const std::vector<int32_t> *a = spsym_array(h->s, which);
+  if (!a) return BA_ERR_INVALID;
+  if (!a->empty()) memcpy(dst, a->data(), a->size() * sizeof(int32_t));
   return BA_OK;
 }

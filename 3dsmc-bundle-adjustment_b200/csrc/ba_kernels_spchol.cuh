@@ -1,0 +1,421 @@
+// ba_kernels_spchol.cuh -- NUMERIC phase of the exact sparse Cholesky of the reduced camera system
+// (BA_SOLVER_SPARSE_SCHUR_CHOLESKY): what the reference asks Ceres for with linear_solver_type = SPARSE_SCHUR
+// (headers/BundleAdjustmentConfig.h:62; ceres::Solve at src/OptimizationUtils.cpp:300) -- the explicit block-sparse
+// S of ba_kernels_sparse.cuh factorised exactly instead of handed to PCG.
+//
+// Supernodal multifrontal Cholesky over the nested-dissection tree built on the host (ba_sparse_symbolic.h):
+//   * ONE thread block per tree node, one launch per tree level (children before parents); nodes of a level are independent.
+//   * A node's FRONT PANEL ((own + border) x own cameras, dense, scalar column-major, leading dimension LD = 6 (m + nb))
+//     lives in shared memory for the whole elimination of its m own cameras: assembled from the stored blocks of S
+//     (+ LM damping on the diagonal) minus the children's update matrices (extend-add through the host-built index maps),
+//     then factorised right-looking with 6x6 pivot blocks.  One thread owns one scalar ROW of the panel: a step costs it
+//     six contiguous loads of its pivot-column entries (kept row-major in a side buffer LT), and per trailing block column
+//     36 warp-broadcast loads of the pivot rows + a conflict-free read-modify-write of its six entries.
+//   * The 6x6 pivot block is factorised by warp 0 with shuffles (lane = row) while the other warps still run the
+//     trailing update of the previous step (look-ahead): two CTA barriers per eliminated camera.
+//   * The right-hand side rides along as one more row (forward substitution fused into the factorisation).
+//   * Afterwards the node's update matrix U = L_B L_B^T (+ what its children pass through) and the panel go to HBM/L2
+//     for the parent / the backward substitution.
+// Backward substitution: one launch per level, parents before children; L_OO and the stored inverses of the pivot blocks
+// come back into shared memory, the border product is a warp-per-column reduction over the panel in L2.
+// Every sum has a fixed order: results are bit-identical from run to run and across ranks.
+#pragma once
+#include "ba_kernels_sparse.cuh"
+#include "ba_sparse_symbolic.h"
+
+#define SPC_THREADS 512
+#define SPC_WARPS (SPC_THREADS / 32)
+// capacity of a front in 6x6 blocks: (m + nb) (m + 1) [panel + the row-major pivot column LT] <= SPC_CAP_BLOCKS, m <= SPC_MAX_OWN
+#define SPC_CAP_BLOCKS 770
+#define SPC_MAX_OWN 24
+
+struct SpChol {
+  const int32_t *node, *bord, *children, *rel, *inv, *aent, *perm, *level_nodes;
+  const double *S, *dsq, *b;  // stored upper blocks of S, LM damping D^2 [6 n_cam], right-hand side [6 n_cam] (by camera)
+  double *panel, *U, *ru;     // per node: factor panel, update matrix (dense lower incl. full diagonal blocks), rhs update [6 nb]
+  double *z, *linv, *ypos;    // by elimination position: forward-substituted rhs [6], inverse pivot blocks [36], solution [6]
+  double *yc;                 // solution by camera [6 n_cam]
+};
+
+__host__ __device__ inline size_t spc_off(const int32_t *N, int lo) { return ((size_t)N[lo + 1] << 31) | (size_t)N[lo]; }
+inline size_t spc_factor_smem(int m, int nb) { return ((size_t)36 * (m + nb) * (m + 1) + 6 * m + 72 + 8) * 8; }
+inline size_t spc_solve_smem(int m, int nb) { return ((size_t)36 * m * m + 36 * m + 6 * nb + 12 * m + 8) * 8; }
+
+// right-hand side b = -g_c - sum (J_c^T J_p V^-1 g_p partials) and LM damping D^2 = (sqrt(diag / radius))^2 per camera column
+__global__ void __launch_bounds__(BA_THREADS)
+k_spchol_rhs(int n_cam, const int32_t *__restrict__ item_ptr, const double *__restrict__ part, const double *__restrict__ gc,
+             const double *__restrict__ dc, double *__restrict__ b, double *__restrict__ dsq, LmState *st, int gate, int keep_b) {
+  if (!gate_open(st, gate)) return;
+  const int c = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (c == 0) st->pcg_iters_last = 0;
+  if (c >= n_cam) return;
+  const double radius = st->radius;
+  if (!keep_b) {
+    double s[6], g[6], bv[6];
+    sum_items6(item_ptr, part, c, s);
+    load6(gc + 6 * (size_t)c, g);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bv[k] = -g[k] - s[k];
+    store6(b + 6 * (size_t)c, bv);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double D = sqrt(dc[6 * (size_t)c + k] / radius);
+    dsq[6 * (size_t)c + k] = D * D;
+  }
+}
+
+// Cholesky of the 6x6 pivot block k of the panel by one warp (lane = row, lanes 0..5 carry data): L back into the panel
+// (upper triangle zeroed), T = L^-1 (lower, row-major) to Tout and to linv_g.  Returns false on a non-positive pivot.
+__device__ __forceinline__ bool spc_chol6(double *P, int LD, int k, int lane, double *Tout, double *linv_g) {
+  double row[6], invd[6];
+  const int r = lane < 6 ? lane : 0;
+  double *D = P + (size_t)(6 * k) * LD + 6 * k;  // D[c * LD + r] = block(r, c)
+#pragma unroll
+  for (int c = 0; c < 6; ++c) row[c] = (c <= r) ? D[(size_t)c * LD + r] : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const double dcc = __shfl_sync(BA_FULL, row[c], c);
+    if (!(dcc > 0.0) || !isfinite(dcc)) ok = false;
+    const double s = sqrt(dcc);
+    const double inv = 1.0 / s;
+    invd[c] = inv;
+    if (lane == c)
+      row[c] = s;
+    else if (lane > c)
+      row[c] *= inv;
+#pragma unroll
+    for (int c2 = c + 1; c2 < 6; ++c2) {
+      const double v = __shfl_sync(BA_FULL, row[c], c2);
+      if (lane >= c2) row[c2] -= row[c] * v;
+    }
+  }
+  if (lane < 6) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) D[(size_t)c * LD + lane] = (c <= lane) ? row[c] : 0.0;
+  }
+  __syncwarp();
+  if (lane < 6) {
+    // column `lane` of T = L^-1 by forward substitution (the reciprocals of the diagonal are in registers)
+    double t[6];
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr) {
+      if (rr < lane) {
+        t[rr] = 0.0;
+      } else if (rr == lane) {
+        t[rr] = invd[rr];
+      } else {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          if (q < rr && q >= lane) acc += D[(size_t)q * LD + rr] * t[q];
+        t[rr] = -acc * invd[rr];
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr) {
+      Tout[rr * 6 + lane] = t[rr];
+      linv_g[rr * 6 + lane] = t[rr];
+    }
+  }
+  __syncwarp();
+  return ok;
+}
+
+// (i, j), i >= j, of the p-th lower block in row-major order of the lower triangle
+__device__ __forceinline__ void spc_tri(int p, int &i, int &j) {
+  int r = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+  while (r * (r + 1) / 2 > p) --r;
+  while ((r + 1) * (r + 2) / 2 <= p) ++r;
+  i = r;
+  j = p - r * (r + 1) / 2;
+}
+
+__global__ void __launch_bounds__(SPC_THREADS, 1)
+k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  extern __shared__ double spc_sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int id = a.level_nodes[lvl_first + blockIdx.x];
+  const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
+  const int k0 = N[SPN_K0], m = N[SPN_M], nb = N[SPN_NB];
+  const int LD = 6 * (m + nb), C6 = 6 * m, NB6 = 6 * nb;
+  double *P = spc_sm;                    // panel, column-major, LD x C6
+  double *LT = P + (size_t)LD * C6;      // current pivot column block, row-major: LT[R * 6 + c]
+  double *zf = LT + (size_t)LD * 6;      // right-hand side of the own cameras
+  double *Tb = zf + C6;                  // two inverse pivot blocks (ping-pong)
+
+  // ---- phase 0: clear, right-hand side
+  for (int i = tid; i < LD * C6; i += SPC_THREADS) P[i] = 0.0;
+  for (int i = tid; i < C6; i += SPC_THREADS) zf[i] = a.b[6 * (size_t)a.perm[k0 + i / 6] + i % 6];
+  __syncthreads();
+  // ---- phase 1a: stored blocks of S (36 threads per block), damping on the diagonal
+  {
+    const int32_t *E = a.aent + 4 * (size_t)N[SPN_AENT];
+    const int ne = N[SPN_NAENT];
+    const int sub = tid / 36, t = tid - 36 * sub, r6 = t / 6, c6 = t - 6 * r6;
+    if (sub < SPC_THREADS / 36)
+      for (int e = sub; e < ne; e += SPC_THREADS / 36) {
+        const uint32_t code = (uint32_t)E[4 * e];
+        const int lr = E[4 * e + 1], lc = E[4 * e + 2], cam = E[4 * e + 3];
+        const uint32_t blk = code & 0x3fffffffu;
+        double v = 0.0;
+        if (code & 0x40000000u) {  // diagonal block: symmetrised from its upper triangle (as k_sp_minv does) + D^2
+          if (blk != 0x3fffffffu) v = a.S[36 * (size_t)blk + (r6 <= c6 ? r6 * 6 + c6 : c6 * 6 + r6)];
+          if (r6 == c6) v += a.dsq[6 * (size_t)cam + r6];
+        } else if (code & 0x80000000u) {
+          v = a.S[36 * (size_t)blk + c6 * 6 + r6];
+        } else {
+          v = a.S[36 * (size_t)blk + r6 * 6 + c6];
+        }
+        P[(size_t)(6 * lc + c6) * LD + 6 * lr + r6] = v;
+      }
+  }
+  __syncthreads();
+  // ---- phase 1b: extend-add of the children (one after the other: fixed order; inside a child the map is injective)
+  for (int ci = 0; ci < N[SPN_NCHILD]; ++ci) {
+    const int ch = a.children[N[SPN_CHILD] + ci];
+    const int32_t *Cn = a.node + (size_t)ch * SPSYM_NODE_INTS;
+    const int nbc6 = 6 * Cn[SPN_NB];
+    const int32_t *rel = a.rel + Cn[SPN_REL];
+    const double *Uc = a.U + 36 * spc_off(Cn, SPN_U_LO);
+    const double *ruc = a.ru + 6 * (size_t)Cn[SPN_BORD];
+    for (int idx = tid; idx < nbc6 * nbc6; idx += SPC_THREADS) {
+      const int col = idx / nbc6, row = idx - col * nbc6;
+      const int j = col / 6, i = row / 6;
+      if (i < j) continue;
+      const int rj = rel[j];
+      if (rj >= m) continue;
+      const int ri = rel[i];
+      P[(size_t)(6 * rj + (col - 6 * j)) * LD + 6 * ri + (row - 6 * i)] -= __ldcg(Uc + idx);
+    }
+    for (int idx = tid; idx < nbc6; idx += SPC_THREADS) {
+      const int ri = rel[idx / 6];
+      if (ri < m) zf[6 * ri + idx % 6] -= __ldcg(ruc + idx);
+    }
+    __syncthreads();
+  }
+  // ---- phase 2: right-looking factorisation, 6 columns (one camera) per step
+  bool ok = true;
+  if (warp == 0) ok = spc_chol6(P, LD, 0, lane, Tb, a.linv + 36 * (size_t)k0);
+  __syncthreads();
+  for (int k = 0; k < m; ++k) {
+    const double *T = Tb + (k & 1) * 36;
+    // (b) pivot column: rows below the pivot block times T^T; forward substitution of the pivot's right-hand side
+    for (int R = 6 * (k + 1) + tid; R < LD; R += SPC_THREADS) {
+      double x[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) x[c] = P[(size_t)(6 * k + c) * LD + R];
+#pragma unroll
+      for (int bb = 0; bb < 6; ++bb) {
+        double o = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          if (c <= bb) o += x[c] * T[bb * 6 + c];
+        P[(size_t)(6 * k + bb) * LD + R] = o;
+        LT[R * 6 + bb] = o;
+      }
+    }
+    if (warp == 0) {
+      double v = 0.0;
+      if (lane < 6) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          if (c <= lane) v += T[lane * 6 + c] * zf[6 * k + c];
+      }
+      __syncwarp();
+      if (lane < 6) zf[6 * k + lane] = v;
+    }
+    __syncthreads();
+    if (k + 1 == m) break;
+    // (c) trailing update with column k.  Warp 0: the rows of the next pivot block, then its Cholesky (look-ahead);
+    //     the other warps: one scalar row each (and a share of the block columns when rows are fewer than threads)
+    if (warp == 0) {
+      if (lane < 6) {
+        const int R = 6 * (k + 1) + lane, j = k + 1;
+        double x[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) x[c] = LT[R * 6 + c];
+#pragma unroll
+        for (int bb = 0; bb < 6; ++bb) {
+          const double *lj = LT + (6 * j + bb) * 6;
+          double s = 0.0;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) s += x[c] * lj[c];
+          P[(size_t)(6 * j + bb) * LD + R] -= s;
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s += x[c] * zf[6 * k + c];
+        zf[R] -= s;
+      }
+      __syncwarp();
+      ok = spc_chol6(P, LD, k + 1, lane, Tb + ((k + 1) & 1) * 36, a.linv + 36 * (size_t)(k0 + k + 1)) && ok;
+    } else {
+      const int base = 6 * (k + 2), nrows = LD - base, avail = SPC_THREADS - 32;
+      if (nrows > 0) {
+        int G = avail / nrows;
+        G = G < 1 ? 1 : (G > 4 ? 4 : G);
+        for (int t = tid - 32; t < G * nrows; t += avail) {
+          const int g = t / nrows, R = base + (t - g * nrows);
+          const int jmax = R / 6 < m - 1 ? R / 6 : m - 1;
+          double x[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) x[c] = LT[R * 6 + c];
+          for (int j = k + 1 + g; j <= jmax; j += G) {
+#pragma unroll
+            for (int bb = 0; bb < 6; ++bb) {
+              const double *lj = LT + (6 * j + bb) * 6;
+              double s = 0.0;
+#pragma unroll
+              for (int c = 0; c < 6; ++c) s += x[c] * lj[c];
+              P[(size_t)(6 * j + bb) * LD + R] -= s;
+            }
+          }
+          if (g == 0 && R < C6) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) s += x[c] * zf[6 * k + c];
+            zf[R] -= s;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0 && lane == 0 && !ok) st->lin_fail = 1;
+  // ---- phase 3: panel and forward-substituted right-hand side to global memory
+  {
+    double *Pg = a.panel + 36 * spc_off(N, SPN_PANEL_LO);
+    for (int i = tid; i < LD * C6; i += SPC_THREADS) Pg[i] = P[i];
+    for (int i = tid; i < C6; i += SPC_THREADS) a.z[6 * (size_t)k0 + i] = zf[i];
+  }
+  if (nb == 0) return;
+  // ---- phase 4: update matrix U = L_B L_B^T + what the children pass through (block lower triangle, full diagonal
+  //      blocks), one half block (3 x 6) per thread; right-hand side update ru = L_B z + children
+  {
+    double *Ug = a.U + 36 * spc_off(N, SPN_U_LO);
+    const double *Pb = P + C6;  // first border row
+    const int n_items = nb * (nb + 1);
+    const int nch = N[SPN_NCHILD];
+    for (int idx = tid; idx < n_items; idx += SPC_THREADS) {
+      int i, j;
+      spc_tri(idx >> 1, i, j);
+      const int h = idx & 1;
+      const int ra = 6 * i + 3 * h, rb = 6 * j;
+      double acc[3][6];
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 6; ++y) acc[x][y] = 0.0;
+      for (int c = 0; c < C6; ++c) {
+        const double *col = Pb + (size_t)c * LD;
+        const double a0 = col[ra], a1 = col[ra + 1], a2 = col[ra + 2];
+#pragma unroll
+        for (int y = 0; y < 6; ++y) {
+          const double bv = col[rb + y];
+          acc[0][y] += a0 * bv;
+          acc[1][y] += a1 * bv;
+          acc[2][y] += a2 * bv;
+        }
+      }
+      for (int ci = 0; ci < nch; ++ci) {
+        const int ch = a.children[N[SPN_CHILD] + ci];
+        const int32_t *Cn = a.node + (size_t)ch * SPSYM_NODE_INTS;
+        const int32_t *inv = a.inv + Cn[SPN_INV];
+        const int ii = inv[i], jj = inv[j];
+        if (ii < 0 || jj < 0) continue;
+        const int nbc6 = 6 * Cn[SPN_NB];
+        const double *Uc = a.U + 36 * spc_off(Cn, SPN_U_LO);
+#pragma unroll
+        for (int y = 0; y < 6; ++y)
+#pragma unroll
+          for (int x = 0; x < 3; ++x) acc[x][y] += __ldcg(Uc + (size_t)(6 * jj + y) * nbc6 + 6 * ii + 3 * h + x);
+      }
+#pragma unroll
+      for (int y = 0; y < 6; ++y)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) Ug[(size_t)(rb + y) * NB6 + ra + x] = acc[x][y];
+    }
+    double *rug = a.ru + 6 * (size_t)N[SPN_BORD];
+    for (int idx = tid; idx < NB6; idx += SPC_THREADS) {
+      double s = 0.0;
+      for (int c = 0; c < C6; ++c) s += Pb[(size_t)c * LD + idx] * zf[c];
+      for (int ci = 0; ci < nch; ++ci) {
+        const int ch = a.children[N[SPN_CHILD] + ci];
+        const int32_t *Cn = a.node + (size_t)ch * SPSYM_NODE_INTS;
+        const int ii = a.inv[Cn[SPN_INV] + idx / 6];
+        if (ii >= 0) s += __ldcg(a.ru + 6 * (size_t)Cn[SPN_BORD] + 6 * ii + idx % 6);
+      }
+      rug[idx] = s;
+    }
+  }
+}
+
+// backward substitution of one tree level (parents are done): y_O = L_OO^-T (z_O - L_BO^T y_B)
+__global__ void __launch_bounds__(SPC_THREADS, 1)
+k_spchol_solve(SpChol a, int lvl_first, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  extern __shared__ double spc_sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int id = a.level_nodes[lvl_first + blockIdx.x];
+  const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
+  const int k0 = N[SPN_K0], m = N[SPN_M], nb = N[SPN_NB];
+  const int LD = 6 * (m + nb), C6 = 6 * m, NB6 = 6 * nb;
+  double *Loo = spc_sm;               // own part of the panel, column-major C6 x C6
+  double *Ti = Loo + (size_t)C6 * C6;  // inverse pivot blocks
+  double *yB = Ti + 36 * m;
+  double *w = yB + NB6;
+  double *y = w + C6;
+  const double *Pg = a.panel + 36 * spc_off(N, SPN_PANEL_LO);
+  const int32_t *bord = a.bord + N[SPN_BORD];
+  for (int idx = tid; idx < C6 * C6; idx += SPC_THREADS) {
+    const int c = idx / C6, r = idx - c * C6;
+    Loo[idx] = Pg[(size_t)c * LD + r];
+  }
+  for (int i = tid; i < 36 * m; i += SPC_THREADS) Ti[i] = a.linv[36 * (size_t)k0 + i];
+  for (int i = tid; i < NB6; i += SPC_THREADS) yB[i] = __ldcg(a.ypos + 6 * (size_t)bord[i / 6] + i % 6);
+  for (int i = tid; i < C6; i += SPC_THREADS) {
+    w[i] = a.z[6 * (size_t)k0 + i];
+    y[i] = 0.0;
+  }
+  __syncthreads();
+  // w -= L_BO^T y_B: one warp per column, lanes stride the border rows (coalesced reads of the panel)
+  for (int c = warp; c < C6; c += SPC_WARPS) {
+    const double *col = Pg + (size_t)c * LD + C6;
+    double s = 0.0;
+    for (int R = lane; R < NB6; R += 32) s += col[R] * yB[R];
+    s = warp_sum(s);
+    if (lane == 0) w[c] -= s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int k = m - 1; k >= 0; --k) {
+      double part[6] = {0, 0, 0, 0, 0, 0};
+      for (int R = 6 * (k + 1) + lane; R < C6; R += 32) {
+        const double yr = y[R];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) part[c] += Loo[(size_t)(6 * k + c) * C6 + R] * yr;
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) part[c] = warp_sum(part[c]);
+      if (lane < 6) {
+        const double *T = Ti + 36 * k;
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          if (c >= lane) v += T[c * 6 + lane] * (w[6 * k + c] - part[c]);
+        y[6 * k + lane] = v;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < C6; i += SPC_THREADS) {
+    const double v = y[i];
+    if (!isfinite(v)) st->lin_fail = 1;
+    a.ypos[6 * (size_t)k0 + i] = v;
+    a.yc[6 * (size_t)a.perm[k0 + i / 6] + i % 6] = v;
+  }
+}

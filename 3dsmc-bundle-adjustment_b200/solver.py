@@ -150,6 +150,23 @@ class GpuSolver:
         self._check(self.lib.ba_gpu_schur_matvec(self._ctx, float(radius), capi.dp(x), capi.dp(y)))
         return y
 
+    def schur_solve(self, radius, rhs):
+        """(S + D^2)^-1 rhs through the sparse Cholesky in force (test hook)."""
+        rhs = capi.f64(rhs).reshape(-1)
+        y = np.zeros_like(rhs)
+        self._check(self.lib.ba_gpu_schur_solve(self._ctx, float(radius), capi.dp(rhs), capi.dp(y)))
+        return y
+
+    def spchol_info(self):
+        """Structure of the sparse Cholesky of the last upload ({} when another solver is in force)."""
+        info = (C.c_int64 * 24)()
+        self._check(self.lib.ba_gpu_spchol_info(self._ctx, info))
+        if info[1] == 0:
+            return {}
+        keys = ["n_cam", "nodes", "levels", "panel_blocks", "update_blocks", "max_front_blocks", "max_own", "max_border",
+                "max_children", "flops", "critical_path_block_ops", "symbolic_us"]
+        return {k: int(info[i]) for i, k in enumerate(keys)}
+
     def se3_plus(self, pose7, delta6):
         pose7 = capi.f64(pose7).reshape(-1, 7)
         delta6 = capi.f64(delta6).reshape(-1, 6)

@@ -48,8 +48,9 @@ BYTES = {
     "tiled": {"linearize": (96, 0, 0), "fused": (36, 52, 0)},
 }
 STORE_NAME = {1: "planes", 2: "factored", 3: "tiled"}
-SOLVERS = {"auto": 0, "implicit": 2, "sparse": 3}
-SOLVER_NAME = {1: "dense explicit Schur + Cholesky", 2: "implicit-Schur PCG", 3: "block-sparse explicit Schur + persistent PCG"}
+SOLVERS = {"auto": 0, "implicit": 2, "sparse": 3, "cholesky": 4}
+SOLVER_NAME = {1: "dense explicit Schur + Cholesky", 2: "implicit-Schur PCG", 3: "block-sparse explicit Schur + persistent PCG",
+               4: "block-sparse explicit Schur + exact sparse Cholesky (supernodal multifrontal, nested dissection)"}
 # PCG iterations per LM iteration of the fixed-count solves (eta = 1e-6, cap 500), as
 # measured by the GPU arm (identical on the oracle for cfg3; within 5% for cfg4/5): the
 # reference arm prices its bounded sample with these, so both arms do the same work.
@@ -188,7 +189,7 @@ def kernel_rooflines(ba_b200, s, problem, wl, solver_used, flush, peak):
     ms_lin = s.time_kernel(cap.BA_KERNEL_LINEARIZE, 3, 20, flush)
     dom = "linearize (%s store)" % store
     roof[dom] = (nbytes(bt["linearize"]), ms_lin)
-    if solver_used == 3:
+    if solver_used in (3, 4):
         # block-CSR product = phase I of the persistent PCG kernel: every stored (upper) block is read twice
         # (as itself and transposed): 288 B block + 8 B entry + 48 B gathered vector per row entry
         n_ent, n_blk = s.sparse_stats()
@@ -363,7 +364,7 @@ def main():
     jac_obs_s = full.n_obs / (maxr(ms_lin) * 1e-3)
     # the matrix-free (north-star) path beside it when AUTO chose the block-sparse solver
     implicit_path = None
-    if solver_used == 3 and world == 1:
+    if solver_used in (3, 4) and world == 1:
         s2 = ba_b200.GpuSolver(max_num_iterations=max(W, 1), **dict(opts, solver=2))
         s2.upload(hp)
         if W > 0:

@@ -46,16 +46,22 @@ enum {
 
 enum {
   BA_SOLVER_AUTO = 0,              /* dense explicit if reduced dim <= explicit_max_dim (or free intrinsics);
-                                      else block-sparse if the co-visibility is sparse (one GPU, NS mode);
+                                      else block-sparse S if the co-visibility is sparse (NS mode), factorised
+                                      exactly (_SPARSE_SCHUR_CHOLESKY) when its fronts fit, else with PCG;
                                       else implicit */
   BA_SOLVER_EXPLICIT_CHOLESKY = 1, /* explicit Schur complement + dense Cholesky
                                       (== Ceres DENSE_SCHUR / SPARSE_SCHUR step) */
   BA_SOLVER_IMPLICIT_PCG = 2,      /* matrix-free Schur + block-Jacobi PCG
                                       (== Ceres ITERATIVE_SCHUR + SCHUR_JACOBI) */
-  BA_SOLVER_SPARSE_SCHUR_PCG = 3   /* explicit BLOCK-SPARSE Schur complement (6x6 blocks, symmetric
+  BA_SOLVER_SPARSE_SCHUR_PCG = 3,  /* explicit BLOCK-SPARSE Schur complement (6x6 blocks, symmetric
                                       storage, device-built structure) + the same PCG
                                       (== ITERATIVE_SCHUR with use_explicit_schur_complement;
                                       the matrix Ceres SPARSE_SCHUR factorises). NS mode only. */
+  BA_SOLVER_SPARSE_SCHUR_CHOLESKY = 4 /* the same block-sparse S factorised EXACTLY by a supernodal multifrontal
+                                      Cholesky over a nested-dissection tree of the camera sequence
+                                      (== Ceres SPARSE_SCHUR, the reference's own setting,
+                                      headers/BundleAdjustmentConfig.h:62). NS mode only; BA_ERR_UNSUPPORTED
+                                      when a front does not fit shared memory (AUTO then keeps PCG). */
 };
 
 enum {
@@ -130,7 +136,7 @@ typedef struct ba_gpu_summary {
   int32_t termination, num_iterations, num_successful, num_unsuccessful;
   double initial_cost, final_cost;
   int64_t total_linear_iters;
-  int32_t solver_used;       /* BA_SOLVER_EXPLICIT_CHOLESKY or _IMPLICIT_PCG */
+  int32_t solver_used;       /* the BA_SOLVER_* that ran (what AUTO resolved to) */
   int32_t reduced_dim;
   double solve_ms;           /* CUDA-event time of ba_gpu_solve on its stream */
   int64_t kernel_launches;   /* kernels launched by this solve */
@@ -180,6 +186,12 @@ int ba_gpu_get_indices(ba_gpu_ctx *ctx, int32_t *perm_pt_major,
 /* y = S x (reduced camera system at the current state, given radius), unscaled
  * coordinates, x,y [n_cam*6] host buffers. Runs the implicit-Schur kernels. */
 int ba_gpu_schur_matvec(ba_gpu_ctx *ctx, double radius, const double *x, double *y);
+/* y = (S + D^2)^-1 rhs through the sparse Cholesky of the last upload (BA_SOLVER_SPARSE_SCHUR_CHOLESKY in force),
+ * same conventions as ba_gpu_schur_matvec: ba_gpu_schur_matvec(radius, ba_gpu_schur_solve(radius, b)) == b */
+int ba_gpu_schur_solve(ba_gpu_ctx *ctx, double radius, const double *rhs, double *y);
+/* structure of the sparse Cholesky of the last upload (zeros when another solver is in force): info[0..10] as
+ * ba_sparse_symbolic_info, info[11] = host microseconds of the symbolic phase */
+int ba_gpu_spchol_info(const ba_gpu_ctx *ctx, int64_t info[24]);
 /* out7[i] = pose7[i] * exp(delta6[i]) on the device (Sophus semantics) */
 int ba_gpu_se3_plus(ba_gpu_ctx *ctx, int32_t n, const double *pose7,
                     const double *delta6, double *out7);
@@ -218,6 +230,20 @@ int ba_gpu_jacobian_store_used(const ba_gpu_ctx *ctx);
 /* block-sparse Schur structure of the last upload (zeros for the other solvers): same-point
  * observation pairs, stored upper blocks, row entries (each off-diagonal block appears twice) */
 int ba_gpu_sparse_stats(const ba_gpu_ctx *ctx, int64_t *n_pairs, int32_t *n_blocks, int32_t *n_entries);
+
+/* ---- symbolic phase of the sparse Cholesky of S (host only, no device needed; CPU tests drive it) ----
+ * n_blk stored upper blocks (blk_i <= blk_j) of the reduced camera matrix; nested-dissection ordering of the camera
+ * sequence, elimination tree, supernodes whose front panel fits cap_blocks 6x6 blocks, levels, extend-add maps
+ * (csrc/ba_sparse_symbolic.h).  info[0..10] = n_cam, nodes, levels, panel blocks, update blocks, largest front (blocks),
+ * largest own / border count, most children, flops, critical-path block operations; info[12 + w] = length of array w.
+ * Arrays (int32): 0 perm, 1 pos, 2 node records (16 ints), 3 border lists, 4 children, 5 rel, 6 inv, 7 entries of S
+ * (4 ints), 8 level_ptr, 9 level_nodes.  BA_ERR_UNSUPPORTED when a front cannot fit. */
+typedef struct ba_spsym ba_spsym;
+int ba_sparse_symbolic_create(int32_t n_cam, int32_t n_blk, const int32_t *blk_i, const int32_t *blk_j, int32_t leaf_cams,
+                              int32_t cap_blocks, int32_t max_own, ba_spsym **out);
+int ba_sparse_symbolic_info(const ba_spsym *h, int64_t info[24]);
+int ba_sparse_symbolic_get(const ba_spsym *h, int32_t which, int32_t *dst);
+void ba_sparse_symbolic_destroy(ba_spsym *h);
 
 /* ---- multi-GPU: one process per GPU, points sharded ---- */
 /* rank 0 makes the id (128 bytes), the launcher broadcasts it, every rank

@@ -24,7 +24,8 @@ def mode_opts(mode, **kw):
     for key, v in kw.items():
         if key == "solver":
             g["solver"] = v
-            o["solver"] = 0 if v in (0, 1) else 1
+            # oracle: 0 dense Schur (exact), 1 implicit PCG, 2 SPARSE_SCHUR-equivalent envelope Cholesky (exact)
+            o["solver"] = 0 if v in (0, 1) else (2 if v == 4 else 1)
         elif key == "jacobian_store":
             g[key] = v
         elif key == "max_num_iterations":

@@ -24,6 +24,10 @@ def _problem(name):
         return syn.make_config(3, scale=0.02)
     if name == "cfg4_small":
         return syn.make_config(4, scale=0.02)
+    if name == "cfg4_tenth":
+        return syn.make_config(4, scale=0.1)
+    if name == "cfg3_tenth":
+        return syn.make_config(3, scale=0.1)
     if name == "window20":
         seq = syn.make_tum_sequence(40, 4000, 24000, seed=5)
         return syn.window_problem(seq, 10, 29).problem
@@ -377,6 +381,89 @@ def test_sparse_schur_rejected_outside_ns(solver_cache):
     with pytest.raises(ba_b200.BAError) as e:
         s.upload(p)
     assert e.value.code == ba_b200.capi.BA_ERR_UNSUPPORTED
+
+
+# ---------------------------------------------------------------- exact sparse Cholesky of the block-sparse S
+@pytest.mark.parametrize("name", ["cfg1", "cfg3_small", "cfg4_small", "cfg4_tenth", "cfg3_tenth"])
+def test_spchol_solve_inverts_the_product(name, solver_cache):
+    """(S + D^2)^-1 through the supernodal multifrontal Cholesky, checked against the block-CSR product of the same
+    matrix (itself checked against the oracle above) and against a dense solve assembled from products with unit vectors."""
+    p = _problem(name)
+    g, _ = mode_opts("NS", solver=4)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    info = s.spchol_info()
+    assert info["nodes"] >= 1 and info["n_cam"] == p.n_cam
+    rng = np.random.default_rng(11)
+    for radius in (1e4, 3.7):
+        b = rng.normal(size=6 * p.n_cam)
+        y = s.schur_solve(radius, b)
+        back = s.schur_matvec(radius, y)
+        assert rel_err(back, b) < 1e-9, (name, radius)
+    if p.n_cam <= 40:
+        n = 6 * p.n_cam
+        A = np.stack([s.schur_matvec(1e4, np.eye(n)[k]) for k in range(n)], axis=1)
+        b = rng.normal(size=n)
+        y = s.schur_solve(1e4, b)
+        yref = np.linalg.solve(A, b)
+        assert rel_err(y, yref) < 1e-9
+
+
+@pytest.mark.parametrize("name,iters", [("cfg1", 8), ("cfg3_small", 8), ("cfg4_small", 8), ("cfg4_tenth", 6), ("cfg3_tenth", 6)])
+def test_solve_spchol_lockstep(name, iters, solver_cache):
+    """Exact step by the sparse Cholesky against the oracle's SPARSE_SCHUR-equivalent (envelope Cholesky): lock step,
+    cost 1e-8, poses 1e-6 -- also on the BAL-shaped loop where the inexact PCG step only reaches 1e-5."""
+    summ, osum = _compare_solve(_problem(name), "NS", 4, iters, solver_cache)
+    assert summ.solver_used == ba_b200.capi.BA_SOLVER_SPARSE_SCHUR_CHOLESKY
+    assert summ.total_linear_iters == 0
+    assert summ.final_cost < 0.5 * summ.initial_cost
+
+
+def test_spchol_fixed_camera_anywhere(solver_cache):
+    p = _problem("cfg3_small")
+    for fixed in (5, -1, p.n_cam - 1):
+        q = p.copy()
+        q.fixed_cam = fixed
+        _compare_solve(q, "NS", 4, 4, solver_cache)
+
+
+def test_auto_picks_sparse_cholesky_on_sequential_data(solver_cache):
+    p = _problem("cfg4_tenth")
+    g, _ = mode_opts("NS", solver=0, max_num_iterations=3)
+    s = _solver(solver_cache, **g)
+    s.upload(p)
+    summ = s.solve()
+    assert summ.solver_used == ba_b200.capi.BA_SOLVER_SPARSE_SCHUR_CHOLESKY and s.spchol_info()["levels"] >= 3
+
+
+def test_spchol_small_leaves_same_result(monkeypatch, solver_cache):
+    """Another dissection (leaves of 6 cameras: deeper tree, more extend-add) solves the same system."""
+    p = _problem("cfg4_tenth")
+    g, _ = mode_opts("NS", solver=4, max_num_iterations=4)
+    out = []
+    for leaf in (None, "6"):
+        if leaf:
+            monkeypatch.setenv("BA_SPCHOL_LEAF", leaf)
+        s = ba_b200.GpuSolver(**g)
+        s.upload(p)
+        summ = s.solve()
+        out.append((summ.final_cost, s.download()[0], s.spchol_info()["levels"]))
+        s.close()
+    assert out[1][2] > out[0][2]
+    assert abs(out[0][0] - out[1][0]) <= 1e-10 * out[0][0]
+    assert pose_err(out[0][1], out[1][1])[0] < 1e-8
+
+
+def test_spchol_repeated_solves_are_deterministic(solver_cache):
+    p = _problem("cfg4_tenth")
+    g, _ = mode_opts("NS", solver=4, max_num_iterations=4)
+    s = _solver(solver_cache, **g)
+    out = []
+    for _ in range(2):
+        s.upload(p)
+        summ = s.solve()
+        out.append((summ.final_cost, s.download()[0].copy()))
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
 
 
 def test_explicit_and_implicit_agree(solver_cache):

@@ -1,0 +1,93 @@
+"""Symbolic phase of the sparse Cholesky of S (host code of libba_gpu.so, no GPU needed) + a numpy emulation of the
+numeric phase that consumes the same structures: the supernodal multifrontal solve must equal a dense solve."""
+import numpy as np
+import pytest
+
+from helpers import ba_b200
+from spchol_emulation import K0, M, NB, PARENT, Symbolic, covisibility_blocks, factor_solve
+
+syn = ba_b200.synthetic
+
+
+def _random_spd(n_cam, bi, bj, rng):
+    """Block matrix with the given upper pattern, made diagonally dominant."""
+    A = np.zeros((n_cam * 6, n_cam * 6))
+    blocks = np.zeros((len(bi), 6, 6))
+    for b, (i, j) in enumerate(zip(bi, bj)):
+        B = rng.normal(size=(6, 6))
+        if i == j:
+            B = B + B.T
+        blocks[b] = B
+        A[6 * i:6 * i + 6, 6 * j:6 * j + 6] = B
+        A[6 * j:6 * j + 6, 6 * i:6 * i + 6] = B.T
+    shift = np.abs(A).sum(axis=1).max() + 1.0
+    dsq = np.full((n_cam, 6), shift)
+    return A + shift * np.eye(6 * n_cam), blocks, dsq
+
+
+def _check(n_cam, bi, bj, seed, **kw):
+    rng = np.random.default_rng(seed)
+    sym = Symbolic(n_cam, bi, bj, **kw)
+    # structure invariants
+    assert sorted(sym.perm.tolist()) == list(range(n_cam))
+    assert int(sym.node[:, M].sum()) == n_cam
+    for id_, N in enumerate(sym.node):
+        assert (N[M] + N[NB]) * N[M] <= kw.get("cap", 760)
+        if N[PARENT] >= 0:
+            assert N[PARENT] > id_ and sym.node[N[PARENT]][5] > N[5]
+    A, blocks, dsq = _random_spd(n_cam, bi, bj, rng)
+    b = rng.normal(size=(n_cam, 6))
+    y = factor_solve(sym, blocks, dsq, b)
+    yref = np.linalg.solve(A, b.reshape(-1)).reshape(-1, 6)
+    assert np.max(np.abs(y - yref)) <= 1e-9 * np.max(np.abs(yref))
+    return sym
+
+
+@pytest.mark.parametrize("cfg,scale,leaf", [(3, 0.05, 8), (4, 0.05, 8), (4, 0.1, 16), (3, 0.1, 12)])
+def test_banded_covisibility(cfg, scale, leaf):
+    p = syn.make_config(cfg, scale=scale)
+    bi, bj = covisibility_blocks(p.cam_idx, p.pt_idx, p.n_cam, p.fixed_cam)
+    sym = _check(p.n_cam, bi, bj, 3, leaf=leaf, cap=300)
+    assert sym.n_levels >= 3  # the dissection really branches
+
+
+def test_small_capacity_splits_supernodes():
+    p = syn.make_config(4, scale=0.05)
+    bi, bj = covisibility_blocks(p.cam_idx, p.pt_idx, p.n_cam, p.fixed_cam)
+    a = _check(p.n_cam, bi, bj, 4, leaf=16, cap=760)
+    b = _check(p.n_cam, bi, bj, 4, leaf=16, cap=120, max_own=4)
+    assert b.n_nodes > a.n_nodes
+
+
+def test_loop_closure_and_disconnected_parts():
+    """Not a band: a loop closure (first cameras see the last ones), an isolated camera, and two unconnected halves."""
+    rng = np.random.default_rng(5)
+    n = 60
+    pairs = set((i, i) for i in range(n) if i != 17)          # camera 17 has no diagonal block (damping only)
+    for i in range(n):
+        for d in (1, 2, 3):
+            if i + d < n and i != 17 and i + d != 17 and not (i < 30 <= i + d):
+                pairs.add((i, i + d))
+    pairs.add((0, 29)); pairs.add((1, 28)); pairs.add((31, 59))
+    pairs = sorted(pairs)
+    bi = np.array([a for a, _ in pairs], dtype=np.int32)
+    bj = np.array([b for _, b in pairs], dtype=np.int32)
+    _check(n, bi, bj, 6, leaf=6, cap=760)
+
+
+def test_dense_window_is_one_chain():
+    n = 7
+    pairs = [(i, j) for i in range(n) for j in range(i, n)]
+    bi = np.array([a for a, _ in pairs], dtype=np.int32)
+    bj = np.array([b for _, b in pairs], dtype=np.int32)
+    sym = _check(n, bi, bj, 7, leaf=32, cap=760)
+    assert sym.n_nodes == 1 and sym.node[0][M] == 7 and sym.node[0][NB] == 0
+
+
+def test_unsupported_when_a_front_cannot_fit():
+    n = 40
+    pairs = [(i, j) for i in range(n) for j in range(i, n)]
+    bi = np.array([a for a, _ in pairs], dtype=np.int32)
+    bj = np.array([b for _, b in pairs], dtype=np.int32)
+    with pytest.raises(RuntimeError):
+        Symbolic(n, bi, bj, leaf=4, cap=20, max_own=64)
