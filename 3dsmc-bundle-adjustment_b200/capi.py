@@ -67,7 +67,7 @@ EXPORTS = [
     "ba_gpu_upload", "ba_gpu_solve", "ba_gpu_get_trace", "ba_gpu_download", "ba_gpu_eval", "ba_gpu_get_indices",
     "ba_gpu_schur_matvec", "ba_gpu_se3_plus", "ba_gpu_time_kernel", "ba_gpu_launch_count", "ba_gpu_comm_unique_id",
     "ba_gpu_comm_init", "ba_gpu_jacobian_store_used", "ba_gpu_sparse_stats", "ba_gpu_backproject",
-    "ba_gpu_schur_solve", "ba_gpu_spchol_info",
+    "ba_gpu_schur_solve", "ba_gpu_spchol_info", "ba_gpu_phase_times", "ba_gpu_phase_name",
     "ba_sparse_symbolic_create", "ba_sparse_symbolic_info", "ba_sparse_symbolic_get", "ba_sparse_symbolic_destroy",
 ]
 
@@ -110,6 +110,9 @@ def load():
     L.ba_gpu_sparse_stats.argtypes = [vp, C.POINTER(C.c_int64), c_int32_p, c_int32_p]
     L.ba_gpu_comm_unique_id.argtypes = [C.c_char_p]
     L.ba_gpu_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
+    L.ba_gpu_phase_times.argtypes = [vp, c_double_p]
+    L.ba_gpu_phase_name.argtypes = [C.c_int32]
+    L.ba_gpu_phase_name.restype = C.c_char_p
     L.ba_gpu_schur_solve.argtypes = [vp, C.c_double, c_double_p, c_double_p]
     L.ba_gpu_spchol_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.ba_sparse_symbolic_create.argtypes = [C.c_int32, C.c_int32, c_int32_p, c_int32_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -119,7 +122,7 @@ def load():
     L.ba_sparse_symbolic_destroy.restype = None
     for name in EXPORTS:
         if name not in ("ba_gpu_destroy", "ba_gpu_default_options", "ba_gpu_last_error", "ba_gpu_launch_count",
-                        "ba_sparse_symbolic_destroy"):
+                        "ba_sparse_symbolic_destroy", "ba_gpu_phase_name"):
             getattr(L, name).restype = C.c_int
     _LIB = L
     return L

@@ -155,6 +155,13 @@ struct ba_gpu_ctx {
   Buf spc_panel, spc_U, spc_ru, spc_z, spc_linv, spc_ypos;
   size_t spc_smem_factor = 0, spc_smem_solve = 0;
   double sym_ms = 0.0;          // host time of the symbolic phase (last upload)
+  // phase timing of the large-problem solvers: CUDA events on the solver stream at the phase boundaries of every LM
+  // iteration of the last solve (a few dozen event records per iteration: < 0.1 % of a multi-millisecond iteration)
+  std::vector<cudaEvent_t> ph_ev;
+  std::vector<int> ph_id;
+  int ph_n = 0;
+  bool ph_on = false;
+  double ph_ms[BA_PHASE_COUNT] = {0};
   Buf p2, pcg_bar, wb_rho, wb_Q, bp_buf, err_flag_bp, row_keys, row_keys2, row_ids, row_order;
   // scaling / diag / gradient / blocks
   Buf sc, sp, sk, dc, dp, dk, gc, gp, gk, U, Uck, Ukk, V, Vinv, Wk, tg, t, yc, yp, yk, rk, Jkk;
@@ -437,6 +444,7 @@ extern "C" void ba_gpu_destroy(ba_gpu_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream3);
     cudaStreamDestroy(ctx->stream3);
   }
+  for (cudaEvent_t e : ctx->ph_ev) cudaEventDestroy(e);
   if (ctx->ev_panel) cudaEventDestroy(ctx->ev_panel);
   if (ctx->ev_trsm) cudaEventDestroy(ctx->ev_trsm);
   for (int i = 0; i < 2; ++i) {
@@ -1438,6 +1446,31 @@ static void join(ba_gpu_ctx *ctx) {
   cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
 }
 
+// ------------------------------------------------------------------ phase timing (large-problem solvers)
+static const char *const g_phase_names[BA_PHASE_COUNT] = {
+    "start", "iteration_zero", "point_inverse", "reduced_rhs", "schur_complement", "linear_solve_factor_or_pcg",
+    "linear_solve_substitution", "back_substitution_model_cost", "candidate_cost", "lm_control", "accept_relinearize"};
+static void phase_mark(ba_gpu_ctx *ctx, int id) {
+  if (!ctx->ph_on) return;
+  if (ctx->ph_n >= (int)ctx->ph_ev.size()) {
+    if (ctx->ph_ev.size() >= 8192) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    ctx->ph_ev.push_back(e);
+    ctx->ph_id.push_back(0);
+  }
+  ctx->ph_id[ctx->ph_n] = id;
+  cudaEventRecord(ctx->ph_ev[ctx->ph_n], ctx->stream);
+  ctx->ph_n++;
+}
+static void phase_collect(ba_gpu_ctx *ctx) {
+  for (int k = 0; k < BA_PHASE_COUNT; ++k) ctx->ph_ms[k] = 0.0;
+  for (int i = 1; i < ctx->ph_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ph_ev[i - 1], ctx->ph_ev[i]) == cudaSuccess) ctx->ph_ms[ctx->ph_id[i]] += ms;
+  }
+}
+
 // ------------------------------------------------------------------ pipeline pieces
 // linearise at the current point in both orders + normal-equation blocks
 static void enqueue_linearize(ba_gpu_ctx *ctx, int gate, const double *sc, const double *sp, const double *sk,
@@ -1661,6 +1694,7 @@ static void enqueue_spchol(ba_gpu_ctx *ctx, int gate) {
   const SpChol a = spchol_args(ctx);
   for (int l = 0; l < S.n_levels; ++l)
     LAUNCH(k_spchol_factor, S.level_ptr[l + 1] - S.level_ptr[l], SPC_THREADS, ctx->spc_smem_factor, a, S.level_ptr[l], st, gate);
+  phase_mark(ctx, BA_PHASE_FACTOR);
   for (int l = S.n_levels - 1; l >= 0; --l)
     LAUNCH(k_spchol_solve, S.level_ptr[l + 1] - S.level_ptr[l], SPC_THREADS, ctx->spc_smem_solve, a, S.level_ptr[l], st, gate);
 }
@@ -1714,8 +1748,10 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
     LAUNCH((k_schur_diag<DD>), ctx->nblk_item, BA_THREADS, 0, ctx->n_items, P<BaItem>(ctx->items), P<int32_t>(ctx->pt_idx), ctx->Jc_,
            P<double>(ctx->Vinv), P<double>(ctx->part21), st, GATE_RUN);
   });
+  phase_mark(ctx, BA_PHASE_RHS);
   enqueue_sparse_values(ctx, GATE_RUN);
   sync_flags(ctx);
+  phase_mark(ctx, BA_PHASE_SCHUR);
   if (ctx->spchol) {
     // exact step: b and the damping, then the factorisation and the two substitutions (yc written by the last kernels)
     ItemRef i6c = reduce_items<6>(ctx, P<double>(ctx->part6), ctx->red6, GATE_RUN);
@@ -1974,8 +2010,10 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
   LmState *st = P<LmState>(ctx->st);
   const int D = ctx->depth, K = ctx->nk;
   if (ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY) enqueue_point_inverse(ctx, GATE_RUN);  // (explicit: inside solve_explicit)
+  phase_mark(ctx, BA_PHASE_POINT_INVERSE);
   int rc = ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY ? solve_implicit(ctx) : solve_explicit(ctx);
   if (rc) return rc;
+  phase_mark(ctx, BA_PHASE_SUBSTITUTION);
   if (ctx->fact) {
     const double *intr = P<double>(ctx->intr);
     LAUNCH(k_pack_camx, ctx->nblk_cam, BA_THREADS, 0, ctx->n_cam, P<double>(ctx->yc), P<double>(ctx->geo), P<double>(ctx->camx), st,
@@ -1997,6 +2035,7 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
            ctx->Jc_, P<double>(ctx->yc), P<double>(ctx->yp), P<double>(ctx->yk), P<double>(ctx->pc_mcc), st, GATE_RUN);
     fork_main(ctx);
   });
+  if (!ctx->forking) phase_mark(ctx, BA_PHASE_BACKSUB);
   LAUNCH(k_candidate, ctx->nblk_ent, BA_THREADS, 0, ctx->n_cam, ctx->n_pt, K, ctx->fixed_cam, P<double>(ctx->pose), P<double>(ctx->pt),
          P<double>(ctx->intr), P<double>(ctx->yc), P<double>(ctx->yp), P<double>(ctx->yk), P<double>(ctx->sc), P<double>(ctx->sp),
          P<double>(ctx->sk), P<double>(ctx->pose_c), P<double>(ctx->pt_c), P<double>(ctx->intr_c), P<double>(ctx->pe_step), st,
@@ -2007,6 +2046,7 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
            ctx->cp, P<double>(ctx->pc_cand), st, GATE_RUN);
   });
   join(ctx);
+  phase_mark(ctx, ctx->forking ? BA_PHASE_BACKSUB : BA_PHASE_CANDIDATE);
   sync_flags(ctx);
   {
     const PartRef rm = reduce_scalar(ctx, P<double>(ctx->pc_mcc), ctx->nblk_obs, 3, false, GATE_RUN);
@@ -2016,6 +2056,7 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
            P<double>(ctx->yk), P<double>(ctx->intr_c), P<double>(ctx->intr_prior), ctx->cp.sw_intr, ctx->lo, st,
            P<BaIterRec>(ctx->trace));
   }
+  phase_mark(ctx, BA_PHASE_CONTROL);
   // accepted: x <- x+, relinearise (all gated on the device-side decision)
   const bool overlap_accept = ctx->forking && !ctx->fact;  // windowed explicit path
   if (overlap_accept) fork_side(ctx);
@@ -2033,6 +2074,7 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
     LAUNCH(k_lm_post, 1, BA_THREADS, 0, rc3.n, rg.n, K, rc3.p, rg.p, rx.p, P<double>(ctx->rk), ctx->lo, st,
            P<BaIterRec>(ctx->trace), GATE_ACCEPTED);
   }
+  phase_mark(ctx, BA_PHASE_RELINEARIZE);
   return 0;
 }
 
@@ -2048,7 +2090,11 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   const bool pdl = !ctx->pdl_off && ctx->solver == BA_SOLVER_EXPLICIT_CHOLESKY && ctx->n_ranks == 1 && ctx->n_red > 0 &&
                    ctx->n_red <= BA_LDLT_MAX_N;
   ctx->pdl = pdl;
+  ctx->ph_on = ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY && getenv("BA_NO_PHASE_TIMES") == nullptr;
+  ctx->ph_n = 0;
+  phase_mark(ctx, BA_PHASE_START);
   enqueue_iteration_zero(ctx);
+  phase_mark(ctx, BA_PHASE_ITER0);
   ctx->pdl = false;
   const int poll = std::max(1, ctx->opt.poll_interval);
   int rc = 0;
@@ -2109,6 +2155,8 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   CK(cudaGetLastError());
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  phase_collect(ctx);
+  ctx->ph_on = false;
   const LmState &h = *ctx->h_st;
   ba_gpu_summary s;
   memset(&s, 0, sizeof(s));
@@ -2144,6 +2192,13 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
     return fail(ctx, BA_ERR_NUMERIC, "non-finite cost or Jacobian at the initial point");
   return BA_OK;
 }
+
+extern "C" int ba_gpu_phase_times(const ba_gpu_ctx *ctx, double ms[BA_PHASE_COUNT]) {
+  if (!ctx || !ms) return BA_ERR_INVALID;
+  for (int k = 0; k < BA_PHASE_COUNT; ++k) ms[k] = ctx->ph_ms[k];
+  return BA_OK;
+}
+extern "C" const char *ba_gpu_phase_name(int32_t phase) { return phase >= 0 && phase < BA_PHASE_COUNT ? g_phase_names[phase] : ""; }
 
 extern "C" int ba_gpu_get_trace(ba_gpu_ctx *ctx, ba_gpu_iter *out, int32_t cap) {
   if (!ctx || (!out && cap > 0)) return BA_ERR_INVALID;

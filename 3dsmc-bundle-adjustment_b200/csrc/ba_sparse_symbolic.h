@@ -122,7 +122,7 @@ inline void nd_order(const Graph &g, int lo, int hi, int leaf, std::vector<int32
 }  // namespace spsym
 
 // n_cam cameras; n_blk stored upper blocks (bi <= bj) of S, any order; leaf = cameras per dissection leaf;
-// cap_blocks = 6x6 blocks of shared memory one front panel may take; max_own = cameras per supernode at most
+// cap_blocks = 6x6 blocks of shared memory one front may take: (own + border) x (own + 1); max_own = cameras per supernode at most
 inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int32_t *bj, int leaf, int cap_blocks, int max_own) {
   SpSymbolic S;
   S.n_cam = n_cam;
@@ -172,7 +172,8 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
     }
   }
   // ---- 3. supernodes
-  auto fits = [&](int m, int nb) { return (long long)(m + nb) * m <= (long long)cap_blocks && m <= max_own; };
+  // shared memory of a front: the panel (m + nb) x m blocks plus one more block column (the pivot column kept row-major)
+  auto fits = [&](int m, int nb) { return (long long)(m + nb) * (m + 1) <= (long long)cap_blocks && m <= max_own; };
   std::vector<int32_t> node_of(n, -1);
   std::vector<int32_t> k0s, ms;
   for (int k = 0; k < n;) {
@@ -220,7 +221,7 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
     N[SPN_U_HI] = (int32_t)(S.u_blocks >> 31);
     S.panel_blocks += (int64_t)(ms[id] + (int)b.size()) * ms[id];
     S.u_blocks += (int64_t)b.size() * (int64_t)b.size();
-    S.max_front_blocks = std::max(S.max_front_blocks, (ms[id] + (int)b.size()) * ms[id]);
+    S.max_front_blocks = std::max(S.max_front_blocks, (ms[id] + (int)b.size()) * (ms[id] + 1));
     S.max_m = std::max(S.max_m, ms[id]);
     S.max_nb = std::max(S.max_nb, (int)b.size());
   }

@@ -167,6 +167,13 @@ class GpuSolver:
                 "max_children", "flops", "critical_path_block_ops", "symbolic_us"]
         return {k: int(info[i]) for i, k in enumerate(keys)}
 
+    def phase_times(self):
+        """{phase name: ms} of the last solve (CUDA events recorded while it ran); empty for the windowed solver."""
+        ms = np.zeros(11)
+        self._check(self.lib.ba_gpu_phase_times(self._ctx, capi.dp(ms)))
+        out = {self.lib.ba_gpu_phase_name(k).decode(): float(ms[k]) for k in range(1, 11)}
+        return out if sum(out.values()) > 0 else {}
+
     def se3_plus(self, pose7, delta6):
         pose7 = capi.f64(pose7).reshape(-1, 7)
         delta6 = capi.f64(delta6).reshape(-1, 6)

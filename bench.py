@@ -339,6 +339,8 @@ def main():
     wall_solve = time.time() - t0
     solve_ms = maxr(summ.solve_ms)
     trace = s.trace()
+    phase_ms = s.phase_times()
+    spchol = s.spchol_info()
     n_iter = summ.num_iterations
     pcg_counts = [t["linear_iters"] for t in trace[1:]]
     # ---- end to end through the C-ABI with host buffers: upload + solve + download
@@ -432,6 +434,8 @@ def main():
                      "timing": "CUDA events on the solver stream, mean of 20 launches after 3 warm-ups",
                      "bytes": kernels[dom]["bytes"]},
         "roofline_kernels": kernels,
+        "phase_ms_per_step": {k: v / max(n_iter, 1) for k, v in phase_ms.items()},
+        "sparse_cholesky": spchol,
         "clocks": clk,
     }
     if args.workload == "cfg2" and world == 1:

@@ -223,6 +223,17 @@ enum {
  * each launch is timed by its own event pair. */
 int ba_gpu_time_kernel(ba_gpu_ctx *ctx, int32_t which, int32_t warmup,
                        int32_t iters, int32_t flush_l2, float *ms_avg);
+/* Where the time of the last ba_gpu_solve went (large-problem solvers: implicit / block-sparse): milliseconds per
+ * phase, summed over the LM iterations, from CUDA events recorded on the solver stream at the phase boundaries
+ * while the solve ran (not a separate profiling run).  All zero for the windowed explicit solver (graph replay). */
+enum {
+  BA_PHASE_START = 0, BA_PHASE_ITER0 = 1, BA_PHASE_POINT_INVERSE = 2, BA_PHASE_RHS = 3, BA_PHASE_SCHUR = 4,
+  BA_PHASE_FACTOR = 5,        /* sparse Cholesky: factorisation (forward substitution fused); PCG solvers: the whole PCG */
+  BA_PHASE_SUBSTITUTION = 6,  /* sparse Cholesky: backward substitution */
+  BA_PHASE_BACKSUB = 7, BA_PHASE_CANDIDATE = 8, BA_PHASE_CONTROL = 9, BA_PHASE_RELINEARIZE = 10, BA_PHASE_COUNT = 11
+};
+int ba_gpu_phase_times(const ba_gpu_ctx *ctx, double ms[BA_PHASE_COUNT]);
+const char *ba_gpu_phase_name(int32_t phase);
 /* kernels launched by this context since creation */
 int64_t ba_gpu_launch_count(const ba_gpu_ctx *ctx);
 /* BA_JAC_* in force after the last upload (what BA_JAC_AUTO resolved to) */

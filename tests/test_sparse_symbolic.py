@@ -32,7 +32,7 @@ def _check(n_cam, bi, bj, seed, **kw):
     assert sorted(sym.perm.tolist()) == list(range(n_cam))
     assert int(sym.node[:, M].sum()) == n_cam
     for id_, N in enumerate(sym.node):
-        assert (N[M] + N[NB]) * N[M] <= kw.get("cap", 760)
+        assert (N[M] + N[NB]) * (N[M] + 1) <= kw.get("cap", 760)
         if N[PARENT] >= 0:
             assert N[PARENT] > id_ and sym.node[N[PARENT]][5] > N[5]
     A, blocks, dsq = _random_spd(n_cam, bi, bj, rng)
