@@ -136,42 +136,51 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_sample(problem, mode, pcg_counts, threads, budget_s=25.0):
-    """Times the CPU oracle (the Ceres-equivalent restatement, all host cores) on
-    a bounded sample of the same problem: ONE LM iteration whose PCG is capped so
-    the sample stays within ~budget_s, then prices the full K-iteration solve
-    with the GPU run's own PCG iteration counts:
-        t_cpu = (K + 2) * t_linearize + sum_it n_pcg(it) * t_pcg_iteration
-    """
+def oracle_problem(problem):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ora
-    op = ora.Problem(problem.pose7, problem.pt3, problem.cam_idx, problem.pt_idx, problem.uv2, problem.depth, problem.intr,
-                     problem.intr_prior, problem.fixed_cam)
-    implicit = mode == (0, 0) and 6 * problem.n_cam > 160
-    # calibrate the cap from the problem size (~60 ns per observation and PCG iteration and core)
-    cap = 500
-    if implicit:
-        est_iter = max(1e-4, problem.n_obs * 150e-9 / max(1, threads) * 2.0)
-        cap = int(max(4, min(500, budget_s / est_iter)))
-    o = ora.default_options(use_depth_prior=mode[0], optimize_intrinsics=mode[1], solver=1 if implicit else 0,
-                            num_threads=threads, max_num_iterations=1, max_pcg_iterations=cap)
+    return ora, ora.Problem(problem.pose7, problem.pt3, problem.cam_idx, problem.pt_idx, problem.uv2, problem.depth, problem.intr,
+                            problem.intr_prior, problem.fixed_cam)
+
+
+def cpu_reference_run(problem, mode, iters, threads, warmup=0):
+    """RUNS the CPU oracle (oracle/ba_oracle.c: the restatement of the reference's cost functors + Ceres 2.0.0 LM) on the
+    same problem for `iters` LM iterations with the reference's own linear solver setting -- SPARSE_SCHUR
+    (headers/BundleAdjustmentConfig.h:62): explicit reduced camera matrix in envelope storage + sparse Cholesky, exact
+    step -- on `threads` OpenMP threads, tolerances disabled.  Nothing is extrapolated: value = iterations / wall seconds
+    of that solve.  `warmup` > 0 runs that many iterations on a copy first (untimed)."""
+    ora, op = oracle_problem(problem)
+    kw = dict(use_depth_prior=mode[0], optimize_intrinsics=mode[1], solver=2, num_threads=threads, function_tolerance=0.0,
+              parameter_tolerance=0.0, gradient_tolerance=0.0)
+    if warmup > 0:
+        ora.solve(op.copy(), ora.default_options(max_num_iterations=warmup, **kw))
     t0 = time.time()
-    rc, s, tr = ora.solve(op, o)
+    rc, s, tr = ora.solve(op, ora.default_options(max_num_iterations=iters, **kw), trace_cap=iters + 8)
     wall = time.time() - t0
-    n_pcg = max(1, int(s.total_linear_iters))
-    t_lin = s.seconds_linearize / 2.0  # iteration zero + the accepted step's relinearisation (or candidate cost)
-    if implicit:
-        t_pcg = s.seconds_linear_solve / n_pcg
-        total = (len(pcg_counts) + 2) * t_lin + float(np.sum(pcg_counts)) * t_pcg
-    else:
-        t_pcg = s.seconds_linear_solve
-        total = (len(pcg_counts) + 2) * t_lin + len(pcg_counts) * t_pcg
-    return {"value": len(pcg_counts) / total, "unit": "LM iterations/s", "cores": threads, "kind": "port",
-            "sample": "oracle (C restatement of Ceres 2.0.0 LM + %s, OpenMP %d threads) timed on 1 LM iteration of the same problem "
-                      "(PCG capped at %d its, %.1f s wall); priced for the K-iteration solve with the GPU run's PCG counts: "
-                      "t_linearize=%.4fs, t_%s=%.5fs" % ("implicit-Schur PCG" if implicit else "dense Schur", threads, cap, wall,
-                                                         t_lin, "pcg_iter" if implicit else "schur_solve", t_pcg),
-            "t_linearize_s": t_lin, "t_linear_unit_s": t_pcg, "jacobian_obs_per_s": problem.n_obs / max(t_lin, 1e-12)}
+    n = max(1, int(s.num_iterations))
+    return {"value": n / wall, "unit": "LM iterations/s", "cores": threads, "kind": "port",
+            "sample": "oracle/ba_oracle.c (C restatement of the reference's cost functors and of Ceres 2.0.0's trust-region loop; "
+                      "linear solver = the reference's SPARSE_SCHUR setting: explicit S in envelope storage + sparse Cholesky, exact "
+                      "step), OpenMP %d threads, %d LM iterations of the SAME problem actually run in %.2f s wall (nothing "
+                      "extrapolated); Ceres itself cannot be built in this image" % (threads, n, wall),
+            "lm_iterations": n, "seconds": wall, "seconds_linearize": s.seconds_linearize, "seconds_linear_solve": s.seconds_linear_solve,
+            "final_cost": s.final_cost, "rc": rc,
+            "jacobian_obs_per_s": problem.n_obs * (n + 1) / max(s.seconds_linearize, 1e-12)}
+
+
+def bench_config(args, wl, full, world, K):
+    """The workload description both arms print (identical for --impl b200 and --impl reference)."""
+    flush = full.n_obs * 36 < 512e6
+    return {"workload": args.workload + ": " + wl["desc"], "n_cam": int(full.n_cam), "n_pt": int(full.n_pt), "n_obs": int(full.n_obs),
+            "scale": args.scale,
+            "cost_model": {(0, 0): "NS: reprojection residuals, fixed intrinsics", (1, 1): "REF: reprojection + depth prior + free "
+                           "intrinsics with prior (the reference's cost)"}.get(tuple(wl["mode"]), str(wl["mode"])),
+            "step": "one Levenberg-Marquardt iteration of a fixed-iteration-count solve (tolerances disabled)", "lm_iterations": K,
+            "linear_solver_requested": args.solver if wl["mode"] == (0, 0) else "auto",
+            "parallelism": "single GPU" if world == 1 else "points and their observations sharded over %d GPUs, cameras replicated" % world,
+            "l2": ("streaming inputs larger than L2 (factored store %.0f MB per pass); L2-resident structures (block-sparse S, fronts "
+                   "of the sparse Cholesky) are timed as they run inside the solve" % (full.n_obs * 36 / 1e6)) if not flush
+                  else "L2 flushed (512 MiB write) between timed launches of the kernel hooks"}
 
 
 def kernel_rooflines(ba_b200, s, problem, wl, solver_used, flush, peak):

@@ -104,8 +104,8 @@ def test_single_camera_window():
 
 
 def test_auto_policy():
-    """AUTO: dense explicit for windows, block-sparse for large sequential NS problems, implicit when the
-    co-visibility is dense (pairs per observation above the threshold)."""
+    """AUTO: dense explicit for windows, block-sparse S factorised exactly for large sequential NS problems, implicit
+    when the co-visibility is dense (pairs per observation above the threshold)."""
     s = _solver()
     try:
         s.upload(syn.make_config(1))
@@ -117,7 +117,7 @@ def test_auto_policy():
     s = _solver(**g)
     try:
         s.upload(p)
-        assert s.solve().solver_used == cap.BA_SOLVER_SPARSE_SCHUR_PCG
+        assert s.solve().solver_used == cap.BA_SOLVER_SPARSE_SCHUR_CHOLESKY
         n_ent, n_blk = s.sparse_stats()
         assert n_blk > 0 and n_ent == 2 * n_blk - p.n_cam + (1 if p.fixed_cam >= 0 else 0)
     finally:

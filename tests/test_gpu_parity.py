@@ -447,9 +447,9 @@ def test_spchol_small_leaves_same_result(monkeypatch, solver_cache):
         s = ba_b200.GpuSolver(**g)
         s.upload(p)
         summ = s.solve()
-        out.append((summ.final_cost, s.download()[0], s.spchol_info()["levels"]))
+        out.append((summ.final_cost, s.download()[0], s.spchol_info()["nodes"]))
         s.close()
-    assert out[1][2] > out[0][2]
+    assert out[1][2] != out[0][2]   # really another tree
     assert abs(out[0][0] - out[1][0]) <= 1e-10 * out[0][0]
     assert pose_err(out[0][1], out[1][1])[0] < 1e-8
 
