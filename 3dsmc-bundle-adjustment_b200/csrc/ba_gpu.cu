@@ -153,7 +153,7 @@ struct ba_gpu_ctx {
   SpSymbolic sym;               // host-side structure of the last upload
   Buf spn_node, spn_bord, spn_children, spn_rel, spn_inv, spn_aent, spn_perm, spn_levels;
   Buf spc_panel, spc_U, spc_ru, spc_z, spc_linv, spc_ypos;
-  size_t spc_smem_factor = 0, spc_smem_solve = 0;
+  size_t spc_smem_factor = 0, spc_smem_solve = 0, spc_smem_update = 0;
   double sym_ms = 0.0;          // host time of the symbolic phase (last upload)
   // phase timing of the large-problem solvers: CUDA events on the solver stream at the phase boundaries of every LM
   // iteration of the last solve (a few dozen event records per iteration: < 0.1 % of a multi-millisecond iteration)
@@ -879,17 +879,21 @@ static int build_spchol(ba_gpu_ctx *ctx) {
   RES(spc_linv, ((size_t)n_cam + 1) * 288);
   RES(spc_ypos, ((size_t)n_cam + 1) * 48);
   RES(dsq, ((size_t)n_cam + 1) * 48);
-  size_t sf = 0, ss = 0;
+  size_t sf = 0, ss = 0, su = 0;
   for (int id = 0; id < S.n_nodes; ++id) {
     const int32_t *N = S.node.data() + (size_t)id * SPSYM_NODE_INTS;
     sf = std::max(sf, spc_factor_smem(N[SPN_M], N[SPN_NB]));
     ss = std::max(ss, spc_solve_smem(N[SPN_M], N[SPN_NB]));
+    su = std::max(su, spc_update_smem(N[SPN_M], N[SPN_NB]));
   }
-  if (sf > 227 * 1024 || ss > 227 * 1024) return fail(ctx, BA_ERR_STATE, "sparse Cholesky: front exceeds shared memory (%zu / %zu bytes)", sf, ss);
+  if (sf > 227 * 1024 || ss > 227 * 1024 || su > 227 * 1024)
+    return fail(ctx, BA_ERR_STATE, "sparse Cholesky: front exceeds shared memory (%zu / %zu / %zu bytes)", sf, ss, su);
   ctx->spc_smem_factor = sf;
   ctx->spc_smem_solve = ss;
+  ctx->spc_smem_update = su;
   CK(cudaFuncSetAttribute(k_spchol_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
   CK(cudaFuncSetAttribute(k_spchol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
+  CK(cudaFuncSetAttribute(k_spchol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)su));
   CK(cudaStreamSynchronize(s));  // host vectors of this call die here
   ctx->spchol = true;
   return 0;
@@ -1223,10 +1227,16 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   CK(cudaMemsetAsync(ctx->cam_cnt.p, 0, (nc + 1) * 4, s));
   CK(cudaMemsetAsync(ctx->cursor.p, 0, (np + 1) * 4, s));
   CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, s));
+  CK(cudaMemsetAsync(ctx->cam_rowptr.p, 0, (nc + 1) * 4, s));  // (no observations at all: every pointer is 0)
   LAUNCH(k_index_count, ctx->nblk_obs, BA_THREADS, 0, n_obs, n_cam, n_pt, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
-         P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->cam_cnt), P<int32_t>(ctx->err_flag));
-  LAUNCH(k_exclusive_scan, 1, 1024, 0, n_pt, P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->pt_rowptr));
-  LAUNCH(k_exclusive_scan, 1, 1024, 0, n_cam, P<int32_t>(ctx->cam_cnt), P<int32_t>(ctx->cam_rowptr));
+         P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->err_flag));
+  if (n_pt > 65536) {
+    // (pt_cnt has n_pt + 1 entries, the last one zero: the scan's last output is the total; library scan, setup only --
+    // the single-CTA scan below took 1.6 ms for 2 M points)
+    CUBCALL(cub::DeviceScan::ExclusiveSum, P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->pt_rowptr), n_pt + 1);
+  } else {
+    LAUNCH(k_exclusive_scan, 1, 1024, 0, n_pt, P<int32_t>(ctx->pt_cnt), P<int32_t>(ctx->pt_rowptr));
+  }
   LAUNCH(k_index_fill, ctx->nblk_obs, BA_THREADS, 0, n_obs, n_cam, n_pt, P<int32_t>(ctx->cam_idx), P<int32_t>(ctx->pt_idx),
          P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->cursor), P<int32_t>(ctx->perm));
   LAUNCH(k_index_sort, ctx->nblk_pt, BA_THREADS, 0, n_pt, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->perm));
@@ -1655,7 +1665,7 @@ static void enqueue_sparse_values(ba_gpu_ctx *ctx, int gate) {
   if (ctx->n_ranks > 1) cudaMemsetAsync(ctx->Sblk.p, 0, (size_t)ctx->n_sblk * 288, ctx->stream);
   int *ticket = reinterpret_cast<int *>(P<char>(ctx->pcg_bar) + 16);
   cudaMemsetAsync(ticket, 0, 4, ctx->stream);
-  LAUNCH(k_sp_schur, std::min(cdiv(ctx->n_sblk_local * 32, BA_THREADS), ctx->n_sm * ctx->sp_ctas_per_sm), BA_THREADS, 0,
+  LAUNCH(k_sp_schur, std::min(cdiv(ctx->n_sblk_local, BA_SPS_CHUNK), ctx->n_sm * ctx->sp_ctas_per_sm), BA_THREADS, 0,
          ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid),
          P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->sp_pair_pt), ctx->Fp_, P<double>(ctx->geo), P<double>(ctx->intr),
          P<double>(ctx->Vs), P<double>(ctx->Sblk), ticket, st, gate);
@@ -1692,11 +1702,22 @@ static void enqueue_spchol(ba_gpu_ctx *ctx, int gate) {
   LmState *st = P<LmState>(ctx->st);
   const SpSymbolic &S = ctx->sym;
   const SpChol a = spchol_args(ctx);
-  for (int l = 0; l < S.n_levels; ++l)
-    LAUNCH(k_spchol_factor, S.level_ptr[l + 1] - S.level_ptr[l], SPC_THREADS, ctx->spc_smem_factor, a, S.level_ptr[l], st, gate);
+  // every kernel of the chain starts with griddepcontrol.wait (gate_open): programmatic dependent launches let the blocks of
+  // the next launch become resident on idle SMs (the upper tree levels have few nodes) while the previous one still runs
+  const bool pdl0 = ctx->pdl;
+  ctx->pdl = !ctx->pdl_off;
+  for (int l = 0; l < S.n_levels; ++l) {
+    const int nodes = S.level_ptr[l + 1] - S.level_ptr[l];
+    LAUNCH(k_spchol_factor, nodes, SPC_THREADS, ctx->spc_smem_factor, a, S.level_ptr[l], st, gate);
+    if (l + 1 < S.n_levels) {  // (roots have no border)
+      const int tiles = std::max(1, std::min(8, ctx->n_sm / std::max(1, nodes)));
+      LAUNCH(k_spchol_update, nodes * tiles, SPU_THREADS, ctx->spc_smem_update, a, S.level_ptr[l], tiles, st, gate);
+    }
+  }
   phase_mark(ctx, BA_PHASE_FACTOR);
   for (int l = S.n_levels - 1; l >= 0; --l)
     LAUNCH(k_spchol_solve, S.level_ptr[l + 1] - S.level_ptr[l], SPC_THREADS, ctx->spc_smem_solve, a, S.level_ptr[l], st, gate);
+  ctx->pdl = pdl0;
 }
 
 static int poll_state(ba_gpu_ctx *ctx) {

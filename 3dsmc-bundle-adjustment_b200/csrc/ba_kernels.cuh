@@ -42,18 +42,25 @@ __device__ __forceinline__ bool gate_open(const LmState *st, int gate, int reset
 // Index construction (device-built, integer-exact)
 // =====================================================================
 // histogram of pt_idx / cam_idx + validation (camera-sorted, in range)
+// The camera CSR comes straight from the sorted camera list (cam_rowptr[c] = first observation with camera >= c: the
+// thread at a camera boundary writes the pointers of the cameras that start there), not from a histogram: 8 M atomic
+// increments on 10 k counters, 32 lanes of a warp on the same address, took 1.0 ms at config 5.
 __global__ void __launch_bounds__(BA_THREADS) k_index_count(int n_obs, int n_cam, int n_pt, const int32_t *__restrict__ cam_idx,
                                                            const int32_t *__restrict__ pt_idx, int32_t *pt_cnt,
-                                                           int32_t *cam_cnt, int32_t *err) {
+                                                           int32_t *cam_rowptr, int32_t *err) {
   const int i = blockIdx.x * BA_THREADS + threadIdx.x;
   if (i >= n_obs) return;
   const int c = cam_idx[i], p = pt_idx[i];
-  if (c < 0 || c >= n_cam || p < 0 || p >= n_pt || (i > 0 && c < cam_idx[i - 1])) {
+  const int prev = i > 0 ? cam_idx[i - 1] : -1;
+  if (c < 0 || c >= n_cam || p < 0 || p >= n_pt || (i > 0 && c < prev)) {
     atomicOr(err, 1);
     return;
   }
   atomicAdd(&pt_cnt[p], 1);
-  atomicAdd(&cam_cnt[c], 1);
+  if (prev < c)  // (an invalid predecessor raises the error flag itself; the clamp only keeps these writes in range)
+    for (int cc = prev < -1 ? 0 : prev + 1; cc <= c; ++cc) cam_rowptr[cc] = i;
+  if (i == n_obs - 1)
+    for (int cc = c + 1; cc <= n_cam; ++cc) cam_rowptr[cc] = n_obs;
 }
 
 // single-CTA exclusive scan: out[0..n] (n+1 entries) from cnt[0..n)
@@ -1439,8 +1446,18 @@ __device__ __forceinline__ void push_trace(LmState *st, BaIterRec *trace, int ca
   st->n_trace++;
 }
 __device__ __forceinline__ double block_max_array(const double *part, int n, double *smem) {
-  double v = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) v = fmax(v, part[i]);
+  double a[4] = {0, 0, 0, 0};
+  const int bd = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * bd < n; i += 4 * bd) {  // four loads in flight (the maximum does not depend on the order)
+    const double t0 = part[i], t1 = part[i + bd], t2 = part[i + 2 * bd], t3 = part[i + 3 * bd];
+    a[0] = fmax(a[0], t0);
+    a[1] = fmax(a[1], t1);
+    a[2] = fmax(a[2], t2);
+    a[3] = fmax(a[3], t3);
+  }
+  for (; i < n; i += bd) a[0] = fmax(a[0], part[i]);
+  double v = fmax(fmax(a[0], a[1]), fmax(a[2], a[3]));
   v = warp_max(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __syncthreads();

@@ -285,61 +285,107 @@ k_sp_minv(int n_cam, const int32_t *__restrict__ diag, const double *__restrict_
   for (int k = 0; k < 36; ++k) Minv[36 * (size_t)c + k] = Bi[k];
 }
 
+// Blocks are handed out in CHUNKS of consecutive blocks (sorted by (row camera, column camera): a chunk is about two
+// camera rows): the CTA takes a chunk from the global ticket counter, its warps take blocks of the chunk from a
+// shared-memory counter (the diagonal block -- the longest pair list of a row -- comes first).  All warps of a CTA then
+// gather the factored records of the SAME cameras' observations at the same time, through L1-allocating loads: the
+// row camera's records are read by every block of the row and hit L1 after the first touch (ncu, round 1 version with
+// one global ticket per block and L1-bypassing loads: 36 % of the stall samples on these gathers at 8 warps per SM).
+#define BA_SPS_CHUNK 32
+__device__ __forceinline__ ObsGeo load_geo_l1(const FPlanes &F, int i, double fx, double fy) {
+  const double2 a = __ldg(F.g0 + i), b = __ldg(F.g1 + i);
+  ObsGeo o;
+  o.xz = a.x;
+  o.yz = a.y;
+  o.iz = b.x;
+  o.wfx = b.y * fx;
+  o.wfy = b.y * fy;
+  return o;
+}
 __global__ void __launch_bounds__(BA_THREADS)
 k_sp_schur(int n_blk, int n_cam, const int32_t *__restrict__ blk_ptr, const unsigned long long *__restrict__ lkeys,
            const int32_t *__restrict__ gid, const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ pair_pt,
            FPlanes F, const double *__restrict__ geo, const double *__restrict__ intr, const double *__restrict__ Vs,
            double *__restrict__ S, int *ticket, const LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
+  __shared__ int s_chunk, s_next;
   const int lane = threadIdx.x & 31;
   const double fx = ldg1(intr), fy = ldg1(intr + 1);
   for (;;) {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(ticket, 1);
-    b = __shfl_sync(BA_FULL, b, 0);
-    if (b >= n_blk) return;
-    const unsigned long long key = lkeys[b];
-    const int ci = (int)(key / (unsigned long long)n_cam), cj = (int)(key % (unsigned long long)n_cam);
-    CamRec ri, rj;
-    load_camrec(geo, ci, ri);
-    load_camrec(geo, cj, rj);
-    double acc[36];
-#pragma unroll
-    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-    for (int e = blk_ptr[b] + lane; e < blk_ptr[b + 1]; e += 32) {
-      const unsigned long long pr = pairs[e];
-      const int p = __ldg(pair_pt + e);
-      const int oa = (int)(pr >> 32), ob = (int)(pr & 0xffffffffu);
-      double vs[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) vs[k] = ldg1(Vs + 6 * (size_t)p + k);
-      const ObsGeo ga = load_geo(F, oa, fx, fy), gb = load_geo(F, ob, fx, fy);
-      double a0[6], a1[6], pa0[3], pa1[3], b0[6], b1[6], pb0[3], pb1[3];
-      sp_rows(ga, ri.R, a0, a1, pa0, pa1);
-      sp_rows(gb, rj.R, b0, b1, pb0, pb1);
-      double v0[3], v1[3];
-      sym3_mul(vs, pa0, v0);
-      sym3_mul(vs, pa1, v1);
-      const double m00 = v0[0] * pb0[0] + v0[1] * pb0[1] + v0[2] * pb0[2];
-      const double m01 = v0[0] * pb1[0] + v0[1] * pb1[1] + v0[2] * pb1[2];
-      const double m10 = v1[0] * pb0[0] + v1[1] * pb0[1] + v1[2] * pb0[2];
-      const double m11 = v1[0] * pb1[0] + v1[1] * pb1[1] + v1[2] * pb1[2];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const double h0 = m00 * b0[c] + m01 * b1[c], h1 = m10 * b0[c] + m11 * b1[c];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) acc[r * 6 + c] += a0[r] * h0 + a1[r] * h1;
-      }
+    __syncthreads();  // every warp is done with the previous chunk's counter
+    if (threadIdx.x == 0) {
+      s_chunk = atomicAdd(ticket, 1);
+      s_next = 0;
     }
+    __syncthreads();
+    const int c0 = s_chunk * BA_SPS_CHUNK;
+    if (c0 >= n_blk) return;
+    const int cend = c0 + BA_SPS_CHUNK < n_blk ? c0 + BA_SPS_CHUNK : n_blk;
+    for (;;) {
+      int b = 0;
+      if (lane == 0) b = c0 + atomicAdd(&s_next, 1);
+      b = __shfl_sync(BA_FULL, b, 0);
+      if (b >= cend) break;
+      const unsigned long long key = lkeys[b];
+      const int ci = (int)(key / (unsigned long long)n_cam), cj = (int)(key % (unsigned long long)n_cam);
+      CamRec ri, rj;
+      load_camrec(geo, ci, ri);
+      load_camrec(geo, cj, rj);
+      double acc[36];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
-    // lanes 0..35 -> lane k writes entry k (two rounds)
-    double *Sb = S + 36 * (size_t)gid[b];
+      for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+      const int e1 = blk_ptr[b + 1];
+      int e = blk_ptr[b] + lane;
+      unsigned long long pr = 0;
+      int p = 0;
+      if (e < e1) {
+        pr = pairs[e];
+        p = __ldg(pair_pt + e);
+      }
+      while (e < e1) {
+        // the next trip's pair record is fetched before this trip's gathers are consumed
+        const int en = e + 32;
+        unsigned long long prn = 0;
+        int pn = 0;
+        if (en < e1) {
+          prn = pairs[en];
+          pn = __ldg(pair_pt + en);
+        }
+        const int oa = (int)(pr >> 32), ob = (int)(pr & 0xffffffffu);
+        double vs[6];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) {
-      if (lane == (k & 31)) {
-        const int r = k / 6, c = k - 6 * (k / 6);
-        Sb[k] = -(acc[k] * (ri.s[r] * rj.s[c]));  // k_sp_add_diag puts U on the diagonal blocks
+        for (int k = 0; k < 6; ++k) vs[k] = ldg1(Vs + 6 * (size_t)p + k);
+        const ObsGeo ga = load_geo_l1(F, oa, fx, fy), gb = load_geo_l1(F, ob, fx, fy);
+        double a0[6], a1[6], pa0[3], pa1[3], b0[6], b1[6], pb0[3], pb1[3];
+        sp_rows(ga, ri.R, a0, a1, pa0, pa1);
+        sp_rows(gb, rj.R, b0, b1, pb0, pb1);
+        double v0[3], v1[3];
+        sym3_mul(vs, pa0, v0);
+        sym3_mul(vs, pa1, v1);
+        const double m00 = v0[0] * pb0[0] + v0[1] * pb0[1] + v0[2] * pb0[2];
+        const double m01 = v0[0] * pb1[0] + v0[1] * pb1[1] + v0[2] * pb1[2];
+        const double m10 = v1[0] * pb0[0] + v1[1] * pb0[1] + v1[2] * pb0[2];
+        const double m11 = v1[0] * pb1[0] + v1[1] * pb1[1] + v1[2] * pb1[2];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const double h0 = m00 * b0[c] + m01 * b1[c], h1 = m10 * b0[c] + m11 * b1[c];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) acc[r * 6 + c] += a0[r] * h0 + a1[r] * h1;
+        }
+        pr = prn;
+        p = pn;
+        e = en;
+      }
+#pragma unroll
+      for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
+      // lanes 0..35 -> lane k writes entry k (two rounds)
+      double *Sb = S + 36 * (size_t)gid[b];
+#pragma unroll
+      for (int k = 0; k < 36; ++k) {
+        if (lane == (k & 31)) {
+          const int r = k / 6, c = k - 6 * (k / 6);
+          Sb[k] = -(acc[k] * (ri.s[r] * rj.s[c]));  // k_sp_add_diag puts U on the diagonal blocks
+        }
       }
     }
   }

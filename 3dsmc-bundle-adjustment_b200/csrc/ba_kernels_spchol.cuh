@@ -14,8 +14,9 @@
 //   * The 6x6 pivot block is factorised by warp 0 with shuffles (lane = row) while the other warps still run the
 //     trailing update of the previous step (look-ahead): two CTA barriers per eliminated camera.
 //   * The right-hand side rides along as one more row (forward substitution fused into the factorisation).
-//   * Afterwards the node's update matrix U = L_B L_B^T (+ what its children pass through) and the panel go to HBM/L2
-//     for the parent / the backward substitution.
+//   * The panel goes to HBM/L2 for the backward substitution; the node's update matrix U = L_B L_B^T (+ what its children
+//     pass through) -- two thirds of the multiply-adds, no dependent chain -- is formed by a second launch per level with
+//     several thread blocks per node (k_spchol_update), for the parent's extend-add.
 // Backward substitution: one launch per level, parents before children; L_OO and the stored inverses of the pivot blocks
 // come back into shared memory, the border product is a warp-per-column reduction over the panel in L2.
 // Every sum has a fixed order: results are bit-identical from run to run and across ranks.
@@ -78,8 +79,9 @@ __device__ __forceinline__ bool spc_chol6(double *P, int LD, int k, int lane, do
   for (int c = 0; c < 6; ++c) {
     const double dcc = __shfl_sync(BA_FULL, row[c], c);
     if (!(dcc > 0.0) || !isfinite(dcc)) ok = false;
-    const double s = sqrt(dcc);
-    const double inv = 1.0 / s;
+    // one reciprocal square root instead of a square root and a division on the dependent chain of the six columns
+    const double inv = rsqrt(dcc);
+    const double s = dcc * inv;
     invd[c] = inv;
     if (lane == c)
       row[c] = s;
@@ -123,6 +125,13 @@ __device__ __forceinline__ bool spc_chol6(double *P, int LD, int k, int lane, do
   return ok;
 }
 
+// six consecutive doubles from shared memory, 16-byte aligned (rows of the row-major pivot column): three LDS.128
+__device__ __forceinline__ void spc_ld6(const double *p, double v[6]) {
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  const double2 a = q[0], b = q[1], c = q[2];
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+
 // (i, j), i >= j, of the p-th lower block in row-major order of the lower triangle
 __device__ __forceinline__ void spc_tri(int p, int &i, int &j) {
   int r = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
@@ -135,12 +144,12 @@ __device__ __forceinline__ void spc_tri(int p, int &i, int &j) {
 __global__ void __launch_bounds__(SPC_THREADS, 1)
 k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  extern __shared__ double spc_sm[];
+  extern __shared__ __align__(16) double spc_sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int id = a.level_nodes[lvl_first + blockIdx.x];
   const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
   const int k0 = N[SPN_K0], m = N[SPN_M], nb = N[SPN_NB];
-  const int LD = 6 * (m + nb), C6 = 6 * m, NB6 = 6 * nb;
+  const int LD = 6 * (m + nb), C6 = 6 * m;
   double *P = spc_sm;                    // panel, column-major, LD x C6
   double *LT = P + (size_t)LD * C6;      // current pivot column block, row-major: LT[R * 6 + c]
   double *zf = LT + (size_t)LD * 6;      // right-hand side of the own cameras
@@ -150,50 +159,61 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
   for (int i = tid; i < LD * C6; i += SPC_THREADS) P[i] = 0.0;
   for (int i = tid; i < C6; i += SPC_THREADS) zf[i] = a.b[6 * (size_t)a.perm[k0 + i / 6] + i % 6];
   __syncthreads();
-  // ---- phase 1a: stored blocks of S (36 threads per block), damping on the diagonal
+  // ---- phase 1a: stored blocks of S (one thread per scalar, entry records through 16-byte broadcast loads), damping on
+  //      the diagonal.  Independent iterations: unrolled so that several dependent load chains are in flight.
   {
-    const int32_t *E = a.aent + 4 * (size_t)N[SPN_AENT];
-    const int ne = N[SPN_NAENT];
-    const int sub = tid / 36, t = tid - 36 * sub, r6 = t / 6, c6 = t - 6 * r6;
-    if (sub < SPC_THREADS / 36)
-      for (int e = sub; e < ne; e += SPC_THREADS / 36) {
-        const uint32_t code = (uint32_t)E[4 * e];
-        const int lr = E[4 * e + 1], lc = E[4 * e + 2], cam = E[4 * e + 3];
-        const uint32_t blk = code & 0x3fffffffu;
-        double v = 0.0;
-        if (code & 0x40000000u) {  // diagonal block: symmetrised from its upper triangle (as k_sp_minv does) + D^2
-          if (blk != 0x3fffffffu) v = a.S[36 * (size_t)blk + (r6 <= c6 ? r6 * 6 + c6 : c6 * 6 + r6)];
-          if (r6 == c6) v += a.dsq[6 * (size_t)cam + r6];
-        } else if (code & 0x80000000u) {
-          v = a.S[36 * (size_t)blk + c6 * 6 + r6];
-        } else {
-          v = a.S[36 * (size_t)blk + r6 * 6 + c6];
-        }
-        P[(size_t)(6 * lc + c6) * LD + 6 * lr + r6] = v;
+    const int4 *E4 = reinterpret_cast<const int4 *>(a.aent) + N[SPN_AENT];
+    const int ne36 = 36 * N[SPN_NAENT];
+#pragma unroll 4
+    for (int idx = tid; idx < ne36; idx += SPC_THREADS) {
+      const int e = idx / 36, t = idx - 36 * e, r6 = t / 6, c6 = t - 6 * r6;
+      const int4 en = __ldg(E4 + e);  // (block | flags, local row, local column, camera of the column)
+      const uint32_t code = (uint32_t)en.x, blk = code & 0x3fffffffu;
+      double v = 0.0;
+      if (code & 0x40000000u) {  // diagonal block: symmetrised from its upper triangle (as k_sp_minv does) + D^2
+        if (blk != 0x3fffffffu) v = a.S[36 * (size_t)blk + (r6 <= c6 ? r6 * 6 + c6 : c6 * 6 + r6)];
+        if (r6 == c6) v += a.dsq[6 * (size_t)en.w + r6];
+      } else if (code & 0x80000000u) {
+        v = a.S[36 * (size_t)blk + c6 * 6 + r6];
+      } else {
+        v = a.S[36 * (size_t)blk + r6 * 6 + c6];
       }
+      P[(size_t)(6 * en.z + c6) * LD + 6 * en.y + r6] = v;
+    }
   }
   __syncthreads();
-  // ---- phase 1b: extend-add of the children (one after the other: fixed order; inside a child the map is injective)
+  // ---- phase 1b: extend-add of the children (one after the other: fixed order; inside a child the map is injective).
+  //      rel is ascending, so the child's border cameras that are OWN cameras of this node come first: only those block
+  //      columns land in the panel (the rest of the child's update matrix passes through to this node's, k_spchol_update)
   for (int ci = 0; ci < N[SPN_NCHILD]; ++ci) {
     const int ch = a.children[N[SPN_CHILD] + ci];
     const int32_t *Cn = a.node + (size_t)ch * SPSYM_NODE_INTS;
-    const int nbc6 = 6 * Cn[SPN_NB];
+    const int nbc = Cn[SPN_NB], nbc6 = 6 * nbc;
     const int32_t *rel = a.rel + Cn[SPN_REL];
+    int n_in = 0;  // first border index with rel >= m (binary search, same on every thread)
+    {
+      int lo = 0, hi = nbc;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(rel + mid) < m)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      n_in = lo;
+    }
     const double *Uc = a.U + 36 * spc_off(Cn, SPN_U_LO);
     const double *ruc = a.ru + 6 * (size_t)Cn[SPN_BORD];
-    for (int idx = tid; idx < nbc6 * nbc6; idx += SPC_THREADS) {
+    const int n_el = 6 * n_in * nbc6;
+#pragma unroll 2
+    for (int idx = tid; idx < n_el; idx += SPC_THREADS) {
       const int col = idx / nbc6, row = idx - col * nbc6;
       const int j = col / 6, i = row / 6;
       if (i < j) continue;
-      const int rj = rel[j];
-      if (rj >= m) continue;
-      const int ri = rel[i];
+      const int rj = __ldg(rel + j), ri = __ldg(rel + i);
       P[(size_t)(6 * rj + (col - 6 * j)) * LD + 6 * ri + (row - 6 * i)] -= __ldcg(Uc + idx);
     }
-    for (int idx = tid; idx < nbc6; idx += SPC_THREADS) {
-      const int ri = rel[idx / 6];
-      if (ri < m) zf[6 * ri + idx % 6] -= __ldcg(ruc + idx);
-    }
+    for (int idx = tid; idx < 6 * n_in; idx += SPC_THREADS) zf[6 * __ldg(rel + idx / 6) + idx % 6] -= __ldcg(ruc + idx);
     __syncthreads();
   }
   // ---- phase 2: right-looking factorisation, 6 columns (one camera) per step
@@ -235,11 +255,11 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
       if (lane < 6) {
         const int R = 6 * (k + 1) + lane, j = k + 1;
         double x[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) x[c] = LT[R * 6 + c];
+        spc_ld6(LT + R * 6, x);
 #pragma unroll
         for (int bb = 0; bb < 6; ++bb) {
-          const double *lj = LT + (6 * j + bb) * 6;
+          double lj[6];
+          spc_ld6(LT + (6 * j + bb) * 6, lj);
           double s = 0.0;
 #pragma unroll
           for (int c = 0; c < 6; ++c) s += x[c] * lj[c];
@@ -261,12 +281,12 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
           const int g = t / nrows, R = base + (t - g * nrows);
           const int jmax = R / 6 < m - 1 ? R / 6 : m - 1;
           double x[6];
-#pragma unroll
-          for (int c = 0; c < 6; ++c) x[c] = LT[R * 6 + c];
+          spc_ld6(LT + R * 6, x);
           for (int j = k + 1 + g; j <= jmax; j += G) {
 #pragma unroll
             for (int bb = 0; bb < 6; ++bb) {
-              const double *lj = LT + (6 * j + bb) * 6;
+              double lj[6];
+              spc_ld6(LT + (6 * j + bb) * 6, lj);
               double s = 0.0;
 #pragma unroll
               for (int c = 0; c < 6; ++c) s += x[c] * lj[c];
@@ -291,65 +311,92 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
     for (int i = tid; i < LD * C6; i += SPC_THREADS) Pg[i] = P[i];
     for (int i = tid; i < C6; i += SPC_THREADS) a.z[6 * (size_t)k0 + i] = zf[i];
   }
+}
+
+// Update matrix of the nodes of one level, after their panels are factorised: U = L_B L_B^T + what the children pass through
+// (block lower triangle, full diagonal blocks) and the right-hand side update ru = L_B z + children.  This is two thirds of a
+// node's multiply-adds and has no dependent chain, so it runs as its own launch with `tiles` thread blocks per node: the upper
+// levels of the tree have fewer nodes than the GPU has SMs.  Every block loads the node's border rows of the panel (L2-resident,
+// just written) into shared memory and takes every tiles-th chunk of the 3 x 6 output pieces.
+#define SPU_THREADS 256
+inline size_t spc_update_smem(int m, int nb) { return ((size_t)36 * nb * m + 6 * m + 8) * 8; }
+__global__ void __launch_bounds__(SPU_THREADS, 1)
+k_spchol_update(SpChol a, int lvl_first, int tiles, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  extern __shared__ __align__(16) double spc_sm[];
+  const int tid = threadIdx.x;
+  const int id = a.level_nodes[lvl_first + blockIdx.x / tiles], tile = blockIdx.x % tiles;
+  const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
+  const int k0 = N[SPN_K0], m = N[SPN_M], nb = N[SPN_NB];
   if (nb == 0) return;
-  // ---- phase 4: update matrix U = L_B L_B^T + what the children pass through (block lower triangle, full diagonal
-  //      blocks), one half block (3 x 6) per thread; right-hand side update ru = L_B z + children
+  const int LD = 6 * (m + nb), C6 = 6 * m, NB6 = 6 * nb;
+  double *LB = spc_sm;              // border rows of the panel, column-major NB6 x C6
+  double *zf = LB + (size_t)NB6 * C6;
   {
-    double *Ug = a.U + 36 * spc_off(N, SPN_U_LO);
-    const double *Pb = P + C6;  // first border row
-    const int n_items = nb * (nb + 1);
-    const int nch = N[SPN_NCHILD];
-    for (int idx = tid; idx < n_items; idx += SPC_THREADS) {
-      int i, j;
-      spc_tri(idx >> 1, i, j);
-      const int h = idx & 1;
-      const int ra = 6 * i + 3 * h, rb = 6 * j;
-      double acc[3][6];
+    const double *Pg = a.panel + 36 * spc_off(N, SPN_PANEL_LO) + C6;
+    for (int idx = tid; idx < NB6 * C6; idx += SPU_THREADS) {
+      const int c = idx / NB6, r = idx - c * NB6;
+      LB[idx] = Pg[(size_t)c * LD + r];
+    }
+    for (int i = tid; i < C6; i += SPU_THREADS) zf[i] = a.z[6 * (size_t)k0 + i];
+  }
+  __syncthreads();
+  double *Ug = a.U + 36 * spc_off(N, SPN_U_LO);
+  const int n_items = nb * (nb + 1);
+  const int nch = N[SPN_NCHILD];
+  for (int idx = tile * SPU_THREADS + tid; idx < n_items; idx += tiles * SPU_THREADS) {
+    int i, j;
+    spc_tri(idx >> 1, i, j);
+    const int h = idx & 1;
+    const int ra = 6 * i + 3 * h, rb = 6 * j;
+    double acc[3][6];
 #pragma unroll
-      for (int x = 0; x < 3; ++x)
+    for (int x = 0; x < 3; ++x)
 #pragma unroll
-        for (int y = 0; y < 6; ++y) acc[x][y] = 0.0;
-      for (int c = 0; c < C6; ++c) {
-        const double *col = Pb + (size_t)c * LD;
-        const double a0 = col[ra], a1 = col[ra + 1], a2 = col[ra + 2];
+      for (int y = 0; y < 6; ++y) acc[x][y] = 0.0;
+#pragma unroll 2
+    for (int c = 0; c < C6; ++c) {
+      const double *col = LB + (size_t)c * NB6;
+      const double a0 = col[ra], a1 = col[ra + 1], a2 = col[ra + 2];
+      const double2 b01 = *reinterpret_cast<const double2 *>(col + rb), b23 = *reinterpret_cast<const double2 *>(col + rb + 2),
+                    b45 = *reinterpret_cast<const double2 *>(col + rb + 4);
+      const double bv[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
 #pragma unroll
-        for (int y = 0; y < 6; ++y) {
-          const double bv = col[rb + y];
-          acc[0][y] += a0 * bv;
-          acc[1][y] += a1 * bv;
-          acc[2][y] += a2 * bv;
-        }
+      for (int y = 0; y < 6; ++y) {
+        acc[0][y] += a0 * bv[y];
+        acc[1][y] += a1 * bv[y];
+        acc[2][y] += a2 * bv[y];
       }
-      for (int ci = 0; ci < nch; ++ci) {
-        const int ch = a.children[N[SPN_CHILD] + ci];
-        const int32_t *Cn = a.node + (size_t)ch * SPSYM_NODE_INTS;
-        const int32_t *inv = a.inv + Cn[SPN_INV];
-        const int ii = inv[i], jj = inv[j];
-        if (ii < 0 || jj < 0) continue;
-        const int nbc6 = 6 * Cn[SPN_NB];
-        const double *Uc = a.U + 36 * spc_off(Cn, SPN_U_LO);
-#pragma unroll
-        for (int y = 0; y < 6; ++y)
-#pragma unroll
-          for (int x = 0; x < 3; ++x) acc[x][y] += __ldcg(Uc + (size_t)(6 * jj + y) * nbc6 + 6 * ii + 3 * h + x);
-      }
+    }
+    for (int ci = 0; ci < nch; ++ci) {
+      const int ch = a.children[N[SPN_CHILD] + ci];
+      const int32_t *Cn = a.node + (size_t)ch * SPSYM_NODE_INTS;
+      const int32_t *inv = a.inv + Cn[SPN_INV];
+      const int ii = inv[i], jj = inv[j];
+      if (ii < 0 || jj < 0) continue;
+      const int nbc6 = 6 * Cn[SPN_NB];
+      const double *Uc = a.U + 36 * spc_off(Cn, SPN_U_LO);
 #pragma unroll
       for (int y = 0; y < 6; ++y)
 #pragma unroll
-        for (int x = 0; x < 3; ++x) Ug[(size_t)(rb + y) * NB6 + ra + x] = acc[x][y];
+        for (int x = 0; x < 3; ++x) acc[x][y] += __ldcg(Uc + (size_t)(6 * jj + y) * nbc6 + 6 * ii + 3 * h + x);
     }
-    double *rug = a.ru + 6 * (size_t)N[SPN_BORD];
-    for (int idx = tid; idx < NB6; idx += SPC_THREADS) {
-      double s = 0.0;
-      for (int c = 0; c < C6; ++c) s += Pb[(size_t)c * LD + idx] * zf[c];
-      for (int ci = 0; ci < nch; ++ci) {
-        const int ch = a.children[N[SPN_CHILD] + ci];
-        const int32_t *Cn = a.node + (size_t)ch * SPSYM_NODE_INTS;
-        const int ii = a.inv[Cn[SPN_INV] + idx / 6];
-        if (ii >= 0) s += __ldcg(a.ru + 6 * (size_t)Cn[SPN_BORD] + 6 * ii + idx % 6);
-      }
-      rug[idx] = s;
+#pragma unroll
+    for (int y = 0; y < 6; ++y)
+#pragma unroll
+      for (int x = 0; x < 3; ++x) Ug[(size_t)(rb + y) * NB6 + ra + x] = acc[x][y];
+  }
+  double *rug = a.ru + 6 * (size_t)N[SPN_BORD];
+  for (int idx = tile * SPU_THREADS + tid; idx < NB6; idx += tiles * SPU_THREADS) {
+    double s = 0.0;
+    for (int c = 0; c < C6; ++c) s += LB[(size_t)c * NB6 + idx] * zf[c];
+    for (int ci = 0; ci < nch; ++ci) {
+      const int ch = a.children[N[SPN_CHILD] + ci];
+      const int32_t *Cn = a.node + (size_t)ch * SPSYM_NODE_INTS;
+      const int ii = a.inv[Cn[SPN_INV] + idx / 6];
+      if (ii >= 0) s += __ldcg(a.ru + 6 * (size_t)Cn[SPN_BORD] + 6 * ii + idx % 6);
     }
+    rug[idx] = s;
   }
 }
 
@@ -357,7 +404,7 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
 __global__ void __launch_bounds__(SPC_THREADS, 1)
 k_spchol_solve(SpChol a, int lvl_first, LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
-  extern __shared__ double spc_sm[];
+  extern __shared__ __align__(16) double spc_sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int id = a.level_nodes[lvl_first + blockIdx.x];
   const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;

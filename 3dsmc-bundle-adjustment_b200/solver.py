@@ -213,6 +213,13 @@ class GpuSolver:
         self._check(self.lib.ba_gpu_sparse_stats(self._ctx, C.byref(npairs), C.byref(nblk), C.byref(nent)))
         return int(nent.value), int(nblk.value)
 
+    def sparse_pairs(self):
+        """Same-point observation pairs behind the block-sparse Schur complement (0 for other solvers)."""
+        import ctypes as C
+        npairs, nblk, nent = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.ba_gpu_sparse_stats(self._ctx, C.byref(npairs), C.byref(nblk), C.byref(nent)))
+        return int(npairs.value)
+
     def jacobian_store_used(self):
         """BA_JAC_* in force after the last upload (what BA_JAC_AUTO resolved to)."""
         rc = int(self.lib.ba_gpu_jacobian_store_used(self._ctx))

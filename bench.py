@@ -51,23 +51,6 @@ STORE_NAME = {1: "planes", 2: "factored", 3: "tiled"}
 SOLVERS = {"auto": 0, "implicit": 2, "sparse": 3, "cholesky": 4}
 SOLVER_NAME = {1: "dense explicit Schur + Cholesky", 2: "implicit-Schur PCG", 3: "block-sparse explicit Schur + persistent PCG",
                4: "block-sparse explicit Schur + exact sparse Cholesky (supernodal multifrontal, nested dissection)"}
-# PCG iterations per LM iteration of the fixed-count solves (eta = 1e-6, cap 500), as
-# measured by the GPU arm (identical on the oracle for cfg3; within 5% for cfg4/5): the
-# reference arm prices its bounded sample with these, so both arms do the same work.
-PCG_COUNTS = {
-    "cfg3": [210, 500, 500, 500, 500, 500, 500, 500, 500, 500],
-    "cfg4": [108, 413, 500, 500, 500, 500, 500, 500, 500, 500],
-    "cfg5": [107, 449, 500, 500, 500, 500, 500, 500, 500, 500],
-}
-
-
-def pcg_counts_for(workload, k):
-    c = PCG_COUNTS.get(workload)
-    if c is None:
-        return [0] * k
-    return (c + [500] * k)[:k]
-
-
 # DRAM traffic per launch from the committed `ncu --set full` captures (dram__bytes_read.sum + dram__bytes_write.sum),
 # cfg5 only; (substring of the roofline kernel name) -> (bytes per launch, source)
 NCU_TRAFFIC_CFG5 = {
@@ -225,6 +208,86 @@ def kernel_rooflines(ba_b200, s, problem, wl, solver_used, flush, peak):
     return kernels, dom, store, ms_lin
 
 
+FP64_NOMINAL_TFLOPS = 40.0  # B200 vector fp64, nominal (MEASURED_PEAKS.json holds no fp64 figure)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this round
+# (profiles/r02_ncu_full_cfg5.csv), config 5 on one GPU
+NCU_TRAFFIC_R02_CFG5 = {}
+
+
+def executed_roofline(workload, phase_ms, n_iter, solver_used, full, n_pairs, n_ent, spchol, pcg_total, peak, peak_src):
+    """The roofline entry of the phase that took the largest share of the timed solve AS EXECUTED (CUDA events recorded on
+    the solver stream at the phase boundaries while the solve ran, ba_gpu_phase_times), with the algorithmic bytes (or
+    flops) of the kernels of that phase."""
+    if not phase_ms or n_iter <= 0:
+        return None, {}
+    per = {k: v / n_iter for k, v in phase_ms.items()}
+    n_o, n_p, n_c = full.n_obs, full.n_pt, full.n_cam
+    total = sum(per.values())
+    table = {}
+
+    def hbm(name, kernels, nbytes, ms, bound, note=None):
+        table[name] = {"kernels": kernels, "bound": bound, "bytes": nbytes, "ms": ms, "share_of_step": ms / total if total else None,
+                       "achieved": nbytes / ms / 1e6 if ms > 0 else None, "peak": peak, "unit": "GB/s",
+                       "frac": nbytes / ms / 1e6 / peak if ms > 0 else None, "note": note}
+
+    if solver_used in (3, 4):
+        hbm("schur_complement", "k_sp_schur (+ k_sp_add_diag)", 124.0 * n_pairs, per.get("schur_complement", 0.0),
+            "l2 / hbm gathers (latency)", "124 B per same-point observation pair: pair 8 + point id 4 + two factored records 64 + Vs 48")
+    if solver_used == 4 and spchol:
+        ms = per.get("linear_solve_factor_or_pcg", 0.0)
+        table["linear_solve_factor"] = {
+            "kernels": "k_spchol_rhs, k_spchol_factor + k_spchol_update per tree level", "bound": "fp64 pipe / dependent chain of tree levels",
+            "flops": spchol.get("flops"), "ms": ms, "share_of_step": ms / total if total else None,
+            "achieved": spchol.get("flops", 0) / ms / 1e9 if ms > 0 else None, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+            "frac": spchol.get("flops", 0) / ms / 1e9 / FP64_NOMINAL_TFLOPS if ms > 0 else None,
+            "note": "fp64 multiply-adds x 2 of the supernodal factorisation; peak = nominal B200 fp64 (not measured); %d nodes in %d "
+                    "levels" % (spchol.get("nodes", 0), spchol.get("levels", 0))}
+        hbm("linear_solve_substitution", "k_spchol_solve per tree level", 288.0 * spchol.get("panel_blocks", 0),
+            per.get("linear_solve_substitution", 0.0), "l2 (panels) / dependent chain of tree levels", "one read of the factor panels")
+    elif solver_used == 3 and pcg_total > 0:
+        ms = per.get("linear_solve_substitution", 0.0) + per.get("linear_solve_factor_or_pcg", 0.0)
+        hbm("pcg", "k_pcg_sparse_persistent (all PCG iterations of a step)", (n_ent * 344.0 + n_c * 96.0) * pcg_total / n_iter, ms,
+            "l2 / latency (S is L2-resident)", "per PCG iteration: 288 B block + 8 B entry + 48 B gathered vector per row entry")
+    # factored store: kf_linearize x2 (96 B/obs each), kf_pt_blocks (48 B/obs + 96 B/pt), kf_cam_blocks (48 B/obs), state copies
+    hbm("accept_relinearize", "k_accept, kf_linearize<0>, kf_pt_blocks, kf_linearize<1>, kf_cam_blocks, k_cam_blocks_fin, k_state_norms",
+        (96.0 + 96.0 + 48.0 + 48.0) * n_o + (96.0 + 2 * 48.0) * n_p + (288.0 + 2 * 112.0) * n_c, per.get("accept_relinearize", 0.0), "hbm")
+    hbm("back_substitution_model_cost", "k_pack_camx, kf_schur_pass1<1,0>, kf_model_cost, k_candidate, k_cost",
+        (48.0 + 48.0 + 44.0) * n_o + (48.0 + 32.0 + 24.0 + 48.0) * n_p, per.get("back_substitution_model_cost", 0.0) + per.get("candidate_cost", 0.0),
+        "hbm")
+    hbm("point_inverse", "kf_point_inverse", (48.0 + 24.0 + 24.0 + 24.0 + 48.0 + 48.0 + 32.0) * n_p, per.get("point_inverse", 0.0), "hbm")
+    hbm("reduced_rhs", "kf_schur_pass2", 68.0 * n_o + 96.0 * n_c, per.get("reduced_rhs", 0.0), "hbm")
+    live = {k: v for k, v in table.items() if v["ms"] and v["ms"] > 0}
+    if not live:
+        return None, table
+    dom = max(live, key=lambda k: live[k]["ms"])
+    d = live[dom]
+    traffic = NCU_TRAFFIC_R02_CFG5.get(dom) if workload == "cfg5" else None
+    roof = {"kernel": "%s: %s" % (dom, d["kernels"]), "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+            "frac": d["frac"], "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
+            "peak_source": peak_src if d["unit"] == "GB/s" else "nominal fp64 peak", "share_of_step": d["share_of_step"],
+            "ms_per_step": d["ms"],
+            "timing": "CUDA events recorded on the solver stream at the phase boundaries of every LM iteration of the timed solve "
+                      "(ba_gpu_phase_times): the phase as executed, not a stand-alone launch",
+            "bytes" if d["unit"] == "GB/s" else "flops": d.get("bytes", d.get("flops"))}
+    return roof, table
+
+
+def parity_vs_n1(workload, scale, solver_used, trace):
+    """Final cost / accept sequence of this run against the committed single-GPU trace of the same workload
+    (tests/golden/bench_trace.json, written by --write-golden on one GPU)."""
+    path = os.path.join(ROOT, "tests", "golden", "bench_trace.json")
+    if not os.path.exists(path) or scale != 1.0:
+        return None
+    g = json.load(open(path)).get("%s/solver%d" % (workload, solver_used))
+    if not g:
+        return None
+    n = min(len(trace), len(g["cost"]))
+    rel = max(abs(trace[i]["cost"] - g["cost"][i]) / abs(g["cost"][i]) for i in range(n))
+    same = [t["step_is_successful"] for t in trace[:n]] == g["successful"][:n]
+    return {"iterations_compared": n - 1, "max_rel_cost_diff": rel, "accept_sequence_equal": same, "ok": bool(same and rel <= 1e-8),
+            "tolerance": 1e-8, "golden": "tests/golden/bench_trace.json (%s, 1 GPU)" % g.get("when", "?")}
+
+
 def pinned_copy(a):
     """numpy view of pinned host memory holding a copy of `a` (H2D at full PCIe speed)."""
     import torch
@@ -246,6 +309,7 @@ def main():
     ap.add_argument("--solver", default="auto", choices=sorted(SOLVERS),
                     help="large NS-mode workloads: auto = the library's choice (block-sparse explicit S on one GPU, "
                          "sharded implicit on several), implicit = matrix-free two/one-pass product, sparse = block-sparse S")
+    ap.add_argument("--write-golden", action="store_true", help="single GPU: store this run's LM trace as the reference of parity_vs_n1")
     ap.add_argument("--store", type=int, default=0, help="BA_JAC_* for the implicit solver (0 auto, 1 planes, 2 factored, 3 tiled)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -257,24 +321,35 @@ def main():
     import ba_b200
     syn = ba_b200.synthetic
 
+    def build_problem():
+        if args.workload == "cfg3ref":
+            c3 = syn.CONFIGS[3]
+            n_kf = max(4, int(round(c3["n_kf"] * args.scale)))
+            seq = syn.make_tum_sequence(n_kf, max(8, int(round(c3["n_lm"] * args.scale))), max(24, int(round(c3["n_obs"] * args.scale))),
+                                        syn.SEED_BASE + 3)
+            return syn.window_problem(seq, 0, n_kf - 1).problem
+        pr = syn.make_config(wl["cfg"], scale=args.scale)
+        if wl["cfg"] == 2:
+            pr = syn.window_problem(pr, 0, 19).problem
+        return pr
+
     if args.impl == "reference":
-        # the reference's CPU implementation of the path = the oracle port (Ceres itself cannot be built here)
+        # the reference's CPU implementation of the path: the oracle port with the reference's own linear solver setting
+        # (SPARSE_SCHUR), RUN for W + K LM iterations on the same problem, all host threads (Ceres itself cannot be built
+        # here: no Ceres / Eigen in the image).  Rank 0 only.
         if rank != 0:
             return 0
-        if args.workload == "cfg3ref":
-            raise SystemExit("cfg3ref has no bounded CPU sample (a dense 4798^2 Schur solve per iteration); use cfg3")
-        problem = syn.make_config(wl["cfg"], scale=args.scale)
-        if wl["cfg"] == 2:
-            problem = syn.window_problem(problem, 0, 19).problem
+        problem = build_problem()
         threads = os.cpu_count() or 1
-        base = cpu_reference_sample(problem, wl["mode"], pcg_counts_for(args.workload, K), threads)
+        base = cpu_reference_run(problem, wl["mode"], K, threads, warmup=W)
+        n_it = base["lm_iterations"]
         line = {"metric": "LM iterations/s", "value": base["value"], "unit": "LM iterations/s", "n_gpus": args.gpus, "steps": K,
-                "warmup": W, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",
+                "warmup": W, "ms_per_step": 1e3 * base["seconds"] / max(n_it, 1), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-                "config": {"workload": args.workload + ": " + wl["desc"], "scale": args.scale,
-                           "pcg_iterations_per_lm": pcg_counts_for(args.workload, K),
-                           "note": "Ceres-equivalent CPU restatement (not Ceres): LM + implicit-Schur PCG / dense Schur; "
-                                   "PCG iterations per LM iteration = the counts the b200 arm measures on this workload"},
+                "config": bench_config(args, wl, problem, args.gpus, K),
+                "final_cost": base["final_cost"],
+                "note": "CPU restatement of the reference path (oracle/, not Ceres), linear solver = the reference's SPARSE_SCHUR "
+                        "setting; every reported iteration was executed inside this run",
                 "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "LM iterations/s", "h2d_bytes_per_step": 0,
                                               "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -288,16 +363,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t_gen = time.time()
-    if args.workload == "cfg3ref":
-        c3 = syn.CONFIGS[3]
-        n_kf = max(4, int(round(c3["n_kf"] * args.scale)))
-        seq = syn.make_tum_sequence(n_kf, max(8, int(round(c3["n_lm"] * args.scale))), max(24, int(round(c3["n_obs"] * args.scale))),
-                                    syn.SEED_BASE + 3)
-        full = syn.window_problem(seq, 0, n_kf - 1).problem
-    else:
-        full = syn.make_config(wl["cfg"], scale=args.scale)
-        if wl["cfg"] == 2:
-            full = syn.window_problem(full, 0, 19).problem
+    full = build_problem()
     t_gen = time.time() - t_gen
     if world > 1 and wl["mode"] != (0, 0):
         raise SystemExit("windowed (explicit) workloads are single-GPU; use --workload cfg4/cfg5 with --gpus > 1")
@@ -407,46 +473,56 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    n_ent, n_blk = s.sparse_stats()
+    n_pairs = s.sparse_pairs()
+    roof, phase_table = executed_roofline(args.workload, phase_ms, n_iter, solver_used, full, n_pairs, n_ent, spchol,
+                                          int(summ.total_linear_iters), peak, peak_src)
+    if roof is None:  # windowed explicit solver (graph replay: no phase events): the stand-alone kernel hook
+        roof = {"kernel": dom, "bound": "launch latency (problem fits L2 many times over)", "achieved": kernels[dom]["achieved_gbs"],
+                "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "timing": "stand-alone launches of the kernel hook, CUDA events, mean of 20 after 3 warm-ups, L2 flushed",
+                "bytes": kernels[dom]["bytes"]}
     line = {
         "metric": "LM iterations/s", "value": n_iter / (solve_ms * 1e-3), "unit": "LM iterations/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": solve_ms / max(n_iter, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"], "solver": SOLVER_NAME.get(solver_used, str(solver_used)),
-                   "solver_requested": args.solver if wl["mode"] == (0, 0) else "auto", "jacobian_store": store,
-                   "n_cam": full.n_cam, "n_pt": full.n_pt, "n_obs": full.n_obs,
-                   "scale": args.scale, "lm_iterations": n_iter, "pcg_iterations_total": int(summ.total_linear_iters),
-                   "pcg_iterations_per_lm": pcg_counts, "tolerances": "disabled (fixed iteration count)",
-                   "parallelism": ("single GPU" if world == 1 else
-                                   ("points sharded x%d: linearisation, point blocks and S formation per shard, NCCL all-reduce of the "
-                                    "block-sparse S (once per LM iteration); persistent PCG with the block-CSR product row-sharded, "
-                                    "exchange through flag-in-data slots in NVLink peer memory inside the kernel" % world)
-                                   if solver_used == 3 else
-                                   ("points sharded x%d, NCCL all-reduce of camera-sized vectors (one per PCG iteration)" % world)),
-                   "l2": ("block-sparse S is L2-resident by design (the product is timed warm, as it runs inside PCG); "
-                          if solver_used == 3 else "") +
-                         ("streaming inputs larger than L2 (factored store %.0f MB per pass)" % (full.n_obs * 36 / 1e6) if not flush
-                          else "L2 flushed (512 MiB write) between timed kernel launches"),
-                   "generate_s": round(t_gen, 2)},
+        "config": bench_config(args, wl, full, world, K),
+        "detail": {"solver": SOLVER_NAME.get(solver_used, str(solver_used)), "jacobian_store": store, "lm_iterations": n_iter,
+                   "pcg_iterations_total": int(summ.total_linear_iters), "pcg_iterations_per_lm": pcg_counts,
+                   "exchange": None if world == 1 else
+                   ("per LM iteration: NCCL all-reduce of camera blocks / reduced rhs / scalars and of the block-sparse S values; "
+                    "the factorisation runs replicated on every rank" if solver_used == 4 else
+                    "per LM iteration: NCCL all-reduce of the block-sparse S; persistent PCG row-sharded, exchange through tagged "
+                    "slots in NVLink peer memory inside the kernel" if solver_used == 3 else
+                    "NCCL all-reduce of camera-sized vectors (one per PCG iteration)"),
+                   "generate_s": round(t_gen, 2), "sparse_blocks": n_blk, "sparse_pairs": n_pairs},
         "jacobian_eval_obs_per_s": jac_obs_s,
-        "jacobian_eval_note": ("materialised r + Jc (2x6) + Jp (2x3), 208 B/obs (k_linearize, planes store)" if planes_kernels is not None
-                               else "kernel of the store in force (see roofline_kernels)"),
+        "jacobian_eval_note": ("materialised r + Jc (2x6) + Jp (2x3), 208 B/obs (k_linearize, planes store; SURVEY 8d's definition)"
+                               if planes_kernels is not None else "kernel of the store in force (see roofline_kernels)"),
         "jacobian_eval_factored_obs_per_s": jac_obs_s_factored,
         "final_cost": summ.final_cost, "initial_cost": summ.initial_cost,
         "solve_wall_ms": wall_solve * 1e3,
         "e2e": {"value": summ2.num_iterations / e2e_s, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d // max(K, 1),
                 "d2h_bytes_per_step": d2h // max(K, 1), "seconds": e2e_s,
-                "note": "upload (pinned host -> HBM, index build) + solve + download through ba_gpu_* with host buffers"},
+                "note": "upload (pinned host -> HBM, index + structure build, symbolic factorisation) + solve + download through "
+                        "ba_gpu_* with host buffers"},
         "gpu_launches": int(summ.kernel_launches),
-        "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["frac"], "traffic": ncu_traffic(args.workload, dom)[0],
-                     "traffic_source": ncu_traffic(args.workload, dom)[1], "peak_source": peak_src,
-                     "timing": "CUDA events on the solver stream, mean of 20 launches after 3 warm-ups",
-                     "bytes": kernels[dom]["bytes"]},
+        "roofline": roof,
+        "phase_rooflines": phase_table,
         "roofline_kernels": kernels,
+        "roofline_kernels_note": "stand-alone launches of single kernels (ba_gpu_time_kernel hook), CUDA events, 20 launches after 3 warm-ups",
         "phase_ms_per_step": {k: v / max(n_iter, 1) for k, v in phase_ms.items()},
         "sparse_cholesky": spchol,
+        "parity_vs_n1": parity_vs_n1(args.workload, args.scale, solver_used, trace),
         "clocks": clk,
     }
+    if args.write_golden and world == 1:
+        path = os.path.join(ROOT, "tests", "golden", "bench_trace.json")
+        g = json.load(open(path)) if os.path.exists(path) else {}
+        g["%s/solver%d" % (args.workload, solver_used)] = {
+            "cost": [t["cost"] for t in trace], "successful": [t["step_is_successful"] for t in trace],
+            "when": time.strftime("%Y-%m-%d"), "solver": SOLVER_NAME.get(solver_used)}
+        json.dump(g, open(path, "w"), indent=1)
     if args.workload == "cfg2" and world == 1:
         # the reference's own loop (src/main.cpp:161-166): windowOptimize over the last 20 keyframes every frame_frequency = 10
         # keyframes, warm-started, through the reference-facing entry point (host extraction + upload + solve + download per call)
@@ -489,10 +565,10 @@ def main():
         line["implicit_path"] = implicit_path
     if planes_kernels is not None:
         line["planes_store_kernels"] = planes_kernels
-    if args.workload == "cfg3ref":
-        line["cpu_baseline"] = None  # a dense 4798^2 Schur solve per LM iteration: no bounded CPU sample
-    elif not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_reference_sample(full, wl["mode"], pcg_counts, os.cpu_count() or 1)
+    if not args.no_cpu_baseline and world == 1:
+        # bounded sample of the same workload on the host cores: a few LM iterations actually run (about 10-30 s at config 5)
+        sample_iters = min(K, 3 if full.n_obs > 100000 else K)
+        line["cpu_baseline"] = cpu_reference_run(full, wl["mode"], sample_iters, os.cpu_count() or 1)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

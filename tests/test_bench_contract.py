@@ -23,6 +23,22 @@ def test_reference_arm_json_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["config"]["workload"].startswith("cfg1")
+    # the arm RUNS what it reports: K iterations inside the timed region, nothing extrapolated
+    assert cb["lm_iterations"] == 3 and abs(cb["seconds"] * 1e3 - line["ms_per_step"] * 3) < 1e-6
+    assert "nothing extrapolated" in cb["sample"] and "projected" not in line
+
+
+def test_both_arms_print_the_same_config():
+    """bench_config() is the one place the workload description comes from."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import ba_b200
+
+    class A:
+        workload, scale, solver = "cfg1", 1.0, "auto"
+    p = ba_b200.synthetic.make_config(1)
+    c = bench.bench_config(A, bench.WORKLOADS["cfg1"], p, 1, 10)
+    assert c["n_obs"] == p.n_obs and c["lm_iterations"] == 10 and "l2" in c and "parallelism" in c
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
