@@ -1404,6 +1404,19 @@ static PartRef reduce_scalar(ba_gpu_ctx *ctx, const double *part, int nblk, int 
   if (nccl_allreduce(ctx, out, 1, is_max)) ctx->comm_error = true;
   return PartRef{out, 1};
 }
+// several sums at once: one collective for the group (a sharded LM iteration is latency-bound: every small all-reduce costs
+// about as much as the kernels between two of them)
+static void reduce_scalar_group(ba_gpu_ctx *ctx, int n, const double *const part[], const int nblk[], int slot0, int gate, PartRef out[]) {
+  for (int k = 0; k < n; ++k) out[k] = PartRef{part[k], nblk[k]};
+  if (ctx->n_ranks == 1) return;
+  double *base = P<double>(ctx->scal) + slot0;
+  for (int k = 0; k < n; ++k) {
+    k_reduce_partials<<<1, BA_THREADS, 0, ctx->stream>>>(nblk[k], part[k], base + k, 0, P<LmState>(ctx->st), gate);
+    ctx->launches++;
+    out[k] = PartRef{base + k, 1};
+  }
+  if (nccl_allreduce(ctx, base, (size_t)n, false)) ctx->comm_error = true;
+}
 // per-camera sums of item partials: single GPU -> (item_ptr, part); sharded ->
 // dense local sums, all-reduce, (identity, dense)
 struct ItemRef {
@@ -1420,14 +1433,20 @@ static ItemRef reduce_items(ba_gpu_ctx *ctx, const double *part, Buf &dense, int
   if (nccl_allreduce(ctx, P<double>(dense), (size_t)ctx->n_cam * NV, false)) ctx->comm_error = true;
   return ItemRef{P<int32_t>(ctx->ident), P<double>(dense)};
 }
-// failure flags must agree on every rank (they steer the control flow)
-static void sync_flags(ba_gpu_ctx *ctx) {
-  if (ctx->n_ranks == 1) return;
+// failure flags must agree on every rank (they steer the control flow); a maximum over per-CTA partials (the gradient
+// norm) can ride on the same collective
+static PartRef sync_flags(ba_gpu_ctx *ctx, const double *max_part = nullptr, int max_nblk = 0, int gate = GATE_RUN) {
+  if (ctx->n_ranks == 1) return PartRef{max_part, max_nblk};
   double *out = P<double>(ctx->scal) + 32;
   k_flags_pack<<<1, 1, 0, ctx->stream>>>(P<LmState>(ctx->st), out);
-  if (nccl_allreduce(ctx, out, 2, true)) ctx->comm_error = true;
+  if (max_part) {
+    k_reduce_partials<<<1, BA_THREADS, 0, ctx->stream>>>(max_nblk, max_part, out + 2, 1, P<LmState>(ctx->st), gate);
+    ctx->launches++;
+  }
+  if (nccl_allreduce(ctx, out, max_part ? 3 : 2, true)) ctx->comm_error = true;
   k_flags_unpack<<<1, 1, 0, ctx->stream>>>(P<LmState>(ctx->st), out);
   ctx->launches += 2;
+  return PartRef{out + 2, 1};
 }
 
 // ------------------------------------------------------------------ fork / join of independent branches
@@ -2070,9 +2089,11 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
   phase_mark(ctx, ctx->forking ? BA_PHASE_BACKSUB : BA_PHASE_CANDIDATE);
   sync_flags(ctx);
   {
-    const PartRef rm = reduce_scalar(ctx, P<double>(ctx->pc_mcc), ctx->nblk_obs, 3, false, GATE_RUN);
-    const PartRef rs = reduce_scalar(ctx, P<double>(ctx->pe_step), ctx->nblk_ent, 4, false, GATE_RUN);
-    const PartRef rc2 = reduce_scalar(ctx, P<double>(ctx->pc_cand), ctx->nblk_obs, 5, false, GATE_RUN);
+    const double *const parts[3] = {P<double>(ctx->pc_mcc), P<double>(ctx->pe_step), P<double>(ctx->pc_cand)};
+    const int nblks[3] = {ctx->nblk_obs, ctx->nblk_ent, ctx->nblk_obs};
+    PartRef grp[3];
+    reduce_scalar_group(ctx, 3, parts, nblks, 3, GATE_RUN, grp);
+    const PartRef rm = grp[0], rs = grp[1], rc2 = grp[2];
     LAUNCH(k_lm_control, 1, BA_THREADS, 0, rm.n, rs.n, K, rm.p, rs.p, rc2.p, P<double>(ctx->rk), P<double>(ctx->Jkk),
            P<double>(ctx->yk), P<double>(ctx->intr_c), P<double>(ctx->intr_prior), ctx->cp.sw_intr, ctx->lo, st,
            P<BaIterRec>(ctx->trace));
@@ -2087,11 +2108,13 @@ static int enqueue_lm_iteration(ba_gpu_ctx *ctx) {
   // (the side stream runs k_accept, then the point-major branch of the relinearisation; enqueue_linearize joins both)
   enqueue_linearize(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk), false, overlap_accept);
   enqueue_state_norms(ctx, GATE_ACCEPTED, P<double>(ctx->sc), P<double>(ctx->sp), P<double>(ctx->sk));
-  sync_flags(ctx);
+  const PartRef rg = sync_flags(ctx, P<double>(ctx->pe_gmax), ctx->nblk_ent, GATE_ACCEPTED);  // flags + gradient norm: one max
   {
-    const PartRef rc3 = reduce_scalar(ctx, P<double>(ctx->pc_lin), ctx->nblk_obs, 6, false, GATE_ACCEPTED);
-    const PartRef rg = reduce_scalar(ctx, P<double>(ctx->pe_gmax), ctx->nblk_ent, 7, true, GATE_ACCEPTED);
-    const PartRef rx = reduce_scalar(ctx, P<double>(ctx->pe_xn), ctx->nblk_ent, 8, false, GATE_ACCEPTED);
+    const double *const parts[2] = {P<double>(ctx->pc_lin), P<double>(ctx->pe_xn)};
+    const int nblks[2] = {ctx->nblk_obs, ctx->nblk_ent};
+    PartRef grp[2];
+    reduce_scalar_group(ctx, 2, parts, nblks, 6, GATE_ACCEPTED, grp);
+    const PartRef rc3 = grp[0], rx = grp[1];
     LAUNCH(k_lm_post, 1, BA_THREADS, 0, rc3.n, rg.n, K, rc3.p, rg.p, rx.p, P<double>(ctx->rk), ctx->lo, st,
            P<BaIterRec>(ctx->trace), GATE_ACCEPTED);
   }
@@ -2164,8 +2187,14 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
       ctx->pdl = false;
       if (rc) return rc;
     }
-    const bool implicit = ctx->solver != BA_SOLVER_EXPLICIT_CHOLESKY;
-    if (!implicit && (it % poll) != 0 && it <= ctx->lo.max_num_iterations) continue;
+    // The launch-per-step PCG loops on the host (it polls the PCG controller itself) and the row-sharded PCG reads its abort
+    // flag after every solve; every other path takes all decisions on the device, so the host only looks at the controller
+    // state every poll_interval iterations and keeps the launch queue full in between (a host synchronisation per LM
+    // iteration left the GPU idle while the ~60 launches of the next iteration were being enqueued).
+    const bool host_in_loop = ctx->solver == BA_SOLVER_IMPLICIT_PCG ||
+                              (ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG && !ctx->spchol &&
+                               (ctx->dist_pcg || !(ctx->opt.persistent_pcg && ctx->pcg_grid > 0)));
+    if (!host_in_loop && (it % poll) != 0 && it <= ctx->lo.max_num_iterations) continue;
     rc = poll_state(ctx);
     if (rc) return rc;
     if (ctx->h_st->done) break;
