@@ -204,14 +204,33 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
     }
     const double *Uc = a.U + 36 * spc_off(Cn, SPN_U_LO);
     const double *ruc = a.ru + 6 * (size_t)Cn[SPN_BORD];
-    const int n_el = 6 * n_in * nbc6;
-#pragma unroll 2
-    for (int idx = tid; idx < n_el; idx += SPC_THREADS) {
-      const int col = idx / nbc6, row = idx - col * nbc6;
-      const int j = col / 6, i = row / 6;
-      if (i < j) continue;
-      const int rj = __ldg(rel + j), ri = __ldg(rel + i);
-      P[(size_t)(6 * rj + (col - 6 * j)) * LD + 6 * ri + (row - 6 * i)] -= __ldcg(Uc + idx);
+    // one warp per scalar column of the child's update matrix (block lower triangle: rows from the column's own block
+    // down), lanes along the rows: coalesced reads of the column from L2, up to four independent loads in flight per lane
+    // before the first one is consumed (this gather was the longest piece of a node's critical path: one dependent
+    // round trip to L2 per element in the first version)
+    for (int col = warp; col < 6 * n_in; col += SPC_WARPS) {
+      const int j = col / 6, cj = col - 6 * j;
+      const int rj = __ldg(rel + j);
+      const double *ucol = Uc + (size_t)col * nbc6;
+      double *pcol = P + (size_t)(6 * rj + cj) * LD;
+      for (int row0 = 6 * j; row0 < nbc6; row0 += 128) {
+        double v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = row0 + lane + 32 * u;
+          v[u] = 0.0;
+          dst[u] = -1;
+          if (row < nbc6) {
+            v[u] = __ldcg(ucol + row);
+            const int i = row / 6;
+            dst[u] = 6 * __ldg(rel + i) + (row - 6 * i);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dst[u] >= 0) pcol[dst[u]] -= v[u];
+      }
     }
     for (int idx = tid; idx < 6 * n_in; idx += SPC_THREADS) zf[6 * __ldg(rel + idx / 6) + idx % 6] -= __ldcg(ruc + idx);
     __syncthreads();
@@ -273,31 +292,61 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
       __syncwarp();
       ok = spc_chol6(P, LD, k + 1, lane, Tb + ((k + 1) & 1) * 36, a.linv + 36 * (size_t)(k0 + k + 1)) && ok;
     } else {
-      const int base = 6 * (k + 2), nrows = LD - base, avail = SPC_THREADS - 32;
-      if (nrows > 0) {
-        int G = avail / nrows;
+      // own rows (R < C6: their block-column range ends at their own block) one per thread; border rows (all block columns)
+      // two per thread, so that the pivot rows lj -- warp-broadcast loads -- are fetched once for two rows
+      const int base = 6 * (k + 2), avail = SPC_THREADS - 32;
+      const int n_own = C6 > base ? C6 - base : 0;
+      const int b0 = C6 > base ? C6 : base, n_bord = LD - b0, n_pair = (n_bord + 1) >> 1;
+      const int n_it = n_own + n_pair;
+      if (n_it > 0) {
+        int G = avail / n_it;
         G = G < 1 ? 1 : (G > 4 ? 4 : G);
-        for (int t = tid - 32; t < G * nrows; t += avail) {
-          const int g = t / nrows, R = base + (t - g * nrows);
-          const int jmax = R / 6 < m - 1 ? R / 6 : m - 1;
-          double x[6];
-          spc_ld6(LT + R * 6, x);
-          for (int j = k + 1 + g; j <= jmax; j += G) {
+        for (int t = tid - 32; t < G * n_it; t += avail) {
+          const int g = t / n_it, u = t - g * n_it;
+          if (u < n_own) {
+            const int R = base + u;
+            const int jmax = R / 6;  // (< m: an own row)
+            double x[6];
+            spc_ld6(LT + R * 6, x);
+            for (int j = k + 1 + g; j <= jmax; j += G) {
 #pragma unroll
-            for (int bb = 0; bb < 6; ++bb) {
-              double lj[6];
-              spc_ld6(LT + (6 * j + bb) * 6, lj);
+              for (int bb = 0; bb < 6; ++bb) {
+                double lj[6];
+                spc_ld6(LT + (6 * j + bb) * 6, lj);
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) s += x[c] * lj[c];
+                P[(size_t)(6 * j + bb) * LD + R] -= s;
+              }
+            }
+            if (g == 0) {
               double s = 0.0;
 #pragma unroll
-              for (int c = 0; c < 6; ++c) s += x[c] * lj[c];
-              P[(size_t)(6 * j + bb) * LD + R] -= s;
+              for (int c = 0; c < 6; ++c) s += x[c] * zf[6 * k + c];
+              zf[R] -= s;
             }
-          }
-          if (g == 0 && R < C6) {
-            double s = 0.0;
+          } else {
+            const int R1 = b0 + (u - n_own), R2 = R1 + n_pair;
+            const bool two = R2 < LD;
+            double x1[6], x2[6];
+            spc_ld6(LT + R1 * 6, x1);
+            spc_ld6(LT + (two ? R2 : R1) * 6, x2);
+            for (int j = k + 1 + g; j < m; j += G) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) s += x[c] * zf[6 * k + c];
-            zf[R] -= s;
+              for (int bb = 0; bb < 6; ++bb) {
+                double lj[6];
+                spc_ld6(LT + (6 * j + bb) * 6, lj);
+                double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                  s1 += x1[c] * lj[c];
+                  s2 += x2[c] * lj[c];
+                }
+                double *pc = P + (size_t)(6 * j + bb) * LD;
+                pc[R1] -= s1;
+                if (two) pc[R2] -= s2;
+              }
+            }
           }
         }
       }
@@ -334,6 +383,7 @@ k_spchol_update(SpChol a, int lvl_first, int tiles, LmState *st, int gate) {
   double *zf = LB + (size_t)NB6 * C6;
   {
     const double *Pg = a.panel + 36 * spc_off(N, SPN_PANEL_LO) + C6;
+#pragma unroll 8
     for (int idx = tid; idx < NB6 * C6; idx += SPU_THREADS) {
       const int c = idx / NB6, r = idx - c * NB6;
       LB[idx] = Pg[(size_t)c * LD + r];
