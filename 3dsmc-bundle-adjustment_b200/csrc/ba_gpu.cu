@@ -137,7 +137,8 @@ struct ba_gpu_ctx {
   bool spmv6 = false;  // BA_SPMV6=1: six-lanes-per-block product kernel in the launch-per-step PCG / product hook (experiment)
   bool pdl = false, pdl_off = false;  // programmatic dependent launches inside the windowed LM iteration (BA_NO_PDL=1: off)
   int legacy_chol = 0;  // BA_LEGACY_CHOL=1: left-looking single-CTA Cholesky, =2: shared-memory L D L^T, =3: grid-barrier blocked substitution (A/B timing only)
-  Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
+  Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal, sp_lrow;
+  bool sp_rows_kernel = false;  // values of S by the row-per-CTA kernel (k_sp_schur_rows)
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
   Buf my_rows, row_flag, row_pos, ipc_stage;
   void *xch = nullptr;          // own exchange buffer (cudaMalloc, cudaIpc-exported)
@@ -152,7 +153,7 @@ struct ba_gpu_ctx {
   bool spchol = false;          // the block-sparse solver factorises S instead of running PCG
   SpSymbolic sym;               // host-side structure of the last upload
   Buf spn_node, spn_bord, spn_children, spn_rel, spn_inv, spn_aent, spn_perm, spn_levels;
-  Buf spc_panel, spc_U, spc_ru, spc_z, spc_linv, spc_ypos;
+  Buf spc_panel, spc_U, spc_ru, spc_z, spc_linv, spc_ypos, spc_prof;
   size_t spc_smem_factor = 0, spc_smem_solve = 0, spc_smem_update = 0;
   double sym_ms = 0.0;          // host time of the symbolic phase (last upload)
   // phase timing of the large-problem solvers: CUDA events on the solver stream at the phase boundaries of every LM
@@ -718,15 +719,15 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   RES(sp_vals, np8);
   RES(sp_keys2, np8);
   RES(sp_pairs, np8);
-  LAUNCH(k_sp_emit, ctx->nblk_pt, BA_THREADS, 0, n_pt, n_cam, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam), ctx->fixed_cam,
-         P<long long>(ctx->sp_off), P<u64>(ctx->sp_keys), P<u64>(ctx->sp_vals));
+  LAUNCH(k_sp_emit, ctx->nblk_pt, BA_THREADS, 0, n_pt, n_cam, P<int32_t>(ctx->pt_rowptr), P<int32_t>(ctx->pm_cam), P<int32_t>(ctx->perm),
+         ctx->fixed_cam, P<long long>(ctx->sp_off), P<u64>(ctx->sp_keys), P<u64>(ctx->sp_vals));
   int bits = 1;
   while (bits < 64 && ((u64)1 << bits) < (u64)n_cam * (u64)n_cam) ++bits;
   CUBCALL(cub::DeviceRadixSort::SortPairs, P<u64>(ctx->sp_keys), P<u64>(ctx->sp_keys2), P<u64>(ctx->sp_vals), P<u64>(ctx->sp_pairs),
           (int)n_pairs, 0, bits);
   RES(sp_pair_pt, ((size_t)n_pairs + 1) * 4);
   LAUNCH(k_sp_pair_points, (int)((n_pairs + BA_THREADS - 1) / BA_THREADS), BA_THREADS, 0, n_pairs, P<u64>(ctx->sp_pairs),
-         P<int32_t>(ctx->pm_pt), P<int32_t>(ctx->sp_pair_pt));
+         P<int32_t>(ctx->pt_idx), P<int32_t>(ctx->sp_pair_pt));
   {
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sp_schur, BA_THREADS, 0));
@@ -749,6 +750,19 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   RES(sp_lkeys, ((size_t)n_blk + 1) * 8);
   RES(sp_gid, ((size_t)n_blk + 1) * 4);
   CK(cudaMemcpyAsync(ctx->sp_lkeys.p, ctx->sp_ukeys.p, (size_t)n_blk * 8, cudaMemcpyDeviceToDevice, s));
+  {
+    // row pointers of the local block list and the largest row (in work items) for the row-per-CTA value kernel
+    RES(sp_lrow, ((size_t)n_cam + 2) * 4);
+    CK(cudaMemsetAsync(ctx->sp_lrow.p, 0, ((size_t)n_cam + 2) * 4, s));
+    CK(cudaMemsetAsync(ctx->sp_nruns.p, 0, 8, s));
+    LAUNCH(k_sp_row_ptr, cdiv(n_blk, BA_THREADS), BA_THREADS, 0, n_blk, n_cam, P<u64>(ctx->sp_lkeys), P<int32_t>(ctx->sp_lrow));
+    LAUNCH(k_sp_row_items, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->sp_lrow), P<int32_t>(ctx->sb_ptr), P<int32_t>(ctx->sp_nruns) + 1);
+    int32_t h_max_items = 0;
+    CK(cudaMemcpyAsync(&h_max_items, P<int32_t>(ctx->sp_nruns) + 1, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->sp_rows_kernel = h_max_items <= BA_SPS_MAX_ITEMS && getenv("BA_SP_SCHUR_BLOCKS") == nullptr;
+    CK(cudaFuncSetAttribute(k_sp_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BA_SPS_SMEM));
+  }
   if (ctx->n_ranks > 1) {
     // point-sharded: every rank holds the blocks its own points touch.  The block structure must be the
     // same everywhere (S is all-reduced, PCG runs replicated): all-gather the key lists, sort, unique.
@@ -878,6 +892,8 @@ static int build_spchol(ba_gpu_ctx *ctx) {
   RES(spc_z, ((size_t)n_cam + 1) * 48);
   RES(spc_linv, ((size_t)n_cam + 1) * 288);
   RES(spc_ypos, ((size_t)n_cam + 1) * 48);
+  RES(spc_prof, 128);
+  CK(cudaMemsetAsync(ctx->spc_prof.p, 0, 128, s));
   RES(dsq, ((size_t)n_cam + 1) * 48);
   size_t sf = 0, ss = 0, su = 0;
   for (int id = 0; id < S.n_nodes; ++id) {
@@ -1684,10 +1700,17 @@ static void enqueue_sparse_values(ba_gpu_ctx *ctx, int gate) {
   if (ctx->n_ranks > 1) cudaMemsetAsync(ctx->Sblk.p, 0, (size_t)ctx->n_sblk * 288, ctx->stream);
   int *ticket = reinterpret_cast<int *>(P<char>(ctx->pcg_bar) + 16);
   cudaMemsetAsync(ticket, 0, 4, ctx->stream);
-  LAUNCH(k_sp_schur, std::min(cdiv(ctx->n_sblk_local, BA_SPS_CHUNK), ctx->n_sm * ctx->sp_ctas_per_sm), BA_THREADS, 0,
-         ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid),
-         P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->sp_pair_pt), ctx->Fp_, P<double>(ctx->geo), P<double>(ctx->intr),
-         P<double>(ctx->Vs), P<double>(ctx->Sblk), ticket, st, gate);
+  // (pair records hold canonical observation indices: both kernels read the CAMERA-major factored planes)
+  if (ctx->sp_rows_kernel)
+    LAUNCH(k_sp_schur_rows, std::min(ctx->n_cam, ctx->n_sm), BA_THREADS, BA_SPS_SMEM, ctx->n_cam, P<int32_t>(ctx->sp_lrow),
+           P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid), P<unsigned long long>(ctx->sp_pairs),
+           P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->pt_idx), ctx->Fc_, P<double>(ctx->geo), P<double>(ctx->intr), P<double>(ctx->Vs),
+           P<double>(ctx->Sblk), ticket, st, gate);
+  else
+    LAUNCH(k_sp_schur, std::min(cdiv(ctx->n_sblk_local, BA_SPS_CHUNK), ctx->n_sm * ctx->sp_ctas_per_sm), BA_THREADS, 0,
+           ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid),
+           P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->sp_pair_pt), ctx->Fc_, P<double>(ctx->geo), P<double>(ctx->intr),
+           P<double>(ctx->Vs), P<double>(ctx->Sblk), ticket, st, gate);
   if (ctx->n_ranks > 1 && nccl_allreduce(ctx, P<double>(ctx->Sblk), (size_t)ctx->n_sblk * 36, false)) ctx->comm_error = true;
   LAUNCH(k_sp_add_diag, cdiv(ctx->n_cam * 36, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->sp_diag), P<double>(ctx->U),
          P<double>(ctx->Sblk), st, gate);
@@ -1715,6 +1738,7 @@ static SpChol spchol_args(ba_gpu_ctx *ctx) {
   a.linv = P<double>(ctx->spc_linv);
   a.ypos = P<double>(ctx->spc_ypos);
   a.yc = P<double>(ctx->yc);
+  a.prof = getenv("BA_SPCHOL_PROF") ? P<unsigned long long>(ctx->spc_prof) : nullptr;
   return a;
 }
 static void enqueue_spchol(ba_gpu_ctx *ctx, int gate) {
@@ -2230,6 +2254,14 @@ extern "C" int ba_gpu_solve(ba_gpu_ctx *ctx, ba_gpu_summary *summary) {
   if (nt) CK(cudaMemcpy(ctx->h_trace.data(), ctx->trace.p, (size_t)nt * sizeof(BaIterRec), cudaMemcpyDeviceToHost));
   ctx->last_summary = s;
   if (summary) *summary = s;
+  if (getenv("BA_SPCHOL_PROF") && ctx->spchol) {
+    unsigned long long pr[8];
+    cudaMemcpy(pr, ctx->spc_prof.p, 64, cudaMemcpyDeviceToHost);
+    cudaMemset(ctx->spc_prof.p, 0, 64);
+    const double n = (double)std::max<unsigned long long>(1, pr[4]);
+    fprintf(stderr, "[BA_SPCHOL_PROF] us per factor launch (thread block 0, %llu launches): assemble S %.2f | extend-add %.2f | factor loop %.2f | "
+                    "write panel %.2f\n", pr[4], pr[0] / n / 1e3, pr[1] / n / 1e3, pr[2] / n / 1e3, pr[3] / n / 1e3);
+  }
   if (getenv("BA_PCG_PROF") && ctx->pcg_bar.p && ctx->solver == BA_SOLVER_SPARSE_SCHUR_PCG) {
     unsigned long long pr[6];
     cudaMemcpy(pr, P<unsigned long long>(ctx->pcg_bar) + 8, 48, cudaMemcpyDeviceToHost);

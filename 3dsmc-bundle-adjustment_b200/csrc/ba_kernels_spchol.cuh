@@ -36,7 +36,15 @@ struct SpChol {
   double *panel, *U, *ru;     // per node: factor panel, update matrix (dense lower incl. full diagonal blocks), rhs update [6 nb]
   double *z, *linv, *ypos;    // by elimination position: forward-substituted rhs [6], inverse pivot blocks [36], solution [6]
   double *yc;                 // solution by camera [6 n_cam]
+  unsigned long long *prof;   // nullable (BA_SPCHOL_PROF=1): ns per phase of thread block 0 of every factor launch, summed
 };
+#define SPC_TICK(slot)                                          \
+  if (a.prof && blockIdx.x == 0 && tid == 0) {                  \
+    unsigned long long t1_;                                     \
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1_));      \
+    a.prof[slot] += t1_ - t0_;                                  \
+    t0_ = t1_;                                                  \
+  }
 
 __host__ __device__ inline size_t spc_off(const int32_t *N, int lo) { return ((size_t)N[lo + 1] << 31) | (size_t)N[lo]; }
 inline size_t spc_factor_smem(int m, int nb) { return ((size_t)36 * (m + nb) * (m + 1) + 6 * m + 72 + 8) * 8; }
@@ -155,6 +163,8 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
   double *zf = LT + (size_t)LD * 6;      // right-hand side of the own cameras
   double *Tb = zf + C6;                  // two inverse pivot blocks (ping-pong)
 
+  unsigned long long t0_ = 0;
+  if (a.prof && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0_));
   // ---- phase 0: clear, right-hand side
   for (int i = tid; i < LD * C6; i += SPC_THREADS) P[i] = 0.0;
   for (int i = tid; i < C6; i += SPC_THREADS) zf[i] = a.b[6 * (size_t)a.perm[k0 + i / 6] + i % 6];
@@ -182,6 +192,7 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
     }
   }
   __syncthreads();
+  SPC_TICK(0)
   // ---- phase 1b: extend-add of the children (one after the other: fixed order; inside a child the map is injective).
   //      rel is ascending, so the child's border cameras that are OWN cameras of this node come first: only those block
   //      columns land in the panel (the rest of the child's update matrix passes through to this node's, k_spchol_update)
@@ -235,6 +246,7 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
     for (int idx = tid; idx < 6 * n_in; idx += SPC_THREADS) zf[6 * __ldg(rel + idx / 6) + idx % 6] -= __ldcg(ruc + idx);
     __syncthreads();
   }
+  SPC_TICK(1)
   // ---- phase 2: right-looking factorisation, 6 columns (one camera) per step
   bool ok = true;
   if (warp == 0) ok = spc_chol6(P, LD, 0, lane, Tb, a.linv + 36 * (size_t)k0);
@@ -354,12 +366,16 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
     __syncthreads();
   }
   if (warp == 0 && lane == 0 && !ok) st->lin_fail = 1;
+  SPC_TICK(2)
   // ---- phase 3: panel and forward-substituted right-hand side to global memory
   {
     double *Pg = a.panel + 36 * spc_off(N, SPN_PANEL_LO);
     for (int i = tid; i < LD * C6; i += SPC_THREADS) Pg[i] = P[i];
     for (int i = tid; i < C6; i += SPC_THREADS) a.z[6 * (size_t)k0 + i] = zf[i];
   }
+  __syncthreads();
+  SPC_TICK(3)
+  if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[4] += 1;
 }
 
 // Update matrix of the nodes of one level, after their panels are factorised: U = L_B L_B^T + what the children pass through

@@ -15,3 +15,5 @@ for l in open(sys.argv[1]):
     elif 'Error' in l or 'error' in l: print(l.strip()[:300])
 PY
 done
+BA_SPCHOL_PROF=1 python profiles/profile_target.py 5 5 500 4 2>&1 | tail -3
+BA_SPCHOL_PROF=1 python profiles/profile_target.py 3 5 500 4 2>&1 | tail -3
