@@ -137,8 +137,7 @@ struct ba_gpu_ctx {
   bool spmv6 = false;  // BA_SPMV6=1: six-lanes-per-block product kernel in the launch-per-step PCG / product hook (experiment)
   bool pdl = false, pdl_off = false;  // programmatic dependent launches inside the windowed LM iteration (BA_NO_PDL=1: off)
   int legacy_chol = 0;  // BA_LEGACY_CHOL=1: left-looking single-CTA Cholesky, =2: shared-memory L D L^T, =3: grid-barrier blocked substitution (A/B timing only)
-  Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal, sp_lrow;
-  bool sp_rows_kernel = false;  // values of S by the row-per-CTA kernel (k_sp_schur_rows)
+  Buf sp_lkeys, sp_gid, sp_gather, sp_gsorted, sp_diag, sp_scal;
   // row-sharded persistent PCG over NVLink peer memory (ba_kernels_dist.cuh)
   Buf my_rows, row_flag, row_pos, ipc_stage;
   void *xch = nullptr;          // own exchange buffer (cudaMalloc, cudaIpc-exported)
@@ -750,19 +749,6 @@ static int build_sparse_structure(ba_gpu_ctx *ctx) {
   RES(sp_lkeys, ((size_t)n_blk + 1) * 8);
   RES(sp_gid, ((size_t)n_blk + 1) * 4);
   CK(cudaMemcpyAsync(ctx->sp_lkeys.p, ctx->sp_ukeys.p, (size_t)n_blk * 8, cudaMemcpyDeviceToDevice, s));
-  {
-    // row pointers of the local block list and the largest row (in work items) for the row-per-CTA value kernel
-    RES(sp_lrow, ((size_t)n_cam + 2) * 4);
-    CK(cudaMemsetAsync(ctx->sp_lrow.p, 0, ((size_t)n_cam + 2) * 4, s));
-    CK(cudaMemsetAsync(ctx->sp_nruns.p, 0, 8, s));
-    LAUNCH(k_sp_row_ptr, cdiv(n_blk, BA_THREADS), BA_THREADS, 0, n_blk, n_cam, P<u64>(ctx->sp_lkeys), P<int32_t>(ctx->sp_lrow));
-    LAUNCH(k_sp_row_items, ctx->nblk_cam, BA_THREADS, 0, n_cam, P<int32_t>(ctx->sp_lrow), P<int32_t>(ctx->sb_ptr), P<int32_t>(ctx->sp_nruns) + 1);
-    int32_t h_max_items = 0;
-    CK(cudaMemcpyAsync(&h_max_items, P<int32_t>(ctx->sp_nruns) + 1, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    ctx->sp_rows_kernel = h_max_items <= BA_SPS_MAX_ITEMS && getenv("BA_SP_SCHUR_BLOCKS") == nullptr;
-    CK(cudaFuncSetAttribute(k_sp_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BA_SPS_SMEM));
-  }
   if (ctx->n_ranks > 1) {
     // point-sharded: every rank holds the blocks its own points touch.  The block structure must be the
     // same everywhere (S is all-reduced, PCG runs replicated): all-gather the key lists, sort, unique.
@@ -1700,17 +1686,11 @@ static void enqueue_sparse_values(ba_gpu_ctx *ctx, int gate) {
   if (ctx->n_ranks > 1) cudaMemsetAsync(ctx->Sblk.p, 0, (size_t)ctx->n_sblk * 288, ctx->stream);
   int *ticket = reinterpret_cast<int *>(P<char>(ctx->pcg_bar) + 16);
   cudaMemsetAsync(ticket, 0, 4, ctx->stream);
-  // (pair records hold canonical observation indices: both kernels read the CAMERA-major factored planes)
-  if (ctx->sp_rows_kernel)
-    LAUNCH(k_sp_schur_rows, std::min(ctx->n_cam, ctx->n_sm), BA_THREADS, BA_SPS_SMEM, ctx->n_cam, P<int32_t>(ctx->sp_lrow),
-           P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid), P<unsigned long long>(ctx->sp_pairs),
-           P<int32_t>(ctx->cam_rowptr), P<int32_t>(ctx->pt_idx), ctx->Fc_, P<double>(ctx->geo), P<double>(ctx->intr), P<double>(ctx->Vs),
-           P<double>(ctx->Sblk), ticket, st, gate);
-  else
-    LAUNCH(k_sp_schur, std::min(cdiv(ctx->n_sblk_local, BA_SPS_CHUNK), ctx->n_sm * ctx->sp_ctas_per_sm), BA_THREADS, 0,
-           ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid),
-           P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->sp_pair_pt), ctx->Fc_, P<double>(ctx->geo), P<double>(ctx->intr),
-           P<double>(ctx->Vs), P<double>(ctx->Sblk), ticket, st, gate);
+  // (pair records hold canonical observation indices: the kernel reads the CAMERA-major factored planes)
+  LAUNCH(k_sp_schur, std::min(cdiv(ctx->n_sblk_local, BA_SPS_CHUNK), ctx->n_sm * ctx->sp_ctas_per_sm), BA_THREADS, 0,
+         ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid),
+         P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->sp_pair_pt), ctx->Fc_, P<double>(ctx->geo), P<double>(ctx->intr),
+         P<double>(ctx->Vs), P<double>(ctx->Sblk), ticket, st, gate);
   if (ctx->n_ranks > 1 && nccl_allreduce(ctx, P<double>(ctx->Sblk), (size_t)ctx->n_sblk * 36, false)) ctx->comm_error = true;
   LAUNCH(k_sp_add_diag, cdiv(ctx->n_cam * 36, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->sp_diag), P<double>(ctx->U),
          P<double>(ctx->Sblk), st, gate);

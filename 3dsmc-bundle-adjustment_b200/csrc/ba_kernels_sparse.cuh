@@ -293,7 +293,13 @@ k_sp_minv(int n_cam, const int32_t *__restrict__ diag, const double *__restrict_
 // shared-memory counter (the diagonal block -- the longest pair list of a row -- comes first).  All warps of a CTA then
 // gather the factored records of the SAME cameras' observations at the same time, through L1-allocating loads: the
 // row camera's records are read by every block of the row and hit L1 after the first touch (ncu, round 1 version with
-// one global ticket per block and L1-bypassing loads: 36 % of the stall samples on these gathers at 8 warps per SM).
+// one global ticket per block and L1-bypassing loads: 36 % of the stall samples on these gathers at 8 warps per SM;
+// 1.43 -> 1.24 ms at config 5).  Pair records hold CANONICAL (camera-major) observation indices, so both sides of a
+// block index the contiguous run of one camera in the camera-major factored planes.
+// Measured and rejected in round 2 (config 5, same results): two CTAs per SM at 128 registers (accumulators spill to
+// local memory: 1.57 ms); one camera ROW per CTA with the row's a side -- rows of Jc and Vs p-rows, 18 doubles per
+// observation -- staged in shared memory, chunked work items and prefetched b-side records (40 B and ~140 multiply-adds
+// per pair instead of 124 B and ~190, but three CTA-wide phases per row at 8 warps per SM: 1.92 ms).
 #define BA_SPS_CHUNK 32
 __device__ __forceinline__ ObsGeo load_geo_l1(const FPlanes &F, int i, double fx, double fy) {
   const double2 a = __ldg(F.g0 + i), b = __ldg(F.g1 + i);
@@ -389,277 +395,6 @@ k_sp_schur(int n_blk, int n_cam, const int32_t *__restrict__ blk_ptr, const unsi
           const int r = k / 6, c = k - 6 * (k / 6);
           Sb[k] = -(acc[k] * (ri.s[r] * rj.s[c]));  // k_sp_add_diag puts U on the diagonal blocks
         }
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Values of S, second version (in force): ONE CAMERA ROW PER CTA.
-//   All upper blocks (i, j >= i) of row camera i read the SAME a-side observations -- those of camera i -- once per block,
-//   ~15 times per row.  The CTA that takes row i first stages, for every observation a of camera i (camera-major factored
-//   planes: one contiguous, coalesced run), the 18 numbers the pairs need from the a side
-//       a0, a1 (the two rows of Jc_a diag(s)^-1, 6 each)   and   v0 = Vs_p pa0, v1 = Vs_p pa1 (3 each; p = the point of a)
-//   in shared memory: a pair then costs one 8-byte pair record, one gathered 32-byte record of the b-side observation
-//   (L1-allocating: the warps of a CTA walk the observations of the same ~15 column cameras) and shared-memory reads --
-//   40 B and ~140 multiply-adds instead of 124 B and ~190 -- and no per-pair gather of Vs at all.
-//   Work items are CHUNKS of <= BA_SPS_ITEM pairs of one block (the diagonal block of a row is 5-8 times longer than the
-//   others: unsplit it sets the CTA's critical path); warps take items from a shared-memory counter; a block that was split
-//   is added up from its chunk partials in chunk order.  The next trip's pair record and b-side record are fetched before
-//   the current trip is consumed.  Pair records hold CANONICAL (camera-major) observation indices.
-//   Fixed summation order per block (chunks of 128 pairs, lanes striding a chunk, butterfly, chunks in order): results do
-//   not depend on the grid, on the order rows are taken, or on the rank count.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double pick6(const double a[6], int k);
-#define BA_SPS_ITEM 128       // pairs per work item
-#define BA_SPS_MAX_OBS 1024   // staged a-side observations (18 doubles each); longer camera rows compute the a side per pair
-#define BA_SPS_MAX_ITEMS 192  // work items of a row
-#define BA_SPS_MAX_SLOTS 64   // chunk partials of split blocks
-#define BA_SPS_MAX_SPLIT 32   // split blocks of a row
-#define BA_SPS_SMEM ((size_t)BA_SPS_MAX_OBS * 18 * 8 + (size_t)BA_SPS_MAX_SLOTS * 36 * 8 + (size_t)BA_SPS_MAX_ITEMS * 16 + \
-                     (size_t)BA_SPS_MAX_SPLIT * 16 + 64)
-
-// local row pointers of the (key-sorted) local block list: lrow_ptr[c] = first local block whose row camera is >= c
-__global__ void __launch_bounds__(BA_THREADS)
-k_sp_row_ptr(int n_blk, int n_cam, const unsigned long long *__restrict__ lkeys, int32_t *__restrict__ lrow_ptr) {
-  const int b = blockIdx.x * BA_THREADS + threadIdx.x;
-  if (b >= n_blk) return;
-  const int ci = (int)(lkeys[b] / (unsigned long long)n_cam);
-  const int prev = b > 0 ? (int)(lkeys[b - 1] / (unsigned long long)n_cam) : -1;
-  for (int cc = prev + 1; cc <= ci; ++cc) lrow_ptr[cc] = b;
-  if (b == n_blk - 1)
-    for (int cc = ci + 1; cc <= n_cam; ++cc) lrow_ptr[cc] = n_blk;
-}
-
-// largest number of work items any row needs (blocks, long ones counted by their chunks): the row kernel is used when it
-// fits BA_SPS_MAX_ITEMS
-__global__ void __launch_bounds__(BA_THREADS)
-k_sp_row_items(int n_cam, const int32_t *__restrict__ lrow_ptr, const int32_t *__restrict__ blk_ptr, int32_t *max_items) {
-  const int c = blockIdx.x * BA_THREADS + threadIdx.x;
-  if (c >= n_cam) return;
-  int n = 0;
-  for (int b = lrow_ptr[c]; b < lrow_ptr[c + 1]; ++b) {
-    const int np = blk_ptr[b + 1] - blk_ptr[b];
-    n += np > BA_SPS_ITEM ? (np + BA_SPS_ITEM - 1) / BA_SPS_ITEM : 1;
-  }
-  if (n > 0) atomicMax(max_items, n);
-}
-
-// the 18 a-side numbers of canonical observation ia (camera rotation Ri, point p = pt_idx[ia])
-__device__ __forceinline__ void sps_a_side(const FPlanes &F, int ia, const int32_t *__restrict__ pt_idx, const double *__restrict__ Vs,
-                                           const double Ri[9], double fx, double fy, double out[18]) {
-  const ObsGeo ga = load_geo_l1(F, ia, fx, fy);
-  double pa0[3], pa1[3];
-  sp_rows(ga, Ri, out, out + 6, pa0, pa1);
-  const int p = __ldg(pt_idx + ia);
-  double vs[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) vs[k] = ldg1(Vs + 6 * (size_t)p + k);
-  sym3_mul(vs, pa0, out + 12);
-  sym3_mul(vs, pa1, out + 15);
-}
-
-__global__ void __launch_bounds__(BA_THREADS, 1)
-k_sp_schur_rows(int n_cam, const int32_t *__restrict__ lrow_ptr, const int32_t *__restrict__ blk_ptr,
-                const unsigned long long *__restrict__ lkeys, const int32_t *__restrict__ gid,
-                const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ cam_rowptr,
-                const int32_t *__restrict__ pt_idx, FPlanes F /* camera-major */, const double *__restrict__ geo,
-                const double *__restrict__ intr, const double *__restrict__ Vs, double *__restrict__ S, int *ticket,
-                const LmState *st, int gate) {
-  if (!gate_open(st, gate)) return;
-  extern __shared__ __align__(16) double sps_sm[];
-  double *A = sps_sm;                                          // [BA_SPS_MAX_OBS][18]
-  double *part = A + (size_t)BA_SPS_MAX_OBS * 18;              // [BA_SPS_MAX_SLOTS][36]
-  int4 *items = reinterpret_cast<int4 *>(part + (size_t)BA_SPS_MAX_SLOTS * 36);  // (block, first pair, end pair, slot or -1)
-  int4 *splits = items + BA_SPS_MAX_ITEMS;                     // (block, first slot, chunks, -)
-  int *ctl = reinterpret_cast<int *>(splits + BA_SPS_MAX_SPLIT);  // [0] row, [1] next item, [2] items, [3] split blocks
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double fx = ldg1(intr), fy = ldg1(intr + 1);
-  for (;;) {
-    __syncthreads();  // the previous row's tables and partials are no longer read
-    if (tid == 0) ctl[0] = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int ci = ctl[0];
-    if (ci >= n_cam) return;
-    const int b0 = __ldg(lrow_ptr + ci), b1 = __ldg(lrow_ptr + ci + 1);
-    if (b0 >= b1) continue;
-    const int o0 = __ldg(cam_rowptr + ci), n_o = __ldg(cam_rowptr + ci + 1) - o0;
-    const bool staged = n_o <= BA_SPS_MAX_OBS;
-    CamRec ri;
-    load_camrec(geo, ci, ri);
-    // ---- a side of the row into shared memory
-    if (staged)
-      for (int t = tid; t < n_o; t += BA_THREADS) {
-        double v[18];
-        sps_a_side(F, o0 + t, pt_idx, Vs, ri.R, fx, fy, v);
-        double2 *dst = reinterpret_cast<double2 *>(A + (size_t)t * 18);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) dst[k] = make_double2(v[2 * k], v[2 * k + 1]);
-      }
-    // ---- work items of the row (warp 0: one lane per block, running offsets through a warp scan)
-    if (warp == 0) {
-      int n_items = 0, n_slots = 0, n_split = 0;
-      for (int bb = b0; bb < b1; bb += 32) {
-        const int b = bb + lane;
-        int e0 = 0, e1 = 0, nch = 0;
-        if (b < b1) {
-          e0 = __ldg(blk_ptr + b);
-          e1 = __ldg(blk_ptr + b + 1);
-          nch = (e1 - e0 + BA_SPS_ITEM - 1) / BA_SPS_ITEM;
-          if (nch < 1) nch = 1;
-        }
-        // exclusive scans over the lanes: items, chunk slots and split-block entries before this lane's block
-        int it_off = nch, sl = nch > 1 ? nch : 0, sp = nch > 1 ? 1 : 0;
-        int it_inc = it_off, sl_inc = sl, sp_inc = sp;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int x = __shfl_up_sync(BA_FULL, it_inc, o), y = __shfl_up_sync(BA_FULL, sl_inc, o), z = __shfl_up_sync(BA_FULL, sp_inc, o);
-          if (lane >= o) {
-            it_inc += x;
-            sl_inc += y;
-            sp_inc += z;
-          }
-        }
-        int my_item = n_items + it_inc - it_off, my_slot = n_slots + sl_inc - sl, my_split = n_split + sp_inc - sp;
-        // a block that cannot be split within the table limits stays one item (longer, still correct and deterministic)
-        const bool can_split = nch > 1 && my_slot + nch <= BA_SPS_MAX_SLOTS && my_split < BA_SPS_MAX_SPLIT;
-        if (b < b1) {
-          if (nch > 1 && can_split) {
-            for (int c = 0; c < nch; ++c)
-              if (my_item + c < BA_SPS_MAX_ITEMS)
-                items[my_item + c] = make_int4(b, e0 + c * BA_SPS_ITEM, min(e1, e0 + (c + 1) * BA_SPS_ITEM), my_slot + c);
-          } else if (my_item < BA_SPS_MAX_ITEMS) {
-            items[my_item] = make_int4(b, e0, e1, -1);
-          }
-          // every long block has an entry in the split table (chunk count 0 = not split: nothing to add up)
-          if (nch > 1 && my_split < BA_SPS_MAX_SPLIT) splits[my_split] = make_int4(b, my_slot, can_split ? nch : 0, 0);
-        }
-        // (the running totals count a block that could not be split as nch items whose first one carries the whole list;
-        // the others are marked empty below)
-        if (b < b1 && nch > 1 && !can_split)
-          for (int c = 1; c < nch; ++c)
-            if (my_item + c < BA_SPS_MAX_ITEMS) items[my_item + c] = make_int4(b, 0, 0, -2);
-        n_items += __shfl_sync(BA_FULL, it_inc, 31);
-        n_slots += __shfl_sync(BA_FULL, sl_inc, 31);
-        n_split += __shfl_sync(BA_FULL, sp_inc, 31);
-      }
-      if (lane == 0) {
-        ctl[1] = 0;
-        ctl[2] = n_items;
-        ctl[3] = n_split < BA_SPS_MAX_SPLIT ? n_split : BA_SPS_MAX_SPLIT;
-      }
-    }
-    __syncthreads();
-    const int n_items = ctl[2];
-    if (n_items > BA_SPS_MAX_ITEMS) {
-      // (more blocks in one row than the table holds: not a sequential co-visibility; the caller never selects this
-      // kernel then -- see the host-side check -- but do not index out of the tables)
-      continue;
-    }
-    // ---- the items
-    for (;;) {
-      int it = 0;
-      if (lane == 0) it = atomicAdd(&ctl[1], 1);
-      it = __shfl_sync(BA_FULL, it, 0);
-      if (it >= n_items) break;
-      const int4 im = items[it];
-      if (im.w == -2) continue;
-      const int b = im.x;
-      const int cj = (int)(lkeys[b] % (unsigned long long)n_cam);
-      CamRec rj;
-      load_camrec(geo, cj, rj);
-      double acc[36];
-#pragma unroll
-      for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-      const int e1 = im.z;
-      int e = im.y + lane;
-      unsigned long long pr = 0, prn = 0;
-      double2 g0 = make_double2(0, 0), g1 = make_double2(0, 0);
-      if (e < e1) {
-        pr = pairs[e];
-        g0 = __ldg(F.g0 + (int)(pr & 0xffffffffu));
-        g1 = __ldg(F.g1 + (int)(pr & 0xffffffffu));
-      }
-      if (e + 32 < e1) prn = pairs[e + 32];
-      while (e < e1) {
-        const int en = e + 32;
-        double2 g0n = make_double2(0, 0), g1n = make_double2(0, 0);
-        unsigned long long prnn = 0;
-        if (en < e1) {
-          g0n = __ldg(F.g0 + (int)(prn & 0xffffffffu));
-          g1n = __ldg(F.g1 + (int)(prn & 0xffffffffu));
-        }
-        if (en + 32 < e1) prnn = pairs[en + 32];
-        const int ia = (int)(pr >> 32);
-        double av[18];
-        if (staged) {
-          const double2 *src = reinterpret_cast<const double2 *>(A + (size_t)(ia - o0) * 18);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            const double2 t = src[k];
-            av[2 * k] = t.x;
-            av[2 * k + 1] = t.y;
-          }
-        } else {
-          sps_a_side(F, ia, pt_idx, Vs, ri.R, fx, fy, av);
-        }
-        ObsGeo gb;
-        gb.xz = g0.x;
-        gb.yz = g0.y;
-        gb.iz = g1.x;
-        gb.wfx = g1.y * fx;
-        gb.wfy = g1.y * fy;
-        double bq0[6], bq1[6], pb0[3], pb1[3];
-        sp_rows(gb, rj.R, bq0, bq1, pb0, pb1);
-        const double *v0 = av + 12, *v1 = av + 15;
-        const double m00 = v0[0] * pb0[0] + v0[1] * pb0[1] + v0[2] * pb0[2];
-        const double m01 = v0[0] * pb1[0] + v0[1] * pb1[1] + v0[2] * pb1[2];
-        const double m10 = v1[0] * pb0[0] + v1[1] * pb0[1] + v1[2] * pb0[2];
-        const double m11 = v1[0] * pb1[0] + v1[1] * pb1[1] + v1[2] * pb1[2];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const double h0 = m00 * bq0[c] + m01 * bq1[c], h1 = m10 * bq0[c] + m11 * bq1[c];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) acc[r * 6 + c] += av[r] * h0 + av[6 + r] * h1;
-        }
-        pr = prn;
-        prn = prnn;
-        g0 = g0n;
-        g1 = g1n;
-        e = en;
-      }
-#pragma unroll
-      for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
-      if (im.w >= 0) {
-        double *dst = part + (size_t)im.w * 36;
-#pragma unroll
-        for (int k = 0; k < 36; ++k)
-          if (lane == (k & 31)) dst[k] = acc[k];
-      } else {
-        double *Sb = S + 36 * (size_t)gid[b];
-#pragma unroll
-        for (int k = 0; k < 36; ++k)
-          if (lane == (k & 31)) {
-            const int r = k / 6, c = k - 6 * (k / 6);
-            Sb[k] = -(acc[k] * (ri.s[r] * rj.s[c]));  // k_sp_add_diag puts U on the diagonal blocks
-          }
-      }
-    }
-    __syncthreads();
-    // ---- split blocks: chunk partials added in chunk order
-    const int n_split = ctl[3];
-    for (int sidx = warp; sidx < n_split; sidx += BA_WARPS) {
-      const int4 sb = splits[sidx];
-      if (sb.z == 0) continue;
-      const int cj = (int)(lkeys[sb.x] % (unsigned long long)n_cam);
-      CamRec rj;
-      load_camrec(geo, cj, rj);
-      double *Sb = S + 36 * (size_t)gid[sb.x];
-      for (int k = lane; k < 36; k += 32) {
-        double v = 0.0;
-        for (int c = 0; c < sb.z; ++c) v += part[(size_t)(sb.y + c) * 36 + k];
-        const int r = k / 6, cc = k - 6 * r;
-        Sb[k] = -(v * (pick6(ri.s, r) * pick6(rj.s, cc)));
       }
     }
   }
