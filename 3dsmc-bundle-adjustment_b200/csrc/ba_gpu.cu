@@ -14,6 +14,7 @@
 #include "ba_kernels_dist.cuh"
 #include "ba_kernels_chol.cuh"
 #include "ba_kernels_spchol.cuh"
+#include "ba_kernels_store.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -149,6 +150,7 @@ struct ba_gpu_ctx {
   int n_my_rows = 0, dist_grid = 0;
   long long n_pairs = 0;
   // exact sparse Cholesky of S (ba_sparse_symbolic.h / ba_kernels_spchol.cuh)
+  bool src_on_device = false;   // the arrays handed to the current upload live in device memory (ba_store_window_solve)
   bool spchol = false;          // the block-sparse solver factorises S instead of running PCG
   SpSymbolic sym;               // host-side structure of the last upload
   Buf spn_node, spn_bord, spn_children, spn_rel, spn_inv, spn_aent, spn_perm, spn_levels;
@@ -1213,15 +1215,17 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
 
   prof.stamp("reserve");
   cudaStream_t s = ctx->stream;
-  CK(cudaMemcpyAsync(ctx->pose.p, pose7, nc * 56, cudaMemcpyHostToDevice, s));
-  if (np) CK(cudaMemcpyAsync(ctx->pt.p, pt3, np * 24, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->intr.p, intr4, 32, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->intr_prior.p, intr_prior4 ? intr_prior4 : intr4, 32, cudaMemcpyHostToDevice, s));
+  // (cudaMemcpyDefault: the arrays are host buffers for a C-ABI caller and device buffers when the device-resident store
+  // assembled the window, ba_store_window_solve)
+  CK(cudaMemcpyAsync(ctx->pose.p, pose7, nc * 56, cudaMemcpyDefault, s));
+  if (np) CK(cudaMemcpyAsync(ctx->pt.p, pt3, np * 24, cudaMemcpyDefault, s));
+  CK(cudaMemcpyAsync(ctx->intr.p, intr4, 32, cudaMemcpyDefault, s));
+  CK(cudaMemcpyAsync(ctx->intr_prior.p, intr_prior4 ? intr_prior4 : intr4, 32, cudaMemcpyDefault, s));
   if (no) {
-    CK(cudaMemcpyAsync(ctx->cam_idx.p, cam_idx, no * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->pt_idx.p, pt_idx, no * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->uv.p, uv2, no * 16, cudaMemcpyHostToDevice, s));
-    if (depth) CK(cudaMemcpyAsync(ctx->depthv.p, depth, no * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->cam_idx.p, cam_idx, no * 4, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(ctx->pt_idx.p, pt_idx, no * 4, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(ctx->uv.p, uv2, no * 16, cudaMemcpyDefault, s));
+    if (depth) CK(cudaMemcpyAsync(ctx->depthv.p, depth, no * 8, cudaMemcpyDefault, s));
   }
   prof.stamp("h2d");
   // ---- device-built indices
@@ -1372,7 +1376,9 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     prof.stamp("rest");
     // windows: device-built pair list; the global REF problem keeps the host-built list of NON-EMPTY blocks
     // (320 k mostly empty blocks at 800 keyframes)
-    const bool dev_pairs = ctx->n_free <= 64 && getenv("BA_HOST_PAIRS") == nullptr;
+    const bool dev_pairs = ctx->n_free <= 64 && (ctx->src_on_device || getenv("BA_HOST_PAIRS") == nullptr);
+    if (!dev_pairs && ctx->src_on_device)
+      return fail(ctx, BA_ERR_UNSUPPORTED, "device-resident windows are limited to 65 keyframes (the pair list of larger explicit problems is host-built)");
     int rc = dev_pairs ? build_pair_list_device(ctx) : build_pair_list(ctx, cam_idx, pt_idx);
     if (rc) return rc;
     prof.stamp("pair list");
@@ -2674,6 +2680,267 @@ extern "C" int ba_gpu_comm_init(ba_gpu_ctx *ctx, const char id128[128], int32_t 
   if (r != 0) return fail(ctx, BA_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   ctx->rank = rank;
   ctx->n_ranks = n_ranks;
+  return BA_OK;
+}
+
+// ------------------------------------------------------------------ device-resident keyframe / landmark store
+// Host bookkeeping of ba_kernels_store.cuh: one observation pool (keyframe segments in container order), world poses by
+// keyframe, world points by landmark id.  Not thread-safe; lives on the stream of its solver context.
+struct ba_store {
+  ba_gpu_ctx *ctx = nullptr;
+  struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+  };
+  DBuf lm, uvf, depth;              // observation pool
+  size_t pool_used = 0;
+  std::vector<long long> seg_off;   // per keyframe: first slot in the pool, -1 = never set
+  std::vector<int32_t> seg_n, seg_cap;
+  DBuf pose_w, pt_w, first;         // [kf * 7], [id * 3], [id]
+  size_t n_kf_cap = 0, n_lm_cap = 0;
+  DBuf stage, win_off, win_seg, flag, pos, isfirst, rank, w_cam, w_pt, w_uv, w_depth, w_pose, w_pt3, w_lm, T0, out_pose, out_pt, cub, cnt;
+  std::vector<DBuf *> all;
+  double ms[3] = {0, 0, 0};         // last window: enumeration + index build, solve, write-back + copies
+  int max_id = -1;                  // largest landmark id any keyframe list refers to
+};
+static int sgrow(ba_gpu_ctx *ctx, ba_store *st, ba_store::DBuf &b, size_t bytes, bool keep) {
+  if (b.cap >= bytes) return 0;
+  const size_t want = std::max(bytes + bytes / 2, (size_t)4096);
+  void *np = nullptr;
+  cudaError_t e = cudaMalloc(&np, want);
+  if (e != cudaSuccess) return fail(ctx, BA_ERR_CUDA, "store: cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+  if (keep && b.p && b.cap) {
+    cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (b.p) cudaFree(b.p);
+  b.p = np;
+  b.cap = want;
+  if (std::find(st->all.begin(), st->all.end(), &b) == st->all.end()) st->all.push_back(&b);
+  return 0;
+}
+#define SGROW(buf, bytes, keep)                              \
+  do {                                                       \
+    int rc_ = sgrow(ctx, st, st->buf, (size_t)(bytes), keep); \
+    if (rc_) return rc_;                                     \
+  } while (0)
+#define BA_STORE_MAX_ID (1 << 24)
+
+extern "C" int ba_store_create(ba_gpu_ctx *ctx, ba_store **out) {
+  if (!ctx || !out) return BA_ERR_INVALID;
+  ba_store *st = new ba_store();
+  st->ctx = ctx;
+  *out = st;
+  return BA_OK;
+}
+extern "C" void ba_store_destroy(ba_store *st) {
+  if (!st) return;
+  if (st->ctx) {
+    cudaSetDevice(st->ctx->device);
+    if (st->ctx->stream) cudaStreamSynchronize(st->ctx->stream);
+  }
+  for (ba_store::DBuf *b : st->all)
+    if (b->p) cudaFree(b->p);
+  delete st;
+}
+static int store_fit_kf(ba_gpu_ctx *ctx, ba_store *st, int kf) {
+  if ((size_t)kf >= st->seg_off.size()) {
+    const size_t n = (size_t)kf + 1 + st->seg_off.size() / 2;
+    st->seg_off.resize(n, -1);
+    st->seg_n.resize(n, 0);
+    st->seg_cap.resize(n, 0);
+  }
+  if ((size_t)kf >= st->n_kf_cap) {
+    const size_t n = (size_t)kf + 64 + st->n_kf_cap / 2;
+    SGROW(pose_w, n * 56, true);
+    st->n_kf_cap = n;
+  }
+  return 0;
+}
+// the observation list of keyframe kf in the iteration order of its global_points_map (replaces any earlier list)
+extern "C" int ba_store_set_keyframe(ba_store *st, int32_t kf, int32_t n, const int32_t *landmark_id, const float *uv2f,
+                                     const double *depth) {
+  if (!st || kf < 0 || n < 0 || (n > 0 && (!landmark_id || !uv2f || !depth))) return BA_ERR_INVALID;
+  ba_gpu_ctx *ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  for (int i = 0; i < n; ++i) {
+    if (landmark_id[i] < 0 || landmark_id[i] >= BA_STORE_MAX_ID)
+      return fail(ctx, BA_ERR_UNSUPPORTED, "store: landmark id %d outside [0, 2^24)", landmark_id[i]);
+    st->max_id = std::max(st->max_id, landmark_id[i]);
+  }
+  int rc = store_fit_kf(ctx, st, kf);
+  if (rc) return rc;
+  if (st->seg_off[kf] < 0 || n > st->seg_cap[kf]) {  // new segment at the end of the pool (with head-room for later inserts)
+    const int cap = n + n / 4 + 16;
+    const size_t need = st->pool_used + (size_t)cap;
+    SGROW(lm, need * 4, true);
+    SGROW(uvf, need * 8, true);
+    SGROW(depth, need * 8, true);
+    st->seg_off[kf] = (long long)st->pool_used;
+    st->seg_cap[kf] = cap;
+    st->pool_used = need;
+  }
+  st->seg_n[kf] = n;
+  if (n) {
+    const size_t o = (size_t)st->seg_off[kf];
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync((int32_t *)st->lm.p + o, landmark_id, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync((float2 *)st->uvf.p + o, uv2f, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync((double *)st->depth.p + o, depth, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // the caller's arrays may be temporaries
+  }
+  return BA_OK;
+}
+extern "C" int ba_store_set_poses(ba_store *st, int32_t kf0, int32_t n, const double *pose7) {
+  if (!st || kf0 < 0 || n <= 0 || !pose7) return BA_ERR_INVALID;
+  ba_gpu_ctx *ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  int rc = store_fit_kf(ctx, st, kf0 + n - 1);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync((double *)st->pose_w.p + 7 * (size_t)kf0, pose7, (size_t)n * 56, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BA_OK;
+}
+extern "C" int ba_store_set_landmarks(ba_store *st, int32_t n, const int32_t *id, const double *xyz) {
+  if (!st || n < 0 || (n > 0 && (!id || !xyz))) return BA_ERR_INVALID;
+  if (n == 0) return BA_OK;
+  ba_gpu_ctx *ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  int mx = 0;
+  for (int i = 0; i < n; ++i) {
+    if (id[i] < 0 || id[i] >= BA_STORE_MAX_ID) return fail(ctx, BA_ERR_UNSUPPORTED, "store: landmark id %d outside [0, 2^24)", id[i]);
+    mx = std::max(mx, id[i]);
+  }
+  if ((size_t)mx >= st->n_lm_cap) {
+    const size_t cap = (size_t)mx + 1024 + st->n_lm_cap / 2;
+    SGROW(pt_w, cap * 24, true);
+    SGROW(first, cap * 4, false);
+    st->n_lm_cap = cap;
+  }
+  const size_t id_bytes = (((size_t)n * 4 + 63) / 64) * 64;
+  SGROW(stage, id_bytes + (size_t)n * 24, false);
+  int32_t *d_id = (int32_t *)st->stage.p;
+  double *d_xyz = (double *)((char *)st->stage.p + id_bytes);
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(d_id, id, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+  ks_scatter_points<<<cdiv(n, BA_THREADS), BA_THREADS, 0, s>>>(n, d_id, d_xyz, (double *)st->pt_w.p);
+  ctx->launches++;
+  CK(cudaStreamSynchronize(s));
+  return BA_OK;
+}
+
+// windowOptimize on the resident data (src/OptimizationUtils.cpp:215-313): enumeration of the admissible observations of
+// keyframes kf_i..kf_f in canonical order, change into the frame of keyframe kf_i, solve with the context's options (REF
+// cost: depth prior + free intrinsics are the caller's choice through ba_gpu_set_options), write-back into the world frame.
+//   intr4: in = current intrinsics, out = optimised;  pose7_out [n_cam * 7] world poses;  landmark_of_pt / pt3_out: the
+//   window's landmarks in order of first appearance and their optimised world points (capacity lm_cap).
+// The store's own poses / points are only touched after a successful solve.
+extern "C" int ba_store_window_solve(ba_store *st, int32_t kf_i, int32_t kf_f, const double intr_prior4[4], double intr4[4],
+                                     ba_gpu_summary *summary, double *pose7_out, int32_t lm_cap, int32_t *n_pt_out,
+                                     int32_t *landmark_of_pt, double *pt3_out, int32_t *n_obs_out, double ms_out[3]) {
+  if (!st || kf_i < 0 || kf_f < kf_i || !intr4 || !pose7_out || !n_pt_out || (lm_cap > 0 && (!landmark_of_pt || !pt3_out)))
+    return BA_ERR_INVALID;
+  ba_gpu_ctx *ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  const int n_cam = kf_f - kf_i + 1;
+  if ((size_t)kf_f >= st->seg_off.size()) return fail(ctx, BA_ERR_STATE, "store: keyframe %d was never set", kf_f);
+  const auto t_begin = std::chrono::steady_clock::now();
+  std::vector<int32_t> off((size_t)n_cam + 1, 0);
+  std::vector<long long> seg((size_t)n_cam, 0);
+  for (int k = 0; k < n_cam; ++k) {
+    if (st->seg_off[kf_i + k] < 0) return fail(ctx, BA_ERR_STATE, "store: keyframe %d was never set", kf_i + k);
+    seg[k] = st->seg_off[kf_i + k];
+    off[k + 1] = off[k] + st->seg_n[kf_i + k];
+  }
+  const int total = off[n_cam];
+  if (st->max_id >= 0 && (size_t)st->max_id >= st->n_lm_cap)  // (the reference would throw from map.at, :270)
+    return fail(ctx, BA_ERR_STATE, "store: a keyframe refers to landmark %d, which was never set", st->max_id);
+  cudaStream_t s = ctx->stream;
+  SGROW(win_off, ((size_t)n_cam + 1) * 4, false);
+  SGROW(win_seg, (size_t)n_cam * 8, false);
+  SGROW(flag, ((size_t)total + 2) * 4, false);
+  SGROW(pos, ((size_t)total + 2) * 4, false);
+  SGROW(isfirst, ((size_t)total + 2) * 4, false);
+  SGROW(rank, ((size_t)total + 2) * 4, false);
+  SGROW(w_cam, ((size_t)total + 1) * 4, false);
+  SGROW(w_pt, ((size_t)total + 1) * 4, false);
+  SGROW(w_uv, ((size_t)total + 1) * 16, false);
+  SGROW(w_depth, ((size_t)total + 1) * 8, false);
+  SGROW(w_lm, ((size_t)total + 1) * 4, false);
+  SGROW(w_pt3, ((size_t)total + 1) * 24, false);
+  SGROW(w_pose, (size_t)n_cam * 56, false);
+  SGROW(T0, 14 * 8, false);
+  SGROW(out_pose, (size_t)n_cam * 56, false);
+  SGROW(cnt, 64, false);
+  CK(cudaMemcpyAsync(st->win_off.p, off.data(), ((size_t)n_cam + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(st->win_seg.p, seg.data(), (size_t)n_cam * 8, cudaMemcpyHostToDevice, s));
+  const int32_t *d_off = (const int32_t *)st->win_off.p;
+  const long long *d_seg = (const long long *)st->win_seg.p;
+  int32_t *d_flag = (int32_t *)st->flag.p, *d_pos = (int32_t *)st->pos.p, *d_isf = (int32_t *)st->isfirst.p, *d_rank = (int32_t *)st->rank.p;
+  const int nb = cdiv(total + 1, BA_THREADS);
+  auto scan = [&](int32_t *in, int32_t *out, int n) -> int {
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s));
+    int rc_ = sgrow(ctx, st, st->cub, tb + 16, false);
+    if (rc_) return rc_;
+    CK(cub::DeviceScan::ExclusiveSum(st->cub.p, tb, in, out, n, s));
+    return 0;
+  };
+  int rc;
+  ks_flags<<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, (const double *)st->depth.p, d_flag);
+  if ((rc = scan(d_flag, d_pos, total + 1))) return rc;
+  int32_t h_cnt[2] = {0, 0};
+  CK(cudaMemcpyAsync(&h_cnt[0], d_pos + total, 4, cudaMemcpyDeviceToHost, s));
+  ks_first<0><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
+  ks_first<1><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
+  CK(cudaMemsetAsync(d_isf, 0, ((size_t)total + 2) * 4, s));
+  ks_first<2><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
+  ctx->launches += 4;
+  CK(cudaStreamSynchronize(s));
+  const int n_obs = h_cnt[0];
+  if ((rc = scan(d_isf, d_rank, n_obs + 1))) return rc;
+  CK(cudaMemcpyAsync(&h_cnt[1], d_rank + n_obs, 4, cudaMemcpyDeviceToHost, s));
+  double *d_T0 = (double *)st->T0.p, *d_T0inv = d_T0 + 7;
+  ks_frame<<<cdiv(std::max(n_cam, 1), 64), 64, 0, s>>>(n_cam, (const double *)st->pose_w.p + 7 * (size_t)kf_i, d_T0, d_T0inv, (double *)st->w_pose.p);
+  ks_emit<<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (const float2 *)st->uvf.p,
+                                    (const double *)st->depth.p, (const int32_t *)st->first.p, d_rank, (const double *)st->pt_w.p, d_T0inv,
+                                    (int32_t *)st->w_cam.p, (int32_t *)st->w_pt.p, (double2 *)st->w_uv.p, (double *)st->w_depth.p,
+                                    (int32_t *)st->w_lm.p, (double *)st->w_pt3.p);
+  ctx->launches += 2;
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  const int n_pt = h_cnt[1];
+  if (n_obs_out) *n_obs_out = n_obs;
+  *n_pt_out = n_pt;
+  if (n_pt > lm_cap) return fail(ctx, BA_ERR_INVALID, "store: %d landmarks in the window, caller's capacity %d", n_pt, lm_cap);
+  ctx->src_on_device = true;
+  rc = ba_gpu_upload(ctx, n_cam, (const double *)st->w_pose.p, 0, n_pt, (const double *)st->w_pt3.p, n_obs, (const int32_t *)st->w_cam.p,
+                     (const int32_t *)st->w_pt.p, (const double *)st->w_uv.p, (const double *)st->w_depth.p, intr4, intr_prior4);
+  ctx->src_on_device = false;
+  if (rc) return rc;
+  st->ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  auto t_ph = std::chrono::steady_clock::now();
+  rc = ba_gpu_solve(ctx, summary);
+  if (rc) return rc;
+  st->ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_ph).count();
+  t_ph = std::chrono::steady_clock::now();
+  SGROW(out_pt, ((size_t)n_pt + 1) * 24, false);
+  ks_writeback<<<cdiv(n_cam + n_pt, BA_THREADS), BA_THREADS, 0, s>>>(n_cam, n_pt, d_T0, P<double>(ctx->pose), P<double>(ctx->pt),
+                                                                    (const int32_t *)st->w_lm.p, (double *)st->pose_w.p + 7 * (size_t)kf_i,
+                                                                    (double *)st->pt_w.p, (double *)st->out_pose.p, (double *)st->out_pt.p);
+  ctx->launches++;
+  CK(cudaMemcpyAsync(pose7_out, st->out_pose.p, (size_t)n_cam * 56, cudaMemcpyDeviceToHost, s));
+  if (n_pt) {
+    CK(cudaMemcpyAsync(pt3_out, st->out_pt.p, (size_t)n_pt * 24, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(landmark_of_pt, st->w_lm.p, (size_t)n_pt * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaMemcpyAsync(intr4, ctx->intr.p, 32, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  st->ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_ph).count();
+  if (ms_out)
+    for (int k = 0; k < 3; ++k) ms_out[k] = st->ms[k];
   return BA_OK;
 }
 

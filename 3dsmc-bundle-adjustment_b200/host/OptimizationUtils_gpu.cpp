@@ -35,6 +35,24 @@ struct Ctx {
 thread_local Ctx g_ctx;
 thread_local BaHostLastProblem g_last;
 thread_local bool g_fixed_iterations = false;
+
+// ---- device-resident store (ba_store_* in include/ba_gpu.h): what this thread has put on the device
+struct StoreState {
+  ba_store *st = nullptr;
+  bool on = false;
+  vector<long long> kf_size;      // global_points_map.size() of every keyframe at its last upload (-1: never)
+  vector<Landmark *> lm_ptr;      // landmark id -> its node in the caller's Map3D (nodes of an unordered_map do not move)
+  ~StoreState() {
+    if (st) ba_store_destroy(st);
+  }
+  void reset() {
+    if (st) ba_store_destroy(st);
+    st = nullptr;
+    kf_size.clear();
+    lm_ptr.clear();
+  }
+};
+thread_local StoreState g_store;
 inline double ms_since(const std::chrono::steady_clock::time_point &t0) {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
@@ -42,6 +60,104 @@ inline double ms_since(const std::chrono::steady_clock::time_point &t0) {
 
 const BaHostLastProblem &ba_host_last_problem() { return g_last; }
 void ba_host_fixed_iterations(bool on) { g_fixed_iterations = on; }
+void ba_host_device_store(bool on) {
+  // (the store is declared after the context in this file, so it is destroyed first at thread exit)
+  g_store.reset();
+  g_store.on = on;
+}
+
+namespace {
+// windowOptimize through the device-resident store: only keyframes whose global_points_map is new or grew since the
+// last call are walked and uploaded; enumeration, frame changes and write-back run on the device.  Returns 1 = done,
+// 0 = failed (inputs untouched), -1 = not applicable (caller takes the full-upload path).
+int window_optimize_store(const ba_gpu_options &opt, int kf_i, int kf_f, vector<KeyFrame> &keyframes, Map3D &map,
+                          const Vector4d &intrinsics_initial, Vector4d &intrinsics_optimized) {
+  const int n_cam = kf_f - kf_i + 1;
+  if (n_cam > 65) return -1;  // (larger explicit problems build their pair list on the host)
+  const auto t_begin = std::chrono::steady_clock::now();
+  int rc = g_ctx.ctx ? ba_gpu_set_options(g_ctx.ctx, &opt) : ba_gpu_create(&opt, &g_ctx.ctx);
+  if (rc == BA_OK && !g_store.st) rc = ba_store_create(g_ctx.ctx, &g_store.st);
+  if (rc != BA_OK) return -1;
+  StoreState &S = g_store;
+  if (S.kf_size.size() < keyframes.size()) S.kf_size.resize(keyframes.size(), -1);
+  vector<int32_t> ids, new_id;
+  vector<float> uvf;
+  vector<double> dep, new_xyz;
+  size_t lm_bound = 0;
+  for (int kf_n = kf_i; kf_n <= kf_f; ++kf_n) {
+    const KeyFrame &kf = keyframes[kf_n];
+    lm_bound += kf.global_points_map.size();
+    if (S.kf_size[kf_n] == (long long)kf.global_points_map.size()) continue;  // unchanged since its last upload
+    ids.clear();
+    uvf.clear();
+    dep.clear();
+    for (const auto &index_pair : kf.global_points_map) {  // container order == canonical order (:257)
+      const int localId = index_pair.first, landmarkId = index_pair.second;
+      if (landmarkId < 0 || landmarkId >= (1 << 24)) return -1;
+      if ((size_t)landmarkId >= S.lm_ptr.size()) S.lm_ptr.resize((size_t)landmarkId + 1 + S.lm_ptr.size() / 2, nullptr);
+      if (!S.lm_ptr[landmarkId]) {  // first time this landmark is referenced: its world point goes to the device
+        auto found = map.find(landmarkId);
+        if (found == map.end()) {
+          std::fprintf(stderr, "windowOptimize: keyframe references a landmark that is not in the map\n");
+          return 0;
+        }
+        S.lm_ptr[landmarkId] = &found->second;
+        new_id.push_back(landmarkId);
+        for (int j = 0; j < 3; ++j) new_xyz.push_back(found->second.point(j));
+      }
+      ids.push_back(landmarkId);
+      uvf.push_back(kf.keypoints[localId].pt.x);
+      uvf.push_back(kf.keypoints[localId].pt.y);
+      dep.push_back(kf.points3d_local[localId](2));
+    }
+    rc = ba_store_set_keyframe(S.st, kf_n, (int32_t)ids.size(), ids.data(), uvf.data(), dep.data());
+    if (rc == BA_ERR_UNSUPPORTED) return -1;
+    if (rc != BA_OK) return 0;
+    S.kf_size[kf_n] = (long long)kf.global_points_map.size();
+  }
+  if (!new_id.empty() && ba_store_set_landmarks(S.st, (int32_t)new_id.size(), new_id.data(), new_xyz.data()) != BA_OK) return 0;
+  vector<double> pose7((size_t)n_cam * 7);
+  for (int k = 0; k < n_cam; ++k)
+    for (int j = 0; j < 7; ++j) pose7[(size_t)k * 7 + j] = keyframes[kf_i + k].T_w_c.data()[j];
+  if (ba_store_set_poses(S.st, kf_i, n_cam, pose7.data()) != BA_OK) return 0;
+  g_last.ms_extract = ms_since(t_begin);
+
+  double intr[4], prior[4], ms3[3] = {0, 0, 0};
+  for (int j = 0; j < 4; ++j) {
+    intr[j] = intrinsics_optimized(j);
+    prior[j] = intrinsics_initial(j);
+  }
+  vector<int32_t> lm_of_pt(lm_bound + 1);
+  vector<double> pt3((lm_bound + 1) * 3);
+  int32_t n_pt = 0, n_obs = 0;
+  ba_gpu_summary summary;
+  rc = ba_store_window_solve(S.st, kf_i, kf_f, prior, intr, &summary, pose7.data(), (int32_t)lm_bound, &n_pt, lm_of_pt.data(), pt3.data(),
+                             &n_obs, ms3);
+  if (rc != BA_OK) {
+    std::fprintf(stderr, "windowOptimize: GPU solve failed (%d): %s\n", rc, ba_gpu_last_error(g_ctx.ctx));
+    // the device copy may no longer mirror the host state: start over at the next call
+    g_store.reset();
+    return 0;
+  }
+  g_last.ms_upload = ms3[0];
+  g_last.ms_solve = ms3[1];
+  g_last.ms_download = ms3[2];
+  const auto t_wb = std::chrono::steady_clock::now();
+  g_last.summary = summary;
+  g_last.admissible_obs = n_obs;
+  g_last.cam_idx.clear();
+  g_last.pt_idx.clear();
+  g_last.landmark_of_pt.assign(lm_of_pt.begin(), lm_of_pt.begin() + n_pt);
+  for (int k = 0; k < n_cam; ++k) keyframes[kf_i + k].T_w_c = se3_from_raw(pose7.data() + (size_t)k * 7);
+  for (int p = 0; p < n_pt; ++p) {
+    Vector3d &x = S.lm_ptr[lm_of_pt[p]]->point;
+    for (int j = 0; j < 3; ++j) x(j) = pt3[(size_t)p * 3 + j];
+  }
+  for (int j = 0; j < 4; ++j) intrinsics_optimized(j) = intr[j];
+  g_last.ms_writeback = ms_since(t_wb);
+  return 1;
+}
+}  // namespace
 
 int countConstraints(const Map3D &map, const vector<KeyFrame> &keyframes, int kf_i, int kf_f) {
   (void)map;
@@ -79,6 +195,10 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   opt.solver = BA_SOLVER_AUTO;   // SPARSE_SCHUR == exact Schur step
   if (g_fixed_iterations)        // measurement only (ba_host_debug.h): exactly max_num_iterations LM iterations
     opt.function_tolerance = opt.parameter_tolerance = opt.gradient_tolerance = 0.0;
+  if (g_store.on) {
+    const int done = window_optimize_store(opt, kf_i, kf_f, keyframes, map, intrinsics_initial, intrinsics_optimized);
+    if (done >= 0) return done == 1;
+  }
   const auto t_begin = std::chrono::steady_clock::now();
 
   // ---- snapshot for the error path: inputs stay untouched on failure

@@ -90,11 +90,33 @@ int ba_host_window_optimize(int n_kf, double *pose7, const int32_t *kf_ptr, cons
 int ba_host_sliding_sequence(int n_kf, double *pose7, const int32_t *kf_ptr, const int32_t *lm, const float *uv,
                              const double *depth, int n_lm, const int32_t *lm_id, double *lm_pt, int window_size,
                              int frame_frequency, int do_global, int max_num_iterations, int fixed_iterations,
-                             const double *intr0, double *intr, double *out_ms, int64_t *out_lm_iterations) {
+                             const double *intr0, double *intr, double *out_ms, int64_t *out_lm_iterations, int use_device_store) {
   if (n_kf <= 0 || frame_frequency <= 0 || window_size <= 0 || window_size > n_kf) return -1;
-  std::vector<KeyFrame> keyframes(n_kf);
+  ba_host_device_store((use_device_store & 1) != 0);  // bit 0: device-resident store, bit 1: maps grow in two steps
+  // Containers grow as the tracking front end would grow them (src/main.cpp:25-82, src/Map3D.cpp:29-74): keyframe k arrives
+  // with its key points and the first part of its global_points_map (its matches as "new_frame"); the rest of its map is
+  // inserted when keyframe k + 1 arrives (its inserts as "old_frame", :52) -- growing != 0 splits every list in two halves
+  // that way, growing == 0 inserts the whole list at arrival.  A landmark enters the map when it is first referenced.
+  const bool growing = (use_device_store & 2) != 0;
+  std::vector<KeyFrame> keyframes;
+  keyframes.reserve(n_kf);
   Map3D map;
-  for (int k = 0; k < n_kf; ++k) {
+  std::unordered_map<int, int> lm_row;  // landmark id -> row of lm_pt
+  for (int l = 0; l < n_lm; ++l) lm_row[lm_id[l]] = l;
+  auto insert_obs = [&](int k, int i0_, int i1_) {
+    KeyFrame &kf = keyframes[k];
+    for (int i = i0_; i < i1_; ++i) {
+      kf.global_points_map.insert({i - kf_ptr[k], lm[i]});
+      if (map.find(lm[i]) == map.end()) {
+        const int l = lm_row.at(lm[i]);
+        Landmark L;
+        L.point = Vector3d(lm_pt[3 * (size_t)l], lm_pt[3 * (size_t)l + 1], lm_pt[3 * (size_t)l + 2]);
+        map.insert({lm[i], L});
+      }
+    }
+  };
+  auto arrive = [&](int k) {
+    keyframes.emplace_back();
     KeyFrame &kf = keyframes[k];
     kf.frame_id = (uint)k;
     kf.T_w_c = se3_from_raw(pose7 + (size_t)k * 7);
@@ -102,18 +124,14 @@ int ba_host_sliding_sequence(int n_kf, double *pose7, const int32_t *kf_ptr, con
     kf.keypoints.resize(b - a);
     kf.points3d_local.resize(b - a);
     for (int i = a; i < b; ++i) {
-      const int local = i - a;
-      kf.keypoints[local].pt.x = uv[2 * (size_t)i];
-      kf.keypoints[local].pt.y = uv[2 * (size_t)i + 1];
-      kf.points3d_local[local] = Vector3d(0.0, 0.0, depth[i]);
-      kf.global_points_map.insert({local, lm[i]});
+      kf.keypoints[i - a].pt.x = uv[2 * (size_t)i];
+      kf.keypoints[i - a].pt.y = uv[2 * (size_t)i + 1];
+      kf.points3d_local[i - a] = Vector3d(0.0, 0.0, depth[i]);
     }
-  }
-  for (int l = 0; l < n_lm; ++l) {
-    Landmark L;
-    L.point = Vector3d(lm_pt[3 * (size_t)l], lm_pt[3 * (size_t)l + 1], lm_pt[3 * (size_t)l + 2]);
-    map.insert({lm_id[l], L});
-  }
+    const int half = growing ? a + (b - a) / 2 : b;
+    insert_obs(k, a, half);
+    if (growing && k > 0) insert_obs(k - 1, kf_ptr[k - 1] + (kf_ptr[k] - kf_ptr[k - 1]) / 2, kf_ptr[k]);
+  };
   ceresGlobalProblem gp;
   gp.options.max_num_iterations = max_num_iterations;
   Vector4d i0(intr0[0], intr0[1], intr0[2], intr0[3]), io(intr[0], intr[1], intr[2], intr[3]);
@@ -136,18 +154,26 @@ int ba_host_sliding_sequence(int n_kf, double *pose7, const int32_t *kf_ptr, con
     ++calls;
   };
   if (do_global) {
+    for (int k = 0; k < n_kf; ++k) arrive(k);
+    if (growing) insert_obs(n_kf - 1, kf_ptr[n_kf - 1] + (kf_ptr[n_kf] - kf_ptr[n_kf - 1]) / 2, kf_ptr[n_kf]);
     run(0, n_kf - 1);
   } else {
-    for (int size = 1; size <= n_kf && ok; ++size)  // keyframes.size() after every tracking step
+    for (int size = 1; size <= n_kf && ok; ++size) {  // keyframes.size() after every tracking step
+      arrive(size - 1);
       if (size % frame_frequency == 0 && size >= window_size) run(size - window_size, size - 1);
+    }
     if (ok && n_kf % frame_frequency != 0) run(n_kf - window_size, n_kf - 1);  // leftovers
   }
   ba_host_fixed_iterations(false);
+  ba_host_device_store(false);
   if (out_ms) std::memcpy(out_ms, ms, sizeof(ms));
   if (out_lm_iterations) *out_lm_iterations = lm_iterations;
   for (int k = 0; k < n_kf; ++k) std::memcpy(pose7 + (size_t)k * 7, keyframes[k].T_w_c.data(), 7 * sizeof(double));
-  for (int l = 0; l < n_lm; ++l)
-    for (int j = 0; j < 3; ++j) lm_pt[3 * (size_t)l + j] = map.at(lm_id[l]).point(j);
+  for (int l = 0; l < n_lm; ++l) {
+    auto found = map.find(lm_id[l]);  // (a landmark nobody referenced never entered the map)
+    if (found != map.end())
+      for (int j = 0; j < 3; ++j) lm_pt[3 * (size_t)l + j] = found->second.point(j);
+  }
   for (int j = 0; j < 4; ++j) intr[j] = io(j);
   return ok ? calls : -1;
 }

@@ -35,11 +35,14 @@ def _ptr(a, t):
 
 
 def sliding_sequence(seq, window_size, frame_frequency=10, max_num_iterations=75, fixed_iterations=False, do_global=False,
-                     intrinsics_initial=None, intrinsics_optimized=None):
+                     intrinsics_initial=None, intrinsics_optimized=None, device_store=False, growing_maps=False):
     """The reference's optimisation schedule (src/main.cpp:161-182) over the whole sequence `seq`
     (synthetic.Sequence) through the compiled windowOptimize.  Mutates seq.pose, seq.pt and
     intrinsics_optimized in place (as windowOptimize does with the caller's containers) and returns
-    a dict: windows, lm_iterations and the accumulated host wall clock per phase in milliseconds."""
+    a dict: windows, lm_iterations and the accumulated host wall clock per phase in milliseconds.
+    device_store=True routes the calls through the device-resident keyframe / landmark store (ba_host_device_store);
+    growing_maps=True inserts the second half of every keyframe's global_points_map when the next keyframe arrives (the
+    "old_frame" inserts of src/Map3D.cpp:52), so that keyframes change between two windows."""
     L = load()
     n_kf = int(seq.pose.shape[0])
     kf_ptr = np.ascontiguousarray(seq.kf_ptr, dtype=np.int32)
@@ -57,7 +60,7 @@ def sliding_sequence(seq, window_size, frame_frequency=10, max_num_iterations=75
                                     _ptr(depth, C.c_double), int(pt.shape[0]), _ptr(lm_id, C.c_int32), _ptr(pt, C.c_double),
                                     int(window_size), int(frame_frequency), int(bool(do_global)), int(max_num_iterations),
                                     int(bool(fixed_iterations)), _ptr(intr0, C.c_double), _ptr(intr, C.c_double),
-                                    _ptr(ms, C.c_double), C.byref(n_it))
+                                    _ptr(ms, C.c_double), C.byref(n_it), int(bool(device_store)) | (2 if growing_maps else 0))
     if rc < 0:
         raise RuntimeError("ba_host_sliding_sequence failed (see stderr)")
     seq.pose[...] = pose

@@ -242,6 +242,29 @@ int ba_gpu_jacobian_store_used(const ba_gpu_ctx *ctx);
  * observation pairs, stored upper blocks, row entries (each off-diagonal block appears twice) */
 int ba_gpu_sparse_stats(const ba_gpu_ctx *ctx, int64_t *n_pairs, int32_t *n_blocks, int32_t *n_entries);
 
+/* ---- device-resident keyframe / landmark store for sliding windows ----
+ * Replaces, for the optimiser's purposes, the host containers the reference re-walks for every window
+ * (std::vector<KeyFrame> + Map3D, headers/CommonTypes.h:15-43, filled by src/Map3D.cpp:7-74; walked at
+ * src/OptimizationUtils.cpp:244-294): observation lists, world poses and world points live in HBM, a window uploads
+ * only what is new or grew.  One store per solver context (its stream, its options), not thread-safe.
+ *   set_keyframe   the list of keyframe kf in the iteration order of its global_points_map: landmark ids in [0, 2^24),
+ *                  float pixels (cv::KeyPoint::pt), local depths points3d_local[localId].z; replaces an earlier list
+ *   set_poses      world poses of keyframes kf0 .. kf0 + n - 1
+ *   set_landmarks  world points by landmark id (new landmarks; the store itself keeps optimised points up to date)
+ *   window_solve   windowOptimize (:215-313) on the resident data: admissible observations (depth > 1e-15) of
+ *                  kf_i..kf_f in canonical order, point ids by first appearance, frame of keyframe kf_i, first pose
+ *                  constant, solve, back to the world frame.  Same bits as ba_gpu_upload / solve / download on the
+ *                  host-built arrays.  ms3 (nullable): enumeration + index build, solve, write-back in milliseconds. */
+typedef struct ba_store ba_store;
+int ba_store_create(ba_gpu_ctx *ctx, ba_store **out);
+void ba_store_destroy(ba_store *st); /* before ba_gpu_destroy of its context */
+int ba_store_set_keyframe(ba_store *st, int32_t kf, int32_t n, const int32_t *landmark_id, const float *uv2f, const double *depth);
+int ba_store_set_poses(ba_store *st, int32_t kf0, int32_t n, const double *pose7);
+int ba_store_set_landmarks(ba_store *st, int32_t n, const int32_t *id, const double *xyz);
+int ba_store_window_solve(ba_store *st, int32_t kf_i, int32_t kf_f, const double intr_prior4[4], double intr4[4],
+                          ba_gpu_summary *summary, double *pose7_out, int32_t lm_cap, int32_t *n_pt, int32_t *landmark_of_pt,
+                          double *pt3_out, int32_t *n_obs, double ms3[3]);
+
 /* ---- symbolic phase of the sparse Cholesky of S (host only, no device needed; CPU tests drive it) ----
  * n_blk stored upper blocks (blk_i <= blk_j) of the reduced camera matrix; nested-dissection ordering of the camera
  * sequence, elimination tree, supernodes whose front panel fits cap_blocks 6x6 blocks, levels, extend-add maps

@@ -14,7 +14,7 @@ from helpers import ba_b200, ora
 def _declared():
     src = open(ba_b200.capi.HEADER_PATH).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ba_(?:gpu|sparse)_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(ba_(?:gpu|sparse|store)_\w+)\s*\(", src)))
 
 
 def test_header_symbols_exported():

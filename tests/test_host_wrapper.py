@@ -179,3 +179,80 @@ def test_no_raw_pointer_se3_constructor_anywhere():
     if os.path.exists(ref):  # (this container only; the GPU box has no /root/reference)
         real = open(ref).read()
         assert re.search(r"SE3\s*\(\s*(Scalar|double)\s+const\s*\*", real) is None and "Scalar* data()" in real
+
+
+# ---------------------------------------------------------------- device-resident store
+@pytest.mark.gpu
+@pytest.mark.parametrize("growing", [False, True], ids=["complete-maps", "maps-grow-between-windows"])
+def test_device_store_sliding_windows_bit_identical(growing):
+    """The reference's schedule (a 20-keyframe window every 10 keyframes, warm-started) through the compiled drop-in, once
+    with every window walked and uploaded in full and once through the device-resident store (only new / grown keyframes
+    and new landmarks are uploaded; enumeration and frame changes on the device): poses, landmarks and intrinsics must
+    be equal BIT FOR BIT after the whole sequence.  With growing maps the second half of every keyframe's map arrives with
+    the next keyframe (the "old_frame" inserts of src/Map3D.cpp:52): such a keyframe is uploaded twice."""
+    hostlib = ba_b200.hostlib
+    out = []
+    for store in (False, True):
+        seq = syn.make_config(2, scale=0.1)   # 80 keyframes, 8000 landmarks
+        intr = seq.K.copy()
+        r = hostlib.sliding_sequence(seq, 20, 10, max_num_iterations=6, fixed_iterations=True, intrinsics_optimized=intr,
+                                     device_store=store, growing_maps=growing)
+        out.append((seq.pose.copy(), seq.pt.copy(), intr.copy(), r))
+    a, b = out
+    assert a[3]["windows"] == b[3]["windows"] == 7 and a[3]["lm_iterations"] == b[3]["lm_iterations"]
+    assert np.array_equal(a[0], b[0]), float(np.max(np.abs(a[0] - b[0])))
+    assert np.array_equal(a[1], b[1]), float(np.max(np.abs(a[1] - b[1])))
+    assert np.array_equal(a[2], b[2])
+    assert not np.array_equal(a[0], syn.make_config(2, scale=0.1).pose)   # the windows did move the poses
+
+
+@pytest.mark.gpu
+def test_device_store_c_abi_direct():
+    """ba_store_* through ctypes: one window assembled on the device equals upload / solve / download of the host-built
+    arrays (synthetic.window_problem does the frame change with numpy: equal to round-off, not bit for bit)."""
+    import ctypes as C
+    cap = ba_b200.capi
+    lib = cap.load()
+    seq = syn.make_tum_sequence(30, 3000, 18000, seed=9)
+    s = ba_b200.GpuSolver(max_num_iterations=6)
+    st = C.c_void_p()
+    assert lib.ba_store_create(s._ctx, C.byref(st)) == 0
+    try:
+        for k in range(30):
+            a, b = int(seq.kf_ptr[k]), int(seq.kf_ptr[k + 1])
+            ids = np.ascontiguousarray(seq.lm[a:b], dtype=np.int32)
+            uvf = np.ascontiguousarray(seq.uv[a:b], dtype=np.float32)
+            dep = np.ascontiguousarray(seq.depth[a:b], dtype=np.float64)
+            assert lib.ba_store_set_keyframe(st, k, b - a, cap.ip(ids), uvf.ctypes.data_as(C.POINTER(C.c_float)), cap.dp(dep)) == 0
+        pose = np.ascontiguousarray(seq.pose, dtype=np.float64)
+        assert lib.ba_store_set_poses(st, 0, 30, cap.dp(pose)) == 0
+        ids = np.arange(seq.pt.shape[0], dtype=np.int32)
+        pts = np.ascontiguousarray(seq.pt, dtype=np.float64)
+        assert lib.ba_store_set_landmarks(st, len(ids), cap.ip(ids), cap.dp(pts)) == 0
+        intr, prior = seq.K.copy(), seq.K.copy()
+        summ = cap.Summary()
+        pose_out = np.zeros((20, 7))
+        lm_of_pt = np.zeros(20000, dtype=np.int32)
+        pt_out = np.zeros((20000, 3))
+        n_pt, n_obs = C.c_int32(0), C.c_int32(0)
+        ms = np.zeros(3)
+        rc = lib.ba_store_window_solve(st, 10, 29, cap.dp(prior), cap.dp(intr), C.byref(summ), cap.dp(pose_out), 20000, C.byref(n_pt),
+                                       cap.ip(lm_of_pt), cap.dp(pt_out), C.byref(n_obs), cap.dp(ms))
+        assert rc == 0, lib.ba_gpu_last_error(s._ctx)
+    finally:
+        lib.ba_store_destroy(st)
+    win = syn.window_problem(seq, 10, 29)
+    assert n_obs.value == win.problem.n_obs and n_pt.value == win.problem.n_pt
+    assert np.array_equal(lm_of_pt[:n_pt.value], win.lm_ids)          # first-appearance order, bit-exact
+    s2 = ba_b200.GpuSolver(max_num_iterations=6)
+    s2.upload(win.problem)
+    summ2 = s2.solve()
+    pose2, pt2, intr2 = s2.download()
+    s2.close()
+    s.close()
+    assert summ.num_iterations == summ2.num_iterations
+    assert abs(summ.final_cost - summ2.final_cost) <= 1e-9 * summ2.final_cost
+    world = ba_b200.se3.mul(np.broadcast_to(win.T0, pose2.shape), pose2)
+    assert np.max(np.abs(world - pose_out)) < 1e-9
+    assert np.max(np.abs(ba_b200.se3.act(win.T0, pt2) - pt_out[:n_pt.value])) < 1e-8
+    assert np.max(np.abs(intr - intr2)) < 1e-7
