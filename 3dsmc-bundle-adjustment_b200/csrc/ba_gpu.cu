@@ -179,6 +179,7 @@ struct ba_gpu_ctx {
   Buf W, WV, S, rhs, blk_i, blk_j, blk_cam, pair_ptr, pair_a, pair_b;
   Buf ex_keys, ex_keys2, ex_vals, ex_vals2, blk_cnt;  // device-built pair list (windows)
   int n_blk = 0;
+  int ex_band_cams = -1;  // largest camera-slot distance of a non-empty block of the dense explicit S (-1: unknown = dense)
   // controller
   Buf st, trace;
   LmState *h_st = nullptr;  // pinned
@@ -591,6 +592,8 @@ static int build_pair_list(ba_gpu_ctx *ctx, const int32_t *cam_idx, const int32_
       }
     }
   ctx->n_blk = (int)bi.size();
+  ctx->ex_band_cams = 0;
+  for (size_t b = 0; b < bi.size(); ++b) ctx->ex_band_cams = std::max(ctx->ex_band_cams, bj[b] - bi[b]);
   RES(blk_i, bi.size() * 4);
   RES(blk_j, bi.size() * 4);
   RES(blk_cam, bi.size() * 4);
@@ -686,6 +689,7 @@ static int build_pair_list_device(ba_gpu_ctx *ctx) {
          P<unsigned long long>(ctx->ex_vals2), P<int32_t>(ctx->pair_a), P<int32_t>(ctx->pair_b), nf, ctx->fixed_cam,
          P<int32_t>(ctx->blk_i), P<int32_t>(ctx->blk_j), P<int32_t>(ctx->blk_cam));
   ctx->n_blk = nb_all;
+  ctx->ex_band_cams = -1;  // (windows: every block of the upper triangle is listed; at most 7 tiles anyway)
   return 0;
 }
 
@@ -1898,6 +1902,29 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
 //   trsm2(k)  <- potrf2(k), column(k-1) [stream order]
 //   column(k) <- trsm2(k) [stream order], bulk(k-1)
 //   bulk(k)   <- trsm2(k), bulk(k-1) [stream order]
+// tile rows below the diagonal of tile column k that can be non-zero: n_band rows right below, then the border rows from bord0
+struct ChActive {
+  int n_band, bord0, n_act;
+};
+static ChActive chol_active(const ba_gpu_ctx *ctx, int n, int nt, int k) {
+  ChActive a;
+  const int below = nt - k - 1;
+  if (ctx->ex_band_cams < 0 || getenv("BA_CHOL_DENSE")) {
+    a.n_band = below;
+    a.bord0 = nt;
+    a.n_act = below;
+    return a;
+  }
+  const int bt = (6 * ctx->ex_band_cams + 5 + CH_NB - 1) / CH_NB;  // tile distance of the furthest camera-camera entry
+  a.n_band = std::min(below, std::max(1, bt));
+  const int kb = k + a.n_band;                                     // last band row
+  int nb0 = nt;                                                    // first tile row that holds intrinsics columns
+  if (ctx->nk) nb0 = (6 * ctx->n_free) / CH_NB;
+  a.bord0 = std::max(nb0, kb + 1);
+  a.n_act = a.n_band + std::max(0, nt - a.bord0);
+  (void)n;
+  return a;
+}
 static int factor_blocked_lookahead2(ba_gpu_ctx *ctx, int n, int nt, double *S, double *Linv, double *Lsub, LmState *st) {
   const size_t tile = (size_t)CH_NB * CH_NB, sm2 = (size_t)2 * CH_NB * CH_LD * 8;
   cudaStream_t A = ctx->stream, B = ctx->stream2, C = ctx->stream3;
@@ -1905,6 +1932,7 @@ static int factor_blocked_lookahead2(ba_gpu_ctx *ctx, int n, int nt, double *S, 
   ctx->pdl = !ctx->pdl_off;
   for (int k = 0; k < nt; ++k) {
     const int below = nt - k - 1, e = k & 1;
+    const ChActive act = chol_active(ctx, n, nt, k);  // band-aware: only the tile rows that can be non-zero (ba_kernels_chol.cuh)
     if (col_rec[e]) CK(cudaStreamWaitEvent(A, ctx->ev_col[e], 0));    // column(k - 2)
     if (bulk_rec[e]) CK(cudaStreamWaitEvent(A, ctx->ev_bulk2[e], 0));  // bulk(k - 2)
     ctx->cur = A;
@@ -1913,16 +1941,19 @@ static int factor_blocked_lookahead2(ba_gpu_ctx *ctx, int n, int nt, double *S, 
     CK(cudaEventRecord(ctx->ev_panel, A));
     CK(cudaStreamWaitEvent(B, ctx->ev_panel, 0));
     ctx->cur = B;
-    LAUNCH(k_chol_trsm2, below, 256, sm2, n, S, Linv + k * tile, Lsub + (size_t)(k + 1) * tile, k, st, GATE_RUN);
-    if (below > 1) {
+    LAUNCH(k_chol_trsm2, act.n_act, 256, sm2, n, S, Linv + k * tile, Lsub + (size_t)(k + 1) * tile, k, act.n_band, act.bord0, st, GATE_RUN);
+    if (act.n_act > 1) {
       CK(cudaEventRecord(ctx->ev_trsm, B));
       if (bulk_rec[e ^ 1]) CK(cudaStreamWaitEvent(B, ctx->ev_bulk2[e ^ 1], 0));  // bulk(k - 1)
-      LAUNCH(k_chol_update, below - 1, 256, CH_UPD_SMEM, n, S, (const double *)(Lsub + (size_t)(k + 1) * tile), k, k, 1, st, GATE_RUN);
+      LAUNCH(k_chol_update, act.n_act - 1, 256, CH_UPD_SMEM, n, S, (const double *)(Lsub + (size_t)(k + 1) * tile), k, k, 1, act.n_band,
+             act.bord0, st, GATE_RUN);
       CK(cudaEventRecord(ctx->ev_col[e], B));
       col_rec[e] = true;
       CK(cudaStreamWaitEvent(C, ctx->ev_trsm, 0));
       ctx->cur = C;
-      LAUNCH(k_chol_update, (below - 1) * below / 2, 256, CH_UPD_SMEM, n, S, (const double *)nullptr, k, k + 1, 0, st, GATE_RUN);
+      // the rest of the trailing update: active rows without the first one (tile row k + 1), as rows from k + 2
+      LAUNCH(k_chol_update, (act.n_act - 1) * act.n_act / 2, 256, CH_UPD_SMEM, n, S, (const double *)nullptr, k, k + 1, 0, act.n_band - 1,
+             act.bord0, st, GATE_RUN);
       CK(cudaEventRecord(ctx->ev_bulk2[e], C));
       bulk_rec[e] = true;
     } else {
@@ -2026,10 +2057,14 @@ static int solve_explicit(ba_gpu_ctx *ctx) {
       } else {
         // diagonal tile: register-resident L D L^T that also yields L^-1; panel: product with L^-1
         LAUNCH(k_chol_potrf2, 1, 1024, chol_potrf2_smem_bytes(), n, S, Linv + (size_t)k * CH_NB * CH_NB, k, 0, st, GATE_RUN);
-        LAUNCH(k_chol_trsm2, below, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv + (size_t)k * CH_NB * CH_NB, (double *)nullptr, k, st,
-               GATE_RUN);
+        const ChActive act = chol_active(ctx, n, nt, k);
+        LAUNCH(k_chol_trsm2, act.n_act, 256, (size_t)2 * CH_NB * CH_LD * 8, n, S, Linv + (size_t)k * CH_NB * CH_NB, (double *)nullptr, k,
+               act.n_band, act.bord0, st, GATE_RUN);
+        LAUNCH(k_chol_update, act.n_act * (act.n_act + 1) / 2, 256, CH_UPD_SMEM, n, S, (const double *)nullptr, k, k, 0, act.n_band,
+               act.bord0, st, GATE_RUN);
+        continue;
       }
-      LAUNCH(k_chol_update, below * (below + 1) / 2, 256, CH_UPD_SMEM, n, S, (const double *)nullptr, k, k, 0, st,
+      LAUNCH(k_chol_update, below * (below + 1) / 2, 256, CH_UPD_SMEM, n, S, (const double *)nullptr, k, k, 0, below, nt, st,
              GATE_RUN);
     }
     int nn = n, n_cam = ctx->n_cam, n_free = ctx->n_free, nk = ctx->nk, gate = GATE_RUN;
@@ -2757,39 +2792,55 @@ static int store_fit_kf(ba_gpu_ctx *ctx, ba_store *st, int kf) {
   }
   return 0;
 }
-// the observation list of keyframe kf in the iteration order of its global_points_map (replaces any earlier list)
-extern "C" int ba_store_set_keyframe(ba_store *st, int32_t kf, int32_t n, const int32_t *landmark_id, const float *uv2f,
-                                     const double *depth) {
-  if (!st || kf < 0 || n < 0 || (n > 0 && (!landmark_id || !uv2f || !depth))) return BA_ERR_INVALID;
+// the observation lists of n_kf keyframes (kf[k] has cnt[k] entries, lists back to back) in the iteration order of their
+// global_points_map; replaces any earlier list of these keyframes.  The lists of one call go to one contiguous piece at the
+// end of the pool: three copies per call, whatever the number of keyframes.  Earlier segments of the same keyframes are
+// abandoned, not reclaimed: a keyframe's map is re-sent once or twice in its life (it grows only while it is one of the two
+// newest keyframes, src/Map3D.cpp:52-53), so the pool holds at most a small multiple of the live lists.
+extern "C" int ba_store_set_keyframes(ba_store *st, int32_t n_kf, const int32_t *kf, const int32_t *cnt, const int32_t *landmark_id,
+                                      const float *uv2f, const double *depth) {
+  if (!st || n_kf < 0 || (n_kf > 0 && (!kf || !cnt))) return BA_ERR_INVALID;
+  if (n_kf == 0) return BA_OK;
   ba_gpu_ctx *ctx = st->ctx;
   CK(cudaSetDevice(ctx->device));
-  for (int i = 0; i < n; ++i) {
+  size_t total = 0;
+  int kf_max = 0;
+  for (int k = 0; k < n_kf; ++k) {
+    if (kf[k] < 0 || cnt[k] < 0) return BA_ERR_INVALID;
+    total += (size_t)cnt[k];
+    kf_max = std::max(kf_max, kf[k]);
+  }
+  if (total > 0 && (!landmark_id || !uv2f || !depth)) return BA_ERR_INVALID;
+  for (size_t i = 0; i < total; ++i) {
     if (landmark_id[i] < 0 || landmark_id[i] >= BA_STORE_MAX_ID)
       return fail(ctx, BA_ERR_UNSUPPORTED, "store: landmark id %d outside [0, 2^24)", landmark_id[i]);
     st->max_id = std::max(st->max_id, landmark_id[i]);
   }
-  int rc = store_fit_kf(ctx, st, kf);
+  int rc = store_fit_kf(ctx, st, kf_max);
   if (rc) return rc;
-  if (st->seg_off[kf] < 0 || n > st->seg_cap[kf]) {  // new segment at the end of the pool (with head-room for later inserts)
-    const int cap = n + n / 4 + 16;
-    const size_t need = st->pool_used + (size_t)cap;
-    SGROW(lm, need * 4, true);
-    SGROW(uvf, need * 8, true);
-    SGROW(depth, need * 8, true);
-    st->seg_off[kf] = (long long)st->pool_used;
-    st->seg_cap[kf] = cap;
-    st->pool_used = need;
+  const size_t need = st->pool_used + total;
+  SGROW(lm, need * 4, true);
+  SGROW(uvf, need * 8, true);
+  SGROW(depth, need * 8, true);
+  size_t o = st->pool_used;
+  for (int k = 0; k < n_kf; ++k) {
+    st->seg_off[kf[k]] = (long long)o;
+    st->seg_n[kf[k]] = cnt[k];
+    o += (size_t)cnt[k];
   }
-  st->seg_n[kf] = n;
-  if (n) {
-    const size_t o = (size_t)st->seg_off[kf];
+  if (total) {
+    // (pageable sources: cudaMemcpyAsync returns once the source has been staged, the caller may reuse its arrays)
     cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync((int32_t *)st->lm.p + o, landmark_id, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync((float2 *)st->uvf.p + o, uv2f, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync((double *)st->depth.p + o, depth, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));  // the caller's arrays may be temporaries
+    CK(cudaMemcpyAsync((int32_t *)st->lm.p + st->pool_used, landmark_id, total * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync((float2 *)st->uvf.p + st->pool_used, uv2f, total * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync((double *)st->depth.p + st->pool_used, depth, total * 8, cudaMemcpyHostToDevice, s));
   }
+  st->pool_used = need;
   return BA_OK;
+}
+extern "C" int ba_store_set_keyframe(ba_store *st, int32_t kf, int32_t n, const int32_t *landmark_id, const float *uv2f,
+                                     const double *depth) {
+  return ba_store_set_keyframes(st, 1, &kf, &n, landmark_id, uv2f, depth);
 }
 extern "C" int ba_store_set_poses(ba_store *st, int32_t kf0, int32_t n, const double *pose7) {
   if (!st || kf0 < 0 || n <= 0 || !pose7) return BA_ERR_INVALID;
@@ -2798,7 +2849,6 @@ extern "C" int ba_store_set_poses(ba_store *st, int32_t kf0, int32_t n, const do
   int rc = store_fit_kf(ctx, st, kf0 + n - 1);
   if (rc) return rc;
   CK(cudaMemcpyAsync((double *)st->pose_w.p + 7 * (size_t)kf0, pose7, (size_t)n * 56, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
   return BA_OK;
 }
 extern "C" int ba_store_set_landmarks(ba_store *st, int32_t n, const int32_t *id, const double *xyz) {
@@ -2826,7 +2876,6 @@ extern "C" int ba_store_set_landmarks(ba_store *st, int32_t n, const int32_t *id
   CK(cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, s));
   ks_scatter_points<<<cdiv(n, BA_THREADS), BA_THREADS, 0, s>>>(n, d_id, d_xyz, (double *)st->pt_w.p);
   ctx->launches++;
-  CK(cudaStreamSynchronize(s));
   return BA_OK;
 }
 
@@ -2892,24 +2941,24 @@ extern "C" int ba_store_window_solve(ba_store *st, int32_t kf_i, int32_t kf_f, c
   if ((rc = scan(d_flag, d_pos, total + 1))) return rc;
   int32_t h_cnt[2] = {0, 0};
   CK(cudaMemcpyAsync(&h_cnt[0], d_pos + total, 4, cudaMemcpyDeviceToHost, s));
-  ks_first<0><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
-  ks_first<1><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
+  // first appearance per landmark as the smallest WINDOW position (monotone in the observation index): the point ranks come
+  // from a scan over window positions, so the host needs the two counts only once, after everything is enqueued
   CK(cudaMemsetAsync(d_isf, 0, ((size_t)total + 2) * 4, s));
-  ks_first<2><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
-  ctx->launches += 4;
-  CK(cudaStreamSynchronize(s));
-  const int n_obs = h_cnt[0];
-  if ((rc = scan(d_isf, d_rank, n_obs + 1))) return rc;
-  CK(cudaMemcpyAsync(&h_cnt[1], d_rank + n_obs, 4, cudaMemcpyDeviceToHost, s));
+  ks_first<0><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
+  ks_first<1><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
+  ks_first<2><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
+  if ((rc = scan(d_isf, d_rank, total + 1))) return rc;
+  CK(cudaMemcpyAsync(&h_cnt[1], d_rank + total, 4, cudaMemcpyDeviceToHost, s));
   double *d_T0 = (double *)st->T0.p, *d_T0inv = d_T0 + 7;
   ks_frame<<<cdiv(std::max(n_cam, 1), 64), 64, 0, s>>>(n_cam, (const double *)st->pose_w.p + 7 * (size_t)kf_i, d_T0, d_T0inv, (double *)st->w_pose.p);
   ks_emit<<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (const float2 *)st->uvf.p,
                                     (const double *)st->depth.p, (const int32_t *)st->first.p, d_rank, (const double *)st->pt_w.p, d_T0inv,
                                     (int32_t *)st->w_cam.p, (int32_t *)st->w_pt.p, (double2 *)st->w_uv.p, (double *)st->w_depth.p,
                                     (int32_t *)st->w_lm.p, (double *)st->w_pt3.p);
-  ctx->launches += 2;
+  ctx->launches += 6;
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
+  const int n_obs = h_cnt[0];
   const int n_pt = h_cnt[1];
   if (n_obs_out) *n_obs_out = n_obs;
   *n_pt_out = n_pt;

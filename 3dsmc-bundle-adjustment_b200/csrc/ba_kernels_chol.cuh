@@ -91,12 +91,18 @@ k_chol_trsm(int n, double *__restrict__ A, int k, const LmState *st, int gate) {
 // schedule splits it into the next column (single_col) and the rest (kmap = k + 1).
 // Bsub != nullptr (single_col only, look-ahead schedule): the column operand L_{k+1,k} comes from the side buffer and the
 // diagonal tile (k + 1, k + 1) is left to the fused k_chol_potrf2: tiles (i, k + 1), i >= k + 2.
+// BAND-AWARE tile rows.  The reduced matrix of a keyframe SEQUENCE is block-banded (a landmark track is a run of neighbouring
+// keyframes) with the 4 intrinsics columns as a dense border at the end; Cholesky creates no fill outside band + border.
+// For tile column k the tile rows that can be non-zero below the diagonal are the n_band rows k + 1 .. k + n_band and the
+// border rows bord0 .. (last); "active row" t of a launch maps to tile row ch_row(first, t, n_band, bord0), first = k + 1 (or
+// k + 2 for the bulk of the look-ahead schedule).  A dense matrix is the special case n_band = all rows, no border rows.
+__device__ __forceinline__ int ch_row(int first, int t, int n_band, int bord0) { return t < n_band ? first + t : bord0 + (t - n_band); }
 #define CH_KH 32               // the 64-deep inner product in two halves: 34 KB of shared memory per CTA instead of 67 KB
 #define CH_HLD (CH_KH + 1)
 #define CH_UPD_SMEM ((size_t)2 * CH_NB * CH_HLD * 8)
 __global__ void __launch_bounds__(256, 4)
-k_chol_update(int n, double *__restrict__ A, const double *__restrict__ Bsub, int k, int kmap, int single_col, const LmState *st,
-              int gate) {
+k_chol_update(int n, double *__restrict__ A, const double *__restrict__ Bsub, int k, int kmap, int single_col, int n_band, int bord0,
+              const LmState *st, int gate) {
   if (!gate_open(st, gate) || st->lin_fail) return;
   extern __shared__ double sh[];
   double *As = sh, *Bs = sh + CH_NB * CH_HLD;
@@ -109,7 +115,7 @@ k_chol_update(int n, double *__restrict__ A, const double *__restrict__ Bsub, in
     while (ti * (ti + 1) / 2 > b) --ti;
     tj = b - ti * (ti + 1) / 2;
   }
-  const int i0 = (kmap + 1 + ti) * CH_NB, c0 = (kmap + 1 + tj) * CH_NB, j0 = k * CH_NB;
+  const int i0 = ch_row(kmap + 1, ti, n_band, bord0) * CH_NB, c0 = ch_row(kmap + 1, tj, n_band, bord0) * CH_NB, j0 = k * CH_NB;
   const int kk = min(CH_NB, n - j0);
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
@@ -668,13 +674,13 @@ k_chol_potrf2(int n, double *__restrict__ A, double *__restrict__ Linv, int k, i
 // Lsub != nullptr (look-ahead schedule): the tile right below the diagonal, (k + 1, k), goes to Lsub (dense 64 x 64) instead
 // of in place -- the fused k_chol_potrf2 of step k + 1 reads the un-solved tile concurrently; k_chol_fixup stores it at the end.
 __global__ void __launch_bounds__(256)
-k_chol_trsm2(int n, double *__restrict__ A, const double *__restrict__ Linv, double *__restrict__ Lsub, int k, const LmState *st,
-             int gate) {
+k_chol_trsm2(int n, double *__restrict__ A, const double *__restrict__ Linv, double *__restrict__ Lsub, int k, int n_band, int bord0,
+             const LmState *st, int gate) {
   if (!gate_open(st, gate) || st->lin_fail) return;
   extern __shared__ double sh[];
   double *As = sh, *Bs = sh + CH_NB * CH_LD;
   const int j0 = k * CH_NB, kk = min(CH_NB, n - j0);
-  const int i0 = (k + 1 + blockIdx.x) * CH_NB;
+  const int i0 = ch_row(k + 1, blockIdx.x, n_band, bord0) * CH_NB;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
     const int r = idx >> 6, c = idx & 63;

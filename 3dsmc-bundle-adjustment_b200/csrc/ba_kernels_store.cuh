@@ -110,17 +110,16 @@ ks_flags(int total, int n_cam, const int32_t *__restrict__ win_off, const long l
 template <int PASS>
 __global__ void __launch_bounds__(BA_THREADS)
 ks_first(int total, int n_cam, const int32_t *__restrict__ win_off, const long long *__restrict__ win_seg,
-         const int32_t *__restrict__ flag, const int32_t *__restrict__ pos, const int32_t *__restrict__ lm, int32_t *first,
-         int32_t *__restrict__ isfirst) {
+         const int32_t *__restrict__ flag, const int32_t *__restrict__ lm, int32_t *first, int32_t *__restrict__ isfirst) {
   const int t = blockIdx.x * BA_THREADS + threadIdx.x;
   if (t >= total || !flag[t]) return;
   int k;
   long long src;
   ks_locate(t, n_cam, win_off, win_seg, k, src);
-  const int l = lm[src], i = pos[t];
+  const int l = lm[src];
   if (PASS == 0) first[l] = 0x7fffffff;
-  if (PASS == 1) atomicMin(first + l, i);
-  if (PASS == 2) isfirst[i] = first[l] == i ? 1 : 0;
+  if (PASS == 1) atomicMin(first + l, t);   // window position of the landmark's first admissible observation
+  if (PASS == 2) isfirst[t] = first[l] == t ? 1 : 0;
 }
 // the window's arrays in canonical order; points (first appearances) moved into the frame of the first keyframe
 __global__ void __launch_bounds__(BA_THREADS)
@@ -134,14 +133,14 @@ ks_emit(int total, int n_cam, const int32_t *__restrict__ win_off, const long lo
   int k;
   long long src;
   ks_locate(t, n_cam, win_off, win_seg, k, src);
-  const int l = lm[src], i = pos[t], fi = first[l];
-  const int p = rank[fi];
+  const int l = lm[src], i = pos[t], ft = first[l];  // ft: window position of the first appearance
+  const int p = rank[ft];
   w_cam[i] = k;
   w_pt[i] = p;
   const float2 f = uvf[src];
   w_uv[i] = make_double2((double)f.x, (double)f.y);  // float -> double (:262)
   w_depth[i] = depth[src];
-  if (fi == i) {
+  if (ft == t) {
     lm_of_pt[p] = l;
     const double x[3] = {pt_w[3 * (size_t)l], pt_w[3 * (size_t)l + 1], pt_w[3 * (size_t)l + 2]};
     double o[3];

@@ -80,17 +80,17 @@ int window_optimize_store(const ba_gpu_options &opt, int kf_i, int kf_f, vector<
   if (rc != BA_OK) return -1;
   StoreState &S = g_store;
   if (S.kf_size.size() < keyframes.size()) S.kf_size.resize(keyframes.size(), -1);
-  vector<int32_t> ids, new_id;
-  vector<float> uvf;
-  vector<double> dep, new_xyz;
+  // (persistent scratch: no allocation per window)
+  static thread_local vector<int32_t> ids, new_id, kf_list, kf_cnt;
+  static thread_local vector<float> uvf;
+  static thread_local vector<double> dep, new_xyz;
+  ids.clear(); new_id.clear(); kf_list.clear(); kf_cnt.clear(); uvf.clear(); dep.clear(); new_xyz.clear();
   size_t lm_bound = 0;
   for (int kf_n = kf_i; kf_n <= kf_f; ++kf_n) {
     const KeyFrame &kf = keyframes[kf_n];
     lm_bound += kf.global_points_map.size();
     if (S.kf_size[kf_n] == (long long)kf.global_points_map.size()) continue;  // unchanged since its last upload
-    ids.clear();
-    uvf.clear();
-    dep.clear();
+    const size_t before = ids.size();
     for (const auto &index_pair : kf.global_points_map) {  // container order == canonical order (:257)
       const int localId = index_pair.first, landmarkId = index_pair.second;
       if (landmarkId < 0 || landmarkId >= (1 << 24)) return -1;
@@ -99,6 +99,7 @@ int window_optimize_store(const ba_gpu_options &opt, int kf_i, int kf_f, vector<
         auto found = map.find(landmarkId);
         if (found == map.end()) {
           std::fprintf(stderr, "windowOptimize: keyframe references a landmark that is not in the map\n");
+          g_store.reset();
           return 0;
         }
         S.lm_ptr[landmarkId] = &found->second;
@@ -110,11 +111,16 @@ int window_optimize_store(const ba_gpu_options &opt, int kf_i, int kf_f, vector<
       uvf.push_back(kf.keypoints[localId].pt.y);
       dep.push_back(kf.points3d_local[localId](2));
     }
-    rc = ba_store_set_keyframe(S.st, kf_n, (int32_t)ids.size(), ids.data(), uvf.data(), dep.data());
-    if (rc == BA_ERR_UNSUPPORTED) return -1;
-    if (rc != BA_OK) return 0;
-    S.kf_size[kf_n] = (long long)kf.global_points_map.size();
+    kf_list.push_back(kf_n);
+    kf_cnt.push_back((int32_t)(ids.size() - before));
   }
+  rc = ba_store_set_keyframes(S.st, (int32_t)kf_list.size(), kf_list.data(), kf_cnt.data(), ids.data(), uvf.data(), dep.data());
+  if (rc == BA_ERR_UNSUPPORTED) {
+    g_store.reset();
+    return -1;
+  }
+  if (rc != BA_OK) return 0;
+  for (int kf_n : kf_list) S.kf_size[kf_n] = (long long)keyframes[kf_n].global_points_map.size();
   if (!new_id.empty() && ba_store_set_landmarks(S.st, (int32_t)new_id.size(), new_id.data(), new_xyz.data()) != BA_OK) return 0;
   vector<double> pose7((size_t)n_cam * 7);
   for (int k = 0; k < n_cam; ++k)

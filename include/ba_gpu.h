@@ -259,6 +259,9 @@ typedef struct ba_store ba_store;
 int ba_store_create(ba_gpu_ctx *ctx, ba_store **out);
 void ba_store_destroy(ba_store *st); /* before ba_gpu_destroy of its context */
 int ba_store_set_keyframe(ba_store *st, int32_t kf, int32_t n, const int32_t *landmark_id, const float *uv2f, const double *depth);
+/* several keyframes in one call (lists back to back, cnt[k] entries for keyframe kf[k]): three copies per call */
+int ba_store_set_keyframes(ba_store *st, int32_t n_kf, const int32_t *kf, const int32_t *cnt, const int32_t *landmark_id,
+                           const float *uv2f, const double *depth);
 int ba_store_set_poses(ba_store *st, int32_t kf0, int32_t n, const double *pose7);
 int ba_store_set_landmarks(ba_store *st, int32_t n, const int32_t *id, const double *xyz);
 int ba_store_window_solve(ba_store *st, int32_t kf_i, int32_t kf_f, const double intr_prior4[4], double intr4[4],
