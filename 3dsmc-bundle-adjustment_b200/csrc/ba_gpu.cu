@@ -2737,10 +2737,40 @@ struct ba_store {
   std::vector<DBuf *> all;
   double ms[3] = {0, 0, 0};         // last window: enumeration + index build, solve, write-back + copies
   int max_id = -1;                  // largest landmark id any keyframe list refers to
+  unsigned long long epoch = 0;     // window counter (stamps the first-appearance table)
+  // pinned staging of the host -> device copies (a pageable source costs ~40 us per copy at these sizes); a slice is reused
+  // only after the stream has been synchronised (window_solve ends with one)
+  char *pin = nullptr;
+  size_t pin_cap = 0, pin_used = 0;
 };
+// copies `bytes` from the caller's array to device memory through the pinned staging area (asynchronous; the caller's
+// array is free on return)
+static int store_h2d(ba_gpu_ctx *ctx, ba_store *st, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return 0;
+  const size_t need = st->pin_used + ((bytes + 63) / 64) * 64;
+  if (need > st->pin_cap) {
+    // no room: drain the copies in flight, then start over (and grow if one request alone does not fit)
+    CK(cudaStreamSynchronize(ctx->stream));
+    st->pin_used = 0;
+    if (((bytes + 63) / 64) * 64 > st->pin_cap) {
+      if (st->pin) cudaFreeHost(st->pin);
+      st->pin = nullptr;
+      st->pin_cap = std::max(((bytes + 63) / 64) * 64 * 4, (size_t)1 << 20);
+      CK(cudaMallocHost((void **)&st->pin, st->pin_cap));
+    }
+  }
+  char *stage = st->pin + st->pin_used;
+  st->pin_used += ((bytes + 63) / 64) * 64;
+  memcpy(stage, src, bytes);
+  CK(cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
 static int sgrow(ba_gpu_ctx *ctx, ba_store *st, ba_store::DBuf &b, size_t bytes, bool keep) {
   if (b.cap >= bytes) return 0;
-  const size_t want = std::max(bytes + bytes / 2, (size_t)4096);
+  // growing tables (keep = true: observation pool, pose / landmark tables) start at 32 MiB and double: a reallocation
+  // (cudaMalloc + copy + cudaFree) was measured at up to 200 ms on this driver, so it must stay a rare event; the scratch
+  // buffers of a window settle at the window size
+  const size_t want = keep ? std::max(bytes * 2, (size_t)32 << 20) : std::max(bytes + bytes / 2, (size_t)65536);
   void *np = nullptr;
   cudaError_t e = cudaMalloc(&np, want);
   if (e != cudaSuccess) return fail(ctx, BA_ERR_CUDA, "store: cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
@@ -2776,6 +2806,7 @@ extern "C" void ba_store_destroy(ba_store *st) {
   }
   for (ba_store::DBuf *b : st->all)
     if (b->p) cudaFree(b->p);
+  if (st->pin) cudaFreeHost(st->pin);
   delete st;
 }
 static int store_fit_kf(ba_gpu_ctx *ctx, ba_store *st, int kf) {
@@ -2829,11 +2860,10 @@ extern "C" int ba_store_set_keyframes(ba_store *st, int32_t n_kf, const int32_t 
     o += (size_t)cnt[k];
   }
   if (total) {
-    // (pageable sources: cudaMemcpyAsync returns once the source has been staged, the caller may reuse its arrays)
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync((int32_t *)st->lm.p + st->pool_used, landmark_id, total * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync((float2 *)st->uvf.p + st->pool_used, uv2f, total * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync((double *)st->depth.p + st->pool_used, depth, total * 8, cudaMemcpyHostToDevice, s));
+    if ((rc = store_h2d(ctx, st, (int32_t *)st->lm.p + st->pool_used, landmark_id, total * 4)) ||
+        (rc = store_h2d(ctx, st, (float2 *)st->uvf.p + st->pool_used, uv2f, total * 8)) ||
+        (rc = store_h2d(ctx, st, (double *)st->depth.p + st->pool_used, depth, total * 8)))
+      return rc;
   }
   st->pool_used = need;
   return BA_OK;
@@ -2848,8 +2878,7 @@ extern "C" int ba_store_set_poses(ba_store *st, int32_t kf0, int32_t n, const do
   CK(cudaSetDevice(ctx->device));
   int rc = store_fit_kf(ctx, st, kf0 + n - 1);
   if (rc) return rc;
-  CK(cudaMemcpyAsync((double *)st->pose_w.p + 7 * (size_t)kf0, pose7, (size_t)n * 56, cudaMemcpyHostToDevice, ctx->stream));
-  return BA_OK;
+  return store_h2d(ctx, st, (double *)st->pose_w.p + 7 * (size_t)kf0, pose7, (size_t)n * 56);
 }
 extern "C" int ba_store_set_landmarks(ba_store *st, int32_t n, const int32_t *id, const double *xyz) {
   if (!st || n < 0 || (n > 0 && (!id || !xyz))) return BA_ERR_INVALID;
@@ -2864,7 +2893,8 @@ extern "C" int ba_store_set_landmarks(ba_store *st, int32_t n, const int32_t *id
   if ((size_t)mx >= st->n_lm_cap) {
     const size_t cap = (size_t)mx + 1024 + st->n_lm_cap / 2;
     SGROW(pt_w, cap * 24, true);
-    SGROW(first, cap * 4, false);
+    SGROW(first, cap * 8, false);  // (epoch << 32 | ~position) per landmark: zero = older than any window
+    CK(cudaMemsetAsync(st->first.p, 0, st->first.cap, ctx->stream));
     st->n_lm_cap = cap;
   }
   const size_t id_bytes = (((size_t)n * 4 + 63) / 64) * 64;
@@ -2872,8 +2902,8 @@ extern "C" int ba_store_set_landmarks(ba_store *st, int32_t n, const int32_t *id
   int32_t *d_id = (int32_t *)st->stage.p;
   double *d_xyz = (double *)((char *)st->stage.p + id_bytes);
   cudaStream_t s = ctx->stream;
-  CK(cudaMemcpyAsync(d_id, id, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+  int rch;
+  if ((rch = store_h2d(ctx, st, d_id, id, (size_t)n * 4)) || (rch = store_h2d(ctx, st, d_xyz, xyz, (size_t)n * 24))) return rch;
   ks_scatter_points<<<cdiv(n, BA_THREADS), BA_THREADS, 0, s>>>(n, d_id, d_xyz, (double *)st->pt_w.p);
   ctx->launches++;
   return BA_OK;
@@ -2908,10 +2938,8 @@ extern "C" int ba_store_window_solve(ba_store *st, int32_t kf_i, int32_t kf_f, c
   cudaStream_t s = ctx->stream;
   SGROW(win_off, ((size_t)n_cam + 1) * 4, false);
   SGROW(win_seg, (size_t)n_cam * 8, false);
-  SGROW(flag, ((size_t)total + 2) * 4, false);
-  SGROW(pos, ((size_t)total + 2) * 4, false);
-  SGROW(isfirst, ((size_t)total + 2) * 4, false);
-  SGROW(rank, ((size_t)total + 2) * 4, false);
+  SGROW(flag, ((size_t)total + 2) * 8, false);  // packed (admissible | first appearance << 32)
+  SGROW(pos, ((size_t)total + 2) * 8, false);   // its exclusive scan
   SGROW(w_cam, ((size_t)total + 1) * 4, false);
   SGROW(w_pt, ((size_t)total + 1) * 4, false);
   SGROW(w_uv, ((size_t)total + 1) * 16, false);
@@ -2922,42 +2950,42 @@ extern "C" int ba_store_window_solve(ba_store *st, int32_t kf_i, int32_t kf_f, c
   SGROW(T0, 14 * 8, false);
   SGROW(out_pose, (size_t)n_cam * 56, false);
   SGROW(cnt, 64, false);
-  CK(cudaMemcpyAsync(st->win_off.p, off.data(), ((size_t)n_cam + 1) * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(st->win_seg.p, seg.data(), (size_t)n_cam * 8, cudaMemcpyHostToDevice, s));
+  {
+    int rch;
+    if ((rch = store_h2d(ctx, st, st->win_off.p, off.data(), ((size_t)n_cam + 1) * 4)) ||
+        (rch = store_h2d(ctx, st, st->win_seg.p, seg.data(), (size_t)n_cam * 8)))
+      return rch;
+  }
   const int32_t *d_off = (const int32_t *)st->win_off.p;
   const long long *d_seg = (const long long *)st->win_seg.p;
-  int32_t *d_flag = (int32_t *)st->flag.p, *d_pos = (int32_t *)st->pos.p, *d_isf = (int32_t *)st->isfirst.p, *d_rank = (int32_t *)st->rank.p;
+  unsigned long long *d_packed = (unsigned long long *)st->flag.p, *d_prefix = (unsigned long long *)st->pos.p;
   const int nb = cdiv(total + 1, BA_THREADS);
-  auto scan = [&](int32_t *in, int32_t *out, int n) -> int {
-    size_t tb = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s));
-    int rc_ = sgrow(ctx, st, st->cub, tb + 16, false);
-    if (rc_) return rc_;
-    CK(cub::DeviceScan::ExclusiveSum(st->cub.p, tb, in, out, n, s));
-    return 0;
-  };
-  int rc;
-  ks_flags<<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, (const double *)st->depth.p, d_flag);
-  if ((rc = scan(d_flag, d_pos, total + 1))) return rc;
-  int32_t h_cnt[2] = {0, 0};
-  CK(cudaMemcpyAsync(&h_cnt[0], d_pos + total, 4, cudaMemcpyDeviceToHost, s));
-  // first appearance per landmark as the smallest WINDOW position (monotone in the observation index): the point ranks come
-  // from a scan over window positions, so the host needs the two counts only once, after everything is enqueued
-  CK(cudaMemsetAsync(d_isf, 0, ((size_t)total + 2) * 4, s));
-  ks_first<0><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
-  ks_first<1><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
-  ks_first<2><<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, (const int32_t *)st->lm.p, (int32_t *)st->first.p, d_isf);
-  if ((rc = scan(d_isf, d_rank, total + 1))) return rc;
-  CK(cudaMemcpyAsync(&h_cnt[1], d_rank + total, 4, cudaMemcpyDeviceToHost, s));
+  const unsigned long long epoch = ++st->epoch;
   double *d_T0 = (double *)st->T0.p, *d_T0inv = d_T0 + 7;
   ks_frame<<<cdiv(std::max(n_cam, 1), 64), 64, 0, s>>>(n_cam, (const double *)st->pose_w.p + 7 * (size_t)kf_i, d_T0, d_T0inv, (double *)st->w_pose.p);
-  ks_emit<<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_flag, d_pos, (const int32_t *)st->lm.p, (const float2 *)st->uvf.p,
-                                    (const double *)st->depth.p, (const int32_t *)st->first.p, d_rank, (const double *)st->pt_w.p, d_T0inv,
+  ks_mark<<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, (const double *)st->depth.p, (const int32_t *)st->lm.p, epoch,
+                                    (unsigned long long *)st->first.p, d_packed);
+  ks_isfirst<<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, (const int32_t *)st->lm.p, epoch, (const unsigned long long *)st->first.p,
+                                       d_packed);
+  {
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_packed, d_prefix, total + 1, s));
+    int rcs = sgrow(ctx, st, st->cub, tb + 16, false);
+    if (rcs) return rcs;
+    CK(cub::DeviceScan::ExclusiveSum(st->cub.p, tb, d_packed, d_prefix, total + 1, s));
+  }
+  unsigned long long h_counts = 0;
+  CK(cudaMemcpyAsync(&h_counts, d_prefix + total, 8, cudaMemcpyDeviceToHost, s));
+  ks_emit<<<nb, BA_THREADS, 0, s>>>(total, n_cam, d_off, d_seg, d_packed, d_prefix, (const int32_t *)st->lm.p, (const float2 *)st->uvf.p,
+                                    (const double *)st->depth.p, (const unsigned long long *)st->first.p, (const double *)st->pt_w.p, d_T0inv,
                                     (int32_t *)st->w_cam.p, (int32_t *)st->w_pt.p, (double2 *)st->w_uv.p, (double *)st->w_depth.p,
                                     (int32_t *)st->w_lm.p, (double *)st->w_pt3.p);
-  ctx->launches += 6;
+  ctx->launches += 4;
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
+  st->pin_used = 0;  // every staged copy has landed
+  int rc;
+  const int32_t h_cnt[2] = {(int32_t)(h_counts & 0xffffffffull), (int32_t)(h_counts >> 32)};
   const int n_obs = h_cnt[0];
   const int n_pt = h_cnt[1];
   if (n_obs_out) *n_obs_out = n_obs;

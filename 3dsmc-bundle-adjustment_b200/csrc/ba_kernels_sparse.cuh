@@ -299,7 +299,8 @@ k_sp_minv(int n_cam, const int32_t *__restrict__ diag, const double *__restrict_
 // Measured and rejected in round 2 (config 5, same results): two CTAs per SM at 128 registers (accumulators spill to
 // local memory: 1.57 ms); one camera ROW per CTA with the row's a side -- rows of Jc and Vs p-rows, 18 doubles per
 // observation -- staged in shared memory, chunked work items and prefetched b-side records (40 B and ~140 multiply-adds
-// per pair instead of 124 B and ~190, but three CTA-wide phases per row at 8 warps per SM: 1.92 ms).
+// per pair instead of 124 B and ~190, but three CTA-wide phases per row at 8 warps per SM: 1.92 ms); a two-trip software
+// pipeline of the gathers in this kernel (252 registers: 1.36 ms).
 #define BA_SPS_CHUNK 32
 __device__ __forceinline__ ObsGeo load_geo_l1(const FPlanes &F, int i, double fx, double fy) {
   const double2 a = __ldg(F.g0 + i), b = __ldg(F.g1 + i);

@@ -90,51 +90,56 @@ __device__ __forceinline__ void ks_locate(int t, int n_cam, const int32_t *__res
   k = lo;
   src = win_seg[lo] + (t - win_off[lo]);
 }
-// admissible observations (local depth > 1e-15, src/OptimizationUtils.cpp:265-268)
+// Enumeration of a window in two kernels and one scan.
+//   ks_mark: admissible observations (local depth > 1e-15, src/OptimizationUtils.cpp:265-268) and, per landmark, the window
+//   position of its first admissible observation: first[lm] = max over (epoch << 32 | ~t) -- an integer atomicMax whose
+//   result does not depend on the execution order; entries of earlier windows carry a smaller epoch and lose, so the table
+//   is never cleared.
+//   ks_isfirst: packed[t] = admissible | is-first-appearance << 32; ONE 64-bit exclusive scan then yields both prefix sums:
+//   low word = observation index (canonical order), high word = point index (order of first appearance, :271-276).
 __global__ void __launch_bounds__(BA_THREADS)
-ks_flags(int total, int n_cam, const int32_t *__restrict__ win_off, const long long *__restrict__ win_seg,
-         const double *__restrict__ depth, int32_t *__restrict__ flag) {
+ks_mark(int total, int n_cam, const int32_t *__restrict__ win_off, const long long *__restrict__ win_seg,
+        const double *__restrict__ depth, const int32_t *__restrict__ lm, unsigned long long epoch, unsigned long long *first,
+        unsigned long long *__restrict__ packed) {
   const int t = blockIdx.x * BA_THREADS + threadIdx.x;
   if (t > total) return;
   if (t == total) {
-    flag[t] = 0;  // (the scan's last output is the count)
+    packed[t] = 0;  // (the scan's last output holds the two counts)
     return;
   }
   int k;
   long long src;
   ks_locate(t, n_cam, win_off, win_seg, k, src);
-  flag[t] = depth[src] > 1e-15 ? 1 : 0;
+  const bool ok = depth[src] > 1e-15;
+  packed[t] = ok ? 1ull : 0ull;
+  if (ok) atomicMax(first + lm[src], (epoch << 32) | (unsigned long long)(0xffffffffu - (unsigned)t));
 }
-// first appearance of every landmark in the window's canonical order: first[lm] = smallest observation index
-// (integer atomicMin: the result does not depend on the execution order)
-template <int PASS>
 __global__ void __launch_bounds__(BA_THREADS)
-ks_first(int total, int n_cam, const int32_t *__restrict__ win_off, const long long *__restrict__ win_seg,
-         const int32_t *__restrict__ flag, const int32_t *__restrict__ lm, int32_t *first, int32_t *__restrict__ isfirst) {
+ks_isfirst(int total, int n_cam, const int32_t *__restrict__ win_off, const long long *__restrict__ win_seg,
+           const int32_t *__restrict__ lm, unsigned long long epoch, const unsigned long long *__restrict__ first,
+           unsigned long long *__restrict__ packed) {
   const int t = blockIdx.x * BA_THREADS + threadIdx.x;
-  if (t >= total || !flag[t]) return;
+  if (t >= total || !packed[t]) return;
   int k;
   long long src;
   ks_locate(t, n_cam, win_off, win_seg, k, src);
-  const int l = lm[src];
-  if (PASS == 0) first[l] = 0x7fffffff;
-  if (PASS == 1) atomicMin(first + l, t);   // window position of the landmark's first admissible observation
-  if (PASS == 2) isfirst[t] = first[l] == t ? 1 : 0;
+  if (first[lm[src]] == ((epoch << 32) | (unsigned long long)(0xffffffffu - (unsigned)t))) packed[t] = 1ull | (1ull << 32);
 }
 // the window's arrays in canonical order; points (first appearances) moved into the frame of the first keyframe
 __global__ void __launch_bounds__(BA_THREADS)
 ks_emit(int total, int n_cam, const int32_t *__restrict__ win_off, const long long *__restrict__ win_seg,
-        const int32_t *__restrict__ flag, const int32_t *__restrict__ pos, const int32_t *__restrict__ lm, const float2 *__restrict__ uvf,
-        const double *__restrict__ depth, const int32_t *__restrict__ first, const int32_t *__restrict__ rank,
+        const unsigned long long *__restrict__ packed, const unsigned long long *__restrict__ prefix, const int32_t *__restrict__ lm,
+        const float2 *__restrict__ uvf, const double *__restrict__ depth, const unsigned long long *__restrict__ first,
         const double *__restrict__ pt_w, const double *__restrict__ T0inv, int32_t *__restrict__ w_cam, int32_t *__restrict__ w_pt,
         double2 *__restrict__ w_uv, double *__restrict__ w_depth, int32_t *__restrict__ lm_of_pt, double *__restrict__ pt3) {
   const int t = blockIdx.x * BA_THREADS + threadIdx.x;
-  if (t >= total || !flag[t]) return;
+  if (t >= total || !packed[t]) return;
   int k;
   long long src;
   ks_locate(t, n_cam, win_off, win_seg, k, src);
-  const int l = lm[src], i = pos[t], ft = first[l];  // ft: window position of the first appearance
-  const int p = rank[ft];
+  const int l = lm[src], i = (int)(prefix[t] & 0xffffffffull);
+  const int ft = (int)(0xffffffffu - (unsigned)(first[l] & 0xffffffffull));  // window position of the first appearance
+  const int p = (int)(prefix[ft] >> 32);
   w_cam[i] = k;
   w_pt[i] = p;
   const float2 f = uvf[src];

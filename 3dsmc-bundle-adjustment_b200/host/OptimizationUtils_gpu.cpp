@@ -15,6 +15,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/ba_gpu.h"
@@ -114,7 +115,11 @@ int window_optimize_store(const ba_gpu_options &opt, int kf_i, int kf_f, vector<
     kf_list.push_back(kf_n);
     kf_cnt.push_back((int32_t)(ids.size() - before));
   }
+  static thread_local double prof[5] = {0, 0, 0, 0, 0};
+  const bool do_prof = std::getenv("BA_STORE_PROF") != nullptr;
+  const double t_walk = ms_since(t_begin);
   rc = ba_store_set_keyframes(S.st, (int32_t)kf_list.size(), kf_list.data(), kf_cnt.data(), ids.data(), uvf.data(), dep.data());
+  const double t_kf = ms_since(t_begin);
   if (rc == BA_ERR_UNSUPPORTED) {
     g_store.reset();
     return -1;
@@ -125,8 +130,15 @@ int window_optimize_store(const ba_gpu_options &opt, int kf_i, int kf_f, vector<
   vector<double> pose7((size_t)n_cam * 7);
   for (int k = 0; k < n_cam; ++k)
     for (int j = 0; j < 7; ++j) pose7[(size_t)k * 7 + j] = keyframes[kf_i + k].T_w_c.data()[j];
+  const double t_lm = ms_since(t_begin);
   if (ba_store_set_poses(S.st, kf_i, n_cam, pose7.data()) != BA_OK) return 0;
   g_last.ms_extract = ms_since(t_begin);
+  if (do_prof) {
+    prof[4] += 1;
+    if ((int)prof[4] % 10 == 0 || g_last.ms_extract > 1.0)
+      std::fprintf(stderr, "[BA_STORE_PROF] window %d ms: options+walk %.3f set_keyframes %.3f set_landmarks %.3f set_poses %.3f (%d kf, %zu obs, %zu new lm)\n",
+                   (int)prof[4], t_walk, t_kf - t_walk, t_lm - t_kf, g_last.ms_extract - t_lm, (int)kf_list.size(), ids.size(), new_id.size());
+  }
 
   double intr[4], prior[4], ms3[3] = {0, 0, 0};
   for (int j = 0; j < 4; ++j) {
