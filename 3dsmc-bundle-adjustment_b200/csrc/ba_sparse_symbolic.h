@@ -151,6 +151,11 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
   std::vector<int32_t> parent(n, -1), nchild(n, 0), mark(n, -1), child_head(n, -1), child_next(n, -1);
   for (int k = 0; k < n; ++k) {
     std::vector<int32_t> &s = st[k];
+    {
+      size_t guess = adjp[k].size();
+      for (int c = child_head[k]; c >= 0; c = child_next[c]) guess = std::max(guess, st[c].size() + adjp[k].size());
+      s.reserve(guess + 4);
+    }
     mark[k] = k;
     for (int j : adjp[k])
       if (mark[j] != k) {
@@ -286,8 +291,23 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
   // ---- 5. entries of S per front: (block | flags, local row, local column, camera of the column)
   //         flags: bit 31 = use the stored block transposed, bit 30 = diagonal block; block 0x3fffffff = no stored block
   {
-    std::vector<std::vector<int32_t>> ent(nn);
+    // two passes (count, fill) straight into the flat table: no per-node vectors
     std::vector<char> has_diag(n, 0);
+    std::vector<int32_t> cnt((size_t)nn + 1, 0);
+    for (int b = 0; b < n_blk; ++b) {
+      cnt[node_of[std::min(S.pos[bi[b]], S.pos[bj[b]])] + 1]++;
+      if (bi[b] == bj[b]) has_diag[bi[b]] = 1;
+    }
+    for (int cam = 0; cam < n; ++cam)
+      if (!has_diag[cam]) cnt[node_of[S.pos[cam]] + 1]++;
+    for (int id = 0; id < nn; ++id) cnt[id + 1] += cnt[id];
+    S.aent.assign((size_t)cnt[nn] * 4, 0);
+    for (int id = 0; id < nn; ++id) {
+      int32_t *N = S.node.data() + (size_t)id * SPSYM_NODE_INTS;
+      N[SPN_AENT] = cnt[id];
+      N[SPN_NAENT] = cnt[id + 1] - cnt[id];
+    }
+    std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
     for (int b = 0; b < n_blk; ++b) {
       const int i = bi[b], j = bj[b];
       const int pi = S.pos[i], pj = S.pos[j];
@@ -308,32 +328,26 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
         lr = m + (int)(it - bb);
       }
       uint32_t code = (uint32_t)b;
-      if (i == j) {
+      if (i == j)
         code |= 0x40000000u;
-        has_diag[i] = 1;
-      } else if (S.perm[r] == j) {
+      else if (S.perm[r] == j)
         code |= 0x80000000u;  // F(r, c) = A(cam r, cam c) = S(i, j)^T when cam r is the stored block's column camera
-      }
-      ent[id].push_back((int32_t)code);
-      ent[id].push_back(lr);
-      ent[id].push_back(c - k0);
-      ent[id].push_back(S.perm[c]);
+      int32_t *e = S.aent.data() + 4 * (size_t)cur[id]++;
+      e[0] = (int32_t)code;
+      e[1] = lr;
+      e[2] = c - k0;
+      e[3] = S.perm[c];
     }
     for (int cam = 0; cam < n; ++cam)
       if (!has_diag[cam]) {  // damping only (fixed camera, camera without observations)
         const int c = S.pos[cam], id = node_of[c];
         const int k0 = S.node[(size_t)id * SPSYM_NODE_INTS + SPN_K0];
-        ent[id].push_back((int32_t)(0x3fffffffu | 0x40000000u));
-        ent[id].push_back(c - k0);
-        ent[id].push_back(c - k0);
-        ent[id].push_back(cam);
+        int32_t *e = S.aent.data() + 4 * (size_t)cur[id]++;
+        e[0] = (int32_t)(0x3fffffffu | 0x40000000u);
+        e[1] = c - k0;
+        e[2] = c - k0;
+        e[3] = cam;
       }
-    for (int id = 0; id < nn; ++id) {
-      int32_t *N = S.node.data() + (size_t)id * SPSYM_NODE_INTS;
-      N[SPN_AENT] = (int)(S.aent.size() / 4);
-      N[SPN_NAENT] = (int)(ent[id].size() / 4);
-      S.aent.insert(S.aent.end(), ent[id].begin(), ent[id].end());
-    }
   }
   // ---- cost model (block operations of 216 multiply-adds)
   {

@@ -406,8 +406,10 @@ def main():
     # ---- timed: K LM iterations, inputs resident in HBM (upload outside the region)
     s.set_options(max_num_iterations=K)
     s.upload(hp)
-    sync_all()
+    # (the sampler is started BEFORE the barrier: spawning nvidia-smi takes ~20 ms on rank 0, and a rank that enters the
+    # solve late makes the others wait inside their first collective -- counted in their solve time)
     clocks = ClockSampler(local_rank) if rank == 0 else None
+    sync_all()
     t0 = time.time()
     summ = s.solve()
     sync_all()
