@@ -68,7 +68,7 @@ EXPORTS = [
     "ba_gpu_schur_matvec", "ba_gpu_se3_plus", "ba_gpu_time_kernel", "ba_gpu_launch_count", "ba_gpu_comm_unique_id",
     "ba_gpu_comm_init", "ba_gpu_jacobian_store_used", "ba_gpu_sparse_stats", "ba_gpu_backproject",
     "ba_gpu_schur_solve", "ba_gpu_spchol_info", "ba_gpu_phase_times", "ba_gpu_phase_name",
-    "ba_store_create", "ba_store_destroy", "ba_store_set_keyframe", "ba_store_set_keyframes", "ba_store_set_poses", "ba_store_set_landmarks",
+    "ba_store_create", "ba_store_destroy", "ba_store_clear", "ba_store_set_keyframe", "ba_store_set_keyframes", "ba_store_set_poses", "ba_store_set_landmarks",
     "ba_store_window_solve",
     "ba_sparse_symbolic_create", "ba_sparse_symbolic_info", "ba_sparse_symbolic_get", "ba_sparse_symbolic_destroy",
 ]
@@ -120,6 +120,7 @@ def load():
     L.ba_store_create.argtypes = [vp, C.POINTER(vp)]
     L.ba_store_destroy.argtypes = [vp]
     L.ba_store_destroy.restype = None
+    L.ba_store_clear.argtypes = [vp]
     L.ba_store_set_keyframe.argtypes = [vp, C.c_int32, C.c_int32, c_int32_p, C.POINTER(C.c_float), c_double_p]
     L.ba_store_set_keyframes.argtypes = [vp, C.c_int32, c_int32_p, c_int32_p, c_int32_p, C.POINTER(C.c_float), c_double_p]
     L.ba_store_set_poses.argtypes = [vp, C.c_int32, C.c_int32, c_double_p]

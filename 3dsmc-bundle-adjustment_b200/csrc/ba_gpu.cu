@@ -154,7 +154,9 @@ struct ba_gpu_ctx {
   bool spchol = false;          // the block-sparse solver factorises S instead of running PCG
   SpSymbolic sym;               // host-side structure of the last upload
   Buf spn_node, spn_bord, spn_children, spn_rel, spn_inv, spn_aent, spn_perm, spn_levels;
-  Buf spc_panel, spc_U, spc_ru, spc_z, spc_linv, spc_ypos, spc_prof;
+  Buf spc_panel, spc_U, spc_ru, spc_z, spc_linv, spc_ypos, spc_prof, spc_queue, spc_tiles, spc_cnt;
+  int spc_n_items = 0;
+  bool spc_tree = true;         // one persistent launch with dependency counters (BA_SPCHOL_LEVELS=1: one launch per tree level)
   size_t spc_smem_factor = 0, spc_smem_solve = 0, spc_smem_update = 0;
   double sym_ms = 0.0;          // host time of the symbolic phase (last upload)
   // phase timing of the large-problem solvers: CUDA events on the solver stream at the phase boundaries of every LM
@@ -902,6 +904,39 @@ static int build_spchol(ba_gpu_ctx *ctx) {
   CK(cudaFuncSetAttribute(k_spchol_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
   CK(cudaFuncSetAttribute(k_spchol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
   CK(cudaFuncSetAttribute(k_spchol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)su));
+  // work queue of the persistent tree kernel: per level (bottom-up) the factor items, then the update tiles; then the
+  // backward substitution level by level top-down.  Update tiles per node: more where a level has few nodes.
+  {
+    std::vector<int32_t> tiles((size_t)S.n_nodes, 0), q;
+    for (int l = 0; l < S.n_levels; ++l) {
+      const int nodes = S.level_ptr[l + 1] - S.level_ptr[l];
+      const int t_lvl = std::max(1, std::min(8, ctx->n_sm / std::max(1, nodes)));
+      for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
+        const int id = S.level_nodes[e];
+        tiles[id] = S.node[(size_t)id * SPSYM_NODE_INTS + SPN_NB] > 0 ? t_lvl : 0;
+        q.push_back(id);
+        q.push_back(-1);
+      }
+      for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
+        const int id = S.level_nodes[e];
+        for (int t = 0; t < tiles[id]; ++t) {
+          q.push_back(id);
+          q.push_back(t);
+        }
+      }
+    }
+    for (int l = S.n_levels - 1; l >= 0; --l)
+      for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
+        q.push_back(S.level_nodes[e]);
+        q.push_back(-2);
+      }
+    ctx->spc_n_items = (int)(q.size() / 2);
+    if ((rc = up(ctx->spc_queue, q)) || (rc = up(ctx->spc_tiles, tiles))) return rc;
+    RES(spc_cnt, ((size_t)3 * S.n_nodes + 8) * 4);
+    const size_t st_ = std::max(std::max(sf, ss), su);
+    CK(cudaFuncSetAttribute(k_spchol_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_));
+    ctx->spc_tree = getenv("BA_SPCHOL_LEVELS") == nullptr;
+  }
   CK(cudaStreamSynchronize(s));  // host vectors of this call die here
   ctx->spchol = true;
   return 0;
@@ -1737,6 +1772,22 @@ static void enqueue_spchol(ba_gpu_ctx *ctx, int gate) {
   const SpChol a = spchol_args(ctx);
   // every kernel of the chain starts with griddepcontrol.wait (gate_open): programmatic dependent launches let the blocks of
   // the next launch become resident on idle SMs (the upper tree levels have few nodes) while the previous one still runs
+  if (ctx->spc_tree) {
+    // the whole linear solve in one persistent launch (k_spchol_tree): dependency counters instead of level barriers
+    SpTree t;
+    t.queue = P<int2>(ctx->spc_queue);
+    t.n_items = ctx->spc_n_items;
+    t.tiles = P<int32_t>(ctx->spc_tiles);
+    t.ticket = P<int>(ctx->spc_cnt);
+    t.fdone = t.ticket + 8;
+    t.udone = t.fdone + S.n_nodes;
+    t.sdone = t.udone + S.n_nodes;
+    cudaMemsetAsync(ctx->spc_cnt.p, 0, ((size_t)3 * S.n_nodes + 8) * 4, ctx->cur);
+    const size_t smem = std::max(std::max(ctx->spc_smem_factor, ctx->spc_smem_solve), ctx->spc_smem_update);
+    LAUNCH(k_spchol_tree, std::min(ctx->n_sm, ctx->spc_n_items), SPC_THREADS, smem, a, t, st, gate);
+    phase_mark(ctx, BA_PHASE_FACTOR);
+    return;
+  }
   const bool pdl0 = ctx->pdl;
   ctx->pdl = !ctx->pdl_off;
   for (int l = 0; l < S.n_levels; ++l) {
@@ -2808,6 +2859,19 @@ extern "C" void ba_store_destroy(ba_store *st) {
     if (b->p) cudaFree(b->p);
   if (st->pin) cudaFreeHost(st->pin);
   delete st;
+}
+// forget every keyframe / landmark (the device buffers are kept: allocating them again costs far more than a window)
+extern "C" int ba_store_clear(ba_store *st) {
+  if (!st) return BA_ERR_INVALID;
+  ba_gpu_ctx *ctx = st->ctx;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::fill(st->seg_off.begin(), st->seg_off.end(), -1);
+  std::fill(st->seg_n.begin(), st->seg_n.end(), 0);
+  st->pool_used = 0;
+  st->pin_used = 0;
+  st->max_id = -1;
+  return BA_OK;
 }
 static int store_fit_kf(ba_gpu_ctx *ctx, ba_store *st, int kf) {
   if ((size_t)kf >= st->seg_off.size()) {

@@ -39,7 +39,7 @@ struct SpChol {
   unsigned long long *prof;   // nullable (BA_SPCHOL_PROF=1): ns per phase of thread block 0 of every factor launch, summed
 };
 #define SPC_TICK(slot)                                          \
-  if (a.prof && blockIdx.x == 0 && tid == 0) {                  \
+  if (a.prof && prof_block && tid == 0) {                       \
     unsigned long long t1_;                                     \
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1_));      \
     a.prof[slot] += t1_ - t0_;                                  \
@@ -149,12 +149,9 @@ __device__ __forceinline__ void spc_tri(int p, int &i, int &j) {
   j = p - r * (r + 1) / 2;
 }
 
-__global__ void __launch_bounds__(SPC_THREADS, 1)
-k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
-  if (!gate_open(st, gate)) return;
-  extern __shared__ __align__(16) double spc_sm[];
+// factorisation of the front of node `id` by the calling thread block (SPC_THREADS threads, spc_factor_smem bytes at spc_sm)
+__device__ __forceinline__ void spc_factor_node(const SpChol &a, int id, bool prof_block, LmState *st, double *spc_sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int id = a.level_nodes[lvl_first + blockIdx.x];
   const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
   const int k0 = N[SPN_K0], m = N[SPN_M], nb = N[SPN_NB];
   const int LD = 6 * (m + nb), C6 = 6 * m;
@@ -164,7 +161,7 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
   double *Tb = zf + C6;                  // two inverse pivot blocks (ping-pong)
 
   unsigned long long t0_ = 0;
-  if (a.prof && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0_));
+  if (a.prof && prof_block && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0_));
   // ---- phase 0: clear, right-hand side
   for (int i = tid; i < LD * C6; i += SPC_THREADS) P[i] = 0.0;
   for (int i = tid; i < C6; i += SPC_THREADS) zf[i] = a.b[6 * (size_t)a.perm[k0 + i / 6] + i % 6];
@@ -375,7 +372,13 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
   }
   __syncthreads();
   SPC_TICK(3)
-  if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[4] += 1;
+  if (a.prof && prof_block && tid == 0) a.prof[4] += 1;
+}
+__global__ void __launch_bounds__(SPC_THREADS, 1)
+k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  extern __shared__ __align__(16) double spc_sm[];
+  spc_factor_node(a, a.level_nodes[lvl_first + blockIdx.x], blockIdx.x == 0, st, spc_sm);
 }
 
 // Update matrix of the nodes of one level, after their panels are factorised: U = L_B L_B^T + what the children pass through
@@ -385,12 +388,10 @@ k_spchol_factor(SpChol a, int lvl_first, LmState *st, int gate) {
 // just written) into shared memory and takes every tiles-th chunk of the 3 x 6 output pieces.
 #define SPU_THREADS 256
 inline size_t spc_update_smem(int m, int nb) { return ((size_t)36 * nb * m + 6 * m + 8) * 8; }
-__global__ void __launch_bounds__(SPU_THREADS, 1)
-k_spchol_update(SpChol a, int lvl_first, int tiles, LmState *st, int gate) {
-  if (!gate_open(st, gate)) return;
-  extern __shared__ __align__(16) double spc_sm[];
+// tile `tile` of `tiles` of the update matrix of node `id`, by the calling thread block (NT threads)
+template <int NT>
+__device__ __forceinline__ void spc_update_node(const SpChol &a, int id, int tile, int tiles, double *spc_sm) {
   const int tid = threadIdx.x;
-  const int id = a.level_nodes[lvl_first + blockIdx.x / tiles], tile = blockIdx.x % tiles;
   const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
   const int k0 = N[SPN_K0], m = N[SPN_M], nb = N[SPN_NB];
   if (nb == 0) return;
@@ -400,17 +401,17 @@ k_spchol_update(SpChol a, int lvl_first, int tiles, LmState *st, int gate) {
   {
     const double *Pg = a.panel + 36 * spc_off(N, SPN_PANEL_LO) + C6;
 #pragma unroll 8
-    for (int idx = tid; idx < NB6 * C6; idx += SPU_THREADS) {
+    for (int idx = tid; idx < NB6 * C6; idx += NT) {
       const int c = idx / NB6, r = idx - c * NB6;
-      LB[idx] = Pg[(size_t)c * LD + r];
+      LB[idx] = __ldcg(Pg + (size_t)c * LD + r);  // (L2: written by another thread block of this or the previous launch)
     }
-    for (int i = tid; i < C6; i += SPU_THREADS) zf[i] = a.z[6 * (size_t)k0 + i];
+    for (int i = tid; i < C6; i += NT) zf[i] = __ldcg(a.z + 6 * (size_t)k0 + i);
   }
   __syncthreads();
   double *Ug = a.U + 36 * spc_off(N, SPN_U_LO);
   const int n_items = nb * (nb + 1);
   const int nch = N[SPN_NCHILD];
-  for (int idx = tile * SPU_THREADS + tid; idx < n_items; idx += tiles * SPU_THREADS) {
+  for (int idx = tile * NT + tid; idx < n_items; idx += tiles * NT) {
     int i, j;
     spc_tri(idx >> 1, i, j);
     const int h = idx & 1;
@@ -453,7 +454,7 @@ k_spchol_update(SpChol a, int lvl_first, int tiles, LmState *st, int gate) {
       for (int x = 0; x < 3; ++x) Ug[(size_t)(rb + y) * NB6 + ra + x] = acc[x][y];
   }
   double *rug = a.ru + 6 * (size_t)N[SPN_BORD];
-  for (int idx = tile * SPU_THREADS + tid; idx < NB6; idx += tiles * SPU_THREADS) {
+  for (int idx = tile * NT + tid; idx < NB6; idx += tiles * NT) {
     double s = 0.0;
     for (int c = 0; c < C6; ++c) s += LB[(size_t)c * NB6 + idx] * zf[c];
     for (int ci = 0; ci < nch; ++ci) {
@@ -465,14 +466,16 @@ k_spchol_update(SpChol a, int lvl_first, int tiles, LmState *st, int gate) {
     rug[idx] = s;
   }
 }
-
-// backward substitution of one tree level (parents are done): y_O = L_OO^-T (z_O - L_BO^T y_B)
-__global__ void __launch_bounds__(SPC_THREADS, 1)
-k_spchol_solve(SpChol a, int lvl_first, LmState *st, int gate) {
+__global__ void __launch_bounds__(SPU_THREADS, 1)
+k_spchol_update(SpChol a, int lvl_first, int tiles, LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
   extern __shared__ __align__(16) double spc_sm[];
+  spc_update_node<SPU_THREADS>(a, a.level_nodes[lvl_first + blockIdx.x / tiles], blockIdx.x % tiles, tiles, spc_sm);
+}
+
+// backward substitution of one tree level (parents are done): y_O = L_OO^-T (z_O - L_BO^T y_B)
+__device__ __forceinline__ void spc_solve_node(const SpChol &a, int id, LmState *st, double *spc_sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int id = a.level_nodes[lvl_first + blockIdx.x];
   const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
   const int k0 = N[SPN_K0], m = N[SPN_M], nb = N[SPN_NB];
   const int LD = 6 * (m + nb), C6 = 6 * m, NB6 = 6 * nb;
@@ -485,12 +488,12 @@ k_spchol_solve(SpChol a, int lvl_first, LmState *st, int gate) {
   const int32_t *bord = a.bord + N[SPN_BORD];
   for (int idx = tid; idx < C6 * C6; idx += SPC_THREADS) {
     const int c = idx / C6, r = idx - c * C6;
-    Loo[idx] = Pg[(size_t)c * LD + r];
+    Loo[idx] = __ldcg(Pg + (size_t)c * LD + r);
   }
-  for (int i = tid; i < 36 * m; i += SPC_THREADS) Ti[i] = a.linv[36 * (size_t)k0 + i];
+  for (int i = tid; i < 36 * m; i += SPC_THREADS) Ti[i] = __ldcg(a.linv + 36 * (size_t)k0 + i);
   for (int i = tid; i < NB6; i += SPC_THREADS) yB[i] = __ldcg(a.ypos + 6 * (size_t)bord[i / 6] + i % 6);
   for (int i = tid; i < C6; i += SPC_THREADS) {
-    w[i] = a.z[6 * (size_t)k0 + i];
+    w[i] = __ldcg(a.z + 6 * (size_t)k0 + i);
     y[i] = 0.0;
   }
   __syncthreads();
@@ -498,7 +501,7 @@ k_spchol_solve(SpChol a, int lvl_first, LmState *st, int gate) {
   for (int c = warp; c < C6; c += SPC_WARPS) {
     const double *col = Pg + (size_t)c * LD + C6;
     double s = 0.0;
-    for (int R = lane; R < NB6; R += 32) s += col[R] * yB[R];
+    for (int R = lane; R < NB6; R += 32) s += __ldcg(col + R) * yB[R];
     s = warp_sum(s);
     if (lane == 0) w[c] -= s;
   }
@@ -530,5 +533,97 @@ k_spchol_solve(SpChol a, int lvl_first, LmState *st, int gate) {
     if (!isfinite(v)) st->lin_fail = 1;
     a.ypos[6 * (size_t)k0 + i] = v;
     a.yc[6 * (size_t)a.perm[k0 + i / 6] + i % 6] = v;
+  }
+}
+__global__ void __launch_bounds__(SPC_THREADS, 1)
+k_spchol_solve(SpChol a, int lvl_first, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  extern __shared__ __align__(16) double spc_sm[];
+  spc_solve_node(a, a.level_nodes[lvl_first + blockIdx.x], st, spc_sm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole linear solve in ONE launch: a persistent grid (one thread block per SM) works through a queue of items --
+// factor(node), update(node, tile), solve(node) -- in an order in which every item follows the items it depends on
+// (levels bottom-up for the factorisation, top-down for the backward substitution).  A block takes the next item from
+// a ticket counter and waits on integer completion counters in global memory:
+//     factor(n)     after every update tile of every child of n
+//     update(n, t)  after factor(n)
+//     solve(n)      after solve(parent(n))   (roots: after their own factor)
+// Items are handed out dynamically, so an item is only ever held by a RUNNING block and every item it waits for has a
+// smaller queue index, i.e. was taken earlier by a running block: no deadlock, whatever the number of resident blocks.
+// Compared with one launch per tree level this removes 3 x levels launches and, more important, lets a node start as
+// soon as ITS children are done instead of when the slowest node of the level below is: the linear solve is bound by
+// the longest root-to-leaf chain of the tree, not by the sum of the per-level maxima.
+// Counters are zeroed by the host before the launch; producers publish with a device-scope fence before the counter
+// update, consumers read other blocks' results through L2 (__ldcg).
+// ---------------------------------------------------------------------------------------------
+struct SpTree {
+  const int2 *queue;       // (node, kind): kind >= 0 update tile, -1 factor, -2 solve
+  int n_items;
+  const int32_t *tiles;    // update tiles per node (0: no border)
+  int *ticket, *fdone, *udone, *sdone;
+};
+__device__ __forceinline__ void spc_wait_ge(const int *flag, int want) {
+  int v;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= want) return;
+    __nanosleep(64);
+  }
+}
+__global__ void __launch_bounds__(SPC_THREADS, 1)
+k_spchol_tree(SpChol a, SpTree t, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  extern __shared__ __align__(16) double spc_sm[];
+  __shared__ int s_item;
+  const int tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();  // (the previous item's shared memory is no longer in use)
+    if (tid == 0) s_item = atomicAdd(t.ticket, 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= t.n_items) return;
+    const int2 q = t.queue[it];
+    const int id = q.x;
+    const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
+    if (q.y == -1) {
+      if (tid == 0)
+        for (int ci = 0; ci < N[SPN_NCHILD]; ++ci) {
+          const int ch = a.children[N[SPN_CHILD] + ci];
+          spc_wait_ge(t.udone + ch, t.tiles[ch]);
+        }
+      __syncthreads();
+      spc_factor_node(a, id, it == 0, st, spc_sm);
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicExch(t.fdone + id, 1);
+      }
+    } else if (q.y >= 0) {
+      if (tid == 0) spc_wait_ge(t.fdone + id, 1);
+      __syncthreads();
+      spc_update_node<SPC_THREADS>(a, id, q.y, t.tiles[id], spc_sm);
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(t.udone + id, 1);
+      }
+    } else {
+      if (tid == 0) {
+        const int par = N[SPN_PARENT];
+        if (par >= 0)
+          spc_wait_ge(t.sdone + par, 1);
+        else
+          spc_wait_ge(t.fdone + id, 1);
+      }
+      __syncthreads();
+      spc_solve_node(a, id, st, spc_sm);
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicExch(t.sdone + id, 1);
+      }
+    }
   }
 }

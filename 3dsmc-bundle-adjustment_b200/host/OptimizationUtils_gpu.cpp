@@ -46,9 +46,11 @@ struct StoreState {
   ~StoreState() {
     if (st) ba_store_destroy(st);
   }
-  void reset() {
-    if (st) ba_store_destroy(st);
-    st = nullptr;
+  void reset() {  // forget what is on the device; the device buffers themselves are kept for the next sequence
+    if (st && ba_store_clear(st) != BA_OK) {
+      ba_store_destroy(st);
+      st = nullptr;
+    }
     kf_size.clear();
     lm_ptr.clear();
   }

@@ -258,6 +258,7 @@ int ba_gpu_sparse_stats(const ba_gpu_ctx *ctx, int64_t *n_pairs, int32_t *n_bloc
 typedef struct ba_store ba_store;
 int ba_store_create(ba_gpu_ctx *ctx, ba_store **out);
 void ba_store_destroy(ba_store *st); /* before ba_gpu_destroy of its context */
+int ba_store_clear(ba_store *st);    /* forget all keyframes / landmarks, keep the device buffers */
 int ba_store_set_keyframe(ba_store *st, int32_t kf, int32_t n, const int32_t *landmark_id, const float *uv2f, const double *depth);
 /* several keyframes in one call (lists back to back, cnt[k] entries for keyframe kf[k]): three copies per call */
 int ba_store_set_keyframes(ba_store *st, int32_t n_kf, const int32_t *kf, const int32_t *cnt, const int32_t *landmark_id,
