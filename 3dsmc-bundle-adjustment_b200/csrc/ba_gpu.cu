@@ -1333,12 +1333,15 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
     }
   }
   if (sparse) {
+    prof.stamp("to sparse");
     int rcs = build_sparse_structure(ctx);
     if (rcs) return rcs;
+    prof.stamp("sparse structure");
     if (want_chol) {
       rcs = build_spchol(ctx);
       if (rcs == BA_ERR_UNSUPPORTED && o.solver == BA_SOLVER_AUTO) rcs = 0;  // falls back to PCG on the same S
       if (rcs) return rcs;
+      prof.stamp("symbolic + tables");
     }
     ctx->dist_pcg = false;
     if (!ctx->spchol && ctx->n_ranks > 1 && o.persistent_pcg == 1 && (rcs = setup_dist_pcg(ctx))) return rcs;

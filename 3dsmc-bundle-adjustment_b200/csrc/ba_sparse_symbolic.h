@@ -142,26 +142,37 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
     for (int k = 0; k < n; ++k) S.pos[S.perm[k]] = k;
   }
   // ---- 2. symbolic factorisation in elimination order
-  std::vector<std::vector<int32_t>> adjp(n), st(n);
+  // adjacency in elimination positions, CSR: adj_ptr[k] .. adj_ptr[k + 1] = later-eliminated neighbours of position k
+  std::vector<std::vector<int32_t>> st(n);
+  std::vector<int32_t> adj_ptr((size_t)n + 1, 0), adj((size_t)g.up.size());
   for (int i = 0; i < n; ++i)
-    for (int e = g.up_ptr[i]; e < g.up_ptr[i + 1]; ++e) {
-      const int a = S.pos[i], b = S.pos[g.up[e]];
-      adjp[std::min(a, b)].push_back(std::max(a, b));
-    }
+    for (int e = g.up_ptr[i]; e < g.up_ptr[i + 1]; ++e) adj_ptr[std::min(S.pos[i], S.pos[g.up[e]]) + 1]++;
+  for (int k = 0; k < n; ++k) adj_ptr[k + 1] += adj_ptr[k];
+  {
+    std::vector<int32_t> cur(adj_ptr.begin(), adj_ptr.end() - 1);
+    for (int i = 0; i < n; ++i)
+      for (int e = g.up_ptr[i]; e < g.up_ptr[i + 1]; ++e) {
+        const int a = S.pos[i], b = S.pos[g.up[e]];
+        adj[cur[std::min(a, b)]++] = std::max(a, b);
+      }
+  }
   std::vector<int32_t> parent(n, -1), nchild(n, 0), mark(n, -1), child_head(n, -1), child_next(n, -1);
   for (int k = 0; k < n; ++k) {
     std::vector<int32_t> &s = st[k];
     {
-      size_t guess = adjp[k].size();
-      for (int c = child_head[k]; c >= 0; c = child_next[c]) guess = std::max(guess, st[c].size() + adjp[k].size());
+      const size_t na = (size_t)(adj_ptr[k + 1] - adj_ptr[k]);
+      size_t guess = na;
+      for (int c = child_head[k]; c >= 0; c = child_next[c]) guess = std::max(guess, st[c].size() + na);
       s.reserve(guess + 4);
     }
     mark[k] = k;
-    for (int j : adjp[k])
+    for (int e = adj_ptr[k]; e < adj_ptr[k + 1]; ++e) {
+      const int j = adj[e];
       if (mark[j] != k) {
         mark[j] = k;
         s.push_back(j);
       }
+    }
     for (int c = child_head[k]; c >= 0; c = child_next[c])
       for (int j : st[c])
         if (j != k && mark[j] != k) {

@@ -115,11 +115,15 @@ class GpuSolver:
         n = self._check(self.lib.ba_gpu_get_trace(self._ctx, buf, cap))
         return [{f[0]: getattr(buf[i], f[0]) for f in capi.IterRecord._fields_} for i in range(n)]
 
-    def download(self):
+    def download(self, out=None):
+        """(pose7 [n_cam,7], pt3 [n_pt,3], intr4).  `out` = a (pose, pt, intr) tuple of preallocated contiguous float64
+        arrays to receive the result -- e.g. views of pinned host memory, which the device writes at PCIe speed (a
+        pageable destination of the 48 MB of config-5 points takes ~11 ms instead of ~1)."""
         n_cam, n_pt, _ = self._shape
-        pose = np.zeros((n_cam, 7))
-        pt = np.zeros((n_pt, 3))
-        intr = np.zeros(4)
+        if out is None:
+            out = (np.zeros((n_cam, 7)), np.zeros((n_pt, 3)), np.zeros(4))
+        pose, pt, intr = out
+        assert pose.shape == (n_cam, 7) and pt.shape == (n_pt, 3) and intr.shape == (4,)
         self._check(self.lib.ba_gpu_download(self._ctx, capi.dp(pose), capi.dp(pt), capi.dp(intr)))
         return pose, pt, intr
 

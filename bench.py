@@ -234,16 +234,19 @@ def executed_roofline(workload, phase_ms, n_iter, solver_used, full, n_pairs, n_
         hbm("schur_complement", "k_sp_schur (+ k_sp_add_diag)", 124.0 * n_pairs, per.get("schur_complement", 0.0),
             "l2 / hbm gathers (latency)", "124 B per same-point observation pair: pair 8 + point id 4 + two factored records 64 + Vs 48")
     if solver_used == 4 and spchol:
-        ms = per.get("linear_solve_factor_or_pcg", 0.0)
-        table["linear_solve_factor"] = {
-            "kernels": "k_spchol_rhs, k_spchol_factor + k_spchol_update per tree level", "bound": "fp64 pipe / dependent chain of tree levels",
+        # (one persistent launch does factorisation and both substitutions; with BA_SPCHOL_LEVELS=1 the backward
+        # substitution shows up as its own phase -- added here either way)
+        ms = per.get("linear_solve_factor_or_pcg", 0.0) + per.get("linear_solve_substitution", 0.0)
+        table["linear_solve"] = {
+            "kernels": "k_spchol_rhs, k_spchol_tree (factor / update / substitution items of the supernodal tree, one persistent launch)",
+            "bound": "fp64 pipe of single SMs along the dependent chain of tree levels (latency)",
             "flops": spchol.get("flops"), "ms": ms, "share_of_step": ms / total if total else None,
             "achieved": spchol.get("flops", 0) / ms / 1e9 if ms > 0 else None, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
             "frac": spchol.get("flops", 0) / ms / 1e9 / FP64_NOMINAL_TFLOPS if ms > 0 else None,
-            "note": "fp64 multiply-adds x 2 of the supernodal factorisation; peak = nominal B200 fp64 (not measured); %d nodes in %d "
-                    "levels" % (spchol.get("nodes", 0), spchol.get("levels", 0))}
-        hbm("linear_solve_substitution", "k_spchol_solve per tree level", 288.0 * spchol.get("panel_blocks", 0),
-            per.get("linear_solve_substitution", 0.0), "l2 (panels) / dependent chain of tree levels", "one read of the factor panels")
+            "note": "fp64 multiply-adds x 2 of the supernodal factorisation over the time of factorisation + substitutions; peak = "
+                    "nominal B200 fp64 (not measured); %d nodes in %d levels, critical path %d block operations of %d total"
+                    % (spchol.get("nodes", 0), spchol.get("levels", 0), spchol.get("critical_path_block_ops", 0),
+                       spchol.get("flops", 0) // 432)}
     elif solver_used == 3 and pcg_total > 0:
         ms = per.get("linear_solve_substitution", 0.0) + per.get("linear_solve_factor_or_pcg", 0.0)
         hbm("pcg", "k_pcg_sparse_persistent (all PCG iterations of a step)", (n_ent * 344.0 + n_c * 96.0) * pcg_total / n_iter, ms,
@@ -420,12 +423,13 @@ def main():
     spchol = s.spchol_info()
     n_iter = summ.num_iterations
     pcg_counts = [t["linear_iters"] for t in trace[1:]]
-    # ---- end to end through the C-ABI with host buffers: upload + solve + download
+    # ---- end to end through the C-ABI with host buffers (pinned, inputs and outputs): upload + solve + download
+    out_bufs = (pinned_copy(np.zeros((problem.n_cam, 7))), pinned_copy(np.zeros((problem.n_pt, 3))), pinned_copy(np.zeros(4)))
     sync_all()
     t0 = time.time()
     s.upload(hp)
     summ2 = s.solve()
-    pose, pt, intr = s.download()
+    pose, pt, intr = s.download(out=out_bufs)
     sync_all()
     e2e_s = maxr(time.time() - t0)
     clk = clocks.stop() if clocks else None
