@@ -39,8 +39,8 @@ $CMD > $O/r02_ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/r02_launches_bench_cfg5.csv $CMD > $O/r02_ncu1.log 2>&1
 CMD2="python profiles/profile_target.py 5 3 500 0"
 $CMD2 > $O/r02_ncu_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_sp_schur|k_spchol_factor|k_spchol_update|k_spchol_solve|kf_pt_blocks|kf_linearize|kf_schur_pass1|kf_cam_blocks" -s 40 -c 60 -o $O/r02_prof_cfg5 $CMD2 > $O/r02_ncu2.log 2>&1
-tail -2 $O/r02_ncu1.log $O/r02_ncu2.log
+ncu --set full --clock-control none --import-source on -k regex:"k_sp_schur|k_spchol_tree|kf_pt_blocks|kf_linearize|kf_schur_pass1|kf_cam_blocks|kf_model_cost|kf_point_inverse" -s 40 -c 24 -o $O/r02_prof_cfg5 $CMD2 > $O/r02_ncu2.log 2>&1
+tail -n 2 $O/r02_ncu1.log; tail -n 2 $O/r02_ncu2.log; ls -la $O | head -40; du -sh $O
 python scripts/summarize_launches.py $O/r02_launches_bench_cfg5.csv > $O/r02_launches_bench_cfg5_summary.txt 2>&1; head -30 $O/r02_launches_bench_cfg5_summary.txt
 for f in $O/r02_bench_*.log; do python - "$f" <<'PY'
 import json,sys
