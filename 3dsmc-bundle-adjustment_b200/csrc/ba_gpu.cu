@@ -154,8 +154,15 @@ struct ba_gpu_ctx {
   bool spchol = false;          // the block-sparse solver factorises S instead of running PCG
   SpSymbolic sym;               // host-side structure of the last upload
   Buf spn_node, spn_bord, spn_children, spn_rel, spn_inv, spn_aent, spn_perm, spn_levels;
-  Buf spc_panel, spc_U, spc_ru, spc_z, spc_linv, spc_ypos, spc_prof, spc_queue, spc_tiles, spc_cnt;
+  Buf spc_panel, spc_U, spc_z, spc_linv, spc_ypos, spc_prof, spc_queue, spc_tiles, spc_cnt, spc_cnt_init, spc_topcams;
   int spc_n_items = 0;
+  // subtree-to-rank partition (spsym_partition): phase A = the subtrees of one part (queue items spc_qA[p] .. spc_qA[p + 1]),
+  // phase B = top part + backward substitution (spc_qB, spc_qB_n).  spc_dist: part p runs on rank p and the head of spc_U
+  // (update matrices of the subtree roots + right-hand-side updates, spc_xchg doubles) is summed over ranks in between;
+  // on one GPU (BA_SPCHOL_PARTS, tests) the parts run one after the other.
+  int spc_parts = 1, spc_qA[BA_MAX_RANKS + 1] = {0}, spc_qB = 0, spc_qB_n = 0, spc_n_topcams = 0;
+  bool spc_dist = false;
+  size_t spc_xchg = 0, spc_ru_off = 0;
   bool spc_tree = true;         // one persistent launch with dependency counters (BA_SPCHOL_LEVELS=1: one launch per tree level)
   size_t spc_smem_factor = 0, spc_smem_solve = 0, spc_smem_update = 0;
   double sym_ms = 0.0;          // host time of the symbolic phase (last upload)
@@ -875,14 +882,45 @@ static int build_spchol(ba_gpu_ctx *ctx) {
     if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice, s));
     return 0;
   };
+  // subtree-to-rank partition: one part per rank (BA_SPCHOL_REPLICATED=1 keeps every rank factorising the whole tree);
+  // on one GPU BA_SPCHOL_PARTS=n runs the n parts one after the other (tests of the queues and of the exchange layout)
+  int want_parts = ctx->n_ranks > 1 ? (getenv("BA_SPCHOL_REPLICATED") ? 1 : ctx->n_ranks)
+                                    : (getenv("BA_SPCHOL_PARTS") ? std::min(BA_MAX_RANKS, std::max(1, atoi(getenv("BA_SPCHOL_PARTS")))) : 1);
+  if (getenv("BA_SPCHOL_LEVELS")) want_parts = 1;
+  const SpPartition part = spsym_partition(S, want_parts);
+  ctx->spc_parts = part.parts;
+  ctx->spc_dist = ctx->n_ranks > 1 && part.parts == ctx->n_ranks;
+  // layout of spc_U (6x6 blocks): [update matrices of the subtree roots | right-hand-side updates of every node | the other
+  // update matrices]: the first two pieces are what the ranks exchange, one contiguous all-reduce
+  const int64_t ru_blocks = ((int64_t)S.bord.size() * 6 + 35) / 36 + 1;
+  {
+    SpSymbolic &W = ctx->sym;
+    auto usize = [&](int id) { const int64_t nb = W.node[(size_t)id * SPSYM_NODE_INTS + SPN_NB]; return nb * nb; };
+    auto is_cut = [&](int id) {
+      const int par = W.node[(size_t)id * SPSYM_NODE_INTS + SPN_PARENT];
+      return part.parts > 1 && part.part[id] >= 0 && par >= 0 && part.part[par] < 0;
+    };
+    int64_t off = 0;
+    auto place = [&](int id) {
+      W.node[(size_t)id * SPSYM_NODE_INTS + SPN_U_LO] = (int32_t)(off & 0x7fffffff);
+      W.node[(size_t)id * SPSYM_NODE_INTS + SPN_U_HI] = (int32_t)(off >> 31);
+      off += usize(id);
+    };
+    for (int id = 0; id < W.n_nodes; ++id)
+      if (is_cut(id)) place(id);
+    ctx->spc_ru_off = (size_t)off * 36;
+    off += ru_blocks;
+    ctx->spc_xchg = (size_t)off * 36;
+    for (int id = 0; id < W.n_nodes; ++id)
+      if (!is_cut(id)) place(id);
+  }
   int rc;
   if ((rc = up(ctx->spn_node, S.node)) || (rc = up(ctx->spn_bord, S.bord)) || (rc = up(ctx->spn_children, S.children)) ||
       (rc = up(ctx->spn_rel, S.rel)) || (rc = up(ctx->spn_inv, S.inv)) || (rc = up(ctx->spn_aent, S.aent)) ||
       (rc = up(ctx->spn_perm, S.perm)) || (rc = up(ctx->spn_levels, S.level_nodes)))
     return rc;
   RES(spc_panel, ((size_t)S.panel_blocks + 1) * 288);
-  RES(spc_U, ((size_t)S.u_blocks + 1) * 288);
-  RES(spc_ru, (S.bord.size() + 1) * 48);
+  RES(spc_U, ((size_t)S.u_blocks + (size_t)ru_blocks + 1) * 288);
   RES(spc_z, ((size_t)n_cam + 1) * 48);
   RES(spc_linv, ((size_t)n_cam + 1) * 288);
   RES(spc_ypos, ((size_t)n_cam + 1) * 48);
@@ -904,38 +942,84 @@ static int build_spchol(ba_gpu_ctx *ctx) {
   CK(cudaFuncSetAttribute(k_spchol_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
   CK(cudaFuncSetAttribute(k_spchol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
   CK(cudaFuncSetAttribute(k_spchol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)su));
-  // work queue of the persistent tree kernel: per level (bottom-up) the factor items, then the update tiles; then the
-  // backward substitution level by level top-down.  Update tiles per node: more where a level has few nodes.
+  // work queues of the persistent tree kernel.  Phase A (one queue per part): per level (bottom-up) the factor items of the
+  // part's nodes, then their update tiles -- more tiles per node where the part has few nodes on a level.  Phase B: the same
+  // for the top part, then the backward substitution level by level top-down (top part first, then the subtrees this GPU
+  // holds).  One part: phase A is the whole factorisation and the substitution follows in the same queue (one launch).
   {
-    std::vector<int32_t> tiles((size_t)S.n_nodes, 0), q;
-    for (int l = 0; l < S.n_levels; ++l) {
-      const int nodes = S.level_ptr[l + 1] - S.level_ptr[l];
-      const int t_lvl = std::max(1, std::min(8, ctx->n_sm / std::max(1, nodes)));
-      for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
-        const int id = S.level_nodes[e];
-        tiles[id] = S.node[(size_t)id * SPSYM_NODE_INTS + SPN_NB] > 0 ? t_lvl : 0;
-        q.push_back(id);
-        q.push_back(-1);
-      }
-      for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
-        const int id = S.level_nodes[e];
-        for (int t = 0; t < tiles[id]; ++t) {
+    const int P_ = part.parts;
+    // -2: this GPU holds every part.  BA_SPCHOL_ONLY_PART=p on one GPU: the queues rank p of a distributed run would execute
+    // (the other parts' subtree roots count as done, their update matrices are whatever the buffer holds): timing experiments
+    const int only = (ctx->n_ranks == 1 && P_ > 1 && getenv("BA_SPCHOL_ONLY_PART")) ? std::min(P_ - 1, std::max(0, atoi(getenv("BA_SPCHOL_ONLY_PART")))) : -1;
+    const int me = ctx->spc_dist ? ctx->rank : (only >= 0 ? only : -2);
+    auto N_ = [&](int id, int f) { return S.node[(size_t)id * SPSYM_NODE_INTS + f]; };
+    std::vector<int32_t> tiles((size_t)S.n_nodes, 0), q, cnt_init((size_t)3 * S.n_nodes + 16, 0), topcams;
+    auto push_factor_levels = [&](int which) {
+      for (int l = 0; l < S.n_levels; ++l) {
+        int nodes = 0;
+        for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) nodes += part.part[S.level_nodes[e]] == which;
+        if (!nodes) continue;
+        const int t_lvl = std::max(1, std::min(8, ctx->n_sm / nodes));
+        for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
+          const int id = S.level_nodes[e];
+          if (part.part[id] != which) continue;
+          tiles[id] = N_(id, SPN_NB) > 0 ? t_lvl : 0;
           q.push_back(id);
-          q.push_back(t);
+          q.push_back(-1);
+        }
+        for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
+          const int id = S.level_nodes[e];
+          if (part.part[id] != which) continue;
+          for (int t = 0; t < tiles[id]; ++t) {
+            q.push_back(id);
+            q.push_back(t);
+          }
         }
       }
+    };
+    auto push_solve_levels = [&](bool top_part) {
+      for (int l = S.n_levels - 1; l >= 0; --l)
+        for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
+          const int id = S.level_nodes[e], pr = part.part[id];
+          if (top_part ? pr >= 0 : (pr < 0 || (me != -2 && pr != me))) continue;
+          q.push_back(id);
+          q.push_back(-2);
+        }
+    };
+    for (int p = 0; p < P_; ++p) {
+      ctx->spc_qA[p] = (int)(q.size() / 2);
+      if (me == -2 || p == me) push_factor_levels(p);
+      ctx->spc_qA[p + 1] = (int)(q.size() / 2);
     }
-    for (int l = S.n_levels - 1; l >= 0; --l)
-      for (int e = S.level_ptr[l]; e < S.level_ptr[l + 1]; ++e) {
-        q.push_back(S.level_nodes[e]);
-        q.push_back(-2);
-      }
+    ctx->spc_qB = (int)(q.size() / 2);
+    if (P_ > 1) {
+      push_factor_levels(-1);
+      push_solve_levels(true);
+    }
+    push_solve_levels(false);
+    ctx->spc_qB_n = (int)(q.size() / 2) - ctx->spc_qB;
     ctx->spc_n_items = (int)(q.size() / 2);
-    if ((rc = up(ctx->spc_queue, q)) || (rc = up(ctx->spc_tiles, tiles))) return rc;
-    RES(spc_cnt, ((size_t)3 * S.n_nodes + 8) * 4);
+    // counters before a solve: zero, except "all update tiles done" for the subtree roots other ranks factorise (their
+    // update matrices arrive with the exchange)
+    for (int id = 0; id < S.n_nodes; ++id) {
+      if (part.part[id] < 0)
+        for (int k = 0; k < N_(id, SPN_M); ++k) topcams.push_back(S.perm[N_(id, SPN_K0) + k]);
+      else if (me != -2 && part.part[id] != me)
+        cnt_init[16 + (size_t)S.n_nodes + id] = 1 << 20;
+    }
+    ctx->spc_n_topcams = (int)topcams.size();
+    if ((rc = up(ctx->spc_queue, q)) || (rc = up(ctx->spc_tiles, tiles)) || (rc = up(ctx->spc_cnt_init, cnt_init)) ||
+        (rc = up(ctx->spc_topcams, topcams)))
+      return rc;
+    RES(spc_cnt, ((size_t)3 * S.n_nodes + 16) * 4);
     const size_t st_ = std::max(std::max(sf, ss), su);
     CK(cudaFuncSetAttribute(k_spchol_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_));
     ctx->spc_tree = getenv("BA_SPCHOL_LEVELS") == nullptr;
+    if (getenv("BA_SPCHOL_DEBUG"))
+      fprintf(stderr, "[spchol] rank %d: %d parts%s, top %d nodes / %d cameras (%.1f %% of the work), heaviest part %.1f %%, "
+              "exchange %.2f MB, items A %d B %d\n", ctx->rank, P_, ctx->spc_dist ? " (distributed)" : "",
+              (int)std::count(part.part.begin(), part.part.end(), -1), ctx->spc_n_topcams, 100.0 * part.top / std::max(1.0, part.total),
+              100.0 * part.heaviest / std::max(1.0, part.total), ctx->spc_xchg * 8e-6, ctx->spc_qB, ctx->spc_qB_n);
   }
   CK(cudaStreamSynchronize(s));  // host vectors of this call die here
   ctx->spchol = true;
@@ -1221,7 +1305,7 @@ extern "C" int ba_gpu_upload(ba_gpu_ctx *ctx, int32_t n_cam, const double *pose7
   RES(Wk, ctx->nk ? np * 96 : 16);
   RES(tg, np * 24);
   RES(t, np * 24);
-  RES(yc, nc * 48);
+  RES(yc, nc * 48 + 16);  // (+ one slot: failure flag riding on the all-reduce of the distributed sparse Cholesky)
   RES(yp, np * 24);
   RES(yk, 32);
   RES(rk, 32);
@@ -1761,7 +1845,7 @@ static SpChol spchol_args(ba_gpu_ctx *ctx) {
   a.b = P<double>(ctx->b);
   a.panel = P<double>(ctx->spc_panel);
   a.U = P<double>(ctx->spc_U);
-  a.ru = P<double>(ctx->spc_ru);
+  a.ru = P<double>(ctx->spc_U) + ctx->spc_ru_off;
   a.z = P<double>(ctx->spc_z);
   a.linv = P<double>(ctx->spc_linv);
   a.ypos = P<double>(ctx->spc_ypos);
@@ -1776,18 +1860,41 @@ static void enqueue_spchol(ba_gpu_ctx *ctx, int gate) {
   // every kernel of the chain starts with griddepcontrol.wait (gate_open): programmatic dependent launches let the blocks of
   // the next launch become resident on idle SMs (the upper tree levels have few nodes) while the previous one still runs
   if (ctx->spc_tree) {
-    // the whole linear solve in one persistent launch (k_spchol_tree): dependency counters instead of level barriers
+    // the whole linear solve in one persistent launch (k_spchol_tree): dependency counters instead of level barriers.
+    // Partitioned tree: one launch for the subtrees (phase A), one for the top part and the backward substitution (phase B).
     SpTree t;
-    t.queue = P<int2>(ctx->spc_queue);
-    t.n_items = ctx->spc_n_items;
+    int *cnt = P<int>(ctx->spc_cnt);
     t.tiles = P<int32_t>(ctx->spc_tiles);
-    t.ticket = P<int>(ctx->spc_cnt);
-    t.fdone = t.ticket + 8;
+    t.fdone = cnt + 16;
     t.udone = t.fdone + S.n_nodes;
     t.sdone = t.udone + S.n_nodes;
-    cudaMemsetAsync(ctx->spc_cnt.p, 0, ((size_t)3 * S.n_nodes + 8) * 4, ctx->cur);
+    cudaMemcpyAsync(cnt, ctx->spc_cnt_init.p, ((size_t)3 * S.n_nodes + 16) * 4, cudaMemcpyDeviceToDevice, ctx->cur);
     const size_t smem = std::max(std::max(ctx->spc_smem_factor, ctx->spc_smem_solve), ctx->spc_smem_update);
-    LAUNCH(k_spchol_tree, std::min(ctx->n_sm, ctx->spc_n_items), SPC_THREADS, smem, a, t, st, gate);
+    auto launch = [&](int first, int n, int slot) {
+      if (n <= 0) return;
+      t.queue = P<int2>(ctx->spc_queue) + first;
+      t.n_items = n;
+      t.ticket = cnt + slot;
+      LAUNCH(k_spchol_tree, std::min(ctx->n_sm, n), SPC_THREADS, smem, a, t, st, gate);
+    };
+    if (ctx->spc_parts == 1) {
+      launch(0, ctx->spc_n_items, 0);
+      phase_mark(ctx, BA_PHASE_FACTOR);
+      return;
+    }
+    if (ctx->spc_dist) cudaMemsetAsync(ctx->spc_U.p, 0, ctx->spc_xchg * 8, ctx->cur);
+    for (int p = 0; p < ctx->spc_parts; ++p) launch(ctx->spc_qA[p], ctx->spc_qA[p + 1] - ctx->spc_qA[p], p);
+    if (ctx->spc_dist && nccl_allreduce(ctx, P<double>(ctx->spc_U), ctx->spc_xchg, false)) ctx->comm_error = true;
+    if (ctx->spc_dist) cudaMemsetAsync(ctx->yc.p, 0, ((size_t)6 * ctx->n_cam + 1) * 8, ctx->cur);
+    launch(ctx->spc_qB, ctx->spc_qB_n, ctx->spc_parts);
+    if (ctx->spc_dist) {
+      // the step: every rank holds the top part's and its own subtrees' cameras; summed over ranks (zeros elsewhere, the top
+      // part kept by rank 0 only) with the failure flag in the extra slot
+      LAUNCH(k_spchol_dist_pre, cdiv(std::max(1, ctx->spc_n_topcams) * 6, BA_THREADS), BA_THREADS, 0, ctx->n_cam, ctx->spc_n_topcams,
+             P<int32_t>(ctx->spc_topcams), ctx->rank, P<double>(ctx->yc), st, gate);
+      if (nccl_allreduce(ctx, P<double>(ctx->yc), (size_t)6 * ctx->n_cam + 1, false)) ctx->comm_error = true;
+      LAUNCH(k_spchol_dist_post, 1, 32, 0, ctx->n_cam, P<double>(ctx->yc), st, gate);
+    }
     phase_mark(ctx, BA_PHASE_FACTOR);
     return;
   }
@@ -2568,6 +2675,7 @@ extern "C" int ba_gpu_spchol_info(const ba_gpu_ctx *ctx, int64_t info[24]) {
   info[0] = s.n_cam; info[1] = s.n_nodes; info[2] = s.n_levels; info[3] = s.panel_blocks; info[4] = s.u_blocks;
   info[5] = s.max_front_blocks; info[6] = s.max_m; info[7] = s.max_nb; info[8] = s.max_children;
   info[9] = (int64_t)s.flops; info[10] = (int64_t)s.crit_blocks; info[11] = (int64_t)(ctx->sym_ms * 1e3);
+  info[12] = ctx->spc_parts; info[13] = ctx->spc_dist ? 1 : 0; info[14] = ctx->spc_n_topcams; info[15] = (int64_t)(ctx->spc_xchg * 8);
   return BA_OK;
 }
 
@@ -3140,6 +3248,17 @@ extern "C" int ba_sparse_symbolic_info(const ba_spsym *h, int64_t info[24]) {
   info[10] = (int64_t)s.crit_blocks;
   for (int w = 0; w < 10; ++w) info[12 + w] = (int64_t)spsym_array(s, w)->size();
   return BA_OK;
+}
+extern "C" int ba_sparse_symbolic_partition(const ba_spsym *h, int32_t parts, int32_t *part, double work[3]) {
+  if (!h || !part || parts < 1) return BA_ERR_INVALID;
+  const SpPartition R = spsym_partition(h->s, parts);
+  if (!R.part.empty()) memcpy(part, R.part.data(), R.part.size() * sizeof(int32_t));
+  if (work) {
+    work[0] = R.total;
+    work[1] = R.top;
+    work[2] = R.heaviest;
+  }
+  return R.parts;
 }
 extern "C" int ba_sparse_symbolic_get(const ba_spsym *h, int32_t which, int32_t *dst) {
   if (!h || !dst) return BA_ERR_INVALID;

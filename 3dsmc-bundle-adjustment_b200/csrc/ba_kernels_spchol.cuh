@@ -627,3 +627,20 @@ k_spchol_tree(SpChol a, SpTree t, LmState *st, int gate) {
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Distributed factorisation (one subtree group per rank, top part replicated): the step is assembled by ONE all-reduce
+// over yc -- every camera's six values are non-zero on exactly one rank (own subtrees; the top part's cameras, which
+// every rank computed bit-identically, are kept by rank 0 only), so the sum is exact and identical on all ranks.  The
+// linear-solver failure flag rides in the extra slot yc[6 n_cam].
+// ---------------------------------------------------------------------------------------------
+__global__ void k_spchol_dist_pre(int n_cam, int n_top, const int32_t *topcams, int rank, double *yc, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rank != 0 && i < 6 * n_top) yc[6 * (size_t)topcams[i / 6] + i % 6] = 0.0;
+  if (i == 0) yc[6 * (size_t)n_cam] = st->lin_fail ? 1.0 : 0.0;
+}
+__global__ void k_spchol_dist_post(int n_cam, const double *yc, LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  if (threadIdx.x == 0 && yc[6 * (size_t)n_cam] != 0.0) st->lin_fail = 1;
+}

@@ -379,3 +379,114 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
   }
   return S;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Subtree-to-rank partition of the supernodal tree (multi-GPU factorisation): a CUT through the tree leaves disjoint
+// subtrees below it, each factorised by one rank, and a small TOP part above it that every rank factorises redundantly
+// from the update matrices of the subtree roots (exchanged once per solve).  The cut starts at the roots and the heaviest
+// subtree is opened (its root moves to the top, its children enter the cut) until the subtrees, taken in the order of the
+// camera sequence, split into `parts` consecutive groups of about equal work.  Consecutive, because the ranks' point
+// shards are consecutive too (landmarks are numbered along the trajectory): a rank then forms most of the blocks of S it
+// factorises itself, and only the blocks near the shard borders and those of the top part have to be summed over ranks.
+// ---------------------------------------------------------------------------------------------
+struct SpPartition {
+  int parts = 1;
+  std::vector<int32_t> part;  // per node: owning part, -1 = top (replicated)
+  std::vector<int32_t> cut;   // roots of the subtrees below the cut, in sequence order
+  double total = 0.0, top = 0.0, heaviest = 0.0;  // work in block operations: all, top part, the most loaded part
+};
+
+inline double spsym_node_ops(const int32_t *N) {
+  const double m = N[SPN_M], nb = N[SPN_NB];
+  double ops = 0.0;
+  for (int k = 0; k < (int)m; ++k) {
+    const double below = m - k - 1 + nb;
+    ops += below + (m - k - 1) * (nb + (m - k) * 0.5);
+  }
+  return ops + m * nb * (nb + 1) * 0.5 + 4.0;
+}
+
+inline SpPartition spsym_partition(const SpSymbolic &S, int parts) {
+  SpPartition R;
+  const int nn = S.n_nodes;
+  R.part.assign((size_t)nn, 0);
+  if (parts <= 1 || nn == 0) return R;
+  auto node = [&](int id) { return S.node.data() + (size_t)id * SPSYM_NODE_INTS; };
+  // subtree work and first position (children have smaller ids than parents)
+  std::vector<double> sub((size_t)nn);
+  std::vector<int32_t> first((size_t)nn);
+  for (int id = 0; id < nn; ++id) {
+    sub[id] = spsym_node_ops(node(id));
+    first[id] = node(id)[SPN_K0];
+    R.total += sub[id];
+  }
+  for (int id = 0; id < nn; ++id) {
+    const int p = node(id)[SPN_PARENT];
+    if (p >= 0) {
+      sub[p] += sub[id];
+      first[p] = std::min(first[p], first[id]);
+    }
+  }
+  std::vector<int32_t> cut;
+  std::vector<char> top((size_t)nn, 0);
+  for (int id = 0; id < nn; ++id)
+    if (node(id)[SPN_PARENT] < 0) cut.push_back(id);
+  // consecutive groups of the cut (sorted along the camera sequence) with about equal work; returns the largest group
+  std::vector<int32_t> group;
+  auto split = [&]() -> double {
+    std::sort(cut.begin(), cut.end(), [&](int a, int b) { return S.perm[first[a]] < S.perm[first[b]]; });
+    double below = 0.0;
+    for (int id : cut) below += sub[id];
+    group.assign(cut.size(), 0);
+    double acc = 0.0, worst = 0.0, cur = 0.0;
+    int g = 0;
+    for (size_t i = 0; i < cut.size(); ++i) {
+      // close the group when the middle of this subtree lies beyond the group's share (and enough subtrees remain)
+      const double mid = acc + 0.5 * sub[cut[i]];
+      while (g + 1 < parts && mid > below * (g + 1) / parts && cur > 0.0) {
+        worst = std::max(worst, cur);
+        cur = 0.0;
+        ++g;
+      }
+      group[i] = g;
+      cur += sub[cut[i]];
+      acc += sub[cut[i]];
+    }
+    return std::max(worst, cur);
+  };
+  double top_w = 0.0, heaviest = 0.0;
+  for (int iter = 0; iter < 2 * nn; ++iter) {
+    heaviest = split();
+    double below = R.total - top_w;
+    if ((int)cut.size() >= parts && heaviest <= 1.10 * below / parts) break;
+    if ((int)cut.size() >= 6 * parts || top_w > 0.3 * R.total) break;  // accept the imbalance rather than a large top part
+    int h = -1;
+    for (int id : cut)
+      if (node(id)[SPN_NCHILD] > 0 && (h < 0 || sub[id] > sub[h])) h = id;
+    if (h < 0) break;
+    top[h] = 1;
+    top_w += spsym_node_ops(node(h));
+    cut.erase(std::find(cut.begin(), cut.end(), h));
+    const int32_t *ch = S.children.data() + node(h)[SPN_CHILD];
+    for (int c = 0; c < node(h)[SPN_NCHILD]; ++c) cut.push_back(ch[c]);
+  }
+  heaviest = split();
+  if ((int)cut.size() < parts) return R;  // (tree too small: one part, replicated)
+  R.parts = parts;
+  R.cut = cut;
+  R.top = top_w;
+  R.heaviest = heaviest;
+  // parents before children (descending ids): a node inherits its parent's part
+  std::vector<int32_t> grp_of((size_t)nn, -2);
+  for (size_t i = 0; i < cut.size(); ++i) grp_of[cut[i]] = group[i];
+  for (int id = nn - 1; id >= 0; --id) {
+    if (top[id]) {
+      R.part[id] = -1;
+    } else if (grp_of[id] >= 0) {
+      R.part[id] = grp_of[id];
+    } else {
+      R.part[id] = R.part[node(id)[SPN_PARENT]];
+    }
+  }
+  return R;
+}

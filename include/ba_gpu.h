@@ -281,6 +281,11 @@ int ba_sparse_symbolic_create(int32_t n_cam, int32_t n_blk, const int32_t *blk_i
                               int32_t cap_blocks, int32_t max_own, ba_spsym **out);
 int ba_sparse_symbolic_info(const ba_spsym *h, int64_t info[24]);
 int ba_sparse_symbolic_get(const ba_spsym *h, int32_t which, int32_t *dst);
+/* Subtree-to-rank partition the multi-GPU factorisation uses for `parts` ranks (csrc/ba_sparse_symbolic.h, spsym_partition):
+ * part[node] = owning rank, -1 = top part (factorised by every rank).  work[0..2] = block operations of the whole tree, of the
+ * top part, of the most loaded rank.  Returns the number of parts in force (1: tree too small, the solve stays replicated). */
+int ba_sparse_symbolic_partition(const ba_spsym *h, int32_t parts, int32_t *part, double work[3]);
+
 void ba_sparse_symbolic_destroy(ba_spsym *h);
 
 /* ---- multi-GPU: one process per GPU, points sharded ---- */

@@ -28,8 +28,14 @@ class Symbolic:
             a = np.zeros(max(1, self.info[12 + w]), dtype=np.int32)
             lib.ba_sparse_symbolic_get(h, w, ba_b200.capi.ip(a))
             setattr(self, name, a[:self.info[12 + w]])
-        lib.ba_sparse_symbolic_destroy(h)
         self.n_cam, self.n_nodes, self.n_levels = self.info[0], self.info[1], self.info[2]
+        self.partitions = {}
+        for parts in (2, 3, 4, 8):  # subtree-to-rank partitions of the multi-GPU factorisation
+            part = np.zeros(max(1, self.n_nodes), dtype=np.int32)
+            work = np.zeros(3)
+            got = lib.ba_sparse_symbolic_partition(h, parts, ba_b200.capi.ip(part), ba_b200.capi.dp(work))
+            self.partitions[parts] = (got, part[:self.n_nodes].copy(), work.copy())
+        lib.ba_sparse_symbolic_destroy(h)
         self.node = self.node.reshape(-1, NI)
         self.aent = self.aent.reshape(-1, 4)
         self.bi, self.bj = bi, bj

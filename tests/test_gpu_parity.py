@@ -454,6 +454,29 @@ def test_spchol_small_leaves_same_result(monkeypatch, solver_cache):
     assert pose_err(out[0][1], out[1][1])[0] < 1e-8
 
 
+@pytest.mark.parametrize("name,parts", [("cfg4_tenth", 2), ("cfg4_tenth", 8), ("cfg3_tenth", 4), ("cfg4_tenth", 3)])
+def test_spchol_partitioned_tree_same_bits(name, parts, monkeypatch):
+    """The subtree-to-rank partition of the multi-GPU factorisation, all parts on this GPU one after the other (phase A per part,
+    then top part + backward substitution): the same arithmetic in the same order per node, so the same bits as one queue."""
+    p = _problem(name)
+    g, _ = mode_opts("NS", solver=4, max_num_iterations=4)
+    out = []
+    monkeypatch.setenv("BA_SPCHOL_LEAF", "6")   # (deep tree on the reduced test sizes)
+    for n in (None, str(parts)):
+        if n:
+            monkeypatch.setenv("BA_SPCHOL_PARTS", n)
+        s = ba_b200.GpuSolver(**g)
+        s.upload(p)
+        summ = s.solve()
+        out.append((summ.final_cost, s.download()[0].copy(), s.spchol_info()))
+        s.close()
+    assert out[0][2]["parts"] == 1
+    if out[1][2]["parts"] == 1:
+        pytest.skip("tree too small for %d parts" % parts)
+    assert out[1][2]["parts"] == parts and out[1][2]["top_cameras"] > 0
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+
+
 def test_spchol_repeated_solves_are_deterministic(solver_cache):
     p = _problem("cfg4_tenth")
     g, _ = mode_opts("NS", solver=4, max_num_iterations=4)

@@ -91,3 +91,36 @@ def test_unsupported_when_a_front_cannot_fit():
     bj = np.array([b for _, b in pairs], dtype=np.int32)
     with pytest.raises(RuntimeError):
         Symbolic(n, bi, bj, leaf=4, cap=20, max_own=64)
+
+
+@pytest.mark.parametrize("cfg,scale,leaf", [(5, 0.1, 32), (4, 0.5, 32), (3, 0.25, 16)])
+def test_subtree_partition(cfg, scale, leaf):
+    """Subtree-to-rank partition of the multi-GPU factorisation: parts are unions of whole subtrees, the top part is closed
+    under `parent`, work is balanced on the sequential co-visibility of the synthetic configurations, and consecutive
+    parts own consecutive stretches of the camera sequence."""
+    p = syn.make_config(cfg, scale=scale)
+    bi, bj = covisibility_blocks(p.cam_idx, p.pt_idx, p.n_cam, p.fixed_cam)
+    sym = Symbolic(p.n_cam, bi, bj, leaf=leaf, cap=770, max_own=24)
+    for parts, (got, part, work) in sym.partitions.items():
+        assert got in (1, parts)
+        if got == 1:
+            assert (part == 0).all()
+            continue
+        assert part.min() == -1 and part.max() == parts - 1
+        for id_, N in enumerate(sym.node):
+            par = N[PARENT]
+            if part[id_] == -1:
+                assert par < 0 or part[par] == -1          # the top part is closed upwards
+            elif par >= 0:
+                assert part[par] in (-1, part[id_])        # subtrees are never split between ranks
+        total, top, heaviest = work
+        assert top <= 0.4 * total           # (opening stops once the top part passes 30 %)
+        if sym.n_nodes >= 40 * parts:       # enough subtrees to balance
+            assert heaviest <= 1.25 * (total - top) / parts
+        # consecutive parts <-> consecutive cameras (median camera index of a part's own cameras is increasing)
+        med = []
+        for r in range(parts):
+            cams = np.concatenate([sym.perm[N[K0]:N[K0] + N[M]] for id_, N in enumerate(sym.node) if part[id_] == r] or [np.zeros(0)])
+            if len(cams):
+                med.append(np.median(cams))
+        assert med == sorted(med)
