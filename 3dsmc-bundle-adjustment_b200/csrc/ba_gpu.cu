@@ -163,6 +163,11 @@ struct ba_gpu_ctx {
   int spc_parts = 1, spc_qA[BA_MAX_RANKS + 1] = {0}, spc_qB = 0, spc_qB_n = 0, spc_n_topcams = 0;
   bool spc_dist = false;
   size_t spc_xchg = 0, spc_ru_off = 0;
+  // distributed factorisation: a rank assembles only its own subtrees and the top part, so only the blocks of S some rank
+  // contributes to WITHOUT factorising them (shard borders, top part) are summed over ranks: spc_nx block ids in spc_xidx
+  Buf spc_xidx, spc_xbuf;
+  int spc_nx = 0;
+  bool sp_full_next = false;  // the next enqueue_sparse_values() completes ALL of S on every rank (product hook)
   bool spc_tree = true;         // one persistent launch with dependency counters (BA_SPCHOL_LEVELS=1: one launch per tree level)
   size_t spc_smem_factor = 0, spc_smem_solve = 0, spc_smem_update = 0;
   double sym_ms = 0.0;          // host time of the symbolic phase (last upload)
@@ -915,6 +920,32 @@ static int build_spchol(ba_gpu_ctx *ctx) {
       if (!is_cut(id)) place(id);
   }
   int rc;
+  ctx->spc_nx = 0;
+  if (ctx->spc_dist) {
+    // exchange set of S: block (i, j) is assembled by the node that owns the earlier-eliminated of its two cameras
+    std::vector<int32_t> node_of((size_t)n_cam, 0), gid((size_t)ctx->n_sblk_local + 1);
+    for (int id = 0; id < S.n_nodes; ++id)
+      for (int k = 0; k < S.node[(size_t)id * SPSYM_NODE_INTS + SPN_M]; ++k) node_of[S.node[(size_t)id * SPSYM_NODE_INTS + SPN_K0] + k] = id;
+    if (ctx->n_sblk_local > 0) CK(cudaMemcpyAsync(gid.data(), ctx->sp_gid.p, (size_t)ctx->n_sblk_local * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<double> mask((size_t)n_blk + 1, 0.0);
+    for (int l = 0; l < ctx->n_sblk_local; ++l) {
+      const int g = gid[l];
+      if (g < 0 || g >= n_blk) return fail(ctx, BA_ERR_STATE, "sparse Cholesky: local block without a global id");
+      if (part.part[node_of[std::min(S.pos[bi[g]], S.pos[bj[g]])]] != ctx->rank) mask[g] = 1.0;
+    }
+    RES(spc_xbuf, ((size_t)n_blk + 1) * 8);
+    CK(cudaMemcpyAsync(ctx->spc_xbuf.p, mask.data(), ((size_t)n_blk + 1) * 8, cudaMemcpyHostToDevice, s));
+    if ((rc = nccl_allreduce(ctx, P<double>(ctx->spc_xbuf), (size_t)n_blk + 1, true))) return rc;
+    CK(cudaMemcpyAsync(mask.data(), ctx->spc_xbuf.p, ((size_t)n_blk + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int32_t> xs;
+    for (int g = 0; g < n_blk; ++g)
+      if (mask[g] != 0.0) xs.push_back(g);
+    ctx->spc_nx = (int)xs.size();
+    if ((rc = up(ctx->spc_xidx, xs))) return rc;
+    RES(spc_xbuf, ((size_t)std::max<size_t>(xs.size(), ((size_t)n_blk + 1) / 36 + 1) + 1) * 288);
+  }
   if ((rc = up(ctx->spn_node, S.node)) || (rc = up(ctx->spn_bord, S.bord)) || (rc = up(ctx->spn_children, S.children)) ||
       (rc = up(ctx->spn_rel, S.rel)) || (rc = up(ctx->spn_inv, S.inv)) || (rc = up(ctx->spn_aent, S.aent)) ||
       (rc = up(ctx->spn_perm, S.perm)) || (rc = up(ctx->spn_levels, S.level_nodes)))
@@ -1823,7 +1854,21 @@ static void enqueue_sparse_values(ba_gpu_ctx *ctx, int gate) {
          ctx->n_sblk_local, ctx->n_cam, P<int32_t>(ctx->sb_ptr), P<unsigned long long>(ctx->sp_lkeys), P<int32_t>(ctx->sp_gid),
          P<unsigned long long>(ctx->sp_pairs), P<int32_t>(ctx->sp_pair_pt), ctx->Fc_, P<double>(ctx->geo), P<double>(ctx->intr),
          P<double>(ctx->Vs), P<double>(ctx->Sblk), ticket, st, gate);
-  if (ctx->n_ranks > 1 && nccl_allreduce(ctx, P<double>(ctx->Sblk), (size_t)ctx->n_sblk * 36, false)) ctx->comm_error = true;
+  if (ctx->n_ranks > 1) {
+    if (ctx->spchol && ctx->spc_dist && !ctx->sp_full_next) {
+      // distributed factorisation: only the blocks another rank needs from this one (and the top part's) are summed
+      if (ctx->spc_nx > 0) {
+        LAUNCH(k_sp_xpack, cdiv(ctx->spc_nx * 36, BA_THREADS), BA_THREADS, 0, ctx->spc_nx, P<int32_t>(ctx->spc_xidx), P<double>(ctx->Sblk),
+               P<double>(ctx->spc_xbuf), 0, st, gate);
+        if (nccl_allreduce(ctx, P<double>(ctx->spc_xbuf), (size_t)ctx->spc_nx * 36, false)) ctx->comm_error = true;
+        LAUNCH(k_sp_xpack, cdiv(ctx->spc_nx * 36, BA_THREADS), BA_THREADS, 0, ctx->spc_nx, P<int32_t>(ctx->spc_xidx), P<double>(ctx->Sblk),
+               P<double>(ctx->spc_xbuf), 1, st, gate);
+      }
+    } else if (nccl_allreduce(ctx, P<double>(ctx->Sblk), (size_t)ctx->n_sblk * 36, false)) {
+      ctx->comm_error = true;
+    }
+    ctx->sp_full_next = false;
+  }
   LAUNCH(k_sp_add_diag, cdiv(ctx->n_cam * 36, BA_THREADS), BA_THREADS, 0, ctx->n_cam, P<int32_t>(ctx->sp_diag), P<double>(ctx->U),
          P<double>(ctx->Sblk), st, gate);
 }
@@ -1965,7 +2010,8 @@ static int solve_implicit(ba_gpu_ctx *ctx) {
   });
   phase_mark(ctx, BA_PHASE_RHS);
   enqueue_sparse_values(ctx, GATE_RUN);
-  sync_flags(ctx);
+  // (the exact solve does not branch on the failure flags; the ranks agree on them after it, before the step is judged)
+  if (!ctx->spchol) sync_flags(ctx);
   phase_mark(ctx, BA_PHASE_SCHUR);
   if (ctx->spchol) {
     // exact step: b and the damping, then the factorisation and the two substitutions (yc written by the last kernels)
@@ -2621,6 +2667,7 @@ extern "C" int ba_gpu_schur_matvec(ba_gpu_ctx *ctx, double radius, const double 
   if (!ctx->uploaded) return fail(ctx, BA_ERR_STATE, "ba_gpu_schur_matvec before ba_gpu_upload");
   if (ctx->nk) return fail(ctx, BA_ERR_UNSUPPORTED, "implicit Schur product needs optimize_intrinsics = 0");
   CK(cudaSetDevice(ctx->device));
+  ctx->sp_full_next = true;  // (the product needs every block of S on every rank)
   int rc = prepare_linear_system(ctx, radius);
   if (rc) return rc;
   LmState *st = P<LmState>(ctx->st);

@@ -239,6 +239,20 @@ k_sp_add_diag(int n_cam, const int32_t *__restrict__ diag, const double *__restr
   if (b >= 0) S[36 * (size_t)b + k] += U[36 * (size_t)c + k];
 }
 
+// gather (unpack = 0) / scatter (unpack = 1) of the blocks of S that are summed over ranks in the distributed factorisation
+__global__ void __launch_bounds__(BA_THREADS)
+k_sp_xpack(int nx, const int32_t *__restrict__ xidx, double *__restrict__ S, double *__restrict__ xbuf, int unpack, const LmState *st, int gate) {
+  if (!gate_open(st, gate)) return;
+  const int i = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (i >= nx * 36) return;
+  const int b = i / 36, k = i - 36 * b;
+  double *src = S + 36 * (size_t)xidx[b] + k;
+  if (unpack)
+    *src = xbuf[i];
+  else
+    xbuf[i] = *src;
+}
+
 // point of every pair (gathered once per upload: one level less in the dependent-load chain of k_sp_schur)
 __global__ void __launch_bounds__(BA_THREADS)
 k_sp_pair_points(long long n_pairs, const unsigned long long *__restrict__ pairs, const int32_t *__restrict__ pt_idx,

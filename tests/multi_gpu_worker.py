@@ -32,6 +32,9 @@ def main():
     dist.broadcast(idbuf, 0)
     s.comm_init(idbuf.cpu().numpy().tobytes(), rank, world)
     s.upload(shard)
+    if len(sys.argv) > 6 and sys.argv[6] == "distributed":
+        info = s.spchol_info()
+        assert info.get("distributed") == 1 and info["parts"] == world, "the distributed factorisation is not in force: %r" % (info,)
     summ = s.solve()
     pose, pt, _ = s.download()
     tr = s.trace()
