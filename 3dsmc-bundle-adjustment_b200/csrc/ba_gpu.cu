@@ -2722,7 +2722,7 @@ extern "C" int ba_gpu_spchol_info(const ba_gpu_ctx *ctx, int64_t info[24]) {
   info[0] = s.n_cam; info[1] = s.n_nodes; info[2] = s.n_levels; info[3] = s.panel_blocks; info[4] = s.u_blocks;
   info[5] = s.max_front_blocks; info[6] = s.max_m; info[7] = s.max_nb; info[8] = s.max_children;
   info[9] = (int64_t)s.flops; info[10] = (int64_t)s.crit_blocks; info[11] = (int64_t)(ctx->sym_ms * 1e3);
-  info[12] = ctx->spc_parts; info[13] = ctx->spc_dist ? 1 : 0; info[14] = ctx->spc_n_topcams; info[15] = (int64_t)(ctx->spc_xchg * 8);
+  info[12] = ctx->spc_parts; info[13] = ctx->spc_dist ? 1 : 0; info[14] = ctx->spc_n_topcams; info[15] = (int64_t)(ctx->spc_xchg * 8); info[16] = ctx->spc_dist ? ctx->spc_nx : 0;
   return BA_OK;
 }
 

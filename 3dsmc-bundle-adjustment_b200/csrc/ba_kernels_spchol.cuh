@@ -150,7 +150,18 @@ __device__ __forceinline__ void spc_tri(int p, int &i, int &j) {
 }
 
 // factorisation of the front of node `id` by the calling thread block (SPC_THREADS threads, spc_factor_smem bytes at spc_sm)
-__device__ __forceinline__ void spc_factor_node(const SpChol &a, int id, bool prof_block, LmState *st, double *spc_sm) {
+__device__ __forceinline__ void spc_wait_ge(const int *flag, int want) {
+  int v;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= want) return;
+    __nanosleep(64);
+  }
+}
+// (udone / tiles: completion counters of the persistent tree kernel -- the node waits for its children's update matrices only
+//  AFTER it has assembled its stored blocks of S, which do not depend on them; nullptr: one launch per level, nothing to wait for)
+__device__ __forceinline__ void spc_factor_node(const SpChol &a, int id, bool prof_block, LmState *st, double *spc_sm,
+                                                const int *udone = nullptr, const int32_t *tiles = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
   const int k0 = N[SPN_K0], m = N[SPN_M], nb = N[SPN_NB];
@@ -188,6 +199,11 @@ __device__ __forceinline__ void spc_factor_node(const SpChol &a, int id, bool pr
       P[(size_t)(6 * en.z + c6) * LD + 6 * en.y + r6] = v;
     }
   }
+  if (udone && tid == 0)
+    for (int ci = 0; ci < N[SPN_NCHILD]; ++ci) {
+      const int ch = a.children[N[SPN_CHILD] + ci];
+      spc_wait_ge(udone + ch, tiles[ch]);
+    }
   __syncthreads();
   SPC_TICK(0)
   // ---- phase 1b: extend-add of the children (one after the other: fixed order; inside a child the map is injective).
@@ -564,14 +580,6 @@ struct SpTree {
   const int32_t *tiles;    // update tiles per node (0: no border)
   int *ticket, *fdone, *udone, *sdone;
 };
-__device__ __forceinline__ void spc_wait_ge(const int *flag, int want) {
-  int v;
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-    if (v >= want) return;
-    __nanosleep(64);
-  }
-}
 __global__ void __launch_bounds__(SPC_THREADS, 1)
 k_spchol_tree(SpChol a, SpTree t, LmState *st, int gate) {
   if (!gate_open(st, gate)) return;
@@ -588,13 +596,7 @@ k_spchol_tree(SpChol a, SpTree t, LmState *st, int gate) {
     const int id = q.x;
     const int32_t *N = a.node + (size_t)id * SPSYM_NODE_INTS;
     if (q.y == -1) {
-      if (tid == 0)
-        for (int ci = 0; ci < N[SPN_NCHILD]; ++ci) {
-          const int ch = a.children[N[SPN_CHILD] + ci];
-          spc_wait_ge(t.udone + ch, t.tiles[ch]);
-        }
-      __syncthreads();
-      spc_factor_node(a, id, it == 0, st, spc_sm);
+      spc_factor_node(a, id, it == 0, st, spc_sm, t.udone, t.tiles);
       __syncthreads();
       if (tid == 0) {
         __threadfence();

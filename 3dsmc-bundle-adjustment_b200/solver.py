@@ -169,7 +169,7 @@ class GpuSolver:
             return {}
         keys = ["n_cam", "nodes", "levels", "panel_blocks", "update_blocks", "max_front_blocks", "max_own", "max_border",
                 "max_children", "flops", "critical_path_block_ops", "symbolic_us", "parts", "distributed", "top_cameras",
-                "exchange_bytes"]
+                "exchange_bytes", "s_exchange_blocks"]
         return {k: int(info[i]) for i, k in enumerate(keys)}
 
     def phase_times(self):

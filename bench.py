@@ -30,11 +30,11 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "cfg1": dict(cfg=1, mode=(1, 1), desc="7-keyframe TUM-shaped window, 500 landmarks, 3000 obs, REF cost, explicit Schur + Cholesky"),
     "cfg2": dict(cfg=2, mode=(1, 1), desc="sliding 20-keyframe windows over 800 keyframes, REF cost, explicit Schur + Cholesky"),
-    "cfg3": dict(cfg=3, mode=(0, 0), desc="global BA 800 keyframes, 60k landmarks, 400k obs, NS cost, implicit-Schur PCG"),
+    "cfg3": dict(cfg=3, mode=(0, 0), desc="global BA 800 keyframes, 60k landmarks, 400k obs, NS cost; linear solver in force: detail.solver (BASELINE.json names implicit-Schur PCG for this config: --solver implicit)"),
     "cfg3ref": dict(cfg=3, mode=(1, 1), desc="the reference's global optimisation: 800 keyframes, 60k landmarks, 400k obs, REF cost (depth prior + "
                                              "free intrinsics), dense explicit Schur + blocked Cholesky (exact LM step)"),
-    "cfg4": dict(cfg=4, mode=(0, 0), desc="BAL-shaped loop 1723 cameras, 156k points, 680k obs, NS cost, implicit-Schur PCG"),
-    "cfg5": dict(cfg=5, mode=(0, 0), desc="large synthetic 10k cameras, 2M points, 8M obs, NS cost, implicit-Schur PCG"),
+    "cfg4": dict(cfg=4, mode=(0, 0), desc="BAL-shaped loop 1723 cameras, 156k points, 680k obs, NS cost; linear solver in force: detail.solver (BASELINE.json names implicit-Schur PCG for this config: --solver implicit)"),
+    "cfg5": dict(cfg=5, mode=(0, 0), desc="large synthetic 10k cameras, 2M points, 8M obs, NS cost; linear solver in force: detail.solver (BASELINE.json names implicit-Schur PCG for this config: --solver implicit)"),
 }
 # Algorithmic bytes per launch: NS mode, fp64, int32 indices.
 # (per observation, per point, per camera) for every Jacobian store; the dominant
@@ -300,6 +300,10 @@ def pinned_copy(a):
     return t.numpy()
 
 
+def n_blk_all(s):
+    return s.sparse_stats()[1]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -312,6 +316,8 @@ def main():
     ap.add_argument("--solver", default="auto", choices=sorted(SOLVERS),
                     help="large NS-mode workloads: auto = the library's choice (block-sparse explicit S on one GPU, "
                          "sharded implicit on several), implicit = matrix-free two/one-pass product, sparse = block-sparse S")
+    ap.add_argument("--with-implicit-path", action="store_true",
+                    help="single GPU: also time the matrix-free implicit-Schur PCG solver on the same problem (adds its W + K LM iterations)")
     ap.add_argument("--write-golden", action="store_true", help="single GPU: store this run's LM trace as the reference of parity_vs_n1")
     ap.add_argument("--store", type=int, default=0, help="BA_JAC_* for the implicit solver (0 auto, 1 planes, 2 factored, 3 tiled)")
     args = ap.parse_args()
@@ -447,7 +453,7 @@ def main():
     jac_obs_s = full.n_obs / (maxr(ms_lin) * 1e-3)
     # the matrix-free (north-star) path beside it when AUTO chose the block-sparse solver
     implicit_path = None
-    if solver_used in (3, 4) and world == 1:
+    if solver_used in (3, 4) and world == 1 and args.with_implicit_path:
         s2 = ba_b200.GpuSolver(max_num_iterations=max(W, 1), **dict(opts, solver=2))
         s2.upload(hp)
         if W > 0:
@@ -496,8 +502,13 @@ def main():
         "detail": {"solver": SOLVER_NAME.get(solver_used, str(solver_used)), "jacobian_store": store, "lm_iterations": n_iter,
                    "pcg_iterations_total": int(summ.total_linear_iters), "pcg_iterations_per_lm": pcg_counts,
                    "exchange": None if world == 1 else
-                   ("per LM iteration: NCCL all-reduce of camera blocks / reduced rhs / scalars and of the block-sparse S values; "
-                    "the factorisation runs replicated on every rank" if solver_used == 4 else
+                   ("per LM iteration: NCCL all-reduce of camera blocks / reduced rhs / scalars; "
+                    + ("distributed factorisation: every rank factorises its own subtrees of the supernodal tree, sums only the blocks of S "
+                       "another rank needs (%d bytes instead of %d), the update matrices of the subtree roots (%d bytes) and the step; the top "
+                       "part of the tree (%d cameras) runs on every rank" % (288 * spchol.get("s_exchange_blocks", 0), 288 * n_blk_all(s),
+                                                                             spchol.get("exchange_bytes", 0), spchol.get("top_cameras", 0))
+                       if spchol.get("distributed") else "all-reduce of the block-sparse S values; the factorisation runs replicated on every rank")
+                    if solver_used == 4 else
                     "per LM iteration: NCCL all-reduce of the block-sparse S; persistent PCG row-sharded, exchange through tagged "
                     "slots in NVLink peer memory inside the kernel" if solver_used == 3 else
                     "NCCL all-reduce of camera-sized vectors (one per PCG iteration)"),
