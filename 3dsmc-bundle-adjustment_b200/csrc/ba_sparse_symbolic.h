@@ -458,7 +458,7 @@ inline SpPartition spsym_partition(const SpSymbolic &S, int parts) {
   for (int iter = 0; iter < 2 * nn; ++iter) {
     heaviest = split();
     double below = R.total - top_w;
-    if ((int)cut.size() >= parts && heaviest <= 1.10 * below / parts) break;
+    if ((int)cut.size() >= parts && heaviest <= 1.30 * below / parts) break;
     if ((int)cut.size() >= 6 * parts || top_w > 0.3 * R.total) break;  // accept the imbalance rather than a large top part
     int h = -1;
     for (int id : cut)
