@@ -211,7 +211,19 @@ def kernel_rooflines(ba_b200, s, problem, wl, solver_used, flush, peak):
 FP64_NOMINAL_TFLOPS = 40.0  # B200 vector fp64, nominal (MEASURED_PEAKS.json holds no fp64 figure)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this round
 # (profiles/r02_ncu_full_cfg5.csv), config 5 on one GPU
-NCU_TRAFFIC_R02_CFG5 = {}
+_NCU_SRC = "ncu --set full, profiles/r02_ncu_full_cfg5.csv / r02_ncu_cfg5_summary.txt (one GPU, cold cache, per launch)"
+NCU_TRAFFIC_R02_CFG5 = {
+    # k_sp_schur 646.4 MB read + 45.0 MB written (the gathers of the 3.0 GB of requested operands hit L1 83 % / L2 52 %)
+    "schur_complement": (691.4e6, _NCU_SRC),
+    # k_spchol_tree 143.6 MB read + 168.7 MB written (fronts and update matrices mostly stay in L2)
+    "linear_solve": (312.3e6, _NCU_SRC),
+    # kf_linearize<0> 567.7 + kf_pt_blocks 617.4 + kf_linearize<1> 569.6 + kf_cam_blocks 394.0 MB
+    "accept_relinearize": (2148.7e6, _NCU_SRC),
+    # kf_schur_pass1<1,0> 582.6 + kf_model_cost 518.2 + k_cost 245.3 MB
+    "back_substitution_model_cost": (1346.1e6, _NCU_SRC),
+    "point_inverse": (445.2e6, _NCU_SRC),
+    "reduced_rhs": (369.0e6, _NCU_SRC),
+}
 
 
 def executed_roofline(workload, phase_ms, n_iter, solver_used, full, n_pairs, n_ent, spchol, pcg_total, peak, peak_src):
@@ -262,6 +274,10 @@ def executed_roofline(workload, phase_ms, n_iter, solver_used, full, n_pairs, n_
     live = {k: v for k, v in table.items() if v["ms"] and v["ms"] > 0}
     if not live:
         return None, table
+    if workload == "cfg5":
+        for k, v in table.items():
+            if k in NCU_TRAFFIC_R02_CFG5:
+                v["traffic"] = NCU_TRAFFIC_R02_CFG5[k][0]
     dom = max(live, key=lambda k: live[k]["ms"])
     d = live[dom]
     traffic = NCU_TRAFFIC_R02_CFG5.get(dom) if workload == "cfg5" else None
