@@ -316,6 +316,30 @@ k_sp_minv(int n_cam, const int32_t *__restrict__ diag, const double *__restrict_
 // per pair instead of 124 B and ~190, but three CTA-wide phases per row at 8 warps per SM: 1.92 ms); a two-trip software
 // pipeline of the gathers in this kernel (252 registers: 1.36 ms).
 #define BA_SPS_CHUNK 32
+// Sum over the warp of 36 per-lane values by recursive halving: at every level a lane keeps one half of its values and
+// receives the partner's partial sums of that half.  Afterwards lane l holds the complete sums of the entries
+// idx .. idx + cnt - 1 (cnt <= 2) in acc[0..1]; the 36 entries are spread over the 32 lanes.
+__device__ __forceinline__ void sp_reduce_scatter36(double (&acc)[36], int lane, int &idx, int &cnt) {
+#define SP_HALVE(N, H, MASK)                                                        \
+  {                                                                                 \
+    const bool up = (lane & MASK) != 0;                                             \
+    _Pragma("unroll") for (int i = 0; i < H; ++i) {                                 \
+      const double lo = acc[i], hi = (i + H < N) ? acc[i + H] : 0.0;                \
+      const double keep = up ? hi : lo, send = up ? lo : hi;                        \
+      acc[i] = keep + __shfl_xor_sync(BA_FULL, send, MASK);                         \
+    }                                                                               \
+  }
+  SP_HALVE(36, 18, 16)
+  SP_HALVE(18, 9, 8)
+  SP_HALVE(9, 5, 4)
+  SP_HALVE(5, 3, 2)
+  SP_HALVE(3, 2, 1)
+#undef SP_HALVE
+  idx = ((lane & 16) ? 18 : 0) + ((lane & 8) ? 9 : 0) + ((lane & 4) ? 5 : 0) + ((lane & 2) ? 3 : 0) + ((lane & 1) ? 2 : 0);
+  int c = (lane & 4) ? 4 : 5;
+  c = (lane & 2) ? c - 3 : 3;
+  cnt = (lane & 1) ? (c > 2 ? c - 2 : 0) : (c < 2 ? c : 2);
+}
 __device__ __forceinline__ ObsGeo load_geo_l1(const FPlanes &F, int i, double fx, double fy) {
   const double2 a = __ldg(F.g0 + i), b = __ldg(F.g1 + i);
   ObsGeo o;
@@ -400,17 +424,16 @@ k_sp_schur(int n_blk, int n_cam, const int32_t *__restrict__ blk_ptr, const unsi
         p = pn;
         e = en;
       }
+      // column scales (compile-time indices), then the warp sum as a recursive halving: every lane ends up with at most two
+      // COMPLETE entries of the block (37 shuffled doubles instead of the 180 of 36 butterflies; SASS of the butterfly
+      // version: 722 SHFL, a quarter of the instructions of a block with ~155 pairs).  Fixed tree: deterministic.
 #pragma unroll
-      for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
-      // lanes 0..35 -> lane k writes entry k (two rounds)
-      double *Sb = S + 36 * (size_t)gid[b];
-#pragma unroll
-      for (int k = 0; k < 36; ++k) {
-        if (lane == (k & 31)) {
-          const int r = k / 6, c = k - 6 * (k / 6);
-          Sb[k] = -(acc[k] * (ri.s[r] * rj.s[c]));  // k_sp_add_diag puts U on the diagonal blocks
-        }
-      }
+      for (int k = 0; k < 36; ++k) acc[k] *= ri.s[k / 6] * rj.s[k % 6];
+      int idx, cnt;
+      sp_reduce_scatter36(acc, lane, idx, cnt);
+      double *Sb = S + 36 * (size_t)gid[b] + idx;
+      if (cnt > 0) Sb[0] = -acc[0];  // k_sp_add_diag puts U on the diagonal blocks
+      if (cnt > 1) Sb[1] = -acc[1];
     }
   }
 }
