@@ -115,6 +115,34 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BA_FULL, v, o);
   return v;
 }
+// Warp sum of N per-lane values by recursive halving: at every level a lane keeps one half of its values and receives the
+// partner's partial sums of that half, so 32 lanes end up with the N COMPLETE sums spread over them -- lane l holds entries
+// idx .. idx + cnt - 1 in acc[0 .. cnt-1], cnt <= ceil(N / 32).  About N shuffled doubles instead of the 5 N of N butterflies
+// (k_sp_schur's 36 butterflies were a quarter of its instructions).  Fixed tree: deterministic.
+template <int N, int MASK>
+__device__ __forceinline__ void warp_halve(double *acc, int lane, int &idx, int &cnt) {
+  constexpr int H = (N + 1) / 2;
+  const bool up = (lane & MASK) != 0;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const double lo = acc[i], hi = (i + H < N) ? acc[i + H] : 0.0;
+    const double keep = up ? hi : lo, send = up ? lo : hi;
+    acc[i] = keep + __shfl_xor_sync(BA_FULL, send, MASK);
+  }
+  if (up) {
+    idx += H;
+    cnt = cnt > H ? cnt - H : 0;
+  } else {
+    cnt = cnt < H ? cnt : H;
+  }
+  if constexpr (MASK > 1) warp_halve<H, MASK / 2>(acc, lane, idx, cnt);
+}
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(double (&acc)[N], int lane, int &idx, int &cnt) {
+  idx = 0;
+  cnt = N;
+  warp_halve<N, 16>(acc, lane, idx, cnt);
+}
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(BA_FULL, v, o));

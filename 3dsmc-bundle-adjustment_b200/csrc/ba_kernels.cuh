@@ -383,13 +383,12 @@ k_cam_blocks(int n_items, const BaItem *__restrict__ items, JPlanes J, double *_
       acc[60] += k1.y * r.y;
     }
   }
-#pragma unroll
-  for (int k = 0; k < NV; ++k) acc[k] = warp_sum(acc[k]);
-  if (lane == 0) {
-    double *o = part + (size_t)wid * NV;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) o[k] = acc[k];
-  }
+  // warp sum by recursive halving (27 / 61 butterflies otherwise): every lane writes the one or two entries it ends up with
+  int idx, cnt;
+  warp_reduce_scatter<NV>(acc, lane, idx, cnt);
+  double *o = part + (size_t)wid * NV + idx;
+  if (cnt > 0) o[0] = acc[0];
+  if (NV > 32 && cnt > 1) o[1] = acc[1];
 }
 
 // per camera: add item partials in order; U (full 6x6), g_c, U_ck, clamped LM diagonal

@@ -188,25 +188,26 @@ kf_cam_blocks(int n_items, const BaItem *__restrict__ items, FPlanes F, const do
 #pragma unroll
     for (int a = 0; a < 6; ++a) acc[21 + a] += j0[a] * r.x + j1[a] * r.y;
   }
-#pragma unroll
-  for (int k = 0; k < 27; ++k) acc[k] = warp_sum(acc[k]);
-  if (lane == 0) {
-    // apply the column scale once per item: U_ab *= s_a s_b, g_a *= s_a
+  {
+    // apply the column scale once per item and lane (compile-time indices): U_ab *= s_a s_b, g_a *= s_a; then the warp sum by
+    // recursive halving (27 butterflies were half of this kernel's instructions): lane l writes the entry it ends up with
     const double *s = geo + (size_t)BA_CAMREC * it.cam + 9;
     double sv[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) sv[k] = s[k];
-    double *o = part + (size_t)wid * 27;
+    for (int k = 0; k < 6; ++k) sv[k] = ldg1(s + k);
     int u = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
       for (int b = a; b < 6; ++b) {
-        o[u] = acc[u] * (sv[a] * sv[b]);
+        acc[u] *= sv[a] * sv[b];
         ++u;
       }
 #pragma unroll
-    for (int a = 0; a < 6; ++a) o[21 + a] = acc[21 + a] * sv[a];
+    for (int a = 0; a < 6; ++a) acc[21 + a] *= sv[a];
+    int idx, cnt;
+    warp_reduce_scatter<27>(acc, lane, idx, cnt);
+    if (cnt > 0) part[(size_t)wid * 27 + idx] = acc[0];
   }
 }
 
