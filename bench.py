@@ -237,40 +237,47 @@ def executed_roofline(workload, phase_ms, n_iter, solver_used, full, n_pairs, n_
     total = sum(per.values())
     table = {}
 
-    def hbm(name, kernels, nbytes, ms, bound, note=None):
-        table[name] = {"kernels": kernels, "bound": bound, "bytes": nbytes, "ms": ms, "share_of_step": ms / total if total else None,
+    def hbm(name, kernels, nbytes, ms, limiter, note=None):
+        # `bound` is the contract's enum (every phase of this path moves bytes: "hbm", against the measured copy bandwidth);
+        # `limiter` says what actually holds the phase back when that is not bandwidth
+        table[name] = {"kernels": kernels, "bound": "hbm", "limiter": limiter, "bytes": nbytes, "ms": ms,
+                       "share_of_step": ms / total if total else None,
                        "achieved": nbytes / ms / 1e6 if ms > 0 else None, "peak": peak, "unit": "GB/s",
                        "frac": nbytes / ms / 1e6 / peak if ms > 0 else None, "note": note}
 
     if solver_used in (3, 4):
         hbm("schur_complement", "k_sp_schur (+ k_sp_add_diag)", 124.0 * n_pairs, per.get("schur_complement", 0.0),
-            "l2 / hbm gathers (latency)", "124 B per same-point observation pair: pair 8 + point id 4 + two factored records 64 + Vs 48")
+            "latency of dependent gathers (pair -> two observation records + Vs) at 8 warps per SM; operands mostly hit L1 / L2",
+            "124 B per same-point observation pair: pair 8 + point id 4 + two factored records 64 + Vs 48")
     if solver_used == 4 and spchol:
         # (one persistent launch does factorisation and both substitutions; with BA_SPCHOL_LEVELS=1 the backward
         # substitution shows up as its own phase -- added here either way)
         ms = per.get("linear_solve_factor_or_pcg", 0.0) + per.get("linear_solve_substitution", 0.0)
-        table["linear_solve"] = {
-            "kernels": "k_spchol_rhs, k_spchol_tree (factor / update / substitution items of the supernodal tree, one persistent launch)",
-            "bound": "fp64 pipe of single SMs along the dependent chain of tree levels (latency)",
-            "flops": spchol.get("flops"), "ms": ms, "share_of_step": ms / total if total else None,
-            "achieved": spchol.get("flops", 0) / ms / 1e9 if ms > 0 else None, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
-            "frac": spchol.get("flops", 0) / ms / 1e9 / FP64_NOMINAL_TFLOPS if ms > 0 else None,
-            "note": "fp64 multiply-adds x 2 of the supernodal factorisation over the time of factorisation + substitutions; peak = "
-                    "nominal B200 fp64 (not measured); %d nodes in %d levels, critical path %d block operations of %d total"
-                    % (spchol.get("nodes", 0), spchol.get("levels", 0), spchol.get("critical_path_block_ops", 0),
-                       spchol.get("flops", 0) // 432)}
+        # algorithmic bytes of one factorisation + both substitutions, 288 B per 6x6 block: stored blocks of S read, panels
+        # written, their border rows read again by the update items, update matrices written and read (extend-add), panels
+        # read by the backward substitution
+        n_sblk = spchol.get("s_blocks", 0)
+        blocks = n_sblk + 3 * spchol.get("panel_blocks", 0) + 2 * spchol.get("update_blocks", 0)
+        flops = spchol.get("flops", 0)
+        hbm("linear_solve", "k_spchol_rhs, k_spchol_tree (factor / update / substitution items of the supernodal tree, one persistent launch)",
+            288.0 * blocks, ms, "latency: dependent chain of %d tree levels on single SMs (fp64); the data stays in L2" % spchol.get("levels", 0),
+            "288 B x (stored blocks of S + 3 x panel blocks + 2 x update-matrix blocks); %d nodes in %d levels, critical path %d block "
+            "operations of %d total; fp64: %.2f GFLOP -> %.2f TFLOP/s of nominal %.0f"
+            % (spchol.get("nodes", 0), spchol.get("levels", 0), spchol.get("critical_path_block_ops", 0), flops // 432, flops / 1e9,
+               flops / ms / 1e9 if ms > 0 else 0.0, FP64_NOMINAL_TFLOPS))
+        table["linear_solve"]["flops"] = flops
     elif solver_used == 3 and pcg_total > 0:
         ms = per.get("linear_solve_substitution", 0.0) + per.get("linear_solve_factor_or_pcg", 0.0)
         hbm("pcg", "k_pcg_sparse_persistent (all PCG iterations of a step)", (n_ent * 344.0 + n_c * 96.0) * pcg_total / n_iter, ms,
-            "l2 / latency (S is L2-resident)", "per PCG iteration: 288 B block + 8 B entry + 48 B gathered vector per row entry")
+            "L2 bandwidth / latency (S is L2-resident)", "per PCG iteration: 288 B block + 8 B entry + 48 B gathered vector per row entry")
     # factored store: kf_linearize x2 (96 B/obs each), kf_pt_blocks (48 B/obs + 96 B/pt), kf_cam_blocks (48 B/obs), state copies
     hbm("accept_relinearize", "k_accept, kf_linearize<0>, kf_pt_blocks, kf_linearize<1>, kf_cam_blocks, k_cam_blocks_fin, k_state_norms",
-        (96.0 + 96.0 + 48.0 + 48.0) * n_o + (96.0 + 2 * 48.0) * n_p + (288.0 + 2 * 112.0) * n_c, per.get("accept_relinearize", 0.0), "hbm")
+        (96.0 + 96.0 + 48.0 + 48.0) * n_o + (96.0 + 2 * 48.0) * n_p + (288.0 + 2 * 112.0) * n_c, per.get("accept_relinearize", 0.0), "bandwidth + L1 request rate of the point-major gathers")
     hbm("back_substitution_model_cost", "k_pack_camx, kf_schur_pass1<1,0>, kf_model_cost, k_candidate, k_cost",
         (48.0 + 48.0 + 44.0) * n_o + (48.0 + 32.0 + 24.0 + 48.0) * n_p, per.get("back_substitution_model_cost", 0.0) + per.get("candidate_cost", 0.0),
-        "hbm")
-    hbm("point_inverse", "kf_point_inverse", (48.0 + 24.0 + 24.0 + 24.0 + 48.0 + 48.0 + 32.0) * n_p, per.get("point_inverse", 0.0), "hbm")
-    hbm("reduced_rhs", "kf_schur_pass2", 68.0 * n_o + 96.0 * n_c, per.get("reduced_rhs", 0.0), "hbm")
+        "bandwidth + L1 request rate of the point-major gathers")
+    hbm("point_inverse", "kf_point_inverse", (48.0 + 24.0 + 24.0 + 24.0 + 48.0 + 48.0 + 32.0) * n_p, per.get("point_inverse", 0.0), "bandwidth")
+    hbm("reduced_rhs", "kf_schur_pass2", 68.0 * n_o + 96.0 * n_c, per.get("reduced_rhs", 0.0), "bandwidth")
     live = {k: v for k, v in table.items() if v["ms"] and v["ms"] > 0}
     if not live:
         return None, table
@@ -281,9 +288,10 @@ def executed_roofline(workload, phase_ms, n_iter, solver_used, full, n_pairs, n_
     dom = max(live, key=lambda k: live[k]["ms"])
     d = live[dom]
     traffic = NCU_TRAFFIC_R02_CFG5.get(dom) if workload == "cfg5" else None
-    roof = {"kernel": "%s: %s" % (dom, d["kernels"]), "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+    roof = {"kernel": "%s: %s" % (dom, d["kernels"]), "bound": d["bound"], "limiter": d.get("limiter"), "achieved": d["achieved"],
+            "peak": d["peak"], "unit": d["unit"],
             "frac": d["frac"], "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
-            "peak_source": peak_src if d["unit"] == "GB/s" else "nominal fp64 peak", "share_of_step": d["share_of_step"],
+            "peak_source": peak_src, "note": d.get("note"), "share_of_step": d["share_of_step"],
             "ms_per_step": d["ms"],
             "timing": "CUDA events recorded on the solver stream at the phase boundaries of every LM iteration of the timed solve "
                       "(ba_gpu_phase_times): the phase as executed, not a stand-alone launch",
@@ -503,6 +511,8 @@ def main():
 
     n_ent, n_blk = s.sparse_stats()
     n_pairs = s.sparse_pairs()
+    if spchol:
+        spchol["s_blocks"] = n_blk
     roof, phase_table = executed_roofline(args.workload, phase_ms, n_iter, solver_used, full, n_pairs, n_ent, spchol,
                                           int(summ.total_linear_iters), peak, peak_src)
     if roof is None:  # windowed explicit solver (graph replay: no phase events): the stand-alone kernel hook
