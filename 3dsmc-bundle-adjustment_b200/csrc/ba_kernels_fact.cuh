@@ -184,9 +184,12 @@ kf_cam_blocks(int n_items, const BaItem *__restrict__ items, FPlanes F, const do
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int b = a; b < 6; ++b) acc[u++] += j0[a] * j0[b] + j1[a] * j1[b];
+      for (int b = a; b < 6; ++b) {
+        acc[u] = fma(j1[a], j1[b], fma(j0[a], j0[b], acc[u]));
+        ++u;
+      }
 #pragma unroll
-    for (int a = 0; a < 6; ++a) acc[21 + a] += j0[a] * r.x + j1[a] * r.y;
+    for (int a = 0; a < 6; ++a) acc[21 + a] = fma(j1[a], r.y, fma(j0[a], r.x, acc[21 + a]));
   }
   {
     // apply the column scale once per item and lane (compile-time indices): U_ab *= s_a s_b, g_a *= s_a; then the warp sum by

@@ -418,6 +418,8 @@ k_sp_schur(int n_blk, int n_cam, const int32_t *__restrict__ blk_ptr, const unsi
         for (int c = 0; c < 6; ++c) {
           const double h0 = m00 * b0[c] + m01 * b1[c], h1 = m10 * b0[c] + m11 * b1[c];
 #pragma unroll
+          // (kept as product-sum + add: an fma chain through acc -- two DFMA instead of DMUL + DFMA + DADD -- measured slower,
+          //  1.03 -> 1.13 ms: with two warps per scheduler the longer dependent chain per accumulator costs more than the instruction)
           for (int r = 0; r < 6; ++r) acc[r * 6 + c] += a0[r] * h0 + a1[r] * h1;
         }
         pr = prn;
