@@ -44,6 +44,10 @@ enum {
   SPN_U_HI = 15
 };
 
+#ifndef SPSYM_STAMP
+#define SPSYM_STAMP(name)  // (profiling hook of the symbolic phase: a harness defines it before including this header)
+#endif
+
 struct SpSymbolic {
   int n_cam = 0, n_nodes = 0, n_levels = 0;
   std::vector<int32_t> perm, pos;  // position -> camera, camera -> position
@@ -129,6 +133,7 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
   const int n = n_cam;
   if (n <= 0) return S;
   const spsym::Graph g = spsym::build_graph(n, n_blk, bi, bj);
+  SPSYM_STAMP("graph");
   // ---- 1. ordering
   {
     std::vector<int32_t> pm((size_t)n + 2);
@@ -141,9 +146,11 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
     S.pos.assign(n, -1);
     for (int k = 0; k < n; ++k) S.pos[S.perm[k]] = k;
   }
+  SPSYM_STAMP("ordering");
   // ---- 2. symbolic factorisation in elimination order
   // adjacency in elimination positions, CSR: adj_ptr[k] .. adj_ptr[k + 1] = later-eliminated neighbours of position k
-  std::vector<std::vector<int32_t>> st(n);
+  // column structures live in one arena (st_off / st_len); a column's structure is the sorted union of its adjacency and its
+  // children's structures without the column itself -- sorted merges (a child's first entry IS its parent), no per-column vectors
   std::vector<int32_t> adj_ptr((size_t)n + 1, 0), adj((size_t)g.up.size());
   for (int i = 0; i < n; ++i)
     for (int e = g.up_ptr[i]; e < g.up_ptr[i + 1]; ++e) adj_ptr[std::min(S.pos[i], S.pos[g.up[e]]) + 1]++;
@@ -156,37 +163,30 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
         adj[cur[std::min(a, b)]++] = std::max(a, b);
       }
   }
-  std::vector<int32_t> parent(n, -1), nchild(n, 0), mark(n, -1), child_head(n, -1), child_next(n, -1);
+  std::vector<int32_t> parent(n, -1), nchild(n, 0), child_head(n, -1), child_next(n, -1), st_len(n, 0);
+  std::vector<int64_t> st_off(n, 0);
+  std::vector<int32_t> arena, ta, tb;
+  arena.reserve((size_t)n * 48 + 64);
   for (int k = 0; k < n; ++k) {
-    std::vector<int32_t> &s = st[k];
-    {
-      const size_t na = (size_t)(adj_ptr[k + 1] - adj_ptr[k]);
-      size_t guess = na;
-      for (int c = child_head[k]; c >= 0; c = child_next[c]) guess = std::max(guess, st[c].size() + na);
-      s.reserve(guess + 4);
+    ta.assign(adj.begin() + adj_ptr[k], adj.begin() + adj_ptr[k + 1]);
+    std::sort(ta.begin(), ta.end());
+    for (int c = child_head[k]; c >= 0; c = child_next[c]) {
+      const int32_t *cb = arena.data() + st_off[c] + 1, *ce = arena.data() + st_off[c] + st_len[c];  // (skips k itself)
+      tb.resize(ta.size() + (size_t)(ce - cb));
+      tb.resize((size_t)(std::set_union(ta.begin(), ta.end(), cb, ce, tb.begin()) - tb.begin()));
+      ta.swap(tb);
     }
-    mark[k] = k;
-    for (int e = adj_ptr[k]; e < adj_ptr[k + 1]; ++e) {
-      const int j = adj[e];
-      if (mark[j] != k) {
-        mark[j] = k;
-        s.push_back(j);
-      }
-    }
-    for (int c = child_head[k]; c >= 0; c = child_next[c])
-      for (int j : st[c])
-        if (j != k && mark[j] != k) {
-          mark[j] = k;
-          s.push_back(j);
-        }
-    std::sort(s.begin(), s.end());
-    if (!s.empty()) {
-      parent[k] = s[0];
-      nchild[s[0]]++;
-      child_next[k] = child_head[s[0]];
-      child_head[s[0]] = k;
+    st_off[k] = (int64_t)arena.size();
+    st_len[k] = (int32_t)ta.size();
+    arena.insert(arena.end(), ta.begin(), ta.end());
+    if (!ta.empty()) {
+      parent[k] = ta[0];
+      nchild[ta[0]]++;
+      child_next[k] = child_head[ta[0]];
+      child_head[ta[0]] = k;
     }
   }
+  SPSYM_STAMP("column structures");
   // ---- 3. supernodes
   // shared memory of a front: the panel (m + nb) x m blocks plus one more block column (the pivot column kept row-major)
   auto fits = [&](int m, int nb) { return (long long)(m + nb) * (m + 1) <= (long long)cap_blocks && m <= max_own; };
@@ -195,11 +195,11 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
   for (int k = 0; k < n;) {
     const int start = k;
     int m = 1;
-    if (!fits(1, (int)st[k].size())) {
+    if (!fits(1, st_len[k])) {
       S.error = 1;
       return S;
     }
-    while (k + 1 < n && parent[k] == k + 1 && nchild[k + 1] == 1 && fits(m + 1, (int)st[k + 1].size())) {
+    while (k + 1 < n && parent[k] == k + 1 && nchild[k + 1] == 1 && fits(m + 1, st_len[k + 1])) {
       ++k;
       ++m;
     }
@@ -217,7 +217,7 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
   for (int id = 0; id < nn; ++id) {
     int32_t *N = S.node.data() + (size_t)id * SPSYM_NODE_INTS;
     const int k1 = k0s[id] + ms[id] - 1;
-    const std::vector<int32_t> &b = st[k1];
+    const std::vector<int32_t> b(arena.begin() + st_off[k1], arena.begin() + st_off[k1] + st_len[k1]);
     N[SPN_K0] = k0s[id];
     N[SPN_M] = ms[id];
     N[SPN_NB] = (int)b.size();
@@ -241,6 +241,7 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
     S.max_m = std::max(S.max_m, ms[id]);
     S.max_nb = std::max(S.max_nb, (int)b.size());
   }
+  SPSYM_STAMP("supernodes");
   // levels: children have smaller ids than parents
   for (int id = 0; id < nn; ++id) {
     const int p = S.node[(size_t)id * SPSYM_NODE_INTS + SPN_PARENT];
@@ -257,6 +258,7 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
     std::vector<int32_t> cur(S.level_ptr.begin(), S.level_ptr.end() - 1);
     for (int id = 0; id < nn; ++id) S.level_nodes[cur[level[id]]++] = id;
   }
+  SPSYM_STAMP("levels");
   // ---- 4. children, extend-add maps
   for (int id = 0; id < nn; ++id) {
     int32_t *N = S.node.data() + (size_t)id * SPSYM_NODE_INTS;
@@ -299,6 +301,7 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
       S.inv.push_back((it != cb + nb && *it == pb[i]) ? (int)(it - cb) : -1);
     }
   }
+  SPSYM_STAMP("children, extend-add maps");
   // ---- 5. entries of S per front: (block | flags, local row, local column, camera of the column)
   //         flags: bit 31 = use the stored block transposed, bit 30 = diagonal block; block 0x3fffffff = no stored block
   {
@@ -360,6 +363,7 @@ inline SpSymbolic spsym_build(int n_cam, int n_blk, const int32_t *bi, const int
         e[3] = cam;
       }
   }
+  SPSYM_STAMP("entries");
   // ---- cost model (block operations of 216 multiply-adds)
   {
     std::vector<double> lev_max(nlev, 0.0);
