@@ -67,15 +67,26 @@ def covisibility_blocks(cam_idx, pt_idx, n_cam, fixed_cam):
     return (k // n_cam).astype(np.int32), (k % n_cam).astype(np.int32)
 
 
-def factor_solve(sym, blocks, dsq, b):
-    """blocks [n_blk,6,6] stored upper blocks of S, dsq [n_cam,6] damping, b [n_cam,6] -> y [n_cam,6]
-    solving (S + diag(dsq)) y = b through the supernodal multifrontal scheme."""
-    n = sym.n_cam
-    nn = sym.n_nodes
-    panels, Us, rus = [None] * nn, [None] * nn, [None] * nn
-    z = np.zeros((n, 6))  # by position
-    for lvl in range(sym.n_levels):
-        for id_ in sym.level_nodes[sym.level_ptr[lvl]:sym.level_ptr[lvl + 1]]:
+class Multifrontal:
+    """Numeric phase, node by node, with the state the kernels keep in global memory (panels, update matrices, rhs updates, z, y by
+    position) -- so that the nodes can be processed in the groups of the distributed factorisation (own subtrees, exchange of the
+    subtree roots' update matrices, top part, backward substitution top-down)."""
+
+    def __init__(self, sym, blocks, dsq, b):
+        self.sym, self.blocks, self.dsq, self.b = sym, blocks, dsq, b
+        nn = sym.n_nodes
+        self.panels, self.Us, self.rus = [None] * nn, [None] * nn, [None] * nn
+        self.z = np.zeros((sym.n_cam, 6))      # by position
+        self.ypos = np.zeros((sym.n_cam, 6))   # by position
+
+    def nodes_bottom_up(self, keep):
+        sym = self.sym
+        return [id_ for lvl in range(sym.n_levels) for id_ in sym.level_nodes[sym.level_ptr[lvl]:sym.level_ptr[lvl + 1]] if keep(id_)]
+
+    def factor(self, ids):
+        sym, blocks, dsq, b = self.sym, self.blocks, self.dsq, self.b
+        panels, Us, rus, z = self.panels, self.Us, self.rus, self.z
+        for id_ in ids:
             N = sym.node[id_]
             k0, m, nb = N[K0], N[M], N[NB]
             F = np.zeros((m + nb, m, 6, 6))
@@ -138,9 +149,10 @@ def factor_solve(sym, blocks, dsq, b):
                         if inv[j] >= 0:
                             U[i, j] += Us[ch][inv[i], inv[j]]
             panels[id_], Us[id_], rus[id_] = F, U, ru
-    ypos = np.zeros((n, 6))
-    for lvl in range(sym.n_levels - 1, -1, -1):
-        for id_ in sym.level_nodes[sym.level_ptr[lvl]:sym.level_ptr[lvl + 1]]:
+
+    def solve(self, ids_top_down):
+        sym, panels, z, ypos = self.sym, self.panels, self.z, self.ypos
+        for id_ in ids_top_down:
             N = sym.node[id_]
             k0, m, nb = N[K0], N[M], N[NB]
             F = panels[id_]
@@ -153,6 +165,27 @@ def factor_solve(sym, blocks, dsq, b):
                 for r in range(k + 1, m):
                     w[k] -= F[r, k].T @ ypos[k0 + r]
                 ypos[k0 + k] = np.linalg.solve(F[k, k].T, w[k])
-    y = np.zeros((n, 6))
-    y[sym.perm] = ypos
-    return y
+
+    def y(self):
+        out = np.zeros((self.sym.n_cam, 6))
+        out[self.sym.perm] = self.ypos
+        return out
+
+
+def factor_solve(sym, blocks, dsq, b):
+    """blocks [n_blk,6,6] stored upper blocks of S, dsq [n_cam,6] damping, b [n_cam,6] -> y [n_cam,6]
+    solving (S + diag(dsq)) y = b through the supernodal multifrontal scheme."""
+    mf = Multifrontal(sym, blocks, dsq, b)
+    order = mf.nodes_bottom_up(lambda id_: True)
+    mf.factor(order)
+    mf.solve(order[::-1])
+    return mf.y()
+
+
+def block_owner(sym, part):
+    """Part that assembles every stored block of S (-1: top part): the part of the node that owns the earlier-eliminated of the
+    block's two cameras -- the rule of build_spchol() (csrc/ba_gpu.cu) for the sparse exchange of S."""
+    node_of = np.zeros(sym.n_cam, dtype=np.int64)
+    for id_, N in enumerate(sym.node):
+        node_of[N[K0]:N[K0] + N[M]] = id_
+    return part[node_of[np.minimum(sym.pos[sym.bi], sym.pos[sym.bj])]]
