@@ -190,7 +190,11 @@ int ba_gpu_schur_matvec(ba_gpu_ctx *ctx, double radius, const double *x, double 
  * same conventions as ba_gpu_schur_matvec: ba_gpu_schur_matvec(radius, ba_gpu_schur_solve(radius, b)) == b */
 int ba_gpu_schur_solve(ba_gpu_ctx *ctx, double radius, const double *rhs, double *y);
 /* structure of the sparse Cholesky of the last upload (zeros when another solver is in force): info[0..10] as
- * ba_sparse_symbolic_info, info[11] = host microseconds of the symbolic phase */
+ * ba_sparse_symbolic_info, info[11] = host microseconds of the symbolic phase, info[12] = parts of the subtree-to-rank
+ * partition in force (1: one queue), info[13] = 1 when the factorisation is distributed over the ranks of the communicator
+ * (every rank its own subtrees, top part replicated), info[14] = cameras of the top part, info[15] = bytes of update matrices +
+ * right-hand-side updates exchanged per solve, info[16] = blocks of S summed over ranks per LM iteration (of all stored blocks
+ * when the factorisation is replicated) */
 int ba_gpu_spchol_info(const ba_gpu_ctx *ctx, int64_t info[24]);
 /* out7[i] = pose7[i] * exp(delta6[i]) on the device (Sophus semantics) */
 int ba_gpu_se3_plus(ba_gpu_ctx *ctx, int32_t n, const double *pose7,
