@@ -189,3 +189,43 @@ def block_owner(sym, part):
     for id_, N in enumerate(sym.node):
         node_of[N[K0]:N[K0] + N[M]] = id_
     return part[node_of[np.minimum(sym.pos[sym.bi], sym.pos[sym.bj])]]
+
+
+def distributed_solve_inprocess(sym, part, world, blocks, dsq, b, touch):
+    """The protocol of the distributed factorisation with the ranks simulated one after the other in this
+    process: touch[r, blk] = rank r's points contribute to the block (contributions sum to `blocks`).  Returns (y, exchanged
+    blocks of S).  Blocks a rank neither assembles itself nor shares in the top part are NaN for it."""
+    owner = block_owner(sym, part)
+    share = touch.sum(axis=0)
+    assert (share > 0).all()
+    local = [np.where(touch[r][:, None, None], blocks / share[:, None, None], 0.0) for r in range(world)]
+    mask = np.zeros(len(blocks), dtype=bool)
+    for r in range(world):
+        mask |= touch[r] & (owner != r)
+    summed = sum(l[mask] for l in local)
+    mfs = []
+    for r in range(world):
+        S = local[r].copy()
+        S[mask] = summed
+        S[~((owner == r) | (owner == -1))] = np.nan
+        mf = Multifrontal(sym, S, dsq, b)
+        mf.factor(mf.nodes_bottom_up(lambda id_: part[id_] == r))
+        mfs.append(mf)
+    for id_, N in enumerate(sym.node):  # exchange of the subtree roots
+        if part[id_] >= 0 and N[PARENT] >= 0 and part[N[PARENT]] == -1:
+            src = mfs[part[id_]]
+            for r in range(world):
+                mfs[r].Us[id_], mfs[r].rus[id_] = src.Us[id_], src.rus[id_]
+    ypos = np.zeros((sym.n_cam, 6))
+    for r in range(world):
+        mf = mfs[r]
+        top = mf.nodes_bottom_up(lambda id_: part[id_] == -1)
+        mf.factor(top)
+        mf.solve(top[::-1])
+        mf.solve(mf.nodes_bottom_up(lambda id_: part[id_] == r)[::-1])
+        for id_, N in enumerate(sym.node):
+            if part[id_] == r or (part[id_] == -1 and r == 0):
+                ypos[N[K0]:N[K0] + N[M]] += mf.ypos[N[K0]:N[K0] + N[M]]
+    y = np.zeros((sym.n_cam, 6))
+    y[sym.perm] = ypos
+    return y, int(mask.sum())

@@ -124,3 +124,48 @@ def test_subtree_partition(cfg, scale, leaf):
             if len(cams):
                 med.append(np.median(cams))
         assert med == sorted(med)
+
+
+def _banded_blocks(n_cam, widths, rng, gaps=()):
+    """Upper block pattern of a camera sequence whose co-visibility reaches `widths[i]` cameras ahead of camera i; cameras in
+    `gaps` see nothing ahead (the sequence falls apart into independent pieces there)."""
+    keys = set()
+    for i in range(n_cam):
+        keys.add((i, i))
+        if i in gaps:
+            continue
+        for d in range(1, widths[i] + 1):
+            if i + d < n_cam and not any(i < g_ < i + d for g_ in gaps) and rng.random() < 0.85:
+                keys.add((i, i + d))
+    k = sorted(keys)
+    return np.array([a for a, _ in k], dtype=np.int32), np.array([b_ for _, b_ in k], dtype=np.int32)
+
+
+@pytest.mark.parametrize("seed,n_cam,maxw,gaps", [(1, 90, 4, ()), (2, 140, 7, ()), (3, 120, 3, (40, 41, 85)), (4, 60, 10, ()),
+                                                  (5, 200, 2, (99,))])
+def test_distributed_protocol_on_varied_structures(seed, n_cam, maxw, gaps):
+    """Partition + exchange rule + subtree / top split (simulated ranks, numpy emulation on the C-ABI's symbolic tables) on band
+    widths that vary along the sequence and on sequences that fall apart into independent pieces (several tree roots)."""
+    from spchol_emulation import distributed_solve_inprocess
+    rng = np.random.default_rng(seed)
+    widths = rng.integers(1, maxw + 1, size=n_cam)
+    bi, bj = _banded_blocks(n_cam, widths, rng, set(gaps))
+    sym = Symbolic(n_cam, bi, bj, leaf=5, cap=300, max_own=8)
+    A, blocks, dsq = _random_spd(n_cam, bi, bj, rng)
+    b = rng.normal(size=(n_cam, 6))
+    yref = np.linalg.solve(A, b.reshape(-1)).reshape(-1, 6)
+    done = 0
+    for world, (got, part, _) in sym.partitions.items():
+        if got != world:
+            continue
+        # every rank's points touch the blocks of its stretch of the sequence (with overlap); stragglers go to one rank
+        touch = np.zeros((world, len(bi)), dtype=bool)
+        for r in range(world):
+            lo, hi = r * n_cam // world - maxw, (r + 1) * n_cam // world + maxw
+            touch[r] = (bi >= lo) & (bi < hi) & (bj >= lo) & (bj < hi)
+        none = ~touch.any(axis=0)
+        touch[np.minimum(bi[none] * world // n_cam, world - 1), np.nonzero(none)[0]] = True
+        y, n_x = distributed_solve_inprocess(sym, part, world, blocks, dsq, b, touch)
+        assert np.max(np.abs(y - yref)) <= 1e-9 * np.max(np.abs(yref)), (world, n_x)
+        done += 1
+    assert done >= 1
