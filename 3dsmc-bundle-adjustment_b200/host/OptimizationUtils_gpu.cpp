@@ -210,6 +210,11 @@ bool windowOptimize(ceresGlobalProblem &globalProblem, int kf_i, int kf_f, vecto
   opt.WEIGHT_INTRINSICS = globalProblem.WEIGHT_INTRINSICS;
   opt.max_num_iterations = globalProblem.options.max_num_iterations;
   opt.eta = globalProblem.options.eta;
+  // convergence tolerances travel in ceres::Solver::Options as they did for ceres::Solve (the reference leaves them at
+  // Ceres' defaults, headers/BundleAdjustmentConfig.h:61-67; bench/ceres_baseline.cpp sets them to zero for fixed-count runs)
+  opt.function_tolerance = globalProblem.options.function_tolerance;
+  opt.gradient_tolerance = globalProblem.options.gradient_tolerance;
+  opt.parameter_tolerance = globalProblem.options.parameter_tolerance;
   opt.use_depth_prior = 1;       // DepthPrior residual per observation (:288-294)
   opt.optimize_intrinsics = 1;   // intrinsics are a free block with a prior (:236-241)
   opt.solver = BA_SOLVER_AUTO;   // SPARSE_SCHUR == exact Schur step

@@ -141,6 +141,9 @@ struct Solver {
     bool minimizer_progress_to_stdout = false;
     int max_num_iterations = 50;
     double eta = 1e-1;
+    double function_tolerance = 1e-6;   // (Ceres 2.0.0 defaults, solver.h)
+    double gradient_tolerance = 1e-10;
+    double parameter_tolerance = 1e-8;
     TrustRegionStrategyType trust_region_strategy_type = LEVENBERG_MARQUARDT;
     int num_threads = 1;
   };
