@@ -10,7 +10,7 @@
 // them against each other (north-star tolerance: poses 1e-6 m / 1e-6 rad) -- the end-to-end parity check against real
 // Ceres that cannot be run inside this repository's container.
 //
-//   ceres_baseline <sequence.bin> <result.bin> [--window 20] [--every 10] [--iterations 10] [--global] [--tolerances]
+//   ceres_baseline <sequence.bin> <result.bin> [--window 20] [--every 10] [--iterations 10] [--passes 2] [--global] [--tolerances]
 //
 // sequence.bin is written by scripts/dump_sequence.py (little endian): int32 magic 0xBA5E0001, n_kf, n_obs, n_lm;
 // int32 kf_ptr[n_kf+1]; int32 lm[n_obs] (landmark id per local feature, insertion order); float uv[2 n_obs];
@@ -22,6 +22,7 @@
 #include "../3dsmc-bundle-adjustment_b200/host/compat/reference_types.h"
 #endif
 
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -41,16 +42,17 @@ bool rd(FILE *f, std::vector<T> &v, size_t n) {
 
 int main(int argc, char **argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: %s sequence.bin result.bin [--window N] [--every N] [--iterations N] [--global] [--tolerances]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s sequence.bin result.bin [--window N] [--every N] [--iterations N] [--passes N] [--global] [--tolerances]\n", argv[0]);
     return 2;
   }
-  int window = 20, every = 10, iterations = 10;
+  int window = 20, every = 10, iterations = 10, passes = 2;  // (pass 1 warms up: device context, allocations, caches)
   bool global = false, tolerances = false;
   for (int a = 3; a < argc; ++a) {
     const std::string s = argv[a];
     if (s == "--window" && a + 1 < argc) window = std::atoi(argv[++a]);
     else if (s == "--every" && a + 1 < argc) every = std::atoi(argv[++a]);
     else if (s == "--iterations" && a + 1 < argc) iterations = std::atoi(argv[++a]);
+    else if (s == "--passes" && a + 1 < argc) passes = std::max(1, std::atoi(argv[++a]));
     else if (s == "--global") global = true;
     else if (s == "--tolerances") tolerances = true;
   }
@@ -76,13 +78,23 @@ int main(int argc, char **argv) {
   std::fclose(f);
   if (window > n_kf) window = n_kf;
 
+  double seconds = 0.0;
+  int calls = 0;
+  bool ok = true;
+  std::vector<KeyFrame> keyframes;
+  Map3D map;
+  Eigen::Vector4d intr0(intr[0], intr[1], intr[2], intr[3]), intr1 = intr0;
+  for (int pass = 0; pass < passes; ++pass) {  // (every pass starts from the recorded state; the last one is reported)
+  seconds = 0.0;
+  calls = 0;
+  keyframes.clear();
+  map.clear();
+  intr1 = intr0;
   // containers as the tracking front end leaves them (src/main.cpp:25-82, src/Map3D.cpp:29-74): key points, local 3-D points
   // (only z is read by the optimiser), local feature id -> landmark id in insertion order, landmarks by id
   std::unordered_map<int, int> lm_row;
   for (int l = 0; l < n_lm; ++l) lm_row[lm_id[l]] = l;
-  std::vector<KeyFrame> keyframes;
   keyframes.reserve(n_kf);
-  Map3D map;
   auto arrive = [&](int k) {
     keyframes.emplace_back();
     KeyFrame &kf = keyframes[k];
@@ -109,10 +121,6 @@ int main(int argc, char **argv) {
   gp.options.max_num_iterations = iterations;
   if (!tolerances)  // fixed iteration count: the throughput metric of BASELINE.json (LM iterations per second)
     gp.options.function_tolerance = gp.options.gradient_tolerance = gp.options.parameter_tolerance = 0.0;
-  Eigen::Vector4d intr0(intr[0], intr[1], intr[2], intr[3]), intr1 = intr0;
-  int calls = 0;
-  bool ok = true;
-  double seconds = 0.0;
   auto run = [&](int kf_i, int kf_f) {
     const auto t0 = std::chrono::steady_clock::now();
     ok = windowOptimize(gp, kf_i, kf_f, keyframes, map, intr0, intr1) && ok;
@@ -129,6 +137,7 @@ int main(int argc, char **argv) {
     }
     if (n_kf % every != 0) run(n_kf - window, n_kf - 1);  // leftovers, :169-175
   }
+  }  // passes
 
   // result: poses, landmarks (rows of the input table; NaN for landmarks nobody referenced), intrinsics
   FILE *o = std::fopen(argv[2], "wb");

@@ -166,6 +166,16 @@ def test_wrapper_compiles_with_reference_headers_macro(src):
     assert r.returncode == 0, r.stderr[-2000:]
 
 
+def test_reference_arm_program_compiles_against_the_reference_interface():
+    """bench/ceres_baseline.cpp (the reference's schedule through windowOptimize, linked either with the reference's own
+    OptimizationUtils.cpp + Ceres or with this drop-in) uses only what the reference's headers declare."""
+    import subprocess
+    src = os.path.join(ROOT, "bench", "ceres_baseline.cpp")
+    for extra in (["-DBA_USE_REFERENCE_HEADERS", "-I", os.path.join(ROOT, "tests", "ref_header_shim")], []):
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror"] + extra + [src], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+
+
 def test_no_raw_pointer_se3_constructor_anywhere():
     """Sophus::SE3 has no constructor from `const double*` (headers/sophus/se3.hpp:407-455): neither the compat class
     nor the wrapper may rely on one; raw storage goes through data() (se3_raw.h)."""
